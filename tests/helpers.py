@@ -1,0 +1,49 @@
+"""Shared test plumbing: product param buffers -> oracle dicts, seeded batches."""
+import numpy as np
+import torch
+
+from sisua_b200 import config as C
+from sisua_b200 import params as PR
+from sisua_b200 import synthetic as SY
+
+
+def oracle_params(cfg, flat, dtype=torch.float64):
+  return {k: torch.tensor(np.array(v), dtype=dtype) for k, v in PR.flat_to_dict(cfg, flat).items()}
+
+
+def oracle_moving(cfg, moving, dtype=torch.float64):
+  return {k: torch.tensor(np.array(v), dtype=dtype) for k, v in PR.moving_to_dict(cfg, moving).items()}
+
+
+def randomize_norm_params(cfg, flat, seed=3):
+  """Make gamma/beta/biases non-trivial so parity tests exercise them."""
+  rng = np.random.default_rng(seed)
+  d = PR.flat_to_dict(cfg, flat)
+  for e in C.param_layout(cfg)[0]:
+    if e.kind == "gamma":
+      d[e.name][...] = rng.uniform(0.5, 1.5, size=e.shape).astype(np.float32)
+    elif e.kind in ("beta", "bias"):
+      d[e.name][...] = rng.normal(0, 0.1, size=e.shape).astype(np.float32)
+  return flat
+
+
+def make_batch(cfg, B, seed=0, S=None, preset_stats=(6.42, 0.28), stress=False):
+  G, P, Z = cfg.n_genes, cfg.n_proteins, cfg.n_latent
+  if stress:
+    data = SY.stress_counts(B, G, P, seed=SY.DATA_SEED + seed)
+  else:
+    data = SY.realistic_counts(B, G, P, preset_stats[0], preset_stats[1], seed=SY.DATA_SEED + seed)
+  rng = np.random.default_rng(1000 + seed)
+  shape = (B,) if S is None else (S, B)
+  batch = dict(x=data["x"])
+  if P > 0:
+    batch["y"] = data["y"]
+    m = (rng.random(B) < 0.3).astype(np.uint8)
+    m[0] = 1
+    batch["mask"] = m
+  if cfg.model_kind == C.MODEL_SCVI:
+    batch["library"] = SY.library_stats(data["x"])
+    batch["eps_l"] = rng.standard_normal(shape).astype(np.float32)
+  if cfg.model_kind != C.MODEL_DCA:
+    batch["eps_z"] = rng.standard_normal(shape + (Z,)).astype(np.float32)
+  return batch
