@@ -1,0 +1,113 @@
+/* sisua_b200 — C ABI of the B200-native SISUA ELBO train / infer step.
+ *
+ * The reference (trungnt13/sisua) is pure Python and has no FFI of its own: the operator boundary of
+ * its hot path is the Python class surface of sisua.models.SingleCellModel
+ * (sisua/models/single_cell_model.py:67-306), whose arithmetic is delegated to odin-ai / TensorFlow.
+ * This library is what that class binds instead (via ctypes); each entry point
+ * names the reference call it replaces.  Conventions: plain pointers and sizes, every data pointer is
+ * caller-owned DEVICE memory (fp32 unless stated), all work is enqueued on the caller's CUDA stream
+ * with no hidden synchronisation, integer return codes (0 = ok) and sisua_last_error() for the text.
+ * One handle per GPU per host thread.
+ */
+#ifndef SISUA_B200_H_
+#define SISUA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SISUA_OK = 0, SISUA_ERR_INVALID = 1, SISUA_ERR_CUDA = 2, SISUA_ERR_UNSUPPORTED = 3, SISUA_ERR_STATE = 4 };
+
+enum { SISUA_MODEL_VAE = 0, SISUA_MODEL_SCVI = 1, SISUA_MODEL_DCA = 2, SISUA_MODEL_SISUA = 3 };
+enum { SISUA_XDIST_ZINBD = 0, SISUA_XDIST_NBD = 1 };
+enum { SISUA_YDIST_NB = 0, SISUA_YDIST_NBD = 1 };
+enum { SISUA_ACT_SOFTPLUS = 0, SISUA_ACT_SOFTPLUS1 = 1, SISUA_ACT_SOFTPLUS_P1 = 2, SISUA_ACT_EXP = 3,
+       SISUA_ACT_IDENTITY = 4 };
+enum { SISUA_GEMM_FP32_UNFUSED = 0, SISUA_GEMM_TC_3XTF32 = 1, SISUA_GEMM_TC_TF32 = 2 };
+
+/* Everything the step needs to know; built on the host from RVmeta / NetConf / configs/base.yaml
+ * (sisua/train.py:71-106).  Field-for-field identical to sisua_b200.config.StepConfig. */
+typedef struct sisua_step_config {
+  int32_t model_kind;        /* SISUA_MODEL_*  (sisua/models/{vae,scvi,dca}.py)                      */
+  int32_t n_genes;           /* G: event_shape of the transcriptomic RVmeta (train.py:79-89)         */
+  int32_t n_proteins;        /* P: label RV of SISUA (vae.py:40), 0 otherwise                        */
+  int32_t n_latent;          /* z: RVmeta(10,'diag') single_cell_model.py:77                         */
+  int32_t n_hidden;          /* NetConf units, 64 (single_cell_model.py:78-81)                       */
+  int32_t n_enc_layers, n_dec_layers, n_encl_layers;
+  int32_t batchnorm;         /* NetConf(batchnorm=True)                                              */
+  int32_t log_norm;          /* log1p on the counts (single_cell_model.py:126-131)                   */
+  int32_t x_dist, y_dist;    /* 'zinbd'|'nbd' ; 'nb'|'nbd' (configs/base.yaml:32-40)                 */
+  int32_t mean_act, disp_act, scale_act;   /* Q1 of SURVEY.md section 8a                             */
+  int32_t scvi_reapply_act;  /* Q2 */
+  int32_t mask_norm;         /* Q3: 0 mean over all cells, 1 over labelled cells                     */
+  int32_t clip_mode;         /* Q5: 0 per-variable clipnorm (Keras), 1 global norm                   */
+  int32_t gemm_mode;         /* SISUA_GEMM_*                                                         */
+  int32_t max_batch;         /* rows the private workspace is sized for (S*B for inference)          */
+  float bn_eps, bn_momentum; /* Keras BatchNormalization defaults 1e-3 / 0.99                        */
+  float input_dropout, enc_dropout, dec_dropout, encl_dropout;
+  float beta, alpha;         /* KL weight (single_cell_model.py:83), label weight (base.yaml:6)      */
+  float clip_library;        /* scvi.py:46,117                                                        */
+} sisua_step_config;
+
+typedef struct sisua_param_desc {
+  char name[32];
+  int64_t offset;            /* floats from the start of the flat buffer */
+  int32_t rows, cols, ld;    /* cols == 0 for vectors; ld = leading dimension in floats */
+  int32_t kind;              /* 0 weight, 1 bias, 2 gamma, 3 beta */
+} sisua_param_desc;
+
+typedef struct sisua_model* sisua_handle;
+
+/* Replaces SingleCellModel.__init__ -> BetaVAE/NetConf/DenseDistribution construction
+ * (single_cell_model.py:74-97, scvi.py:33-86).  Allocates only the private workspace. */
+int sisua_create(const sisua_step_config* cfg, int device, sisua_handle* out);
+int sisua_destroy(sisua_handle h);
+
+/* Names / offsets of every trainable tensor inside ONE flat fp32 buffer (what keras `model.weights`
+ * enumerates for save_weights/load_weights, single_cell_model.py:283-306). *n: in = capacity, out = count. */
+int sisua_param_layout(sisua_handle h, sisua_param_desc* out, int* n, int64_t* total_floats);
+
+/* Caller-owned device buffers: params/grads/adam_m/adam_v [total_floats]; bn_moving [n_bn,2,H]. */
+int sisua_bind_buffers(sisua_handle h, float* params, float* grads, float* adam_m, float* adam_v, float* bn_moving);
+
+/* One minibatch forward + backward: replaces the body of odin-ai's `optimize` under GradientTape —
+ * train_steps -> encode -> decode -> _elbo -> tape.gradient (call site
+ * single_cell_model.py:236).  x [B,G] counts; y [B,P] or NULL; library [B,2] (mean,var) or NULL;
+ * mask [B] bytes or NULL; eps_z [B,z]; eps_l [B] (scVI).  Outputs: terms [5,B] =
+ * (elbo | llk_x | llk_y | kl_z | kl_l), loss [1].  Gradients land in the bound `grads` buffer and
+ * BN moving statistics are updated.  The optimiser is a separate call so the host can all-reduce
+ * `grads` across GPUs in between. */
+int sisua_train_step(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                     const float* eps_z, const float* eps_l, int B, float* terms, float* loss, void* stream);
+
+/* Replaces one `self(**data, training=False, sample_shape=S)` call of SingleCellModel.predict
+ * (single_cell_model.py:176-181) plus the parameter tensors the returned distributions hold.
+ * eps_z [S,B,z], eps_l [S,B]; terms [5,S*B]; z_loc/z_scale [B,z]; out_mean/out_disp/out_pi [S*B,G]
+ * (NB mean = "imputed" mean of posterior.py:210-220, inverse dispersion, dropout logit), y_mean
+ * [S*B,P]; any output may be NULL. */
+int sisua_infer(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                const float* eps_z, const float* eps_l, int B, int S, float* terms, float* z_loc, float* z_scale,
+                float* lib_loc, float* lib_scale, float* out_mean, float* out_disp, float* out_pi, float* y_mean,
+                void* stream);
+
+/* Replaces keras Adam.apply_gradients with clipnorm (configs/base.yaml:46-50). grad_scale multiplies
+ * the gradients first (1/world_size after a sum all-reduce). t >= 1 sets the step index; t <= 0
+ * advances the device-side counter (CUDA-graph friendly). */
+int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float eps_hat, float clipnorm,
+                    float grad_scale, int64_t t, void* stream);
+
+/* Workspace peeks for tests (device pointers valid until destroy): "d" decoder output [rows,H],
+ * "delta1" first-layer pre-activation gradient. Returns NULL for unknown names. */
+const float* sisua_debug_buffer(sisua_handle h, const char* name);
+
+int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
+
+const char* sisua_last_error(sisua_handle h);
+const char* sisua_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SISUA_B200_H_ */

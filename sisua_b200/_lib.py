@@ -1,0 +1,61 @@
+"""ctypes binding of include/sisua_b200.h.  There is no CPU fallback: if the shared library is
+missing or a call fails the error is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .config import StepConfig
+
+_LIB = None
+
+EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
+           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_last_error", "sisua_version"]
+
+
+class ParamDesc(ctypes.Structure):
+  _fields_ = [("name", ctypes.c_char * 32), ("offset", ctypes.c_int64), ("rows", ctypes.c_int32),
+              ("cols", ctypes.c_int32), ("ld", ctypes.c_int32), ("kind", ctypes.c_int32)]
+
+
+class SisuaError(RuntimeError):
+  pass
+
+
+def lib_path() -> str:
+  return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsisua_b200.so")
+
+
+def load():
+  global _LIB
+  if _LIB is not None:
+    return _LIB
+  path = lib_path()
+  if not os.path.exists(path):
+    raise SisuaError(f"{path} is missing: run `python -m sisua_b200.build` (there is no CPU fallback)")
+  L = ctypes.CDLL(path)
+  vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+  L.sisua_create.argtypes = [ctypes.POINTER(StepConfig), ci, ctypes.POINTER(vp)]
+  L.sisua_create.restype = ci
+  L.sisua_destroy.argtypes = [vp]
+  L.sisua_destroy.restype = ci
+  L.sisua_param_layout.argtypes = [vp, ctypes.POINTER(ParamDesc), ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_int64)]
+  L.sisua_param_layout.restype = ci
+  L.sisua_bind_buffers.argtypes = [vp, vp, vp, vp, vp, vp]
+  L.sisua_bind_buffers.restype = ci
+  L.sisua_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+  L.sisua_train_step.restype = ci
+  L.sisua_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci] + [vp] * 10
+  L.sisua_infer.restype = ci
+  L.sisua_adam_step.argtypes = [vp, cf, cf, cf, cf, cf, cf, ctypes.c_int64, vp]
+  L.sisua_adam_step.restype = ci
+  L.sisua_debug_buffer.argtypes = [vp, ctypes.c_char_p]
+  L.sisua_debug_buffer.restype = vp
+  L.sisua_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]
+  L.sisua_debug_copy.restype = ci
+  L.sisua_last_error.argtypes = [vp]
+  L.sisua_last_error.restype = ctypes.c_char_p
+  L.sisua_version.argtypes = []
+  L.sisua_version.restype = ctypes.c_char_p
+  _LIB = L
+  return L

@@ -1,0 +1,684 @@
+// C ABI + step orchestration (include/sisua_b200.h).  Host code here only sequences kernel launches on
+// the caller's stream; all arithmetic is in the .cuh kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sisua_b200.h"
+#include "adam.cuh"
+#include "device_math.cuh"
+#include "kernels_mid.cuh"
+#include "kernels_unfused.cuh"
+#ifdef SISUA_WITH_TC
+#include "kernels_tc.cuh"
+#endif
+
+using namespace sisua;
+
+namespace {
+
+struct ParamRef {
+  std::string name;
+  long long off;
+  int rows, cols, ld, kind;   // kind: 0 weight 1 bias 2 gamma 3 beta
+  long long size() const { return cols == 0 ? rows : (long long)rows * ld; }
+};
+
+struct Layer {          // one Dense -> (BN | bias) -> ReLU unit
+  long long w_off;      // weight [H, Kin] offset
+  int ldw, Kin;
+  long long g_off, b_off;   // gamma / beta (bias in b_off when no BN)
+  int bn_index;         // index into bn_moving, -1 without BN
+  int stat_index;       // index into the per-step statistics buffer
+  float* A;             // pre-activation buffer
+  int lda;
+  float dropout;
+};
+
+}  // namespace
+
+struct sisua_model {
+  sisua_step_config cfg;
+  int device;
+  std::string err;
+  std::vector<ParamRef> params;
+  long long total_floats = 0;
+  // bound buffers
+  float *P = nullptr, *Gd = nullptr, *M = nullptr, *V = nullptr, *moving = nullptr;
+  // layers
+  std::vector<Layer> enc, encl, dec;
+  long long lat_w, lat_b, lib_w, lib_b, out_w, out_b, y_w, y_b;
+  int n_bn = 0;
+  int NO = 0;          // output head columns (nheads * G)
+  int Gp = 0;
+  int ld0 = 0;         // leading dim of the first-layer pre-activation buffer (64 or 128)
+  // workspace
+  std::vector<void*> allocs;
+  float *A0 = nullptr, *PL = nullptr, *loc = nullptr, *scale = nullptr, *Zs = nullptr, *PLIB = nullptr,
+        *lib_loc = nullptr, *lib_scale = nullptr, *lib = nullptr, *dZ = nullptr, *dPL = nullptr, *dPLIB = nullptr,
+        *dLib = nullptr, *D = nullptr, *dD = nullptr, *dHa = nullptr, *dHb = nullptr, *delta1 = nullptr,
+        *PY = nullptr, *dPY = nullptr, *OUT = nullptr, *mask_scale = nullptr, *scratch_terms = nullptr;
+  int n_units = 0;             // hidden units (layers) that own a statistics slot
+  double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
+  double* sq = nullptr;        // [kMaxSegments]
+  long long* d_step = nullptr;
+  SegTable seg;
+  int num_sms = 148;
+  int last_train_B = 0;
+};
+
+#define SET_ERR(h, code, ...)                         \
+  do {                                                \
+    char _b[512];                                     \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+    (h)->err = _b;                                    \
+    return code;                                      \
+  } while (0)
+
+#define CUDA_OK(h, expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) SET_ERR(h, SISUA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_OK(h, what)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess) SET_ERR(h, SISUA_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+static long long align64(long long n) { return (n + 63) / 64 * 64; }
+
+// ---- parameter table: must agree with sisua_b200/config.py:param_layout -------------------------
+static void build_layout(sisua_model* h) {
+  const sisua_step_config& c = h->cfg;
+  const int H = c.n_hidden, G = c.n_genes, Z = c.n_latent, P = c.n_proteins;
+  const int Gp = (G + 3) / 4 * 4;
+  h->Gp = Gp;
+  long long off = 0;
+  auto add = [&](const std::string& name, int rows, int cols, int ld, int kind) {
+    ParamRef p{name, off, rows, cols, ld, kind};
+    h->params.push_back(p);
+    off = align64(off + p.size());
+    return p.off;
+  };
+  const bool bn = c.batchnorm != 0;
+  const bool scvi = c.model_kind == SISUA_MODEL_SCVI;
+  int bn_counter = 0;
+  auto add_norm = [&](const std::string& prefix, Layer& L) {
+    if (bn) {
+      L.g_off = add(prefix + ".gamma", H, 0, H, 2);
+      L.b_off = add(prefix + ".beta", H, 0, H, 3);
+    } else {
+      L.g_off = -1;
+      L.b_off = add(prefix + ".b", H, 0, H, 1);
+    }
+  };
+  h->enc.resize(c.n_enc_layers);
+  h->encl.resize(scvi ? c.n_encl_layers : 0);
+  h->dec.resize(c.n_dec_layers);
+  h->enc[0].w_off = add("enc.0.W", H, G, Gp, 0); h->enc[0].ldw = Gp; h->enc[0].Kin = G;
+  if (scvi) { h->encl[0].w_off = add("encl.0.W", H, G, Gp, 0); h->encl[0].ldw = Gp; h->encl[0].Kin = G; }
+  add_norm("enc.0", h->enc[0]);
+  for (int i = 1; i < c.n_enc_layers; ++i) {
+    std::string p = "enc." + std::to_string(i);
+    h->enc[i].w_off = add(p + ".W", H, H, H, 0); h->enc[i].ldw = H; h->enc[i].Kin = H;
+    add_norm(p, h->enc[i]);
+  }
+  if (scvi) {
+    add_norm("encl.0", h->encl[0]);
+    for (int i = 1; i < c.n_encl_layers; ++i) {
+      std::string p = "encl." + std::to_string(i);
+      h->encl[i].w_off = add(p + ".W", H, H, H, 0); h->encl[i].ldw = H; h->encl[i].Kin = H;
+      add_norm(p, h->encl[i]);
+    }
+  }
+  const int ZP = c.model_kind == SISUA_MODEL_DCA ? Z : 2 * Z;
+  h->lat_w = add("lat.W", ZP, H, H, 0);
+  h->lat_b = add("lat.b", ZP, 0, ZP, 1);
+  h->lib_w = h->lib_b = -1;
+  if (scvi) { h->lib_w = add("lib.W", 2, H, H, 0); h->lib_b = add("lib.b", 2, 0, 2, 1); }
+  h->dec[0].w_off = add("dec.0.W", H, Z, Z, 0); h->dec[0].ldw = Z; h->dec[0].Kin = Z;
+  add_norm("dec.0", h->dec[0]);
+  for (int i = 1; i < c.n_dec_layers; ++i) {
+    std::string p = "dec." + std::to_string(i);
+    h->dec[i].w_off = add(p + ".W", H, H, H, 0); h->dec[i].ldw = H; h->dec[i].Kin = H;
+    add_norm(p, h->dec[i]);
+  }
+  const int nheads = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  h->NO = nheads * G;
+  h->out_w = add("out.W", h->NO, H, H, 0);
+  h->out_b = add("out.b", h->NO, 0, h->NO, 1);
+  h->y_w = h->y_b = -1;
+  if (P > 0) { h->y_w = add("y.W", 2 * P, H, H, 0); h->y_b = add("y.b", 2 * P, 0, 2 * P, 1); }
+  h->total_floats = off;
+  // BN indices follow config.py:bn_layer_names (enc, encl, dec)
+  for (auto& L : h->enc) L.bn_index = bn ? bn_counter++ : -1;
+  for (auto& L : h->encl) L.bn_index = bn ? bn_counter++ : -1;
+  for (auto& L : h->dec) L.bn_index = bn ? bn_counter++ : -1;
+  h->n_bn = bn_counter;
+  int sc = 0;
+  for (auto& L : h->enc) L.stat_index = sc++;
+  for (auto& L : h->encl) L.stat_index = sc++;
+  for (auto& L : h->dec) L.stat_index = sc++;
+  h->n_units = sc;
+  h->seg.n = (int)h->params.size();
+  for (int i = 0; i < h->seg.n; ++i) { h->seg.off[i] = h->params[i].off; h->seg.size[i] = h->params[i].size(); }
+}
+
+template <typename T>
+static int ws_alloc(sisua_model* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) SET_ERR(h, SISUA_ERR_CUDA, "workspace cudaMalloc(%zu B) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return SISUA_OK;
+}
+
+extern "C" const char* sisua_version(void) { return "sisua_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* sisua_last_error(sisua_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+static std::string g_create_err;
+
+extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_handle* out) {
+  if (!cfg || !out) return SISUA_ERR_INVALID;
+  *out = nullptr;
+  sisua_model* h = new sisua_model();
+  h->cfg = *cfg;
+  h->device = device;
+  *out = h;   // returned even on failure so the caller can read last_error, then destroy
+  const sisua_step_config& c = h->cfg;
+  if (c.n_hidden != kH) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "n_hidden=%d: kernels are built for 64 hidden units", c.n_hidden);
+  if (c.n_latent < 1 || c.n_latent > 32) SET_ERR(h, SISUA_ERR_INVALID, "n_latent must be in [1,32]");
+  if (c.n_proteins < 0 || c.n_proteins > 32) SET_ERR(h, SISUA_ERR_INVALID, "n_proteins must be in [0,32]");
+  if (c.n_genes < 1) SET_ERR(h, SISUA_ERR_INVALID, "n_genes must be positive");
+  if (c.n_enc_layers < 1 || c.n_enc_layers > 4 || c.n_dec_layers < 1 || c.n_dec_layers > 4)
+    SET_ERR(h, SISUA_ERR_INVALID, "hidden layer counts must be in [1,4]");
+  if (c.model_kind == SISUA_MODEL_SCVI && (c.n_encl_layers < 1 || c.n_encl_layers > 4))
+    SET_ERR(h, SISUA_ERR_INVALID, "scVI needs 1..4 library-encoder layers");
+  if (c.model_kind == SISUA_MODEL_SISUA && c.n_proteins < 1) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs proteins");
+  if (c.model_kind != SISUA_MODEL_SISUA && c.n_proteins != 0) SET_ERR(h, SISUA_ERR_INVALID, "proteins only with SISUA");
+  if (c.max_batch < 1) SET_ERR(h, SISUA_ERR_INVALID, "max_batch must be positive");
+  if (c.input_dropout > 0.f || c.enc_dropout > 0.f || c.dec_dropout > 0.f || c.encl_dropout > 0.f)
+    SET_ERR(h, SISUA_ERR_UNSUPPORTED, "dropout > 0 is not implemented in the sm_100a step yet");
+#ifndef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
+#endif
+  CUDA_OK(h, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(h, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  build_layout(h);
+  const size_t R = c.max_batch;
+  const int H = kH, Z = c.n_latent, P = c.n_proteins;
+  const bool scvi = c.model_kind == SISUA_MODEL_SCVI;
+  h->ld0 = scvi ? 2 * H : H;
+  int rc;
+#define WS(ptr, count) if ((rc = ws_alloc(h, &(ptr), (count))) != SISUA_OK) return rc
+  WS(h->A0, R * h->ld0);
+  h->enc[0].A = h->A0; h->enc[0].lda = h->ld0;
+  for (int i = 1; i < c.n_enc_layers; ++i) { WS(h->enc[i].A, R * H); h->enc[i].lda = H; }
+  if (scvi) {
+    h->encl[0].A = h->A0 + H; h->encl[0].lda = h->ld0;
+    for (int i = 1; i < c.n_encl_layers; ++i) { WS(h->encl[i].A, R * H); h->encl[i].lda = H; }
+  }
+  for (int i = 0; i < c.n_dec_layers; ++i) { WS(h->dec[i].A, R * H); h->dec[i].lda = H; }
+  WS(h->PL, R * 2 * Z); WS(h->loc, R * Z); WS(h->scale, R * Z); WS(h->Zs, R * Z);
+  WS(h->dZ, R * Z); WS(h->dPL, R * 2 * Z);
+  if (scvi) {
+    WS(h->PLIB, R * 2); WS(h->lib_loc, R); WS(h->lib_scale, R); WS(h->lib, R); WS(h->dPLIB, R * 2); WS(h->dLib, R);
+  }
+  WS(h->D, R * H); WS(h->dD, R * H); WS(h->dHa, R * H); WS(h->dHb, R * H); WS(h->delta1, R * h->ld0);
+  if (P > 0) { WS(h->PY, R * 2 * P); WS(h->dPY, R * 2 * P); }
+  if (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED) WS(h->OUT, R * (size_t)h->NO);
+  WS(h->mask_scale, 1);
+  WS(h->scratch_terms, 5 * R);
+  WS(h->stats, (size_t)h->n_units * 4 * H);
+  WS(h->sq, kMaxSegments);
+  WS(h->d_step, 1);
+#undef WS
+  CUDA_OK(h, cudaMemset(h->d_step, 0, sizeof(long long)));
+  CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
+  CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (scvi && c.n_genes * sizeof(float) > 200 * 1024 && c.gemm_mode == SISUA_GEMM_FP32_UNFUSED)
+    SET_ERR(h, SISUA_ERR_UNSUPPORTED, "un-fused scVI row kernel caches one softmax row in shared memory: n_genes <= 51200");
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    rc = tc_create(h);
+    if (rc != SISUA_OK) return rc;
+  }
+#endif
+  return SISUA_OK;
+}
+
+extern "C" int sisua_destroy(sisua_handle h) {
+  if (!h) return SISUA_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return SISUA_OK;
+}
+
+extern "C" int sisua_param_layout(sisua_handle h, sisua_param_desc* out, int* n, int64_t* total_floats) {
+  if (!h || !n) return SISUA_ERR_INVALID;
+  int cap = *n;
+  *n = (int)h->params.size();
+  if (total_floats) *total_floats = h->total_floats;
+  if (!out) return SISUA_OK;
+  if (cap < (int)h->params.size()) SET_ERR(h, SISUA_ERR_INVALID, "param_layout: capacity %d < %zu", cap, h->params.size());
+  for (size_t i = 0; i < h->params.size(); ++i) {
+    const ParamRef& p = h->params[i];
+    memset(&out[i], 0, sizeof(out[i]));
+    strncpy(out[i].name, p.name.c_str(), sizeof(out[i].name) - 1);
+    out[i].offset = p.off; out[i].rows = p.rows; out[i].cols = p.cols; out[i].ld = p.ld; out[i].kind = p.kind;
+  }
+  return SISUA_OK;
+}
+
+extern "C" int sisua_bind_buffers(sisua_handle h, float* params, float* grads, float* adam_m, float* adam_v,
+                                  float* bn_moving) {
+  if (!h) return SISUA_ERR_INVALID;
+  if (!params) SET_ERR(h, SISUA_ERR_INVALID, "bind_buffers: params is null");
+  if (h->cfg.batchnorm && !bn_moving) SET_ERR(h, SISUA_ERR_INVALID, "bind_buffers: bn_moving is null but batchnorm is on");
+  h->P = params; h->Gd = grads; h->M = adam_m; h->V = adam_v; h->moving = bn_moving;
+  return SISUA_OK;
+}
+
+extern "C" const float* sisua_debug_buffer(sisua_handle h, const char* name) {
+  if (!h || !name) return nullptr;
+  std::string n(name);
+  if (n == "d") return h->D;
+  if (n == "delta1") return h->delta1;
+  if (n == "out") return h->OUT;
+  if (n == "dD") return h->dD;
+  if (n == "a0") return h->A0;
+  if (n == "z") return h->Zs;
+  return nullptr;
+}
+
+extern "C" int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  const float* src = sisua_debug_buffer(h, name);
+  if (!src) SET_ERR(h, SISUA_ERR_INVALID, "debug_copy: unknown buffer '%s'", name ? name : "");
+  CUDA_OK(h, cudaMemcpyAsync(dst, src, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SISUA_OK;
+}
+
+// ---- helpers ------------------------------------------------------------------------------------
+static NormSpec make_norm(sisua_model* h, const Layer& L, bool training, int rows) {
+  NormSpec ns;
+  memset(&ns, 0, sizeof(ns));
+  ns.eps = h->cfg.bn_eps;
+  if (L.bn_index >= 0) {
+    ns.gamma = h->P + L.g_off; ns.beta = h->P + L.b_off;
+    if (training) {
+      ns.mode = NORM_BN_BATCH;
+      ns.sum = h->stats + (size_t)L.stat_index * 4 * kH;
+      ns.sumsq = ns.sum + kH;
+      ns.inv_count = 1.0f / (float)rows;
+    } else {
+      ns.mode = NORM_BN_MOVING;
+      ns.moving = h->moving + (size_t)L.bn_index * 2 * kH;
+    }
+  } else {
+    ns.mode = NORM_BIAS;
+    ns.beta = h->P + L.b_off;
+  }
+  return ns;
+}
+static NormSpec raw_norm() { NormSpec ns; memset(&ns, 0, sizeof(ns)); ns.mode = NORM_RAW; return ns; }
+
+static int mid_grid(sisua_model* h, int rows) { return std::max(1, std::min((rows + kTileR - 1) / kTileR, 2 * h->num_sms)); }
+
+template <int AOP, int BOP>
+static void launch_sgemm(sisua_model* h, cudaStream_t st, const float* A, long long a_rs, long long a_cs, const float* B,
+                         long long b_rs, long long b_cs, float* C, long long ldc, const float* bias, int M, int N, int K,
+                         bool accumulate) {
+  int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
+  int want = (2 * h->num_sms + tiles - 1) / tiles;
+  int max_splits = std::max(1, K / 256);
+  int splits = accumulate ? std::max(1, std::min(want, max_splits)) : 1;   // split-K adds atomically: needs a zeroed C
+  int k_chunk = ((K + splits - 1) / splits + kGemmBK - 1) / kGemmBK * kGemmBK;
+  splits = (K + k_chunk - 1) / k_chunk;
+  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM, splits);
+  int atomic_out = (accumulate || splits > 1) ? 1 : 0;
+  sgemm_kernel<AOP, BOP><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, k_chunk, atomic_out);
+}
+
+static void launch_dense_fwd(sisua_model* h, cudaStream_t st, const float* A_in, int lda, int Kin, const NormSpec& ns,
+                             const float* W, int ldw, const float* bias, int Nout, float* A_out, int ldo, int R) {
+  dense_fwd_kernel<<<mid_grid(h, R), kMidThreads, 0, st>>>(A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R);
+}
+
+static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, int R) {
+  double* s = h->stats + (size_t)L.stat_index * 4 * kH;
+  int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+  col_stats_kernel<<<grid, 256, 0, st>>>(L.A, L.lda, R, kH, s, s + kH);
+}
+
+// hidden stack forward: layer 0's pre-activation is already in L[0].A; leaves the last layer's
+// pre-activation (plus statistics when training with BN) ready for the consumer.
+static void stack_forward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, bool training, int R) {
+  for (size_t i = 0; i < Ls.size(); ++i) {
+    if (training && Ls[i].bn_index >= 0) launch_col_stats(h, st, Ls[i], R);
+    if (i + 1 < Ls.size()) {
+      NormSpec ns = make_norm(h, Ls[i], training, R);
+      launch_dense_fwd(h, st, Ls[i].A, Ls[i].lda, kH, ns, h->P + Ls[i + 1].w_off, Ls[i + 1].ldw, nullptr, kH,
+                       Ls[i + 1].A, Ls[i + 1].lda, R);
+    }
+  }
+}
+
+// shared forward; rows_dec = S*B
+static int forward_common(sisua_model* h, cudaStream_t st, bool training, const float* x, const float* y,
+                          const float* library, const uint8_t* mask, const float* eps_z, const float* eps_l, int B,
+                          int S, float* terms, float* loss, float* out_mean, float* out_disp, float* out_pi,
+                          float* y_mean) {
+  const sisua_step_config& c = h->cfg;
+  const int H = kH, G = c.n_genes, Z = c.n_latent, P = c.n_proteins;
+  const bool scvi = c.model_kind == SISUA_MODEL_SCVI, dca = c.model_kind == SISUA_MODEL_DCA;
+  const int R = S * B;
+  if (!h->P) SET_ERR(h, SISUA_ERR_STATE, "bind_buffers has not been called");
+  if (B < 1 || S < 1 || R > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "rows S*B=%d exceed max_batch=%d", R, c.max_batch);
+  if (!x || !terms) SET_ERR(h, SISUA_ERR_INVALID, "x / terms must not be null");
+  if (!dca && !eps_z) SET_ERR(h, SISUA_ERR_INVALID, "eps_z is required (stochastic latent)");
+  if (scvi && (!library || !eps_l)) SET_ERR(h, SISUA_ERR_INVALID, "scVI needs library [B,2] and eps_l");
+  if (P > 0 && !y) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs y [B,P]");
+  if (training) CUDA_OK(h, cudaMemsetAsync(h->stats, 0, (size_t)h->n_units * 4 * H * sizeof(double), st));
+  if (loss) CUDA_OK(h, cudaMemsetAsync(loss, 0, sizeof(float), st));
+
+  // ---- first layer: log1p(x) . W1^T  (z encoder and, for scVI, the library encoder in one pass)
+  const int N0 = scvi ? 2 * H : H;
+  bool first_done = false;
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    int rc = tc_encoder_first(h, st, x, B, N0);
+    if (rc != SISUA_OK) return rc;
+    first_done = true;
+  }
+#endif
+  if (!first_done) {
+    if (c.log_norm)
+      launch_sgemm<LOAD_LOG1P, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false);
+    else
+      launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false);
+    // split-K accumulates atomically: the buffer must start from zero in that case
+  }
+  LAUNCH_OK(h, "first-layer gemm");
+  stack_forward(h, st, h->enc, training, B);
+  {
+    Layer& L = h->enc.back();
+    NormSpec ns = make_norm(h, L, training, B);
+    const int ZP = dca ? Z : 2 * Z;
+    launch_dense_fwd(h, st, L.A, L.lda, H, ns, h->P + h->lat_w, H, h->P + h->lat_b, ZP, h->PL, ZP, B);
+  }
+  if (scvi) {
+    stack_forward(h, st, h->encl, training, B);
+    Layer& L = h->encl.back();
+    NormSpec ns = make_norm(h, L, training, B);
+    launch_dense_fwd(h, st, L.A, L.lda, H, ns, h->P + h->lib_w, H, h->P + h->lib_b, 2, h->PLIB, 2, B);
+  }
+  LAUNCH_OK(h, "encoder stack");
+  {
+    LatentArgs a;
+    memset(&a, 0, sizeof(a));
+    a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
+    a.kl_z = terms + (size_t)3 * R; a.kl_l = terms + (size_t)4 * R;
+    if (scvi) {
+      a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc; a.lib_scale = h->lib_scale;
+      a.lib = h->lib;
+    }
+    a.B = B; a.S = S; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
+    latent_fwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    LAUNCH_OK(h, "latent_fwd_kernel");
+  }
+  // ---- decoder
+  launch_dense_fwd(h, st, h->Zs, Z, Z, raw_norm(), h->P + h->dec[0].w_off, h->dec[0].ldw, nullptr, H, h->dec[0].A,
+                   h->dec[0].lda, R);
+  stack_forward(h, st, h->dec, training, R);
+  NormSpec ns_d = make_norm(h, h->dec.back(), training, R);
+  norm_relu_kernel<<<std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms)), 256, 0, st>>>(
+      h->dec.back().A, h->dec.back().lda, ns_d, h->D, R);
+  LAUNCH_OK(h, "decoder stack");
+  // ---- protein head (before the output layer so dD can be initialised by its backward)
+  if (P > 0) {
+    launch_dense_fwd(h, st, h->D, H, H, raw_norm(), h->P + h->y_w, H, h->P + h->y_b, 2 * P, h->PY, 2 * P, R);
+    if (c.mask_norm == 1) mask_scale_kernel<<<1, 256, 0, st>>>(mask, B, h->mask_scale);
+    YHeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.PY = h->PY; a.y = y; a.mask = mask; a.llk_y = terms + (size_t)2 * R; a.dPY = training ? h->dPY : nullptr;
+    a.y_mean = y_mean; a.R = R; a.B = B; a.P = P; a.y_dist = c.y_dist; a.mean_act = c.mean_act; a.disp_act = c.disp_act;
+    a.upstream = -c.alpha / (float)R;
+    a.mask_scale = c.mask_norm == 1 ? h->mask_scale : nullptr;
+    yhead_kernel<<<(R + 127) / 128, 128, 0, st>>>(a);
+    LAUNCH_OK(h, "yhead_kernel");
+  } else {
+    CUDA_OK(h, cudaMemsetAsync(terms + (size_t)2 * R, 0, (size_t)R * sizeof(float), st));
+  }
+  // ---- output heads + count likelihood
+  bool out_done = false;
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi);
+    if (rc != SISUA_OK) return rc;
+    out_done = true;
+  }
+#endif
+  if (!out_done) {
+    launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->D, H, 1, h->P + h->out_w, 1, H, h->OUT, h->NO, h->P + h->out_b, R, h->NO, H, false);
+    CountRowArgs a;
+    memset(&a, 0, sizeof(a));
+    a.OUT = h->OUT; a.ldo = h->NO; a.x = x; a.lib = scvi ? h->lib : nullptr; a.llk_x = terms + (size_t)R;
+    a.dlib = (scvi && training) ? h->dLib : nullptr;
+    a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
+    a.R = R; a.B = B; a.G = G; a.scvi = scvi ? 1 : 0; a.zero_inflated = c.x_dist == SISUA_XDIST_ZINBD;
+    a.train = training ? 1 : 0; a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.reapply = c.scvi_reapply_act;
+    a.upstream = -1.0f / (float)R; a.clip_library = c.clip_library;
+    size_t smem = scvi ? (size_t)G * sizeof(float) : 0;
+    if (a.zero_inflated) count_row_kernel<true><<<R, 256, smem, st>>>(a);
+    else count_row_kernel<false><<<R, 256, smem, st>>>(a);
+    LAUNCH_OK(h, "count_row_kernel");
+  }
+  // ---- ELBO
+  {
+    ElboArgs a;
+    a.terms = terms; a.mask = P > 0 ? mask : nullptr; a.mask_scale = (P > 0 && c.mask_norm == 1) ? h->mask_scale : nullptr;
+    a.R = R; a.B = B; a.alpha = c.alpha; a.beta = c.beta; a.loss = loss;
+    elbo_kernel<<<std::max(1, std::min((R + 255) / 256, h->num_sms)), 256, 0, st>>>(a);
+    LAUNCH_OK(h, "elbo_kernel");
+  }
+  if (training && c.batchnorm) {
+    MovingUpdateArgs mu;
+    memset(&mu, 0, sizeof(mu));
+    auto reg = [&](const Layer& L, int rows) {
+      mu.sum[L.bn_index] = h->stats + (size_t)L.stat_index * 4 * kH;
+      mu.sumsq[L.bn_index] = mu.sum[L.bn_index] + kH;
+      mu.inv_count[L.bn_index] = 1.0f / (float)rows;
+    };
+    for (auto& L : h->enc) reg(L, B);
+    for (auto& L : h->encl) reg(L, B);
+    for (auto& L : h->dec) reg(L, R);
+    bn_moving_update_kernel<<<h->n_bn, kH, 0, st>>>(mu, h->moving, c.bn_momentum);
+    LAUNCH_OK(h, "bn_moving_update_kernel");
+  }
+  return SISUA_OK;
+}
+
+// backward of a hidden stack. dH_top: gradient wrt the activated output of the last layer.
+// in0: source of layer 0's input for dW_0 (null -> dW_0 comes from the big first-layer GEMM),
+// dIn0: where the gradient wrt layer 0's input goes (null -> not needed), dA0: pre-activation
+// gradient of layer 0 (delta1) when requested.
+static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, int R, float* dH_top,
+                          const float* in0, int ld_in0, int Kin0, float* dIn0, int ld_dIn0, float* dA0, int ld_dA0) {
+  float* dH = dH_top;
+  for (int i = (int)Ls.size() - 1; i >= 0; --i) {
+    Layer& L = Ls[i];
+    NormSpec ns = make_norm(h, L, true, R);
+    double* sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH;
+    double* sdyx = sdy + kH;
+    float* dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr;
+    float* dbeta = h->Gd + L.b_off;
+    int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
+    DenseBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_mode = 1; a.dOut = dH; a.ldd = kH; a.A_out = L.A; a.lda_out = L.lda; a.ns_out = ns; a.sdy = sdy; a.sdyx = sdyx;
+    a.Nout = kH; a.R = R;
+    float* dH_next = (dH == h->dHa) ? h->dHb : h->dHa;
+    if (i > 0) {
+      a.A_in = Ls[i - 1].A; a.lda_in = Ls[i - 1].lda; a.Kin = kH; a.ns_in = make_norm(h, Ls[i - 1], true, R);
+      a.W = h->P + L.w_off; a.ldw = L.ldw; a.dW = h->Gd + L.w_off;
+      a.dIn = dH_next; a.ldi = kH; a.accumulate_dIn = 0;
+    } else {
+      a.A_in = in0; a.lda_in = ld_in0; a.Kin = in0 ? Kin0 : kH; a.ns_in = raw_norm();
+      a.W = in0 ? h->P + L.w_off : nullptr; a.ldw = L.ldw; a.dW = in0 ? h->Gd + L.w_off : nullptr;
+      a.dIn = dIn0; a.ldi = ld_dIn0; a.accumulate_dIn = 0;
+      a.dA = dA0; a.ldda = ld_dA0;
+    }
+    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
+    LAUNCH_OK(h, "hidden backward");
+    dH = dH_next;
+  }
+  return SISUA_OK;
+}
+
+extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, const float* library,
+                                const uint8_t* mask, const float* eps_z, const float* eps_l, int B, float* terms,
+                                float* loss, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const sisua_step_config& c = h->cfg;
+  if (!h->Gd) SET_ERR(h, SISUA_ERR_STATE, "train_step needs a bound grads buffer");
+  if (c.batchnorm && B < 2) SET_ERR(h, SISUA_ERR_INVALID, "training-mode batch norm needs B >= 2");
+  const int H = kH, G = c.n_genes, Z = c.n_latent, P = c.n_proteins, R = B;
+  const bool scvi = c.model_kind == SISUA_MODEL_SCVI, dca = c.model_kind == SISUA_MODEL_DCA;
+  CUDA_OK(h, cudaMemsetAsync(h->Gd, 0, (size_t)h->total_floats * sizeof(float), st));
+  int rc = forward_common(h, st, true, x, y, library, mask, eps_z, eps_l, B, 1, terms, loss, nullptr, nullptr, nullptr, nullptr);
+  if (rc != SISUA_OK) return rc;
+  h->last_train_B = B;
+  // ---- gradient wrt decoder output D
+  if (P > 0) {
+    DenseBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_mode = 0; a.dOut = h->dPY; a.ldd = 2 * P; a.Nout = 2 * P; a.A_in = h->D; a.lda_in = H; a.Kin = H;
+    a.ns_in = raw_norm(); a.W = h->P + h->y_w; a.ldw = H; a.dW = h->Gd + h->y_w; a.db = h->Gd + h->y_b;
+    a.dIn = h->dD; a.ldi = H; a.accumulate_dIn = 0; a.R = R;
+    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
+    LAUNCH_OK(h, "protein head backward");
+  } else {
+    CUDA_OK(h, cudaMemsetAsync(h->dD, 0, (size_t)R * H * sizeof(float), st));
+  }
+  bool out_done = false;
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) out_done = true;   // fused kernel already produced dW_out, db_out, dD
+#endif
+  if (!out_done) {
+    // dW_out[NO,H] += G_out^T . D ; db_out += colsum(G_out) ; dD += G_out . W_out
+    launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, 1, h->NO, h->D, H, 1, h->Gd + h->out_w, H, nullptr, h->NO, H, R, true);
+    int rows_per_block = std::max(64, (R + 63) / 64);
+    dim3 g((h->NO + 255) / 256, (R + rows_per_block - 1) / rows_per_block);
+    col_sum_kernel<<<g, 256, 0, st>>>(h->OUT, h->NO, R, h->NO, rows_per_block, h->Gd + h->out_b);
+    launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, h->NO, 1, h->P + h->out_w, H, 1, h->dD, H, nullptr, R, H, h->NO, true);
+    LAUNCH_OK(h, "output-layer backward");
+  }
+  // ---- decoder stack, latent, encoder stack(s)
+  rc = stack_backward(h, st, h->dec, R, h->dD, h->Zs, Z, Z, h->dZ, Z, nullptr, 0);
+  if (rc != SISUA_OK) return rc;
+  {
+    LatentBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dZ = h->dZ; a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.dPL = h->dPL;
+    if (scvi) {
+      a.dLib = h->dLib; a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc;
+      a.lib_scale = h->lib_scale; a.dPLIB = h->dPLIB;
+    }
+    a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
+    latent_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    LAUNCH_OK(h, "latent_bwd_kernel");
+  }
+  {
+    const int ZP = dca ? Z : 2 * Z;
+    Layer& L = h->enc.back();
+    DenseBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_mode = 0; a.dOut = h->dPL; a.ldd = ZP; a.Nout = ZP; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
+    a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lat_w; a.ldw = H; a.dW = h->Gd + h->lat_w; a.db = h->Gd + h->lat_b;
+    a.dIn = h->dHa; a.ldi = H; a.R = B;
+    dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
+    LAUNCH_OK(h, "latent projection backward");
+    rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0);
+    if (rc != SISUA_OK) return rc;
+  }
+  if (scvi) {
+    Layer& L = h->encl.back();
+    DenseBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_mode = 0; a.dOut = h->dPLIB; a.ldd = 2; a.Nout = 2; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
+    a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lib_w; a.ldw = H; a.dW = h->Gd + h->lib_w; a.db = h->Gd + h->lib_b;
+    a.dIn = h->dHa; a.ldi = H; a.R = B;
+    dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
+    LAUNCH_OK(h, "library projection backward");
+    rc = stack_backward(h, st, h->encl, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1 + H, h->ld0);
+    if (rc != SISUA_OK) return rc;
+  }
+  // ---- first-layer weight gradient: dW1[N0, G] = delta1^T . log1p(x)
+  const int N0 = scvi ? 2 * H : H;
+  bool w1_done = false;
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    rc = tc_encoder_first_bwd(h, st, x, B, N0);
+    if (rc != SISUA_OK) return rc;
+    w1_done = true;
+  }
+#endif
+  if (!w1_done) {
+    if (c.log_norm)
+      launch_sgemm<LOAD_NONE, LOAD_LOG1P>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true);
+    else
+      launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true);
+    LAUNCH_OK(h, "first-layer weight gradient");
+  }
+  return SISUA_OK;
+}
+
+extern "C" int sisua_infer(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                           const float* eps_z, const float* eps_l, int B, int S, float* terms, float* z_loc,
+                           float* z_scale, float* lib_loc, float* lib_scale, float* out_mean, float* out_disp,
+                           float* out_pi, float* y_mean, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const sisua_step_config& c = h->cfg;
+  float* t = terms ? terms : h->scratch_terms;
+  int rc = forward_common(h, st, false, x, y, library, mask, eps_z, eps_l, B, S, t, nullptr, out_mean, out_disp, out_pi, y_mean);
+  if (rc != SISUA_OK) return rc;
+  const size_t zb = (size_t)B * c.n_latent * sizeof(float);
+  if (z_loc) CUDA_OK(h, cudaMemcpyAsync(z_loc, h->loc, zb, cudaMemcpyDeviceToDevice, st));
+  if (z_scale) CUDA_OK(h, cudaMemcpyAsync(z_scale, h->scale, zb, cudaMemcpyDeviceToDevice, st));
+  if (c.model_kind == SISUA_MODEL_SCVI) {
+    if (lib_loc) CUDA_OK(h, cudaMemcpyAsync(lib_loc, h->lib_loc, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (lib_scale) CUDA_OK(h, cudaMemcpyAsync(lib_scale, h->lib_scale, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return SISUA_OK;
+}
+
+extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float eps_hat, float clipnorm,
+                               float grad_scale, int64_t t, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->P || !h->Gd || !h->M || !h->V) SET_ERR(h, SISUA_ERR_STATE, "adam_step needs params, grads, m and v bound");
+  CUDA_OK(h, cudaMemsetAsync(h->sq, 0, kMaxSegments * sizeof(double), st));
+  dim3 grid(std::max(1, std::min(64, (int)((h->total_floats / h->seg.n + 2047) / 2048))), h->seg.n);
+  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->sq, h->d_step, (long long)t);
+  adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->sq, h->d_step, lr, beta1, beta2, eps_hat,
+                                     clipnorm, h->cfg.clip_mode, grad_scale);
+  LAUNCH_OK(h, "adam");
+  return SISUA_OK;
+}

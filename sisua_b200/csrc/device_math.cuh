@@ -1,0 +1,191 @@
+// Per-element mathematics of the SISUA ELBO step (forward value + derivative), shared by the
+// un-fused cross-check kernels and the fused tcgen05 epilogues so both paths agree by construction.
+// Formulas: SURVEY.md Appendix A (restating odin-ai's NegativeBinomialDisp / ZeroInflated, which
+// follow scVI's log_zinb_positive / log_nb_positive, eps = 1e-8) and sisua/models/scvi.py:117-138.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace sisua {
+
+constexpr float kEps = 1e-8f;
+constexpr float kSoftplus1Shift = 0.5413248546129181f;
+
+enum Act : int { ACT_SOFTPLUS = 0, ACT_SOFTPLUS1 = 1, ACT_SOFTPLUS_P1 = 2, ACT_EXP = 3, ACT_IDENTITY = 4 };
+
+// log(1 + t) for t in [0, 1]; series below 2^-6 keeps full relative accuracy where logf(1+t) cannot.
+__device__ __forceinline__ float log1p_unit(float t) {
+  if (t < 0.015625f) return t * (1.0f - t * (0.5f - t * (0.33333334f - 0.25f * t)));
+  return __logf(1.0f + t);
+}
+
+// softplus(x) and sigmoid(x) from one exponential
+__device__ __forceinline__ void softplus_sigmoid(float x, float& sp, float& sg) {
+  float e = __expf(-fabsf(x));
+  float r = __frcp_rn(1.0f + e);
+  sp = fmaxf(x, 0.0f) + log1p_unit(e);
+  sg = (x >= 0.0f) ? r : e * r;
+}
+
+__device__ __forceinline__ float softplus_only(float x) {
+  float e = __expf(-fabsf(x));
+  return fmaxf(x, 0.0f) + log1p_unit(e);
+}
+
+// value v = act(x) and dv = d act / dx
+__device__ __forceinline__ void activation(int kind, float x, float& v, float& dv) {
+  switch (kind) {
+    case ACT_SOFTPLUS: softplus_sigmoid(x, v, dv); break;
+    case ACT_SOFTPLUS1: softplus_sigmoid(x + kSoftplus1Shift, v, dv); break;
+    case ACT_SOFTPLUS_P1: softplus_sigmoid(x, v, dv); v += 1.0f; break;
+    case ACT_EXP: v = __expf(x); dv = v; break;
+    default: v = x; dv = 1.0f; break;
+  }
+}
+
+// psi(t), t > 0
+__device__ __forceinline__ float digamma_pos(float t) {
+  float r = 0.0f;
+#pragma unroll 1
+  while (t < 6.0f) { r -= __frcp_rn(t); t += 1.0f; }
+  float it = __frcp_rn(t), it2 = it * it;
+  return r + __logf(t) - 0.5f * it - it2 * (0.083333336f - it2 * (0.008333334f - it2 * 0.003968254f));
+}
+
+// lg = lgamma(x + th) - lgamma(th) - lgamma(x + 1),  dg = psi(x + th) - psi(th);  x > 0.
+// Small integer counts (the bulk of non-zero entries) use the exact product form
+//   Gamma(x+th) / (Gamma(th) x!) = prod_{k<x} (th + k)/(k + 1)
+// -> one log and one division instead of three lgamma + two digamma.
+__device__ __forceinline__ void nb_gamma_terms(float x, float th, bool want_grad, float& lg, float& dg) {
+  float xr = rintf(x);
+  if (x == xr && x <= 8.0f && th < 1.0e4f) {
+    float q = th, dq = 1.0f, f = 1.0f;   // q = prod (th+k), dq = dq/dth, f = x!
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      if ((float)k < x) {
+        float tk = th + (float)k;
+        dq = fmaf(dq, tk, q);
+        q *= tk;
+        f *= (float)(k + 1);
+      }
+    }
+    lg = __logf(q) - __logf(f);
+    dg = want_grad ? __fdividef(dq, q) : 0.0f;
+  } else {
+    lg = lgammaf(x + th) - lgammaf(th) - lgammaf(x + 1.0f);
+    dg = want_grad ? (digamma_pos(x + th) - digamma_pos(th)) : 0.0f;
+  }
+}
+
+struct CountGrad {  // d llk / d(mu, theta, pi_logit)
+  float dmu, dth, dpi;
+};
+
+// Zero-inflated NB (mean / inverse dispersion / dropout logit). Returns log-likelihood of one entry.
+template <bool kZeroInflated, bool kGrad>
+__device__ __forceinline__ float count_llk(float x, float mu, float th, float pi, CountGrad& g) {
+  float tm = th + mu + kEps;
+  float lt = __logf(th + kEps);
+  float ltm = __logf(tm);
+  float r_tm = __frcp_rn(tm);
+  float dlog = lt - ltm;
+  float n0 = th * dlog;   // log NB(0)
+  float dn0_dmu = 0.f, dn0_dth = 0.f;
+  if (kGrad) {
+    dn0_dmu = -th * r_tm;
+    dn0_dth = dlog + th * (__frcp_rn(th + kEps) - r_tm);
+  }
+  float llk;
+  if (x < kEps) {
+    if (kZeroInflated) {
+      float sp_a, sg_a, sp_b, sg_b;
+      softplus_sigmoid(n0 - pi, sp_a, sg_a);   // sg_a = w = sigmoid(n0 - pi)
+      softplus_sigmoid(-pi, sp_b, sg_b);
+      llk = sp_a - sp_b;
+      if (kGrad) { g.dpi = sg_b - sg_a; g.dmu = sg_a * dn0_dmu; g.dth = sg_a * dn0_dth; }
+    } else {
+      llk = n0;
+      if (kGrad) { g.dpi = 0.f; g.dmu = dn0_dmu; g.dth = dn0_dth; }
+    }
+  } else {
+    float lm = __logf(mu + kEps);
+    float lg, dg;
+    nb_gamma_terms(x, th, kGrad, lg, dg);
+    llk = n0 + x * (lm - ltm) + lg;
+    if (kGrad) {
+      g.dmu = dn0_dmu + x * (__frcp_rn(mu + kEps) - r_tm);
+      g.dth = dn0_dth - x * r_tm + dg;
+      g.dpi = 0.f;
+    }
+    if (kZeroInflated) {
+      float sp_p, sg_p;
+      softplus_sigmoid(pi, sp_p, sg_p);
+      llk -= sp_p;                     // log sigmoid(-pi) = -softplus(pi)
+      if (kGrad) g.dpi = -sg_p;
+    }
+  }
+  return llk;
+}
+
+// TFP NegativeBinomial(total_count = exp(a), logits = b) for real-valued y (protein head,
+// configs/base.yaml:38-40). Returns log-prob; da, db = d/d(a, b).
+template <bool kGrad>
+__device__ __forceinline__ float nb_tfp_llk(float y, float a, float b, float& da, float& db) {
+  float r = __expf(a);
+  float sp_b, sg_b;
+  softplus_sigmoid(b, sp_b, sg_b);          // log sigmoid(b) = b - sp_b ; log sigmoid(-b) = -sp_b
+  float llk = lgammaf(r + y) - lgammaf(r) - lgammaf(y + 1.0f) - r * sp_b + y * (b - sp_b);
+  if (kGrad) {
+    float dr = digamma_pos(r + y) - digamma_pos(r) - sp_b;
+    da = dr * r;
+    db = y - (r + y) * sg_b;
+  }
+  return llk;
+}
+
+// warp / block reductions -------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; every thread gets the result. `scratch` needs >= 33 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    T t = (lane < nw) ? scratch[lane] : T(0);
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = (lane < nw) ? scratch[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+}  // namespace sisua

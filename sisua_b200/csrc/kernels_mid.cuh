@@ -1,0 +1,488 @@
+// The 64-wide "middle" of the network: BN statistics, BN/bias + ReLU applied on load, the small
+// dense layers (hidden x hidden, latent / library / protein heads, first decoder layer), the
+// reparameterisation + analytic KL, and their backward passes.  These kernels are shared by the
+// un-fused cross-check path and the fused tcgen05 path (which only replaces the genes x hidden
+// contractions).  Reference semantics: SURVEY.md section 8a rows a4-a6, a10-a12, Appendix A.
+#pragma once
+#include "device_math.cuh"
+
+namespace sisua {
+
+constexpr int kH = 64;          // hidden width (single_cell_model.py:78-81)
+constexpr int kTileR = 64;      // rows per CTA tile in the mid kernels
+constexpr int kMidThreads = 256;
+
+enum NormMode : int { NORM_RAW = 0, NORM_BN_BATCH = 1, NORM_BN_MOVING = 2, NORM_BIAS = 3 };
+
+struct NormSpec {
+  int mode;
+  const double* sum;     // [64] column sums of the pre-activation (NORM_BN_BATCH)
+  const double* sumsq;   // [64]
+  const float* moving;   // [2,64] moving mean, moving var (NORM_BN_MOVING)
+  const float* gamma;    // [64]
+  const float* beta;     // [64]  (bias when NORM_BIAS)
+  float inv_count;       // 1 / rows that entered the batch statistics
+  float eps;
+};
+
+// per-column affine (h = relu(a*sc + sh)) and the standardisation (xhat = (a - mean)*rstd)
+__device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc, float& sh, float& mean,
+                                            float& rstd) {
+  if (ns.mode == NORM_BN_BATCH) {
+    double m = ns.sum[c] * (double)ns.inv_count;
+    double v = ns.sumsq[c] * (double)ns.inv_count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(v + (double)ns.eps));
+    sc = ns.gamma[c] * rstd;
+    sh = ns.beta[c] - mean * sc;
+  } else if (ns.mode == NORM_BN_MOVING) {
+    mean = ns.moving[c];
+    rstd = rsqrtf(ns.moving[kH + c] + ns.eps);
+    sc = ns.gamma[c] * rstd;
+    sh = ns.beta[c] - mean * sc;
+  } else if (ns.mode == NORM_BIAS) {
+    mean = 0.f; rstd = 1.f; sc = 1.f; sh = ns.beta[c];
+  } else {
+    mean = 0.f; rstd = 1.f; sc = 1.f; sh = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums / sums of squares of A[R, ncols<=128] in double (BN batch statistics)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ A, int lda, int R, int ncols,
+                                                        double* __restrict__ sum, double* __restrict__ sumsq) {
+  __shared__ double s1[256], s2[256];
+  int groups = 256 / ncols;                    // ncols in {64,128}
+  int c = threadIdx.x % ncols, grp = threadIdx.x / ncols;
+  double a1 = 0.0, a2 = 0.0;
+  for (int r = blockIdx.x * groups + grp; r < R; r += gridDim.x * groups) {
+    double v = (double)A[(size_t)r * lda + c];
+    a1 += v; a2 += v * v;
+  }
+  s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < groups; ++g) { a1 += s1[g * ncols + c]; a2 += s2[g * ncols + c]; }
+    atomicAdd(&sum[c], a1);
+    atomicAdd(&sumsq[c], a2);
+  }
+}
+
+// moving <- m * moving + (1-m) * batch   (one block of 64 threads per BN layer)
+struct MovingUpdateArgs {
+  const double* sum[16];
+  const double* sumsq[16];
+  float inv_count[16];
+};
+__global__ void bn_moving_update_kernel(MovingUpdateArgs a, float* __restrict__ moving, float momentum) {
+  int l = blockIdx.x, c = threadIdx.x;
+  double m = a.sum[l][c] * (double)a.inv_count[l];
+  double v = a.sumsq[l][c] * (double)a.inv_count[l] - m * m;
+  if (v < 0.0) v = 0.0;
+  float* mv = moving + (size_t)l * 2 * kH;
+  mv[c] = momentum * mv[c] + (1.f - momentum) * (float)m;
+  mv[kH + c] = momentum * mv[kH + c] + (1.f - momentum) * (float)v;
+}
+
+// D = relu(norm(A))  (materialises the activated decoder output for the output heads)
+__global__ void __launch_bounds__(256) norm_relu_kernel(const float* __restrict__ A, int lda, NormSpec ns,
+                                                        float* __restrict__ D, int R) {
+  __shared__ float sc[kH], sh[kH];
+  if (threadIdx.x < kH) { float m, r; norm_coeffs(ns, threadIdx.x, sc[threadIdx.x], sh[threadIdx.x], m, r); }
+  __syncthreads();
+  size_t n = (size_t)R * kH;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % kH); size_t r = i / kH;
+    float v = A[r * lda + c] * sc[c] + sh[c];
+    D[i] = ns.mode == NORM_RAW ? v : fmaxf(v, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// A_out[R, Nout] = act_in(A_in)[R, Kin] . W[Nout, Kin]^T (+ bias);  Kin, Nout <= 64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
+    const float* __restrict__ A_in, int lda, int Kin, NormSpec ns, const float* __restrict__ W, int ldw,
+    const float* __restrict__ bias, int Nout, float* __restrict__ A_out, int ldo, int R) {
+  __shared__ float Ws[kH][kH + 1];
+  __shared__ float Hs[kTileR][kH + 1];
+  __shared__ float sc[kH], sh[kH];
+  int t = threadIdx.x;
+  for (int i = t; i < kH * kH; i += kMidThreads) {
+    int n = i / kH, k = i % kH;
+    Ws[n][k] = (n < Nout && k < Kin) ? W[(size_t)n * ldw + k] : 0.f;
+  }
+  if (t < kH) {
+    float m, r;
+    if (t < Kin) norm_coeffs(ns, t, sc[t], sh[t], m, r); else { sc[t] = 0.f; sh[t] = 0.f; }
+  }
+  __syncthreads();
+  int rl = t >> 2, cq = t & 3;
+  for (int r0 = blockIdx.x * kTileR; r0 < R; r0 += gridDim.x * kTileR) {
+    for (int i = t; i < kTileR * Kin; i += kMidThreads) {
+      int r = i / Kin, k = i % Kin;
+      float v = 0.f;
+      if (r0 + r < R) {
+        v = A_in[(size_t)(r0 + r) * lda + k] * sc[k] + sh[k];
+        if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f);
+      }
+      Hs[r][k] = v;
+    }
+    __syncthreads();
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int k = 0; k < Kin; ++k) {
+      float h = Hs[rl][k];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(h, Ws[cq + 4 * j][k], acc[j]);
+    }
+    if (r0 + rl < R) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int n = cq + 4 * j;
+        if (n < Nout) A_out[(size_t)(r0 + rl) * ldo + n] = acc[j] + (bias ? bias[n] : 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// latent head: loc/scale, reparameterised sample, analytic KL (rows a5, a6, a10, a14)
+// ------------------------------------------------------------------------------------------
+struct LatentArgs {
+  const float* PL;     // [B, ZP] raw latent projection (ZP = 2Z, or Z for the deterministic DCA latent)
+  const float* eps_z;  // [S, B, Z]
+  float* loc;          // [B, Z]
+  float* scale;        // [B, Z]
+  float* z;            // [S*B, Z]
+  float* kl_z;         // [B]
+  // scVI library latent
+  const float* PLIB;   // [B, 2] raw (loc, scale_raw) or null
+  const float* eps_l;  // [S, B]
+  const float* library;  // [B, 2] prior (mean, var)
+  float* lib_loc; float* lib_scale;  // [B]
+  float* lib;          // [S*B] sampled log-library
+  float* kl_l;         // [B]
+  int B, S, Z, deterministic, scale_act;
+};
+__global__ void latent_fwd_kernel(LatentArgs a) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  int Z = a.Z;
+  if (a.deterministic) {
+    for (int j = 0; j < Z; ++j) {
+      float v = fmaxf(a.PL[(size_t)b * Z + j], 0.f);
+      a.loc[(size_t)b * Z + j] = v; a.scale[(size_t)b * Z + j] = 0.f; a.z[(size_t)b * Z + j] = v;
+    }
+    a.kl_z[b] = 0.f;
+  } else {
+    float kl = 0.f;
+    for (int j = 0; j < Z; ++j) {
+      float mu = a.PL[(size_t)b * 2 * Z + j];
+      float sg, dsg;
+      activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], sg, dsg);
+      a.loc[(size_t)b * Z + j] = mu; a.scale[(size_t)b * Z + j] = sg;
+      kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
+      for (int s = 0; s < a.S; ++s)
+        a.z[((size_t)s * a.B + b) * Z + j] = fmaf(sg, a.eps_z[((size_t)s * a.B + b) * Z + j], mu);
+    }
+    a.kl_z[b] = 0.5f * kl;
+  }
+  if (a.PLIB) {
+    float mu = a.PLIB[(size_t)b * 2];
+    float sg, dsg;
+    activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], sg, dsg);
+    float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
+    a.lib_loc[b] = mu; a.lib_scale[b] = sg;
+    a.kl_l[b] = logf(sqrtf(pv) / sg) + (sg * sg + (mu - pm) * (mu - pm)) / (2.f * pv) - 0.5f;
+    for (int s = 0; s < a.S; ++s) a.lib[(size_t)s * a.B + b] = fmaf(sg, a.eps_l[(size_t)s * a.B + b], mu);
+  } else if (a.kl_l) {
+    a.kl_l[b] = 0.f;
+  }
+}
+
+struct LatentBwdArgs {
+  const float* dZ;     // [B, Z] d loss / d z
+  const float* PL; const float* eps_z; const float* loc; const float* scale;
+  float* dPL;          // [B, ZP]
+  const float* dLib;   // [B] d loss / d sampled log-library (scVI) or null
+  const float* PLIB; const float* eps_l; const float* library; const float* lib_loc; const float* lib_scale;
+  float* dPLIB;        // [B, 2]
+  int B, Z, deterministic, scale_act;
+  float kl_weight;     // beta / B : d loss / d KL_b
+};
+__global__ void latent_bwd_kernel(LatentBwdArgs a) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  int Z = a.Z;
+  if (a.deterministic) {
+    for (int j = 0; j < Z; ++j)
+      a.dPL[(size_t)b * Z + j] = a.PL[(size_t)b * Z + j] > 0.f ? a.dZ[(size_t)b * Z + j] : 0.f;
+  } else {
+    for (int j = 0; j < Z; ++j) {
+      float dz = a.dZ[(size_t)b * Z + j];
+      float mu = a.loc[(size_t)b * Z + j], sg = a.scale[(size_t)b * Z + j];
+      float v, dv;
+      activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], v, dv);
+      float dmu = dz + a.kl_weight * mu;
+      float dsg = dz * a.eps_z[(size_t)b * Z + j] + a.kl_weight * (sg - 1.f / sg);
+      a.dPL[(size_t)b * 2 * Z + j] = dmu;
+      a.dPL[(size_t)b * 2 * Z + Z + j] = dsg * dv;
+    }
+  }
+  if (a.dPLIB) {
+    float dl = a.dLib[b];
+    float mu = a.lib_loc[b], sg = a.lib_scale[b];
+    float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
+    float v, dv;
+    activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], v, dv);
+    a.dPLIB[(size_t)b * 2] = dl + a.kl_weight * (mu - pm) / pv;
+    a.dPLIB[(size_t)b * 2 + 1] = (dl * a.eps_l[b] + a.kl_weight * (sg / pv - 1.f / sg)) * dv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// semi-supervised protein head (row a11): llk_y per row and d loss / d raw head outputs
+// ------------------------------------------------------------------------------------------
+struct YHeadArgs {
+  const float* PY;       // [R, 2P] raw (a | b)
+  const float* y;        // [B, P]
+  const uint8_t* mask;   // [B] or null (== unlabelled)
+  float* llk_y;          // [R]
+  float* dPY;            // [R, 2P] or null (inference)
+  float* y_mean;         // [R, P] or null
+  int R, B, P, y_dist, mean_act, disp_act;
+  float upstream;        // -alpha / B   (d loss / d llk_y for a labelled cell, before mask weighting)
+  const float* mask_scale;  // device scalar: 1 (Q3 default) or B / n_labelled
+};
+__global__ void yhead_kernel(YHeadArgs a) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  int b = r % a.B, P = a.P;
+  float w = (a.mask && a.mask[b]) ? 1.f : 0.f;
+  if (a.mask_scale) w *= *a.mask_scale;
+  float acc = 0.f;
+  for (int j = 0; j < P; ++j) {
+    float ra = a.PY[(size_t)r * 2 * P + j], rb = a.PY[(size_t)r * 2 * P + P + j];
+    float yv = a.y[(size_t)b * P + j];
+    float da = 0.f, db = 0.f, llk, mean;
+    if (a.y_dist == 0) {
+      llk = a.dPY ? nb_tfp_llk<true>(yv, ra, rb, da, db) : nb_tfp_llk<false>(yv, ra, rb, da, db);
+      mean = __expf(ra + rb);
+    } else {
+      float mu, dmu, th, dth;
+      activation(a.mean_act, ra, mu, dmu);
+      activation(a.disp_act, rb, th, dth);
+      CountGrad g;
+      llk = count_llk<false, true>(yv, mu, th, 0.f, g);
+      da = g.dmu * dmu; db = g.dth * dth; mean = mu;
+    }
+    acc += llk;
+    if (a.dPY) {
+      a.dPY[(size_t)r * 2 * P + j] = a.upstream * w * da;
+      a.dPY[(size_t)r * 2 * P + P + j] = a.upstream * w * db;
+    }
+    if (a.y_mean) a.y_mean[(size_t)r * P + j] = mean;
+  }
+  a.llk_y[r] = acc;
+}
+
+// n_labelled -> mask_scale = B / max(n_labelled, 1)   (Q3 alternative)
+__global__ void mask_scale_kernel(const uint8_t* mask, int B, float* out) {
+  __shared__ float scratch[33];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) c += mask[i] ? 1.f : 0.f;
+  c = block_sum(c, scratch);
+  if (threadIdx.x == 0) *out = (float)B / fmaxf(c, 1.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// ELBO assembly (row a12): terms = [elbo | llk_x | llk_y | kl_z | kl_l] each [R]; loss = -mean
+// ------------------------------------------------------------------------------------------
+struct ElboArgs {
+  float* terms; const uint8_t* mask; const float* mask_scale;
+  int R, B; float alpha, beta; float* loss;  // loss: device scalar, pre-zeroed
+};
+__global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
+  __shared__ float scratch[33];
+  float local = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.R; r += gridDim.x * blockDim.x) {
+    int b = r % a.B;
+    float w = (a.mask && a.mask[b]) ? 1.f : 0.f;
+    if (a.mask_scale) w *= *a.mask_scale;
+    float e = a.terms[(size_t)1 * a.R + r] + a.alpha * w * a.terms[(size_t)2 * a.R + r] -
+              a.beta * (a.terms[(size_t)3 * a.R + b] + a.terms[(size_t)4 * a.R + b]);
+    a.terms[r] = e;
+    local += e;
+  }
+  local = block_sum(local, scratch);
+  if (threadIdx.x == 0 && a.loss) atomicAdd(a.loss, -local / (float)a.R);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of norm+relu: column sums of dY and dY*xhat (double) + d gamma / d beta
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
+    const float* __restrict__ dH, int ldd, const float* __restrict__ A, int lda, NormSpec ns, int R,
+    double* __restrict__ sdy, double* __restrict__ sdyx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double s1[256], s2[256];
+  int c = threadIdx.x % kH, grp = threadIdx.x / kH;  // 4 row groups
+  float sc, sh, mean, rstd;
+  norm_coeffs(ns, c, sc, sh, mean, rstd);
+  double a1 = 0.0, a2 = 0.0;
+  for (int r = blockIdx.x * 4 + grp; r < R; r += gridDim.x * 4) {
+    float av = A[(size_t)r * lda + c];
+    float dy = (av * sc + sh > 0.f) ? dH[(size_t)r * ldd + c] : 0.f;
+    a1 += (double)dy;
+    a2 += (double)(dy * ((av - mean) * rstd));
+  }
+  s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < 4; ++g) { a1 += s1[g * kH + c]; a2 += s2[g * kH + c]; }
+    atomicAdd(&sdy[c], a1);
+    atomicAdd(&sdyx[c], a2);
+    if (ns.mode == NORM_BIAS) {
+      atomicAdd(&dbeta[c], (float)a1);             // bias gradient
+    } else {
+      atomicAdd(&dgamma[c], (float)a2);
+      atomicAdd(&dbeta[c], (float)a1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of one dense unit:  given the gradient at its output, produce dW (atomic), db (atomic),
+// the gradient wrt its input activations, and optionally the gradient wrt its pre-activation.
+//   out_mode 0: dOut[R, Nout] is given directly (heads with bias, no norm)
+//   out_mode 1: dOut = BN/bias backward of dH[R,64] applied on load (needs A_out, ns_out, sdy, sdyx)
+// ------------------------------------------------------------------------------------------
+constexpr size_t kDenseBwdSmem = (size_t)(kH + 2 * kTileR) * (kH + 1) * sizeof(float) + 9 * kH * sizeof(float);
+struct DenseBwdArgs {
+  int out_mode;
+  const float* dOut; int ldd;          // dOut (mode 0) or dH (mode 1)
+  const float* A_out; int lda_out;     // pre-activation of this unit (mode 1)
+  NormSpec ns_out;
+  const double* sdy; const double* sdyx;
+  int Nout;
+  const float* A_in; int lda_in; int Kin; NormSpec ns_in;   // source of the unit's input (null -> no dW)
+  const float* W; int ldw;             // [Nout, Kin]
+  float* dW;                           // [Nout, Kin] ld = ldw, atomic accumulate (nullable)
+  float* db;                           // [Nout] atomic accumulate (nullable)
+  float* dIn; int ldi; int accumulate_dIn;   // [R, Kin] (nullable)
+  float* dA; int ldda;                 // [R, Nout] d loss / d pre-activation (nullable)
+  int R;
+};
+__global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) {
+  extern __shared__ float dyn_smem[];
+  typedef float Row[kH + 1];
+  Row* Ws = reinterpret_cast<Row*>(dyn_smem);
+  Row* Hs = Ws + kH;
+  Row* Gs = Hs + kTileR;
+  float* sc_i = reinterpret_cast<float*>(Gs + kTileR);
+  float *sh_i = sc_i + kH, *sc_o = sh_i + kH, *sh_o = sc_o + kH, *mean_o = sh_o + kH, *rstd_o = mean_o + kH,
+        *m1 = rstd_o + kH, *m2 = m1 + kH, *gsc = m2 + kH;
+  int t = threadIdx.x;
+  const int Nout = a.Nout, Kin = a.Kin;
+  const bool has_in = a.A_in != nullptr;
+  for (int i = t; i < kH * kH; i += kMidThreads) {
+    int n = i / kH, k = i % kH;
+    Ws[n][k] = (n < Nout && k < Kin && a.W) ? a.W[(size_t)n * a.ldw + k] : 0.f;
+  }
+  if (t < kH) {
+    float m, r;
+    if (has_in && t < Kin) norm_coeffs(a.ns_in, t, sc_i[t], sh_i[t], m, r); else { sc_i[t] = 0.f; sh_i[t] = 0.f; }
+    if (a.out_mode == 1) {
+      norm_coeffs(a.ns_out, t, sc_o[t], sh_o[t], mean_o[t], rstd_o[t]);
+      if (a.ns_out.mode == NORM_BN_BATCH) {
+        m1[t] = (float)(a.sdy[t] * (double)a.ns_out.inv_count);
+        m2[t] = (float)(a.sdyx[t] * (double)a.ns_out.inv_count);
+        gsc[t] = sc_o[t];           // gamma * rstd
+      } else {                      // bias (or moving-stat BN): no batch coupling
+        m1[t] = 0.f; m2[t] = 0.f; gsc[t] = sc_o[t];
+      }
+    }
+  }
+  __syncthreads();
+  const int rl = t >> 2, cq = t & 3;
+  float accW[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) accW[j] = 0.f;
+  float accb = 0.f;
+  for (int r0 = blockIdx.x * kTileR; r0 < a.R; r0 += gridDim.x * kTileR) {
+    // gradient wrt pre-activation of this unit -> Gs[r][n]
+    for (int i = t; i < kTileR * kH; i += kMidThreads) {
+      int r = i / kH, n = i % kH;
+      float g = 0.f;
+      if (r0 + r < a.R && n < Nout) {
+        if (a.out_mode == 0) {
+          g = a.dOut[(size_t)(r0 + r) * a.ldd + n];
+        } else {
+          float av = a.A_out[(size_t)(r0 + r) * a.lda_out + n];
+          float dy = (av * sc_o[n] + sh_o[n] > 0.f) ? a.dOut[(size_t)(r0 + r) * a.ldd + n] : 0.f;
+          float xh = (av - mean_o[n]) * rstd_o[n];
+          g = gsc[n] * (dy - m1[n] - xh * m2[n]);
+        }
+        if (a.dA) a.dA[(size_t)(r0 + r) * a.ldda + n] = g;
+      }
+      Gs[r][n] = g;
+    }
+    if (has_in) {
+      for (int i = t; i < kTileR * kH; i += kMidThreads) {
+        int r = i / kH, k = i % kH;
+        float v = 0.f;
+        if (r0 + r < a.R && k < Kin) {
+          v = a.A_in[(size_t)(r0 + r) * a.lda_in + k] * sc_i[k] + sh_i[k];
+          if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f);
+        }
+        Hs[r][k] = v;
+      }
+    }
+    __syncthreads();
+    if (has_in && a.dW) {   // dW[n][k] += sum_r Gs[r][n] * Hs[r][k];  n = rl, k = cq + 4j
+      for (int r = 0; r < kTileR; ++r) {
+        float g = Gs[r][rl];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accW[j] = fmaf(g, Hs[r][cq + 4 * j], accW[j]);
+      }
+    }
+    if (a.db && t < Nout) {
+      for (int r = 0; r < kTileR; ++r) accb += Gs[r][t];
+    }
+    if (a.dIn) {            // dIn[r][k] = sum_n Gs[r][n] * W[n][k];  r = rl, k = cq + 4j
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int n = 0; n < Nout; ++n) {
+        float g = Gs[rl][n];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(g, Ws[n][cq + 4 * j], acc[j]);
+      }
+      if (r0 + rl < a.R) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int k = cq + 4 * j;
+          if (k < Kin) {
+            float* p = a.dIn + (size_t)(r0 + rl) * a.ldi + k;
+            *p = a.accumulate_dIn ? (*p + acc[j]) : acc[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (has_in && a.dW && rl < Nout) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int k = cq + 4 * j;
+      if (k < Kin) atomicAdd(&a.dW[(size_t)rl * a.ldw + k], accW[j]);
+    }
+  }
+  if (a.db && t < Nout) atomicAdd(&a.db[t], accb);
+}
+
+}  // namespace sisua

@@ -1,0 +1,152 @@
+"""Thin owner of one C-ABI handle plus the device buffers it is bound to.  torch is used only to
+hold device memory and the CUDA stream; every computation goes through libsisua_b200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import StepConfig, bn_layer_names, param_layout
+from .params import init_bn_moving, init_flat_params
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return ctypes.c_void_p(0) if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+  """One model replica on one GPU."""
+
+  def __init__(self, cfg: StepConfig, device: int = 0, flat_params: Optional[np.ndarray] = None,
+               bn_moving: Optional[np.ndarray] = None, seed: int = 8, train: bool = True):
+    if not torch.cuda.is_available():
+      raise _lib.SisuaError("no CUDA device: the SISUA B200 step has no CPU path")
+    self.lib = _lib.load()
+    self.cfg = cfg
+    self.device = torch.device("cuda", device)
+    self.handle = ctypes.c_void_p()
+    with torch.cuda.device(self.device):
+      rc = self.lib.sisua_create(ctypes.byref(cfg), device, ctypes.byref(self.handle))
+    if rc != 0:
+      msg = self.lib.sisua_last_error(self.handle).decode() if self.handle else "create failed"
+      if self.handle:
+        self.lib.sisua_destroy(self.handle)
+        self.handle = ctypes.c_void_p()
+      raise _lib.SisuaError(f"sisua_create: {msg}")
+    self.entries, self.total = param_layout(cfg)
+    n = ctypes.c_int(0)
+    tot = ctypes.c_int64(0)
+    self._check(self.lib.sisua_param_layout(self.handle, None, ctypes.byref(n), ctypes.byref(tot)))
+    if tot.value != self.total or n.value != len(self.entries):
+      raise _lib.SisuaError("host / library parameter layouts disagree")
+    flat = init_flat_params(cfg, seed) if flat_params is None else np.asarray(flat_params, dtype=np.float32)
+    mov = init_bn_moving(cfg) if bn_moving is None else np.asarray(bn_moving, dtype=np.float32)
+    self.params = torch.from_numpy(flat.copy()).to(self.device)
+    self.bn_moving = torch.from_numpy(mov.copy()).to(self.device)
+    if train:
+      self.grads = torch.zeros_like(self.params)
+      self.adam_m = torch.zeros_like(self.params)
+      self.adam_v = torch.zeros_like(self.params)
+    else:
+      self.grads = self.adam_m = self.adam_v = None
+    self._check(self.lib.sisua_bind_buffers(self.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m),
+                                            _ptr(self.adam_v), _ptr(self.bn_moving)))
+    self.step_count = 0
+
+  # -------------------------------------------------------------------------------------------
+  def _check(self, rc: int):
+    if rc != 0:
+      raise _lib.SisuaError(self.lib.sisua_last_error(self.handle).decode())
+
+  def close(self):
+    if getattr(self, "handle", None):
+      self.lib.sisua_destroy(self.handle)
+      self.handle = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def layout(self):
+    n = ctypes.c_int(64)
+    arr = (_lib.ParamDesc * 64)()
+    tot = ctypes.c_int64(0)
+    self._check(self.lib.sisua_param_layout(self.handle, arr, ctypes.byref(n), ctypes.byref(tot)))
+    return [(arr[i].name.decode(), arr[i].offset, arr[i].rows, arr[i].cols, arr[i].ld, arr[i].kind)
+            for i in range(n.value)], tot.value
+
+  def _dev(self, a, dtype=torch.float32):
+    if a is None:
+      return None
+    if isinstance(a, torch.Tensor):
+      t = a.to(device=self.device, dtype=dtype)
+    else:
+      t = torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+    return t.contiguous()
+
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  # -------------------------------------------------------------------------------------------
+  def train_step(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, terms=None, loss=None):
+    """forward + backward on device tensors (or host arrays, copied). Returns (terms [5,B], loss [1])."""
+    x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
+    mask = self._dev(mask, torch.uint8)
+    B = x.shape[0]
+    if terms is None:
+      terms = torch.empty((5, B), dtype=torch.float32, device=self.device)
+    if loss is None:
+      loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_train_step(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
+                                            _ptr(eps_l), B, _ptr(terms), _ptr(loss), self._stream()))
+    return terms, loss
+
+  def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps_hat=1e-7, clipnorm=100.0, grad_scale=1.0, t=0):
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_adam_step(self.handle, lr, beta1, beta2, eps_hat, clipnorm or 0.0, grad_scale,
+                                           int(t), self._stream()))
+    self.step_count = t if t > 0 else self.step_count + 1
+
+  def infer(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, S=1, want_mean=True,
+            want_disp=False, want_pi=False) -> Dict[str, torch.Tensor]:
+    cfg = self.cfg
+    x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
+    mask = self._dev(mask, torch.uint8)
+    B, G, Z, P = x.shape[0], cfg.n_genes, cfg.n_latent, cfg.n_proteins
+    R = S * B
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+    out = dict(terms=f(5, R), z_loc=f(B, Z), z_scale=f(B, Z))
+    out["mean"] = f(R, G) if want_mean else None
+    out["disp"] = f(R, G) if want_disp else None
+    out["pi_logit"] = f(R, G) if (want_pi and cfg.x_dist == 0) else None
+    out["lib_loc"] = f(B) if cfg.model_kind == 1 else None
+    out["lib_scale"] = f(B) if cfg.model_kind == 1 else None
+    out["y_mean"] = f(R, P) if P > 0 else None
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_infer(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
+                                       _ptr(eps_l), B, S, _ptr(out["terms"]), _ptr(out["z_loc"]), _ptr(out["z_scale"]),
+                                       _ptr(out["lib_loc"]), _ptr(out["lib_scale"]), _ptr(out["mean"]),
+                                       _ptr(out["disp"]), _ptr(out["pi_logit"]), _ptr(out["y_mean"]), self._stream()))
+    return out
+
+  # -------------------------------------------------------------------------------------------
+  def debug_buffer(self, name: str, rows: int, cols: int) -> torch.Tensor:
+    """Copy of a private workspace buffer (tests only)."""
+    out = torch.empty((rows, cols), dtype=torch.float32, device=self.device)
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_debug_copy(self.handle, name.encode(), _ptr(out), rows * cols, self._stream()))
+    return out
+
+  def params_dict(self) -> Dict[str, np.ndarray]:
+    from .params import flat_to_dict
+    return flat_to_dict(self.cfg, self.params.detach().cpu().numpy())
+
+  def grads_dict(self) -> Dict[str, np.ndarray]:
+    from .params import flat_to_dict
+    return flat_to_dict(self.cfg, self.grads.detach().cpu().numpy())

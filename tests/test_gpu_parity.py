@@ -1,0 +1,165 @@
+"""CUDA path vs the CPU oracle on identical synthetic counts, weights and injected eps.
+Tolerance (BASELINE.json north_star): per-cell ELBO, latent means and imputed means within 1e-4
+relative in fp32 (gemm_mode 0 = exact fp32 FFMA, gemm_mode 1 = error-compensated 3xTF32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import step_oracle as O
+from sisua_b200 import config as C
+from sisua_b200 import params as PR
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _engine(cfg, flat, mov):
+  from sisua_b200.engine import Engine
+  return Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+
+
+def _close(a, b, rtol=RTOL, atol=0.0, what=""):
+  a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+  err = np.abs(a - b)
+  tol = rtol * np.abs(b) + atol
+  bad = err > tol
+  assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} off; worst rel {np.max(err / (np.abs(b) + 1e-30)):.3e} abs {err.max():.3e}"
+
+
+MODELS = [("vae", {}), ("scvi", {}), ("dca", {}), ("sisua", dict(n_proteins=10))]
+MODES = [C.GEMM_FP32_UNFUSED]
+
+
+def _setup(model, kw, G, B, mode, seed=0, trained_moving=True, **cfgkw):
+  cfg = C.make_step_config(model, n_genes=G, gemm_mode=mode, max_batch=max(B * 4, 256), **kw, **cfgkw)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  if trained_moving:
+    rng = np.random.default_rng(5)
+    mov[:, 0, :] = rng.normal(0, 0.3, mov[:, 0, :].shape)
+    mov[:, 1, :] = rng.uniform(0.5, 2.0, mov[:, 1, :].shape)
+  batch = Hh.make_batch(cfg, B, seed=seed)
+  return cfg, flat, mov, batch
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw", MODELS)
+@pytest.mark.parametrize("G,B", [(558, 96), (50, 33)])
+def test_inference_parity(model, kw, G, B, mode):
+  cfg, flat, mov, batch = _setup(model, kw, G, B, mode)
+  eng = _engine(cfg, flat, mov)
+  out = eng.infer(want_mean=True, want_disp=True, want_pi=True, **batch)
+  torch.cuda.synchronize()
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=False, **batch)
+  terms = out["terms"].cpu().numpy()
+  _close(terms[0], ref["elbo"].numpy(), what="elbo")
+  _close(terms[1], ref["llk_x"].numpy(), what="llk_x")
+  _close(terms[3], ref["kl_z"].numpy(), atol=1e-5, what="kl_z")
+  _close(out["z_loc"].cpu().numpy(), ref["z_loc"].numpy(), atol=1e-5, what="z_loc")
+  _close(out["z_scale"].cpu().numpy(), ref["z_scale"].numpy(), atol=1e-6, what="z_scale")
+  _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="imputed mean")
+  _close(out["disp"].cpu().numpy(), ref["theta"].numpy(), atol=1e-7, what="dispersion")
+  if model == "sisua":
+    _close(terms[2], ref["llk_y"].numpy(), what="llk_y")
+    _close(out["y_mean"].cpu().numpy(), ref["y_mean"].numpy(), what="y_mean")
+  if model == "scvi":
+    _close(terms[4], ref["kl_l"].numpy(), atol=1e-5, what="kl_l")
+  eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_inference_mc_samples(mode):
+  cfg, flat, mov, _ = _setup("vae", {}, 200, 40, mode)
+  batch = Hh.make_batch(cfg, 40, S=3)
+  eng = _engine(cfg, flat, mov)
+  out = eng.infer(S=3, **batch)
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy().reshape(3, 40), ref["elbo"].numpy(), what="elbo[S,B]")
+  _close(out["mean"].cpu().numpy().reshape(3, 40, 200), ref["mu"].numpy(), atol=1e-7, what="mean[S,B,G]")
+  eng.close()
+
+
+def _grad_check(cfg, flat, mov, batch, eng, gtol=2e-3):
+  terms, loss = eng.train_step(**batch)
+  torch.cuda.synchronize()
+  P = Hh.oracle_params(cfg, flat)
+  for p in P.values():
+    p.requires_grad_(True)
+  om = Hh.oracle_moving(cfg, mov)
+  ref = O.forward(cfg, P, om, training=True, **batch)
+  ref["loss"].backward()
+  _close(terms[0].cpu().numpy(), ref["elbo"].detach().numpy(), what="train elbo")
+  _close(loss.cpu().numpy()[0], float(ref["loss"]), what="loss")
+  got = eng.grads_dict()
+  for name, p in P.items():
+    g_ref = p.grad.numpy() if p.grad is not None else np.zeros(p.shape)
+    scale = np.abs(g_ref).max() + 1e-12
+    err = np.abs(got[name] - g_ref).max()
+    assert err <= gtol * scale + 1e-9, f"grad {name}: max err {err:.3e} vs scale {scale:.3e}"
+  # BN moving statistics
+  new_mov = PR.moving_to_dict(cfg, eng.bn_moving.cpu().numpy())
+  for k, v in ref["new_moving"].items():
+    _close(new_mov[k], v.numpy(), rtol=1e-4, atol=1e-6, what=k)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw", MODELS)
+@pytest.mark.parametrize("G,B", [(558, 128), (50, 33)])
+def test_train_step_gradients(model, kw, G, B, mode):
+  cfg, flat, mov, batch = _setup(model, kw, G, B, mode, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng)
+  eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_variants_nbd_nobn_stress(mode):
+  # 'nbd' likelihood, no batch norm (bias path), dense stress counts (tests/test_scalability.py recipe)
+  cfg = C.make_step_config("sisua", n_genes=120, n_proteins=10, x_dist="nbd", y_dist="nbd", batchnorm=False,
+                           gemm_mode=mode, max_batch=256)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  batch = Hh.make_batch(cfg, 64, stress=True)
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng)
+  eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw", [("vae", {}), ("scvi", {}), ("sisua", dict(n_proteins=10))])
+def test_multi_step_training_matches_oracle(model, kw, mode):
+  G, B, T = 300, 64, 5
+  cfg, flat, mov, _ = _setup(model, kw, G, B, mode, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  P = Hh.oracle_params(cfg, flat)
+  om = Hh.oracle_moving(cfg, mov)
+  m = {k: torch.zeros_like(v) for k, v in P.items()}
+  v = {k: torch.zeros_like(p) for k, p in P.items()}
+  for t in range(1, T + 1):
+    batch = Hh.make_batch(cfg, B, seed=t)
+    terms, loss = eng.train_step(**batch)
+    eng.adam_step(lr=1e-3, clipnorm=100.0, t=t)
+    out, _ = O.train_step(cfg, P, om, m, v, t, batch, lr=1e-3, clipnorm=100.0)
+    _close(loss.cpu().numpy()[0], float(out["loss"]), rtol=2e-4, what=f"loss step {t}")
+  got = eng.params_dict()
+  for name, p in P.items():
+    # Adam's normalised update amplifies tiny gradient differences: compare against the step size
+    err = np.abs(got[name] - p.numpy()).max()
+    assert err <= 2e-4, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
+  eng.close()
+
+
+def test_errors_are_loud():
+  from sisua_b200 import _lib
+  cfg = C.make_step_config("scvi", n_genes=40, max_batch=64)
+  from sisua_b200.engine import Engine
+  eng = Engine(cfg, 0)
+  b = Hh.make_batch(cfg, 16)
+  with pytest.raises(_lib.SisuaError):
+    eng.infer(x=b["x"], eps_z=b["eps_z"])          # scVI without library
+  with pytest.raises(_lib.SisuaError):
+    big = Hh.make_batch(cfg, 128)
+    eng.infer(**big)                               # exceeds max_batch
+  eng.close()
