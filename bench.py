@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — train cells/s of the ZINB-VAE ELBO step (BASELINE.json metric) on N B200s.
+
+Workload (BASELINE.json configs[4]): ZINB-VAE, 2000 genes, latent 10, 2x64 hidden
+units, cells sharded over the GPUs; each rank streams minibatches out of its HBM-resident shard
+(synthetic NB counts, pbmc8k-calibrated statistics).  A step = one minibatch forward + backward (+ gradient
+all-reduce when N > 1) + Adam.  Prints ONE JSON line (see the driver contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--genes G]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENES, LATENT, SHARD_CELLS, TOTAL_CELLS = 2000, 10, 131072, 1_000_000
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=60)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--batch", type=int, default=8192, help="cells per GPU per step")
+  ap.add_argument("--genes", type=int, default=GENES)
+  ap.add_argument("--shard-cells", type=int, default=SHARD_CELLS)
+  ap.add_argument("--gemm-mode", type=int, default=-1, help="-1: best available (tcgen05 3xTF32 if built)")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--cpu-steps", type=int, default=6)
+  return ap.parse_args()
+
+
+def workload_name(a):
+  return (f"ZINB-VAE train step, synthetic {TOTAL_CELLS // 1000}k-cell x {a.genes}-gene epoch "
+          f"(BASELINE.json configs[4]); per-GPU shard {a.shard_cells} cells resident in HBM")
+
+
+# ----------------------------------------------------------------------------------------------
+def synth_on_device(n_cells, n_genes, device, seed):
+  """pbmc8k-calibrated NB counts generated on the GPU (same recipe as sisua_b200.synthetic.realistic_counts;
+  1M x 2000 on the host would take minutes)."""
+  import torch
+  g = torch.Generator(device=device); g.manual_seed(seed)
+  log_m = torch.randn(n_genes, device=device, generator=g) * 1.5
+  m = torch.softmax(log_m, 0)
+  theta = torch.distributions.Gamma(torch.full((n_genes,), 2.0, device=device), torch.ones(n_genes, device=device)).sample() + 1e-3
+  X = torch.empty((n_cells, n_genes), device=device)
+  for s in range(0, n_cells, 16384):
+    e = min(n_cells, s + 16384)
+    lib = torch.exp(6.42 + 0.28 * torch.randn(e - s, 1, device=device, generator=g))
+    mean = lib * m[None, :]
+    lam = torch.distributions.Gamma(theta[None, :].expand_as(mean), (theta[None, :] / mean.clamp_min(1e-8))).sample()
+    c = torch.poisson(lam)
+    c = c * (torch.rand(c.shape, device=device, generator=g) >= 0.1)
+    X[s:e] = c
+  return X
+
+
+def cpu_batches(cfg, B, n, seed=0):
+  from sisua_b200 import synthetic as SY
+  out = []
+  for i in range(n):
+    d = SY.realistic_counts(B, cfg.n_genes, 0, 6.42, 0.28, seed=SY.DATA_SEED + seed + i)
+    rng = np.random.default_rng(seed + i)
+    out.append(dict(x=d["x"], eps_z=rng.standard_normal((B, cfg.n_latent)).astype(np.float32)))
+  return out
+
+
+def run_cpu(cfg, B, steps, warmup):
+  from oracle import cpu_baseline as CB
+  from sisua_b200 import params as PR
+  flat = PR.init_flat_params(cfg)
+  times, threads = CB.time_train_steps(cfg, PR.flat_to_dict(cfg, flat), PR.moving_to_dict(cfg, PR.init_bn_moving(cfg)),
+                                       cpu_batches(cfg, B, min(4, steps + warmup)), steps, warmup)
+  return times, threads
+
+
+class ClockSampler:
+  Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+  def __init__(self, index):
+    self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    try:
+      self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                 "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+    except Exception:
+      self.p = None
+
+  def stop(self):
+    if self.p is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.p.terminate()
+    try:
+      self.p.wait(timeout=5)
+    except Exception:
+      self.p.kill()
+    self.f.flush(); self.f.seek(0)
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in self.f.read().strip().splitlines():
+      parts = [p.strip() for p in line.split(",")]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0])); mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, parts[3:7]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    os.unlink(self.f.name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      d = json.load(f)
+    return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+  a = parse()
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+
+  from sisua_b200 import config as C
+  have_tc = os.path.exists(os.path.join(ROOT, "sisua_b200", "csrc", "kernels_tc.cuh"))
+  mode = a.gemm_mode if a.gemm_mode >= 0 else (C.GEMM_TC_3XTF32 if have_tc else C.GEMM_FP32_UNFUSED)
+  cfg = C.make_step_config("vae", n_genes=a.genes, n_latent=LATENT, gemm_mode=mode, max_batch=a.batch)
+  base = {"metric": "train cells/sec (ZINB-VAE step)", "unit": "cells/s", "n_gpus": a.gpus, "steps": a.steps,
+          "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic",
+          "config": {"workload": workload_name(a), "model": "vae/zinbd", "genes": a.genes, "latent": LATENT,
+                     "hidden": [64, 64], "batch_per_gpu": a.batch, "global_batch": a.batch * a.gpus,
+                     "parallelism": f"dp{a.gpus} (cells sharded, grads all-reduced)",
+                     "l2": "inputs larger than L2: each step streams a fresh minibatch of a >= 1 GB resident shard"}}
+
+  # ------------------------------------------------------------------ reference arm (CPU)
+  if a.impl == "reference":
+    if rank != 0:
+      return
+    times, threads = run_cpu(cfg, a.batch, a.steps, a.warmup)
+    sec = float(np.mean(times))
+    val = a.batch / sec
+    out = dict(base)
+    out.update({"impl": "reference", "value": val, "ms_per_step": sec * 1e3, "n_gpus": a.gpus,
+                "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port",
+                                 "sample": f"{a.steps} train steps of {a.batch} cells x {a.genes} genes, torch fp32 "
+                                           "oracle (reference TF/odin-ai stack not installable: DESIGN.md)"},
+                "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0})
+    out["config"] = dict(out["config"], parallelism="cpu")
+    print(json.dumps(out))
+    return
+
+  # ------------------------------------------------------------------ our arm
+  import torch
+  import torch.distributed as dist
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  from sisua_b200.engine import Engine
+  eng = Engine(cfg, local_rank, seed=8)
+  B, G = a.batch, a.genes
+  X = synth_on_device(a.shard_cells, G, dev, seed=87654321 + rank)
+  n_batches = a.shard_cells // B
+  gen = torch.Generator(device=dev); gen.manual_seed(8 + rank)
+  eps_pool = torch.randn((16, B, LATENT), device=dev, generator=gen)
+  terms = torch.empty((5, B), device=dev)
+  loss = torch.empty((1,), device=dev)
+  step_no = [0]
+
+  def one_step(xb):
+    step_no[0] += 1
+    eng.train_step(xb, eps_z=eps_pool[step_no[0] % 16], terms=terms, loss=loss, seed=rank, step=step_no[0])
+    if world > 1:
+      dist.all_reduce(eng.grads)
+    eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=1.0 / world, t=step_no[0])
+
+  def sync_all():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(a.warmup):
+    one_step(X[(i % n_batches) * B:(i % n_batches + 1) * B])
+  sync_all()
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  launches0 = eng.launch_count()
+  eng.profile(True)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(a.steps):
+    j = (a.warmup + i) % n_batches
+    one_step(X[j * B:(j + 1) * B])
+  e1.record()
+  sync_all()
+  ms = e0.elapsed_time(e1)
+  prof = eng.profile_read()
+  eng.profile(False)
+  launches = eng.launch_count() - launches0
+  clocks = sampler.stop() if sampler else None
+  t = torch.tensor([ms], device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = float(t.item())
+  value = world * B * a.steps / (ms * 1e-3)
+  final_loss = float(loss.item())
+
+  # ---- end-to-end arm: host-resident minibatches through the host-buffer entry point
+  from sisua_b200.pipeline import HostTrainPipeline
+  pipe = HostTrainPipeline(eng, B)
+  n_host = 6
+  host_batches = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
+  for i, hb in enumerate(host_batches):
+    hb.copy_(X[i * B:(i + 1) * B])
+  host_eps = [torch.randn((B, LATENT)).pin_memory() for _ in range(n_host)]
+  e2e_steps = max(10, a.steps // 2)
+
+  def e2e_run(n):
+    losses = []
+    for i in range(n):
+      step_no[0] += 1
+      l = pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
+                    allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None)
+      losses.append(l)
+    return pipe.flush(losses)
+
+  e2e_run(3)
+  sync_all()
+  t0 = time.perf_counter()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  e2e_losses = e2e_run(e2e_steps)
+  ev1.record()
+  sync_all()
+  e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+  t = torch.tensor([e2e_ms], device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_val = world * B * e2e_steps / (float(t.item()) * 1e-3)
+
+  if rank == 0:
+    hbm_peak, peak_src = measured_peaks()
+    # dominant kernel / section from the live CUDA-event profile of the timed region
+    per_step = {k: (v[0] / a.steps) for k, v in prof.items()}
+    dom = max(per_step, key=per_step.get)
+    # algorithmic bytes of one launch of the decoder-output + likelihood path: the
+    # count tile (4 G B/cell) + decoder activations in/out (2 * 256 B/cell) + per-cell terms
+    alg_bytes = {"out_heads": B * (4 * G + 2 * 256 + 8), "enc_first": B * (4 * G + 256), "enc_first_bwd": B * (4 * G + 256),
+                 "mid_fwd": B * 256 * 8, "mid_bwd": B * 256 * 12, "adam": eng.total * 28}
+    dur_s = per_step[dom] * 1e-3
+    achieved = alg_bytes[dom] / dur_s / 1e9
+    out = dict(base)
+    out.update({
+        "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss,
+        "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 3xTF32 fused", 2: "tcgen05 TF32 fused"}[mode],
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4),
+                "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "api": "HostTrainPipeline.step (pinned host minibatch -> H2D -> sisua_train_step -> sisua_adam_step -> D2H loss)"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "ms_per_launch": per_step[dom], "share_of_step": per_step[dom] / (ms / a.steps),
+                     "sections_ms_per_step": per_step},
+    })
+    if not a.no_cpu_baseline:
+      times, threads = run_cpu(cfg, B, a.cpu_steps, 1)
+      out["cpu_baseline"] = {"value": B / float(np.mean(times)), "unit": "cells/s", "cores": threads, "kind": "port",
+                             "sample": f"{a.cpu_steps} train steps of {B} cells x {G} genes (torch fp32 oracle, all host threads)"}
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -77,10 +77,13 @@ int sisua_bind_buffers(sisua_handle h, float* params, float* grads, float* adam_
  * single_cell_model.py:236).  x [B,G] counts; y [B,P] or NULL; library [B,2] (mean,var) or NULL;
  * mask [B] bytes or NULL; eps_z [B,z]; eps_l [B] (scVI).  Outputs: terms [5,B] =
  * (elbo | llk_x | llk_y | kl_z | kl_l), loss [1].  Gradients land in the bound `grads` buffer and
- * BN moving statistics are updated.  The optimiser is a separate call so the host can all-reduce
+ * BN moving statistics are updated.  Dropout masks (NetConf input_dropout / dropout) are the pure function
+ * Philox4x32-10(seed; row, col/4, step, stream) regenerated in forward and backward; step < 0 uses an
+ * internal call counter.  The optimiser is a separate call so the host can all-reduce
  * `grads` across GPUs in between. */
 int sisua_train_step(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
-                     const float* eps_z, const float* eps_l, int B, float* terms, float* loss, void* stream);
+                     const float* eps_z, const float* eps_l, int B, uint64_t seed, int64_t step, float* terms,
+                     float* loss, void* stream);
 
 /* Replaces one `self(**data, training=False, sample_shape=S)` call of SingleCellModel.predict
  * (single_cell_model.py:176-181) plus the parameter tensors the returned distributions hold.
@@ -103,6 +106,13 @@ int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float ep
 const float* sisua_debug_buffer(sisua_handle h, const char* name);
 
 int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
+
+/* Measurement hooks for bench.py: kernels launched so far through this handle; per-section device time
+ * (CUDA events on the caller's stream). Sections: 0 first encoder layer, 1 mid forward, 2 output heads +
+ * count likelihood (fused: one kernel), 3 mid backward, 4 first-layer weight gradient, 5 Adam. */
+int64_t sisua_launch_count(sisua_handle h);
+int sisua_profile_enable(sisua_handle h, int on);
+int sisua_profile_read(sisua_handle h, float* ms_out, int* counts_out);
 
 const char* sisua_last_error(sisua_handle h);
 const char* sisua_version(void);

@@ -1,0 +1,38 @@
+"""Timed CPU baseline: the oracle's train step (torch fp32, autograd, TF-formulation Adam) on the
+host cores.  Stands in for the reference's TensorFlow-CPU path, which cannot be installed here
+(odin-ai / TensorFlow absent, no network: DESIGN.md).  TEST / BENCH INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from oracle import step_oracle as O
+
+
+def host_threads() -> int:
+  try:
+    return len(os.sched_getaffinity(0))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
+def time_train_steps(cfg, params_np, moving_np, batches, steps: int, warmup: int = 1, lr: float = 1e-3):
+  """batches: list of oracle-style batch dicts (cycled). Returns (seconds_per_step list, threads)."""
+  threads = host_threads()
+  torch.set_num_threads(threads)
+  P = {k: torch.tensor(np.array(v), dtype=torch.float32) for k, v in params_np.items()}
+  mov = {k: torch.tensor(np.array(v), dtype=torch.float32) for k, v in moving_np.items()}
+  m = {k: torch.zeros_like(v) for k, v in P.items()}
+  v = {k: torch.zeros_like(p) for k, p in P.items()}
+  times = []
+  for t in range(1, warmup + steps + 1):
+    b = batches[(t - 1) % len(batches)]
+    t0 = time.perf_counter()
+    O.train_step(cfg, P, mov, m, v, t, b, lr=lr, clipnorm=100.0)
+    dt = time.perf_counter() - t0
+    if t > warmup:
+      times.append(dt)
+  return times, threads

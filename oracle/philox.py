@@ -1,0 +1,38 @@
+"""NumPy replica of the product's counter-based dropout masks.  TEST INFRASTRUCTURE ONLY.
+
+The CUDA step draws its dropout masks as Philox4x32-10(key = seed; counter = (row, col // 4, step,
+stream))[col % 4] (sisua_b200/csrc/device_math.cuh: philox4x32_10 / dropout_mult).  Philox is the
+published counter-based generator of Salmon et al. (SC'11); this file restates it so the oracle can
+be fed the very same masks.  Known-answer vectors from the Random123 distribution pin it
+(tests/test_oracle_kat.py)."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+  c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+  k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+  for _ in range(10):
+    p0 = M0 * c0
+    p1 = M1 * c2
+    hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+    hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+    c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)) & MASK, lo1, (hi0 ^ c3 ^ np.uint64(k1)) & MASK, lo0
+    k0 = (k0 + W0) & 0xFFFFFFFF
+    k1 = (k1 + W1) & 0xFFFFFFFF
+  return c0, c1, c2, c3
+
+
+def dropout_mask(rows: int, cols: int, rate: float, seed: int, step: int, stream: int) -> np.ndarray:
+  """[rows, cols] array of {0, 1}: 1 = kept."""
+  c4 = (cols + 3) // 4
+  r = np.repeat(np.arange(rows, dtype=np.uint64)[:, None], c4, axis=1)
+  c = np.repeat(np.arange(c4, dtype=np.uint64)[None, :], rows, axis=0)
+  out = philox4x32_10(r, c, np.full_like(r, step & 0xFFFFFFFF), np.full_like(r, stream),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+  u = np.stack(out, axis=-1).reshape(rows, c4 * 4)[:, :cols]
+  uf = (u >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+  return (uf >= np.float32(rate)).astype(np.float64)

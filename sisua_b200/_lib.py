@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
-           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -43,7 +43,7 @@ def load():
   L.sisua_param_layout.restype = ci
   L.sisua_bind_buffers.argtypes = [vp, vp, vp, vp, vp, vp]
   L.sisua_bind_buffers.restype = ci
-  L.sisua_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+  L.sisua_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
   L.sisua_train_step.restype = ci
   L.sisua_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci] + [vp] * 10
   L.sisua_infer.restype = ci
@@ -53,6 +53,12 @@ def load():
   L.sisua_debug_buffer.restype = vp
   L.sisua_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]
   L.sisua_debug_copy.restype = ci
+  L.sisua_launch_count.argtypes = [vp]
+  L.sisua_launch_count.restype = ctypes.c_int64
+  L.sisua_profile_enable.argtypes = [vp, ci]
+  L.sisua_profile_enable.restype = ci
+  L.sisua_profile_read.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ci)]
+  L.sisua_profile_read.restype = ci
   L.sisua_last_error.argtypes = [vp]
   L.sisua_last_error.restype = ctypes.c_char_p
   L.sisua_version.argtypes = []

@@ -69,7 +69,34 @@ struct sisua_model {
   SegTable seg;
   int num_sms = 148;
   int last_train_B = 0;
+  // dropout stream of the current training step
+  uint64_t drop_seed = 0;
+  uint32_t drop_step = 0;
+  long long train_calls = 0;
+  long long launches = 0;       // kernels launched through this handle (bench.py reports it)
+  // optional per-section device timing (CUDA events on the caller's stream)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sec_events[8];
+  size_t sec_used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+enum Section { SEC_ENC_FIRST = 0, SEC_MID_FWD = 1, SEC_OUT_HEADS = 2, SEC_MID_BWD = 3, SEC_ENC_FIRST_BWD = 4, SEC_ADAM = 5, SEC_COUNT = 6 };
+
+static void sec_begin(sisua_model* h, cudaStream_t st, int id) {
+  if (!h->profiling) return;
+  if (h->sec_used[id] == h->sec_events[id].size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->sec_events[id].push_back({a, b});
+  }
+  cudaEventRecord(h->sec_events[id][h->sec_used[id]].first, st);
+}
+static void sec_end(sisua_model* h, cudaStream_t st, int id) {
+  if (!h->profiling) return;
+  cudaEventRecord(h->sec_events[id][h->sec_used[id]].second, st);
+  h->sec_used[id] += 1;
+}
+
 
 #define SET_ERR(h, code, ...)                         \
   do {                                                \
@@ -166,6 +193,9 @@ static void build_layout(sisua_model* h) {
   for (auto& L : h->encl) L.stat_index = sc++;
   for (auto& L : h->dec) L.stat_index = sc++;
   h->n_units = sc;
+  for (auto& L : h->enc) L.dropout = c.enc_dropout;
+  for (auto& L : h->encl) L.dropout = c.encl_dropout;
+  for (auto& L : h->dec) L.dropout = c.dec_dropout;
   h->seg.n = (int)h->params.size();
   for (int i = 0; i < h->seg.n; ++i) { h->seg.off[i] = h->params[i].off; h->seg.size[i] = h->params[i].size(); }
 }
@@ -205,8 +235,8 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   if (c.model_kind == SISUA_MODEL_SISUA && c.n_proteins < 1) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs proteins");
   if (c.model_kind != SISUA_MODEL_SISUA && c.n_proteins != 0) SET_ERR(h, SISUA_ERR_INVALID, "proteins only with SISUA");
   if (c.max_batch < 1) SET_ERR(h, SISUA_ERR_INVALID, "max_batch must be positive");
-  if (c.input_dropout > 0.f || c.enc_dropout > 0.f || c.dec_dropout > 0.f || c.encl_dropout > 0.f)
-    SET_ERR(h, SISUA_ERR_UNSUPPORTED, "dropout > 0 is not implemented in the sm_100a step yet");
+  for (float r : {c.input_dropout, c.enc_dropout, c.dec_dropout, c.encl_dropout})
+    if (r < 0.f || r >= 1.f) SET_ERR(h, SISUA_ERR_INVALID, "dropout rates must be in [0, 1)");
 #ifndef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
 #endif
@@ -263,6 +293,8 @@ extern "C" int sisua_destroy(sisua_handle h) {
   if (!h) return SISUA_ERR_INVALID;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  for (auto& v : h->sec_events)
+    for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete h;
   return SISUA_OK;
 }
@@ -313,10 +345,22 @@ extern "C" int sisua_debug_copy(sisua_handle h, const char* name, float* dst, in
 }
 
 // ---- helpers ------------------------------------------------------------------------------------
+static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool training) {
+  DropSpec d;
+  memset(&d, 0, sizeof(d));
+  if (training && rate > 0.f) {
+    d.rate = rate; d.scale = 1.0f / (1.0f - rate);
+    d.seed_lo = (uint32_t)(h->drop_seed & 0xffffffffu); d.seed_hi = (uint32_t)(h->drop_seed >> 32);
+    d.step = h->drop_step; d.stream = stream;
+  }
+  return d;
+}
+
 static NormSpec make_norm(sisua_model* h, const Layer& L, bool training, int rows) {
   NormSpec ns;
   memset(&ns, 0, sizeof(ns));
   ns.eps = h->cfg.bn_eps;
+  ns.drop = make_drop(h, L.dropout, 1u + (uint32_t)L.stat_index, training);
   if (L.bn_index >= 0) {
     ns.gamma = h->P + L.g_off; ns.beta = h->P + L.b_off;
     if (training) {
@@ -341,7 +385,7 @@ static int mid_grid(sisua_model* h, int rows) { return std::max(1, std::min((row
 template <int AOP, int BOP>
 static void launch_sgemm(sisua_model* h, cudaStream_t st, const float* A, long long a_rs, long long a_cs, const float* B,
                          long long b_rs, long long b_cs, float* C, long long ldc, const float* bias, int M, int N, int K,
-                         bool accumulate) {
+                         bool accumulate, DropSpec drop = DropSpec{0.f, 1.f, 0u, 0u, 0u, 0u}) {
   int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
   int want = (2 * h->num_sms + tiles - 1) / tiles;
   int max_splits = std::max(1, K / 256);
@@ -350,17 +394,20 @@ static void launch_sgemm(sisua_model* h, cudaStream_t st, const float* A, long l
   splits = (K + k_chunk - 1) / k_chunk;
   dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM, splits);
   int atomic_out = (accumulate || splits > 1) ? 1 : 0;
-  sgemm_kernel<AOP, BOP><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, k_chunk, atomic_out);
+  ++h->launches;
+  sgemm_kernel<AOP, BOP><<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, M, N, K, k_chunk, atomic_out, drop);
 }
 
 static void launch_dense_fwd(sisua_model* h, cudaStream_t st, const float* A_in, int lda, int Kin, const NormSpec& ns,
                              const float* W, int ldw, const float* bias, int Nout, float* A_out, int ldo, int R) {
+  ++h->launches;
   dense_fwd_kernel<<<mid_grid(h, R), kMidThreads, 0, st>>>(A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R);
 }
 
 static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, int R) {
   double* s = h->stats + (size_t)L.stat_index * 4 * kH;
   int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+  ++h->launches;
   col_stats_kernel<<<grid, 256, 0, st>>>(L.A, L.lda, R, kH, s, s + kH);
 }
 
@@ -398,6 +445,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   // ---- first layer: log1p(x) . W1^T  (z encoder and, for scVI, the library encoder in one pass)
   const int N0 = scvi ? 2 * H : H;
   bool first_done = false;
+  sec_begin(h, st, SEC_ENC_FIRST);
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
     int rc = tc_encoder_first(h, st, x, B, N0);
@@ -406,13 +454,15 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   }
 #endif
   if (!first_done) {
+    DropSpec din = make_drop(h, c.input_dropout, 0u, training);
     if (c.log_norm)
-      launch_sgemm<LOAD_LOG1P, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false);
+      launch_sgemm<LOAD_LOG1P, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false, din);
     else
-      launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false);
-    // split-K accumulates atomically: the buffer must start from zero in that case
+      launch_sgemm<LOAD_RAW_DROP, LOAD_NONE>(h, st, x, G, 1, h->P + h->enc[0].w_off, 1, h->Gp, h->A0, h->ld0, nullptr, B, N0, G, false, din);
   }
   LAUNCH_OK(h, "first-layer gemm");
+  sec_end(h, st, SEC_ENC_FIRST);
+  sec_begin(h, st, SEC_MID_FWD);
   stack_forward(h, st, h->enc, training, B);
   {
     Layer& L = h->enc.back();
@@ -437,6 +487,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
       a.lib = h->lib;
     }
     a.B = B; a.S = S; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
+    ++h->launches;
     latent_fwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
     LAUNCH_OK(h, "latent_fwd_kernel");
   }
@@ -445,25 +496,29 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
                    h->dec[0].lda, R);
   stack_forward(h, st, h->dec, training, R);
   NormSpec ns_d = make_norm(h, h->dec.back(), training, R);
+  ++h->launches;
   norm_relu_kernel<<<std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms)), 256, 0, st>>>(
       h->dec.back().A, h->dec.back().lda, ns_d, h->D, R);
   LAUNCH_OK(h, "decoder stack");
   // ---- protein head (before the output layer so dD can be initialised by its backward)
   if (P > 0) {
     launch_dense_fwd(h, st, h->D, H, H, raw_norm(), h->P + h->y_w, H, h->P + h->y_b, 2 * P, h->PY, 2 * P, R);
-    if (c.mask_norm == 1) mask_scale_kernel<<<1, 256, 0, st>>>(mask, B, h->mask_scale);
+    if (c.mask_norm == 1) { ++h->launches; mask_scale_kernel<<<1, 256, 0, st>>>(mask, B, h->mask_scale); }
     YHeadArgs a;
     memset(&a, 0, sizeof(a));
     a.PY = h->PY; a.y = y; a.mask = mask; a.llk_y = terms + (size_t)2 * R; a.dPY = training ? h->dPY : nullptr;
     a.y_mean = y_mean; a.R = R; a.B = B; a.P = P; a.y_dist = c.y_dist; a.mean_act = c.mean_act; a.disp_act = c.disp_act;
     a.upstream = -c.alpha / (float)R;
     a.mask_scale = c.mask_norm == 1 ? h->mask_scale : nullptr;
+    ++h->launches;
     yhead_kernel<<<(R + 127) / 128, 128, 0, st>>>(a);
     LAUNCH_OK(h, "yhead_kernel");
   } else {
     CUDA_OK(h, cudaMemsetAsync(terms + (size_t)2 * R, 0, (size_t)R * sizeof(float), st));
   }
+  sec_end(h, st, SEC_MID_FWD);
   // ---- output heads + count likelihood
+  sec_begin(h, st, SEC_OUT_HEADS);
   bool out_done = false;
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
@@ -483,15 +538,18 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     a.train = training ? 1 : 0; a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.reapply = c.scvi_reapply_act;
     a.upstream = -1.0f / (float)R; a.clip_library = c.clip_library;
     size_t smem = scvi ? (size_t)G * sizeof(float) : 0;
+    ++h->launches;
     if (a.zero_inflated) count_row_kernel<true><<<R, 256, smem, st>>>(a);
     else count_row_kernel<false><<<R, 256, smem, st>>>(a);
     LAUNCH_OK(h, "count_row_kernel");
   }
+  sec_end(h, st, SEC_OUT_HEADS);
   // ---- ELBO
   {
     ElboArgs a;
     a.terms = terms; a.mask = P > 0 ? mask : nullptr; a.mask_scale = (P > 0 && c.mask_norm == 1) ? h->mask_scale : nullptr;
     a.R = R; a.B = B; a.alpha = c.alpha; a.beta = c.beta; a.loss = loss;
+    ++h->launches;
     elbo_kernel<<<std::max(1, std::min((R + 255) / 256, h->num_sms)), 256, 0, st>>>(a);
     LAUNCH_OK(h, "elbo_kernel");
   }
@@ -506,6 +564,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     for (auto& L : h->enc) reg(L, B);
     for (auto& L : h->encl) reg(L, B);
     for (auto& L : h->dec) reg(L, R);
+    ++h->launches;
     bn_moving_update_kernel<<<h->n_bn, kH, 0, st>>>(mu, h->moving, c.bn_momentum);
     LAUNCH_OK(h, "bn_moving_update_kernel");
   }
@@ -527,6 +586,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
     float* dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr;
     float* dbeta = h->Gd + L.b_off;
     int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+    ++h->launches;
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
     DenseBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -543,6 +603,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
       a.dIn = dIn0; a.ldi = ld_dIn0; a.accumulate_dIn = 0;
       a.dA = dA0; a.ldda = ld_dA0;
     }
+    ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "hidden backward");
     dH = dH_next;
@@ -551,11 +612,14 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
 }
 
 extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, const float* library,
-                                const uint8_t* mask, const float* eps_z, const float* eps_l, int B, float* terms,
-                                float* loss, void* stream) {
+                                const uint8_t* mask, const float* eps_z, const float* eps_l, int B, uint64_t seed,
+                                int64_t step, float* terms, float* loss, void* stream) {
   if (!h) return SISUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const sisua_step_config& c = h->cfg;
+  h->train_calls += 1;
+  h->drop_seed = seed;
+  h->drop_step = (uint32_t)(step >= 0 ? step : h->train_calls);
   if (!h->Gd) SET_ERR(h, SISUA_ERR_STATE, "train_step needs a bound grads buffer");
   if (c.batchnorm && B < 2) SET_ERR(h, SISUA_ERR_INVALID, "training-mode batch norm needs B >= 2");
   const int H = kH, G = c.n_genes, Z = c.n_latent, P = c.n_proteins, R = B;
@@ -571,6 +635,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.out_mode = 0; a.dOut = h->dPY; a.ldd = 2 * P; a.Nout = 2 * P; a.A_in = h->D; a.lda_in = H; a.Kin = H;
     a.ns_in = raw_norm(); a.W = h->P + h->y_w; a.ldw = H; a.dW = h->Gd + h->y_w; a.db = h->Gd + h->y_b;
     a.dIn = h->dD; a.ldi = H; a.accumulate_dIn = 0; a.R = R;
+    ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "protein head backward");
   } else {
@@ -581,15 +646,19 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) out_done = true;   // fused kernel already produced dW_out, db_out, dD
 #endif
   if (!out_done) {
+    sec_begin(h, st, SEC_OUT_HEADS);
     // dW_out[NO,H] += G_out^T . D ; db_out += colsum(G_out) ; dD += G_out . W_out
     launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, 1, h->NO, h->D, H, 1, h->Gd + h->out_w, H, nullptr, h->NO, H, R, true);
     int rows_per_block = std::max(64, (R + 63) / 64);
     dim3 g((h->NO + 255) / 256, (R + rows_per_block - 1) / rows_per_block);
+    ++h->launches;
     col_sum_kernel<<<g, 256, 0, st>>>(h->OUT, h->NO, R, h->NO, rows_per_block, h->Gd + h->out_b);
     launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, h->NO, 1, h->P + h->out_w, H, 1, h->dD, H, nullptr, R, H, h->NO, true);
     LAUNCH_OK(h, "output-layer backward");
+    sec_end(h, st, SEC_OUT_HEADS);
   }
   // ---- decoder stack, latent, encoder stack(s)
+  sec_begin(h, st, SEC_MID_BWD);
   rc = stack_backward(h, st, h->dec, R, h->dD, h->Zs, Z, Z, h->dZ, Z, nullptr, 0);
   if (rc != SISUA_OK) return rc;
   {
@@ -601,6 +670,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
       a.lib_scale = h->lib_scale; a.dPLIB = h->dPLIB;
     }
     a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
+    ++h->launches;
     latent_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
     LAUNCH_OK(h, "latent_bwd_kernel");
   }
@@ -612,6 +682,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.out_mode = 0; a.dOut = h->dPL; a.ldd = ZP; a.Nout = ZP; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
     a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lat_w; a.ldw = H; a.dW = h->Gd + h->lat_w; a.db = h->Gd + h->lat_b;
     a.dIn = h->dHa; a.ldi = H; a.R = B;
+    ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "latent projection backward");
     rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0);
@@ -624,14 +695,17 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.out_mode = 0; a.dOut = h->dPLIB; a.ldd = 2; a.Nout = 2; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
     a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lib_w; a.ldw = H; a.dW = h->Gd + h->lib_w; a.db = h->Gd + h->lib_b;
     a.dIn = h->dHa; a.ldi = H; a.R = B;
+    ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "library projection backward");
     rc = stack_backward(h, st, h->encl, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1 + H, h->ld0);
     if (rc != SISUA_OK) return rc;
   }
+  sec_end(h, st, SEC_MID_BWD);
   // ---- first-layer weight gradient: dW1[N0, G] = delta1^T . log1p(x)
   const int N0 = scvi ? 2 * H : H;
   bool w1_done = false;
+  sec_begin(h, st, SEC_ENC_FIRST_BWD);
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
     rc = tc_encoder_first_bwd(h, st, x, B, N0);
@@ -640,12 +714,14 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   }
 #endif
   if (!w1_done) {
+    DropSpec din = make_drop(h, c.input_dropout, 0u, true);
     if (c.log_norm)
-      launch_sgemm<LOAD_NONE, LOAD_LOG1P>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true);
+      launch_sgemm<LOAD_NONE, LOAD_LOG1P>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true, din);
     else
-      launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true);
+      launch_sgemm<LOAD_NONE, LOAD_RAW_DROP>(h, st, h->delta1, 1, h->ld0, x, G, 1, h->Gd + h->enc[0].w_off, h->Gp, nullptr, N0, G, B, true, din);
     LAUNCH_OK(h, "first-layer weight gradient");
   }
+  sec_end(h, st, SEC_ENC_FIRST_BWD);
   return SISUA_OK;
 }
 
@@ -674,11 +750,42 @@ extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta
   if (!h) return SISUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (!h->P || !h->Gd || !h->M || !h->V) SET_ERR(h, SISUA_ERR_STATE, "adam_step needs params, grads, m and v bound");
+  sec_begin(h, st, SEC_ADAM);
   CUDA_OK(h, cudaMemsetAsync(h->sq, 0, kMaxSegments * sizeof(double), st));
   dim3 grid(std::max(1, std::min(64, (int)((h->total_floats / h->seg.n + 2047) / 2048))), h->seg.n);
+  ++h->launches;
   grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->sq, h->d_step, (long long)t);
+  ++h->launches;
   adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->sq, h->d_step, lr, beta1, beta2, eps_hat,
                                      clipnorm, h->cfg.clip_mode, grad_scale);
   LAUNCH_OK(h, "adam");
+  sec_end(h, st, SEC_ADAM);
+  return SISUA_OK;
+}
+
+extern "C" int64_t sisua_launch_count(sisua_handle h) { return h ? h->launches : -1; }
+
+extern "C" int sisua_profile_enable(sisua_handle h, int on) {
+  if (!h) return SISUA_ERR_INVALID;
+  h->profiling = on != 0;
+  for (int i = 0; i < 8; ++i) h->sec_used[i] = 0;
+  return SISUA_OK;
+}
+
+// Sum of the device time (ms) spent in each section since profile_enable(1); synchronises the device.
+// ms_out[6] = enc_first, mid_fwd, out_heads, mid_bwd, enc_first_bwd, adam; counts_out[6] = timed intervals.
+extern "C" int sisua_profile_read(sisua_handle h, float* ms_out, int* counts_out) {
+  if (!h || !ms_out) return SISUA_ERR_INVALID;
+  CUDA_OK(h, cudaDeviceSynchronize());
+  for (int i = 0; i < SEC_COUNT; ++i) {
+    double tot = 0.0;
+    for (size_t j = 0; j < h->sec_used[i]; ++j) {
+      float ms = 0.f;
+      CUDA_OK(h, cudaEventElapsedTime(&ms, h->sec_events[i][j].first, h->sec_events[i][j].second));
+      tot += ms;
+    }
+    ms_out[i] = (float)tot;
+    if (counts_out) counts_out[i] = (int)h->sec_used[i];
+  }
   return SISUA_OK;
 }

@@ -144,6 +144,45 @@ __device__ __forceinline__ float nb_tfp_llk(float y, float a, float b, float& da
   return llk;
 }
 
+// Counter-based dropout masks (Philox4x32-10): mask(seed, step, stream, row, col) is a pure function, so
+// forward and backward regenerate it instead of storing it, and the CPU oracle reproduces it exactly
+// (oracle/philox.py).  stream 0 = input dropout on log1p(x); stream 1+u = hidden unit u.
+struct DropSpec {
+  float rate;      // 0 -> disabled
+  float scale;     // 1 / (1 - rate)
+  uint32_t seed_lo, seed_hi, step, stream;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// four consecutive columns (col4*4 .. col4*4+3) of one row: multiplier is 0 or 1/(1-rate)
+__device__ __forceinline__ float4 dropout_mult4(const DropSpec& d, uint32_t row, uint32_t col4) {
+  uint4 r = philox4x32_10(make_uint4(row, col4, d.step, d.stream), make_uint2(d.seed_lo, d.seed_hi));
+  const float u = 1.0f / 16777216.0f;
+  float4 m;
+  m.x = ((r.x >> 8) * u >= d.rate) ? d.scale : 0.f;
+  m.y = ((r.y >> 8) * u >= d.rate) ? d.scale : 0.f;
+  m.z = ((r.z >> 8) * u >= d.rate) ? d.scale : 0.f;
+  m.w = ((r.w >> 8) * u >= d.rate) ? d.scale : 0.f;
+  return m;
+}
+__device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, uint32_t col) {
+  if (d.rate <= 0.f) return 1.f;
+  float4 m = dropout_mult4(d, row, col >> 2);
+  uint32_t j = col & 3u;
+  return j == 0 ? m.x : (j == 1 ? m.y : (j == 2 ? m.z : m.w));
+}
+
 // warp / block reductions -------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -23,6 +23,7 @@ struct NormSpec {
   const float* beta;     // [64]  (bias when NORM_BIAS)
   float inv_count;       // 1 / rows that entered the batch statistics
   float eps;
+  DropSpec drop;         // dropout applied after the ReLU (training only; rate 0 = off)
 };
 
 // per-column affine (h = relu(a*sc + sh)) and the standardisation (xhat = (a - mean)*rstd)
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(256) norm_relu_kernel(const float* __restrict_
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % kH); size_t r = i / kH;
     float v = A[r * lda + c] * sc[c] + sh[c];
-    D[i] = ns.mode == NORM_RAW ? v : fmaxf(v, 0.f);
+    if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(ns.drop, (uint32_t)r, (uint32_t)c);
+    D[i] = v;
   }
 }
 
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
       float v = 0.f;
       if (r0 + r < R) {
         v = A_in[(size_t)(r0 + r) * lda + k] * sc[k] + sh[k];
-        if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f);
+        if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(ns.drop, (uint32_t)(r0 + r), (uint32_t)k);
       }
       Hs[r][k] = v;
     }
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
   double a1 = 0.0, a2 = 0.0;
   for (int r = blockIdx.x * 4 + grp; r < R; r += gridDim.x * 4) {
     float av = A[(size_t)r * lda + c];
-    float dy = (av * sc + sh > 0.f) ? dH[(size_t)r * ldd + c] : 0.f;
+    float dy = (av * sc + sh > 0.f) ? dH[(size_t)r * ldd + c] * dropout_mult(ns.drop, (uint32_t)r, (uint32_t)c) : 0.f;
     a1 += (double)dy;
     a2 += (double)(dy * ((av - mean) * rstd));
   }
@@ -423,7 +425,9 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
           g = a.dOut[(size_t)(r0 + r) * a.ldd + n];
         } else {
           float av = a.A_out[(size_t)(r0 + r) * a.lda_out + n];
-          float dy = (av * sc_o[n] + sh_o[n] > 0.f) ? a.dOut[(size_t)(r0 + r) * a.ldd + n] : 0.f;
+          float dy = (av * sc_o[n] + sh_o[n] > 0.f)
+                         ? a.dOut[(size_t)(r0 + r) * a.ldd + n] * dropout_mult(a.ns_out.drop, (uint32_t)(r0 + r), (uint32_t)n)
+                         : 0.f;
           float xh = (av - mean_o[n]) * rstd_o[n];
           g = gsc[n] * (dy - m1[n] - xh * m2[n]);
         }
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
         float v = 0.f;
         if (r0 + r < a.R && k < Kin) {
           v = a.A_in[(size_t)(r0 + r) * a.lda_in + k] * sc_i[k] + sh_i[k];
-          if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f);
+          if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_in.drop, (uint32_t)(r0 + r), (uint32_t)k);
         }
         Hs[r][k] = v;
       }

@@ -7,7 +7,7 @@
 
 namespace sisua {
 
-enum LoadOp : int { LOAD_NONE = 0, LOAD_LOG1P = 1 };
+enum LoadOp : int { LOAD_NONE = 0, LOAD_LOG1P = 1, LOAD_RAW_DROP = 2 };   // 1, 2: the operand is the count matrix (input dropout applies)
 
 // C[M,N] (+)= op_a(A)(m,k) * op_b(B)(k,n);  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
 // gridDim.z splits K; with splits > 1 or accumulate the result is added atomically into C.
@@ -17,7 +17,7 @@ template <int AOP, int BOP>
 __global__ void __launch_bounds__(256) sgemm_kernel(
     const float* __restrict__ A, long long a_rs, long long a_cs, const float* __restrict__ Bm, long long b_rs,
     long long b_cs, float* __restrict__ Cm, long long ldc, const float* __restrict__ bias, int M, int N, int K,
-    int k_chunk, int atomic_out) {
+    int k_chunk, int atomic_out, DropSpec drop) {
   __shared__ float As[kGemmBK][kGemmBM + 4];
   __shared__ float Bs[kGemmBK][kGemmBN + 4];
   const int t = threadIdx.x;
@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(
       if (m0 + m < M && k0 + k < kend) {
         v = A[(long long)(m0 + m) * a_rs + (long long)(k0 + k) * a_cs];
         if (AOP == LOAD_LOG1P) v = log1pf(v);
+        if (AOP != LOAD_NONE) v *= dropout_mult(drop, (uint32_t)(m0 + m), (uint32_t)(k0 + k));
       }
       As[k][m] = v;
       int n, kb;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(
       if (n0 + n < N && k0 + kb < kend) {
         w = Bm[(long long)(k0 + kb) * b_rs + (long long)(n0 + n) * b_cs];
         if (BOP == LOAD_LOG1P) w = log1pf(w);
+        if (BOP != LOAD_NONE) w *= dropout_mult(drop, (uint32_t)(k0 + kb), (uint32_t)(n0 + n));
       }
       Bs[kb][n] = w;
     }

@@ -245,3 +245,20 @@ class VectorDeterministic(Distribution):
   def log_prob(self, x):
     x = torch.as_tensor(x, device=self.loc.device, dtype=self.loc.dtype)
     return torch.where((x == self.loc).all(dim=-1), 0.0, -float("inf"))
+
+
+class MeanOnly(Distribution):
+  """Carrier for a head of which only the mean was requested from the CUDA step."""
+
+  def __init__(self, loc, name="MeanOnly"):
+    self.loc, self.name = loc, name
+
+  @property
+  def batch_shape(self):
+    return tuple(self.loc.shape)
+
+  def mean(self):
+    return self.loc
+
+  def log_prob(self, x):
+    raise NotImplementedError("only the mean of this head is materialised; per-cell log-likelihood is in elbo_terms")

@@ -93,7 +93,8 @@ class Engine:
     return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
   # -------------------------------------------------------------------------------------------
-  def train_step(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, terms=None, loss=None):
+  def train_step(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, terms=None, loss=None,
+                 seed: int = 0, step: int = -1):
     """forward + backward on device tensors (or host arrays, copied). Returns (terms [5,B], loss [1])."""
     x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
     mask = self._dev(mask, torch.uint8)
@@ -104,7 +105,7 @@ class Engine:
       loss = torch.empty((1,), dtype=torch.float32, device=self.device)
     with torch.cuda.device(self.device):
       self._check(self.lib.sisua_train_step(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
-                                            _ptr(eps_l), B, _ptr(terms), _ptr(loss), self._stream()))
+                                            _ptr(eps_l), B, int(seed), int(step), _ptr(terms), _ptr(loss), self._stream()))
     return terms, loss
 
   def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps_hat=1e-7, clipnorm=100.0, grad_scale=1.0, t=0):
@@ -136,6 +137,21 @@ class Engine:
     return out
 
   # -------------------------------------------------------------------------------------------
+  SECTIONS = ("enc_first", "mid_fwd", "out_heads", "mid_bwd", "enc_first_bwd", "adam")
+
+  def launch_count(self) -> int:
+    return int(self.lib.sisua_launch_count(self.handle))
+
+  def profile(self, on: bool):
+    self._check(self.lib.sisua_profile_enable(self.handle, 1 if on else 0))
+
+  def profile_read(self):
+    ms = (ctypes.c_float * 8)()
+    cnt = (ctypes.c_int * 8)()
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_profile_read(self.handle, ms, cnt))
+    return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.SECTIONS)}
+
   def debug_buffer(self, name: str, rows: int, cols: int) -> torch.Tensor:
     """Copy of a private workspace buffer (tests only)."""
     out = torch.empty((rows, cols), dtype=torch.float32, device=self.device)

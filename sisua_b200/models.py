@@ -1,0 +1,640 @@
+"""Host-side mirror of ``sisua.models`` for the ELBO train / infer hot path.
+
+Same class names, constructor arguments, ``fit / predict / encode / decode / save_weights /
+load_weights / create_posterior`` surface and error behaviour as the reference
+(sisua/models/single_cell_model.py:67-306, vae.py:15-44, scvi.py:20-171, dca.py:13-28,
+__init__.py:11-38); the arithmetic goes to libsisua_b200.so through ``Engine`` (ctypes).
+Two HEAD defects are deliberately not copied: ``fit`` passing the undefined
+name ``analytic`` and ``predict`` shuffling / truncating plain arrays."""
+from __future__ import annotations
+
+import os
+import pickle
+import warnings
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import config as C
+from . import distributions as D
+from . import synthetic
+from .config import NetConf, RVmeta
+from .engine import Engine
+
+__all__ = ["SingleCellModel", "VAE", "SISUA", "SCVI", "DeepCountAutoencoder", "NetConf", "RVmeta",
+           "SingleCellData", "get_model", "get_all_models", "load_model"]
+
+
+# ----------------------------------------------------------------------------------------------
+# input contract (stands in for SingleCellOMIC.create_dataset, _single_cell_base.py:539-602)
+# ----------------------------------------------------------------------------------------------
+class SingleCellData:
+  """Minimal stand-in for the slice of ``SingleCellOMIC`` the step consumes: a named count matrix,
+  optional protein levels, variable names, dataset-level library statistics and the frozen
+  semi-supervision mask of ``create_dataset(labels_percent=...)``."""
+
+  def __init__(self, X, Y=None, name: str = "synthetic", var_names: Optional[Dict[str, Sequence[str]]] = None,
+               labels_percent: float = 0.0, mask_seed: int = 1):
+    self.X = np.ascontiguousarray(X, dtype=np.float32)
+    self.Y = None if Y is None else np.ascontiguousarray(Y, dtype=np.float32)
+    self.name = name
+    self.var_names = var_names or {
+        "transcriptomic": [f"gene{i}" for i in range(self.X.shape[1])],
+        **({"proteomic": [f"prot{i}" for i in range(self.Y.shape[1])]} if self.Y is not None else {})}
+    self.library = synthetic.library_stats(self.X)
+    lp = 0.0 if self.Y is None else float(np.clip(labels_percent, 0.0, 1.0))   # forced to 0 for one OMIC (:578-579)
+    self.mask = synthetic.label_mask(self.X.shape[0], lp, mask_seed) if lp > 0 else \
+        np.zeros(self.X.shape[0], dtype=np.uint8)
+
+  def __len__(self):
+    return self.X.shape[0]
+
+  @property
+  def n_genes(self):
+    return self.X.shape[1]
+
+  def split(self, train_percent: float = 0.8, seed: int = 1):
+    rng = np.random.RandomState(seed)
+    idx = rng.permutation(len(self))
+    n = int(train_percent * len(self))
+    mk = lambda ids, tag: self._take(ids, f"{self.name}_{tag}")
+    return mk(np.sort(idx[:n]), "train"), mk(np.sort(idx[n:]), "test")
+
+  def _take(self, ids, name):
+    out = SingleCellData.__new__(SingleCellData)
+    out.X = self.X[ids]; out.Y = None if self.Y is None else self.Y[ids]
+    out.name = name; out.var_names = self.var_names
+    out.library = self.library[ids]; out.mask = self.mask[ids]
+    return out
+
+
+def _to_data(x, require_meta=False) -> SingleCellData:
+  if isinstance(x, SingleCellData):
+    return x
+  if isinstance(x, dict):
+    return SingleCellData(x["x"], x.get("y"), name=x.get("name", "array"))
+  if isinstance(x, (tuple, list)):
+    return SingleCellData(x[0], x[1] if len(x) > 1 else None, name="array")
+  return SingleCellData(x, name="array")
+
+
+# ----------------------------------------------------------------------------------------------
+class _Posterior:
+  """What callers read from ``model.posteriors[i]`` / ``model.output_layers[i]``."""
+
+  def __init__(self, rv: RVmeta):
+    self.name = rv.name
+    self.event_shape = (rv.dim,)
+    self.posterior = rv.posterior
+    self.is_zero_inflated = rv.is_zero_inflated
+    self.trainable = True
+
+
+class SingleCellModel:
+  r""" Note: seed the model (``seed=...``) for reproducible results. """
+
+  _kind = C.MODEL_VAE
+
+  def __init__(self,
+               outputs: RVmeta,
+               latents: RVmeta = None,
+               encoder: NetConf = None,
+               decoder: NetConf = None,
+               log_norm=True,
+               beta=1.0,
+               name=None,
+               **kwargs):
+    latents = RVmeta(10, 'diag', True, 'Latents') if latents is None else latents
+    encoder = NetConf([64, 64], batchnorm=True, input_dropout=0.3) if encoder is None else encoder
+    decoder = NetConf([64, 64], batchnorm=True) if decoder is None else decoder
+    outs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
+    labels = kwargs.pop("labels", None)
+    labels = [] if labels is None else (list(labels) if isinstance(labels, (list, tuple)) else [labels])
+    self.init_args = dict(outputs=outputs, latents=latents, encoder=encoder, decoder=decoder, log_norm=log_norm,
+                          beta=beta, name=name, **({"labels": labels} if labels else {}), **kwargs)
+    self._outputs, self.labels, self._latents = outs, labels, latents
+    self._encoder, self._decoder = encoder, decoder
+    self._log_norm = bool(log_norm)
+    self.beta = float(beta)
+    self.alpha = float(kwargs.pop("alpha", 10.0))
+    self.name = name or type(self).__name__
+    self._device_index = int(kwargs.pop("device", torch.cuda.current_device() if torch.cuda.is_available() else 0))
+    self._gemm_mode = int(kwargs.pop("gemm_mode", C.GEMM_FP32_UNFUSED))
+    self._seed = int(kwargs.pop("seed", 8))
+    self._max_batch = int(kwargs.pop("max_batch", 8192))
+    self._cfg_overrides = {k: kwargs.pop(k) for k in list(kwargs) if k in (
+        "mean_act", "disp_act", "scale_act", "scvi_reapply_act", "mask_norm", "clip_mode")}
+    for k in ("reduce_latent", "input_shape", "step", "path", "analytic"):
+      kwargs.pop(k, None)
+    if kwargs:
+      raise TypeError(f"unexpected arguments: {sorted(kwargs)}")
+    self.dataset = None
+    self.metadata: Dict[str, Any] = dict()
+    self.posteriors = [_Posterior(rv) for rv in self._outputs + self.labels]
+    self.output_layers = self.posteriors[:len(self._outputs)]
+    self.train_history: Dict[str, List[float]] = {}
+    self.valid_history: Dict[str, List[float]] = {}
+    self.is_fitted = False
+    self._engine: Optional[Engine] = None
+    self._pending_weights = None
+    self.step = 0
+
+  # ---------------------------------------------------------------- configuration -> StepConfig
+  def _step_config(self) -> C.StepConfig:
+    rv = self._outputs[0]
+    if rv.posterior not in ("zinbd", "nbd"):
+      raise ValueError(f"posterior '{rv.posterior}' is outside the B200 hot path (zinbd, nbd)")
+    enc, dec = self._encoder, self._decoder
+    if len(set(enc.units + dec.units)) != 1:
+      raise ValueError("all hidden layers must share one width")
+    kw = dict(self._cfg_overrides)
+    for k in ("mean_act", "disp_act", "scale_act"):
+      if k in rv.kwargs:
+        kw.setdefault(k, rv.kwargs[k])
+    n_prot, y_dist = 0, "nb"
+    if self.labels:
+      if len(self.labels) != 1 or self.labels[0].posterior not in ("nb", "nbd"):
+        raise ValueError("the semi-supervised head on the hot path is one 'nb' / 'nbd' protein RV")
+      n_prot, y_dist = self.labels[0].dim, self.labels[0].posterior
+    extra = self._extra_config()
+    return C.make_step_config(
+        C.MODEL_NAMES[self._kind], n_genes=rv.dim, n_proteins=n_prot, n_latent=self._latents.dim,
+        n_hidden=enc.units[0], n_enc_layers=len(enc.units), n_dec_layers=len(dec.units), batchnorm=enc.batchnorm,
+        log_norm=self._log_norm, x_dist=rv.posterior, y_dist=y_dist, gemm_mode=self._gemm_mode,
+        max_batch=self._max_batch, input_dropout=enc.input_dropout, enc_dropout=enc.dropout,
+        dec_dropout=dec.dropout, beta=self.beta, alpha=self.alpha, **extra, **kw)
+
+  def _extra_config(self) -> Dict[str, Any]:
+    return {}
+
+  @property
+  def engine(self) -> Engine:
+    if self._engine is None:
+      self._engine = Engine(self._step_config(), self._device_index, seed=self._seed)
+      if self._pending_weights is not None:
+        self._restore(self._pending_weights)
+        self._pending_weights = None
+    return self._engine
+
+  # ---------------------------------------------------------------- reference attribute surface
+  def set_metadata(self, sco):
+    if not isinstance(sco, SingleCellData):
+      raise AssertionError(f"sco must be instance of SingleCellData but given: {type(sco)}")
+    self.dataset = sco.name
+    for k, v in sco.var_names.items():
+      self.metadata[k] = list(v)
+    return self
+
+  @property
+  def log_norm(self):
+    return self._log_norm
+
+  @property
+  def is_zero_inflated(self):
+    return self.posteriors[0].is_zero_inflated
+
+  @property
+  def is_semi_supervised(self):
+    return len(self.labels) > 0
+
+  @classmethod
+  def _id(cls):
+    return ''.join(c for c in cls.__name__ if c.isupper()).lower()
+
+  class _ClassProp:
+    def __get__(self, obj, owner):
+      return owner._id()
+
+  id = _ClassProp()
+
+  # ---------------------------------------------------------------- one batch through the C ABI
+  def _batch_tensors(self, data: SingleCellData, idx: torch.Tensor, dev_cache: Dict[str, torch.Tensor]):
+    b = dict(x=dev_cache["x"][idx])
+    if self.labels:
+      b["y"] = dev_cache["y"][idx]
+      b["mask"] = dev_cache["mask"][idx]
+    if self._kind == C.MODEL_SCVI:
+      b["library"] = dev_cache["library"][idx]
+    return b
+
+  def _upload(self, data: SingleCellData) -> Dict[str, torch.Tensor]:
+    dev = self.engine.device
+    cache = dict(x=torch.from_numpy(data.X).to(dev))
+    if self.labels:
+      if data.Y is None:
+        raise ValueError("semi-supervised model needs the protein matrix Y")
+      cache["y"] = torch.from_numpy(data.Y).to(dev)
+      cache["mask"] = torch.from_numpy(data.mask).to(dev)
+    if self._kind == C.MODEL_SCVI:
+      cache["library"] = torch.from_numpy(data.library).to(dev)
+    return cache
+
+  def _eps(self, B: int, S: Optional[int], gen: torch.Generator):
+    eng = self.engine
+    shape = (B,) if S is None else (S, B)
+    out = {}
+    if self._kind != C.MODEL_DCA:
+      out["eps_z"] = torch.randn(shape + (eng.cfg.n_latent,), device=eng.device, generator=gen)
+    if self._kind == C.MODEL_SCVI:
+      out["eps_l"] = torch.randn(shape, device=eng.device, generator=gen)
+    return out
+
+  def __call__(self, inputs, library=None, mask=None, training=False, sample_shape=(), eps=None, **kwargs):
+    """One batch -> (pX_Z, qZ_X) like ``self(**data, training=False, sample_shape=S)``
+    (single_cell_model.py:178)."""
+    if training:
+      raise NotImplementedError("use fit() for training-mode steps")
+    eng = self.engine
+    xs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+    x = eng._dev(xs[0])
+    y = eng._dev(xs[1]) if len(xs) > 1 and self.labels else None
+    B = x.shape[0]
+    S = int(np.prod(sample_shape)) if sample_shape not in ((), None, 0) else None
+    if eps is None:
+      gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + self.step)
+      eps = self._eps(B, S, gen)
+    if self._kind == C.MODEL_SCVI and library is None:
+      raise ValueError("scVI needs the `library` [B,2] statistics of the batch")
+    if self.labels and y is None:
+      y = torch.zeros((B, eng.cfg.n_proteins), device=eng.device)
+    out = eng.infer(x, y=y, library=library, mask=mask, S=S or 1, want_mean=True, want_disp=True, want_pi=True, **eps)
+    return self._wrap(out, B, S)
+
+  def _wrap(self, out, B, S):
+    cfg = self.engine.cfg
+    G = cfg.n_genes
+    shp = (lambda t, n: t.reshape(S, B, n)) if S else (lambda t, n: t.reshape(B, n))
+    nb = D.NegativeBinomialDisp(shp(out["mean"], G), shp(out["disp"], G))
+    base = D.ZeroInflated(nb, shp(out["pi_logit"], G)) if cfg.x_dist == C.XDIST_ZINBD else nb
+    pX = D.Independent(base, 1, name=self.posteriors[0].name)
+    pX.elbo_terms = out["terms"]
+    if self._kind == C.MODEL_DCA:
+      qZ = D.VectorDeterministic(out["z_loc"], name=self._latents.name)
+    else:
+      qZ = D.MultivariateNormalDiag(out["z_loc"], out["z_scale"], name=self._latents.name)
+    if self._kind == C.MODEL_SCVI:
+      qL = D.Independent(D.Normal(out["lib_loc"][:, None], out["lib_scale"][:, None]), 1, name="Library")
+      qZ = (qZ, qL)
+    if self.labels:
+      pY = D.Independent(D.MeanOnly(shp(out["y_mean"], cfg.n_proteins)), 1, name=self.posteriors[1].name)
+      return (pX, pY), qZ
+    return pX, qZ
+
+  def encode(self, inputs, library=None, training=None, mask=None, sample_shape=(), **kwargs):
+    return self(inputs, library=library, mask=mask, training=False, sample_shape=sample_shape, **kwargs)[1]
+
+  def decode(self, latents=None, training=None, mask=None, sample_shape=(), inputs=None, **kwargs):
+    if inputs is None:
+      raise NotImplementedError("the fused step decodes inside encode->decode; pass `inputs=`")
+    return self(inputs, mask=mask, training=False, sample_shape=sample_shape, **kwargs)[0]
+
+  # ---------------------------------------------------------------- predict
+  def predict(self, inputs, sample_shape=(), batch_size=32, verbose=True, device="GPU"):
+    r""" Predict on minibatches then return a single distribution by concatenation
+    (single_cell_model.py:153-211).  Row order is preserved and every cell is kept. """
+    assert device in ("CPU", "GPU"), f"Only support device CPU or GPU, but given: {device}"
+    data = _to_data(inputs)
+    eng = self.engine
+    cache = self._upload(data)
+    N = len(data)
+    S = int(np.prod(sample_shape)) if sample_shape not in ((), None, 0) else None
+    rows_per_call = max(1, eng.cfg.max_batch // (S or 1))
+    bs = min(max(int(batch_size), 1), rows_per_call)
+    # minibatch size does not change inference results (moving-average BN); use the largest that fits
+    bs = rows_per_call if N > bs else bs
+    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 12345)
+    parts = []
+    for s in range(0, N, bs):
+      idx = torch.arange(s, min(N, s + bs), device=eng.device)
+      b = self._batch_tensors(data, idx, cache)
+      eps = self._eps(idx.numel(), S, gen)
+      out = eng.infer(S=S or 1, want_mean=True, want_disp=True, want_pi=True, **b, **eps)
+      parts.append((out, idx.numel()))
+    cfg = eng.cfg
+
+    def cat(key, width):
+      ts = []
+      for out, n in parts:
+        t = out[key]
+        ts.append(t.reshape(S, n, width) if S else t.reshape(n, width))
+      return torch.cat(ts, dim=1 if S else 0)
+
+    merged = dict(mean=cat("mean", cfg.n_genes), disp=cat("disp", cfg.n_genes),
+                  z_loc=torch.cat([o["z_loc"] for o, _ in parts]), z_scale=torch.cat([o["z_scale"] for o, _ in parts]),
+                  terms=torch.cat([o["terms"].reshape(5, S or 1, n) for o, n in parts], dim=2))
+    merged["pi_logit"] = cat("pi_logit", cfg.n_genes) if cfg.x_dist == C.XDIST_ZINBD else None
+    if self._kind == C.MODEL_SCVI:
+      merged["lib_loc"] = torch.cat([o["lib_loc"] for o, _ in parts])
+      merged["lib_scale"] = torch.cat([o["lib_scale"] for o, _ in parts])
+    if self.labels:
+      merged["y_mean"] = cat("y_mean", cfg.n_proteins)
+    if device == "CPU":
+      merged = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in merged.items()}
+    flat = {k: (v.reshape(-1, v.shape[-1]) if (isinstance(v, torch.Tensor) and k in ("mean", "disp", "pi_logit", "y_mean")) else v)
+            for k, v in merged.items()}
+    return self._wrap(flat, N, S)
+
+  # ---------------------------------------------------------------- fit
+  def fit(self,
+          train,
+          valid=None,
+          metadata=None,
+          batch_size=64,
+          optimizer='adam',
+          learning_rate=1e-3,
+          clipnorm=100.,
+          epochs=-1,
+          max_iter=-1,
+          valid_freq=500,
+          sample_shape=(),
+          checkpoint=None,
+          earlystop_threshold=0.001,
+          earlystop_patience=20,
+          earlystop_min_epoch=-1,
+          terminate_on_nan=True,
+          logging_interval=2,
+          shuffle=True,
+          seed=None,
+          verbose=False,
+          **kwargs):
+    r""" `Model.compile` + `Model.fit` of the reference in one call
+    (single_cell_model.py:213-236; keys of configs/base.yaml:45-62). """
+    if isinstance(train, SingleCellData):
+      self.set_metadata(train)
+    elif isinstance(valid, SingleCellData):
+      self.set_metadata(valid)
+    elif isinstance(metadata, SingleCellData):
+      self.set_metadata(metadata)
+    if self.dataset is None or len(self.metadata) == 0:
+      raise RuntimeError("First time call `fit`, set the 'metadata' argument to a "
+                         "SingleCellData dataset to keep the dataset name and OMICs' "
+                         "variables description.")
+    if str(optimizer).lower() != 'adam':
+      raise ValueError("the fused optimiser on the hot path is Adam (configs/base.yaml:46)")
+    if sample_shape not in ((), None, [], 0, 1, (1,)):
+      raise NotImplementedError("training uses sample_shape=() (configs/base.yaml:53)")
+    train = _to_data(train)
+    valid = _to_data(valid) if valid is not None else None
+    eng = self.engine
+    B = int(batch_size)
+    if B > eng.cfg.max_batch:
+      raise ValueError(f"batch_size {B} > max_batch {eng.cfg.max_batch}")
+    N = len(train)
+    if N < B:
+      raise ValueError("dataset smaller than one batch (drop_remainder=True, train.py:126-135)")
+    steps_per_epoch = N // B
+    if epochs is None or epochs <= 0:
+      epochs = 1 if (max_iter is None or max_iter <= 0) else int(np.ceil(max_iter / steps_per_epoch))
+    total = epochs * steps_per_epoch if (max_iter is None or max_iter <= 0) else min(int(max_iter), epochs * steps_per_epoch)
+    cache = self._upload(train)
+    vcache = self._upload(valid) if valid is not None else None
+    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed if seed is None else int(seed))
+    terms = torch.empty((5, B), device=eng.device)
+    loss = torch.empty((1,), device=eng.device)
+    names = ["loss", "llk_" + self.posteriors[0].name] + (["llk_" + self.posteriors[1].name] if self.labels else []) + \
+        ["kl_" + self._latents.name] + (["kl_Library"] if self._kind == C.MODEL_SCVI else [])
+    for n in names:
+      self.train_history.setdefault(n, [])
+      self.valid_history.setdefault(n, [])
+    best, patience, done = float("inf"), 0, 0
+    log_buf: List[torch.Tensor] = []
+    stop = False
+    for ep in range(epochs):
+      perm = torch.randperm(N, device=eng.device, generator=gen) if shuffle else torch.arange(N, device=eng.device)
+      for s in range(steps_per_epoch):
+        if done >= total:
+          stop = True
+          break
+        idx = perm[s * B:(s + 1) * B]
+        b = self._batch_tensors(train, idx, cache)
+        eps = self._eps(B, None, gen)
+        eng.train_step(terms=terms, loss=loss, **b, **eps)
+        self.step += 1
+        eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), t=self.step)
+        done += 1
+        if logging_interval and done % int(logging_interval) == 0:
+          log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
+        if valid is not None and valid_freq and done % int(valid_freq) == 0:
+          v = self._evaluate(valid, vcache, B)
+          self._log(self.valid_history, names, v)
+          if terminate_on_nan and not np.isfinite(v[0]):
+            raise FloatingPointError("validation loss is not finite")
+          if v[0] < best - abs(earlystop_threshold) * abs(best if np.isfinite(best) else 1.0):
+            best, patience = v[0], 0
+            if checkpoint is not None:
+              checkpoint()
+          else:
+            patience += 1
+            if earlystop_patience and patience >= earlystop_patience and ep >= earlystop_min_epoch:
+              stop = True
+              break
+      if log_buf:
+        vals = torch.stack(log_buf).cpu().numpy()
+        log_buf = []
+        for row in vals:
+          self._log(self.train_history, names, self._select(row))
+        if terminate_on_nan and not np.isfinite(vals[:, 0]).all():
+          raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
+        if verbose:
+          print(f"epoch {ep + 1}/{epochs} loss {vals[-1, 0]:.3f}")
+      if stop:
+        break
+    torch.cuda.current_stream(eng.device).synchronize()
+    self.is_fitted = True
+    return self
+
+  def _select(self, row):
+    # row = [loss, llk_x, llk_y, kl_z, kl_l] -> the metric names of this model
+    out = [row[0], row[1]]
+    if self.labels:
+      out.append(row[2])
+    out.append(row[3])
+    if self._kind == C.MODEL_SCVI:
+      out.append(row[4])
+    return out
+
+  @staticmethod
+  def _log(hist, names, vals):
+    for n, v in zip(names, vals):
+      hist[n].append(float(v))
+
+  def _evaluate(self, data: SingleCellData, cache, B):
+    eng = self.engine
+    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 777)
+    acc, cnt = torch.zeros(5, device=eng.device), 0
+    for s in range(0, len(data), B):
+      idx = torch.arange(s, min(len(data), s + B), device=eng.device)
+      b = self._batch_tensors(data, idx, cache)
+      out = eng.infer(want_mean=False, **b, **self._eps(idx.numel(), None, gen))
+      acc += out["terms"].sum(dim=1)
+      cnt += idx.numel()
+    m = (acc / cnt).cpu().numpy()
+    return self._select(np.concatenate([[-m[0]], m[1:]]))
+
+  def marginal_log_prob(self, inputs, library=None, mask=None, sample_shape=100, **kwargs):
+    """Importance-weighted estimate log p(x) ~= logsumexp_s[log p(x|z_s) + log p(z_s) - log q(z_s|x)] - log S
+    (used by sisua/analysis/posterior.py:941-976)."""
+    S = int(sample_shape)
+    eng = self.engine
+    x = eng._dev(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
+    B = x.shape[0]
+    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 4242)
+    eps = self._eps(B, S, gen)
+    out = eng.infer(x, library=library, mask=mask, S=S, want_mean=False, **eps)
+    llk = out["terms"][1].reshape(S, B)
+    if self._kind == C.MODEL_DCA:
+      return llk.mean(0)
+    e = eps["eps_z"]
+    z = out["z_loc"] + out["z_scale"] * e
+    log_q = (-0.5 * e * e - torch.log(out["z_scale"]) - 0.9189385332).sum(-1)
+    log_p = (-0.5 * z * z - 0.9189385332).sum(-1)
+    return torch.logsumexp(llk + log_p - log_q, dim=0) - float(np.log(S))
+
+  # ---------------------------------------------------------------- posterior / persistence
+  def create_posterior(self, test_sco=None, dropout_rate=0.2, retain_rate=0.2, corrupt_distribution='binomial',
+                       batch_size=8, sample_shape=10, reduce_latents=None, verbose=True, train_percent=0.8,
+                       random_state=1):
+    r""" Create a `Posterior` object for evaluation (single_cell_model.py:247-281) """
+    if not self.is_fitted:
+      raise RuntimeError("fit() must be called before creating Posterior.")
+    if isinstance(test_sco, SingleCellData):
+      test = test_sco
+    elif self.dataset is None:
+      raise ValueError("Call SingleCellModel.set_metadata() to track the fitted dataset.")
+    else:
+      raise ValueError(f"dataset '{self.dataset}' cannot be re-loaded here (no dataset registry on the hot path); "
+                       "pass test_sco=")
+    from .posterior import Posterior
+    return Posterior(self, test, dropout_rate=dropout_rate, retain_rate=retain_rate,
+                     corrupt_distribution=corrupt_distribution, batch_size=batch_size, sample_shape=sample_shape,
+                     random_state=random_state, name=f"{self.id}_{self.dataset}")
+
+  def _snapshot(self):
+    eng = self.engine
+    return dict(params=eng.params.cpu().numpy(), bn_moving=eng.bn_moving.cpu().numpy(),
+                adam_m=eng.adam_m.cpu().numpy(), adam_v=eng.adam_v.cpu().numpy(), step=self.step,
+                layout=[(e.name, e.offset, e.shape, e.ld) for e in eng.entries])
+
+  def _restore(self, snap):
+    eng = self._engine
+    if [(e.name, e.offset, e.shape, e.ld) for e in eng.entries] != [tuple(x) for x in snap["layout"]]:
+      raise ValueError("checkpoint layout does not match this model")
+    eng.params.copy_(torch.from_numpy(snap["params"]))
+    eng.bn_moving.copy_(torch.from_numpy(snap["bn_moving"]))
+    eng.adam_m.copy_(torch.from_numpy(snap["adam_m"]))
+    eng.adam_v.copy_(torch.from_numpy(snap["adam_v"]))
+    self.step = int(snap["step"])
+
+  def save_weights(self, filepath, overwrite=True):
+    r""" weights blob + ``.metamodel`` pickle ``[class_name, dataset, metadata, init_args]``
+    (single_cell_model.py:295-306); Adam state and BN moving statistics are persisted too. """
+    if os.path.exists(filepath) and not overwrite:
+      raise FileExistsError(filepath)
+    snap = self._snapshot()
+    snap["layout"] = [list(x) for x in snap["layout"]]
+    with open(filepath, "wb") as f:
+      pickle.dump(snap, f)
+    with open(f"{filepath}.metamodel", "wb") as f:
+      pickle.dump([self.__class__.__name__, self.dataset, self.metadata, dict(self.init_args)], f)
+    return self
+
+  def load_weights(self, filepath, raise_notfound=False, verbose=False):
+    r""" Load all the saved weights at given path (single_cell_model.py:283-293) """
+    if not os.path.exists(filepath):
+      if raise_notfound:
+        raise FileNotFoundError(filepath)
+      return self
+    with open(filepath, "rb") as f:
+      snap = pickle.load(f)
+    if self._engine is None and not torch.cuda.is_available():
+      self._pending_weights = snap
+    else:
+      _ = self.engine
+      self._restore(snap)
+    meta = f"{filepath}.metamodel"
+    if os.path.exists(meta):
+      with open(meta, "rb") as f:
+        class_name, dataset, metadata, _ = pickle.load(f)
+      assert class_name == self.__class__.__name__
+      self.dataset, self.metadata = dataset, metadata
+    self.is_fitted = True
+    return self
+
+  def plot_learning_curves(self, path=None):
+    raise NotImplementedError("plotting is host-side tooling outside the hot path (SURVEY.md section 2, rows 9, 15)")
+
+
+class VAE(SingleCellModel):
+  r""" Variational Auto Encoder (sisua/models/vae.py:15-16) """
+  _kind = C.MODEL_VAE
+
+
+class SISUA(SingleCellModel):
+  r""" Multi-task SemI-SUpervised Autoencoder (sisua/models/vae.py:19-44):
+  transcriptomic ZINB/NB output + a protein head read from the same decoder output. """
+  _kind = C.MODEL_SISUA
+
+  def __init__(self, outputs, labels, **kwargs):
+    super().__init__(outputs=outputs, labels=labels, **kwargs)
+    if not self.labels:
+      raise ValueError("SISUA needs `labels`")
+
+
+class SCVI(SingleCellModel):
+  r""" scVI re-implementation (sisua/models/scvi.py:20-171): library-size latent, softmax gene scale. """
+  _kind = C.MODEL_SCVI
+
+  def __init__(self, outputs, latents=None, library=None, encoder=None, encoder_l=None, clip_library=1e3, **kwargs):
+    latents = RVmeta(10, 'diag', True, "Latents") if latents is None else latents
+    self._library = RVmeta(1, 'normal', True, "Library") if library is None else library
+    encoder = NetConf([64, 64], batchnorm=True, dropout=0.1, name='Encoder') if encoder is None else encoder
+    self._encoder_l = NetConf([64], batchnorm=True, dropout=0.1, name='EncoderL') if encoder_l is None else encoder_l
+    out0 = outputs[0] if isinstance(outputs, (list, tuple)) else outputs
+    assert out0.posterior in ('zinbd', 'nbd'), \
+        "scVI only support transcriptomic distribution: 'zinbd' or 'nbd', but given: %s" % str(outputs)
+    self.clip_library = float(clip_library)
+    super().__init__(outputs, latents=latents, encoder=encoder, **kwargs)
+    self.init_args.update(library=self._library, encoder_l=self._encoder_l, clip_library=clip_library)
+
+  def _extra_config(self):
+    return dict(n_encl_layers=len(self._encoder_l.units), encl_dropout=self._encoder_l.dropout,
+                clip_library=self.clip_library)
+
+
+class DeepCountAutoencoder(SingleCellModel):
+  r""" Deep Count Autoencoder (sisua/models/dca.py:13-28): deterministic latent, no KL. """
+  _kind = C.MODEL_DCA
+
+  def __init__(self, outputs, latents=None, **kwargs):
+    latents = RVmeta(10, 'relu', True, name="Latents") if latents is None else latents
+    if not latents.is_deterministic:
+      warnings.warn("DeepCountAutoencoder only support deterministic latents, "
+                    f"but given {latents}, use default linear Dense layer for latents.")
+      latents = latents.copy(posterior='relu')
+    super().__init__(outputs=outputs, latents=latents, **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------
+def get_all_models() -> list:
+  found = [v for v in globals().values() if isinstance(v, type) and issubclass(v, SingleCellModel)]
+  return sorted(found, key=lambda cls: cls.id)
+
+
+def get_model(model):
+  if isinstance(model, type):
+    model = model.__name__
+  model = str(model).lower()
+  for key, val in list(globals().items()):
+    if isinstance(val, type) and issubclass(val, SingleCellModel):
+      if model == key.lower() or model == val.id:
+        return val
+  raise RuntimeError(f"Cannot find SingleCellModel with type '{model}'")
+
+
+def load_model(filepath: str) -> SingleCellModel:
+  with open(f"{filepath}.metamodel", 'rb') as f:
+    class_name, dataset, metadata, kwargs = pickle.load(f)
+  model = get_model(class_name)(**kwargs)
+  model.load_weights(filepath, raise_notfound=True)
+  return model

@@ -47,3 +47,23 @@ def make_batch(cfg, B, seed=0, S=None, preset_stats=(6.42, 0.28), stress=False):
   if cfg.model_kind != C.MODEL_DCA:
     batch["eps_z"] = rng.standard_normal(shape + (Z,)).astype(np.float32)
   return batch
+
+
+def oracle_dropout_masks(cfg, B, seed, step, dtype=torch.float64):
+  """The masks the CUDA step regenerates from (seed, step): stream 0 = input, 1+u = hidden unit u
+  (units numbered enc, encl, dec — sisua_b200/csrc/abi.cu stat_index)."""
+  from oracle.philox import dropout_mask
+  units = [f"enc.{i}" for i in range(cfg.n_enc_layers)]
+  rates = [cfg.enc_dropout] * cfg.n_enc_layers
+  if cfg.model_kind == C.MODEL_SCVI:
+    units += [f"encl.{i}" for i in range(cfg.n_encl_layers)]
+    rates += [cfg.encl_dropout] * cfg.n_encl_layers
+  units += [f"dec.{i}" for i in range(cfg.n_dec_layers)]
+  rates += [cfg.dec_dropout] * cfg.n_dec_layers
+  drop = {}
+  if cfg.input_dropout > 0:
+    drop["input"] = torch.tensor(dropout_mask(B, cfg.n_genes, cfg.input_dropout, seed, step, 0), dtype=dtype)
+  for u, (name, rate) in enumerate(zip(units, rates)):
+    if rate > 0:
+      drop[name] = torch.tensor(dropout_mask(B, cfg.n_hidden, rate, seed, step, 1 + u), dtype=dtype)
+  return drop

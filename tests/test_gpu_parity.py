@@ -81,14 +81,14 @@ def test_inference_mc_samples(mode):
   eng.close()
 
 
-def _grad_check(cfg, flat, mov, batch, eng, gtol=2e-3):
-  terms, loss = eng.train_step(**batch)
+def _grad_check(cfg, flat, mov, batch, eng, gtol=2e-3, drop=None, seed=0, step=-1):
+  terms, loss = eng.train_step(seed=seed, step=step, **batch)
   torch.cuda.synchronize()
   P = Hh.oracle_params(cfg, flat)
   for p in P.values():
     p.requires_grad_(True)
   om = Hh.oracle_moving(cfg, mov)
-  ref = O.forward(cfg, P, om, training=True, **batch)
+  ref = O.forward(cfg, P, om, training=True, drop=drop, **batch)
   ref["loss"].backward()
   _close(terms[0].cpu().numpy(), ref["elbo"].detach().numpy(), what="train elbo")
   _close(loss.cpu().numpy()[0], float(ref["loss"]), what="loss")
@@ -148,6 +148,23 @@ def test_multi_step_training_matches_oracle(model, kw, mode):
     # Adam's normalised update amplifies tiny gradient differences: compare against the step size
     err = np.abs(got[name] - p.numpy()).max()
     assert err <= 2e-4, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
+  eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw", [("vae", {}), ("scvi", {}), ("sisua", dict(n_proteins=10))])
+def test_train_step_with_dropout(model, kw, mode):
+  # reference defaults: input_dropout 0.3 (single_cell_model.py:80), hidden dropout 0.1 (base.yaml:10-17)
+  G, B = 200, 64
+  cfg, flat, mov, batch = _setup(model, kw, G, B, mode, trained_moving=False, input_dropout=0.3,
+                                 enc_dropout=0.1, dec_dropout=0.1, **({"encl_dropout": 0.1} if model == "scvi" else {}))
+  eng = _engine(cfg, flat, mov)
+  drop = Hh.oracle_dropout_masks(cfg, B, seed=99, step=3)
+  _grad_check(cfg, flat, mov, batch, eng, drop=drop, seed=99, step=3)
+  # inference ignores dropout
+  out = eng.infer(**batch)
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, eng.bn_moving.cpu().numpy()), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo (inference, dropout model)")
   eng.close()
 
 

@@ -161,3 +161,18 @@ def test_library_stats_follow_reference_recipe():
   s = O.library_size_stats(X)
   np.testing.assert_allclose(s[:, 0], lc.mean(), rtol=1e-6)
   np.testing.assert_allclose(s[:, 1], lc.var(), rtol=1e-6)
+
+
+def test_philox_known_answers():
+  # Random123 kat_vectors for philox4x32-10
+  from oracle.philox import dropout_mask, philox4x32_10
+  kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+         ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+         ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+          (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+  for ctr, key, exp in kat:
+    got = tuple(int(v) for v in philox4x32_10(*ctr, *key))
+    assert got == exp
+  m = dropout_mask(512, 200, 0.3, seed=1234, step=7, stream=0)
+  assert m.shape == (512, 200) and abs(m.mean() - 0.7) < 0.01
+  assert not np.array_equal(m, dropout_mask(512, 200, 0.3, seed=1234, step=8, stream=0))
