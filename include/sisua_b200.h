@@ -114,6 +114,10 @@ int64_t sisua_launch_count(sisua_handle h);
 int sisua_profile_enable(sisua_handle h, int on);
 int sisua_profile_read(sisua_handle h, float* ms_out, int* counts_out);
 
+/* tcgen05 descriptor self-test used by the GPU tests: D[128,N] = A[128,K] . B[N,K]^T (device pointers, fp32 in/out,
+ * fp16 operands inside); a_mn_major / b_mn_major pick the shared-memory operand layout handed to the MMA. */
+int sisua_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
+
 const char* sisua_last_error(sisua_handle h);
 const char* sisua_version(void);
 

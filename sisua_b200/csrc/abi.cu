@@ -15,6 +15,7 @@
 #include "kernels_unfused.cuh"
 #ifdef SISUA_WITH_TC
 #include "kernels_tc.cuh"
+#include "kernels_tc_selftest.cuh"
 #endif
 
 using namespace sisua;
@@ -67,6 +68,8 @@ struct sisua_model {
   double* sq = nullptr;        // [kMaxSegments]
   long long* d_step = nullptr;
   SegTable seg;
+  uint8_t* packed_wout = nullptr;   // pre-packed fp16 (hi | lo | bias) output-head weight tiles (tcgen05 path)
+  int n_gene_tiles = 0;
   int num_sms = 148;
   int last_train_B = 0;
   // dropout stream of the current training step
@@ -210,6 +213,70 @@ static int ws_alloc(sisua_model* h, T** p, size_t count) {
   return SISUA_OK;
 }
 
+#ifdef SISUA_WITH_TC
+static bool tc_heads_enabled(const sisua_model* h) {
+  return h->cfg.gemm_mode != SISUA_GEMM_FP32_UNFUSED && h->cfg.model_kind != SISUA_MODEL_SCVI;
+}
+
+template <int NH, bool TRAIN, bool VEC>
+static int tc_set_attr(sisua_model* h) {
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::OutSmem::total(NH, TRAIN)));
+  return SISUA_OK;
+}
+
+static int tc_create(sisua_model* h) {
+  if (!tc_heads_enabled(h)) return SISUA_OK;
+  const int nh = h->cfg.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  h->n_gene_tiles = (h->cfg.n_genes + tc::kGeneTile - 1) / tc::kGeneTile;
+  int rc = ws_alloc(h, &h->packed_wout, (size_t)h->n_gene_tiles * tc::packed_tile_stride(nh));
+  if (rc != SISUA_OK) return rc;
+#define TC_ATTR(NH) \
+  if ((rc = tc_set_attr<NH, true, true>(h)) || (rc = tc_set_attr<NH, true, false>(h)) || \
+      (rc = tc_set_attr<NH, false, true>(h)) || (rc = tc_set_attr<NH, false, false>(h))) return rc
+  if (nh == 3) { TC_ATTR(3); } else { TC_ATTR(2); }
+#undef TC_ATTR
+  return SISUA_OK;
+}
+
+// fused output heads + count likelihood (+ backward of the heads when training)
+static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const float* x, int B, int S, float* llk_x,
+                           float* out_mean, float* out_disp, float* out_pi) {
+  const sisua_step_config& c = h->cfg;
+  const int nh = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  const int R = S * B, G = c.n_genes;
+  ++h->launches;
+  tc::pack_wout_kernel<<<h->n_gene_tiles, 256, 0, st>>>(h->P + h->out_w, h->P + h->out_b, h->packed_wout, G, nh, h->n_gene_tiles);
+  CUDA_OK(h, cudaMemsetAsync(llk_x, 0, (size_t)R * sizeof(float), st));
+  tc::OutHeadsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.D = h->D; a.x = x; a.packed = h->packed_wout; a.llk_x = llk_x;
+  a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
+  a.dD = h->dD; a.dW = h->Gd ? h->Gd + h->out_w : nullptr; a.db = h->Gd ? h->Gd + h->out_b : nullptr;
+  a.R = R; a.B = B; a.G = G; a.n_tiles = h->n_gene_tiles;
+  a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.upstream = -1.0f / (float)R;
+  const int cell_tiles = (R + tc::kCellTile - 1) / tc::kCellTile;
+  int chunks = std::max(1, std::min(h->n_gene_tiles, (h->num_sms + cell_tiles / 2) / cell_tiles));
+  a.tiles_per_chunk = (h->n_gene_tiles + chunks - 1) / chunks;
+  chunks = (h->n_gene_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  dim3 grid(cell_tiles, chunks);
+  const bool vec = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  ++h->launches;
+#define TC_LAUNCH(NH, TRAIN, VEC) \
+  tc::out_heads_kernel<NH, TRAIN, VEC><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a)
+  if (nh == 3) {
+    if (training) { if (vec) TC_LAUNCH(3, true, true); else TC_LAUNCH(3, true, false); }
+    else { if (vec) TC_LAUNCH(3, false, true); else TC_LAUNCH(3, false, false); }
+  } else {
+    if (training) { if (vec) TC_LAUNCH(2, true, true); else TC_LAUNCH(2, true, false); }
+    else { if (vec) TC_LAUNCH(2, false, true); else TC_LAUNCH(2, false, false); }
+  }
+#undef TC_LAUNCH
+  LAUNCH_OK(h, "out_heads_kernel (tcgen05)");
+  return SISUA_OK;
+}
+#endif  // SISUA_WITH_TC
+
 extern "C" const char* sisua_version(void) { return "sisua_b200 0.1 (sm_100a)"; }
 
 extern "C" const char* sisua_last_error(sisua_handle h) { return h ? h->err.c_str() : "null handle"; }
@@ -267,7 +334,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   }
   WS(h->D, R * H); WS(h->dD, R * H); WS(h->dHa, R * H); WS(h->dHb, R * H); WS(h->delta1, R * h->ld0);
   if (P > 0) { WS(h->PY, R * 2 * P); WS(h->dPY, R * 2 * P); }
-  if (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED) WS(h->OUT, R * (size_t)h->NO);
+  if (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED || scvi) WS(h->OUT, R * (size_t)h->NO);   // scVI heads (gene softmax) stay un-fused
   WS(h->mask_scale, 1);
   WS(h->scratch_terms, 5 * R);
   WS(h->stats, (size_t)h->n_units * 4 * H);
@@ -278,7 +345,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  if (scvi && c.n_genes * sizeof(float) > 200 * 1024 && c.gemm_mode == SISUA_GEMM_FP32_UNFUSED)
+  if (scvi && c.n_genes * sizeof(float) > 200 * 1024)
     SET_ERR(h, SISUA_ERR_UNSUPPORTED, "un-fused scVI row kernel caches one softmax row in shared memory: n_genes <= 51200");
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
@@ -424,6 +491,24 @@ static void stack_forward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
   }
 }
 
+// d loss / d D starts from the protein head's backward (SISUA) or from zero; the output heads add to it
+static int init_dD(sisua_model* h, cudaStream_t st, int R) {
+  const int H = kH, P = h->cfg.n_proteins;
+  if (P > 0) {
+    DenseBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_mode = 0; a.dOut = h->dPY; a.ldd = 2 * P; a.Nout = 2 * P; a.A_in = h->D; a.lda_in = H; a.Kin = H;
+    a.ns_in = raw_norm(); a.W = h->P + h->y_w; a.ldw = H; a.dW = h->Gd + h->y_w; a.db = h->Gd + h->y_b;
+    a.dIn = h->dD; a.ldi = H; a.accumulate_dIn = 0; a.R = R;
+    ++h->launches;
+    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
+    LAUNCH_OK(h, "protein head backward");
+  } else {
+    CUDA_OK(h, cudaMemsetAsync(h->dD, 0, (size_t)R * H * sizeof(float), st));
+  }
+  return SISUA_OK;
+}
+
 // shared forward; rows_dec = S*B
 static int forward_common(sisua_model* h, cudaStream_t st, bool training, const float* x, const float* y,
                           const float* library, const uint8_t* mask, const float* eps_z, const float* eps_l, int B,
@@ -446,13 +531,6 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   const int N0 = scvi ? 2 * H : H;
   bool first_done = false;
   sec_begin(h, st, SEC_ENC_FIRST);
-#ifdef SISUA_WITH_TC
-  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
-    int rc = tc_encoder_first(h, st, x, B, N0);
-    if (rc != SISUA_OK) return rc;
-    first_done = true;
-  }
-#endif
   if (!first_done) {
     DropSpec din = make_drop(h, c.input_dropout, 0u, training);
     if (c.log_norm)
@@ -521,7 +599,11 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   sec_begin(h, st, SEC_OUT_HEADS);
   bool out_done = false;
 #ifdef SISUA_WITH_TC
-  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+  if (tc_heads_enabled(h)) {
+    if (training) {   // the fused kernel adds its d loss / d D on top of the protein head's contribution
+      int rc0 = init_dD(h, st, R);
+      if (rc0 != SISUA_OK) return rc0;
+    }
     int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi);
     if (rc != SISUA_OK) return rc;
     out_done = true;
@@ -628,24 +710,13 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   int rc = forward_common(h, st, true, x, y, library, mask, eps_z, eps_l, B, 1, terms, loss, nullptr, nullptr, nullptr, nullptr);
   if (rc != SISUA_OK) return rc;
   h->last_train_B = B;
-  // ---- gradient wrt decoder output D
-  if (P > 0) {
-    DenseBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.out_mode = 0; a.dOut = h->dPY; a.ldd = 2 * P; a.Nout = 2 * P; a.A_in = h->D; a.lda_in = H; a.Kin = H;
-    a.ns_in = raw_norm(); a.W = h->P + h->y_w; a.ldw = H; a.dW = h->Gd + h->y_w; a.db = h->Gd + h->y_b;
-    a.dIn = h->dD; a.ldi = H; a.accumulate_dIn = 0; a.R = R;
-    ++h->launches;
-    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
-    LAUNCH_OK(h, "protein head backward");
-  } else {
-    CUDA_OK(h, cudaMemsetAsync(h->dD, 0, (size_t)R * H * sizeof(float), st));
-  }
   bool out_done = false;
 #ifdef SISUA_WITH_TC
-  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) out_done = true;   // fused kernel already produced dW_out, db_out, dD
+  if (tc_heads_enabled(h)) out_done = true;   // fused kernel already produced dW_out, db_out, dD
 #endif
   if (!out_done) {
+    rc = init_dD(h, st, R);
+    if (rc != SISUA_OK) return rc;
     sec_begin(h, st, SEC_OUT_HEADS);
     // dW_out[NO,H] += G_out^T . D ; db_out += colsum(G_out) ; dD += G_out . W_out
     launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, 1, h->NO, h->D, H, 1, h->Gd + h->out_w, H, nullptr, h->NO, H, R, true);
@@ -706,13 +777,6 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   const int N0 = scvi ? 2 * H : H;
   bool w1_done = false;
   sec_begin(h, st, SEC_ENC_FIRST_BWD);
-#ifdef SISUA_WITH_TC
-  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
-    rc = tc_encoder_first_bwd(h, st, x, B, N0);
-    if (rc != SISUA_OK) return rc;
-    w1_done = true;
-  }
-#endif
   if (!w1_done) {
     DropSpec din = make_drop(h, c.input_dropout, 0u, true);
     if (c.log_norm)
@@ -761,6 +825,21 @@ extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta
   LAUNCH_OK(h, "adam");
   sec_end(h, st, SEC_ADAM);
   return SISUA_OK;
+}
+
+// tcgen05 descriptor self-test (tests only): D[128,N] = A[128,K] . B[N,K]^T, fp16 operands, fp32 accumulate.
+extern "C" int sisua_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
+                                 void* stream) {
+#ifdef SISUA_WITH_TC
+  if (N % 16 != 0 || N < 16 || N > 256 || K % 16 != 0 || K < 16 || K > 256) return SISUA_ERR_INVALID;
+  size_t smem = (size_t)(128 + N) * K * 2;
+  if (cudaFuncSetAttribute(tc::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return SISUA_ERR_CUDA;
+  tc::tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, a_mn_major, b_mn_major);
+  return cudaGetLastError() == cudaSuccess ? SISUA_OK : SISUA_ERR_CUDA;
+#else
+  return SISUA_ERR_UNSUPPORTED;
+#endif
 }
 
 extern "C" int64_t sisua_launch_count(sisua_handle h) { return h ? h->launches : -1; }

@@ -1,0 +1,403 @@
+// Fused tcgen05 kernel for the decoder output heads:
+//   out = d . W_out^T + b   (tensor cores, accumulators in TMEM, never written to HBM)
+//   -> mean / dispersion / dropout-logit activations -> ZINB / NB log-likelihood per cell (epilogue)
+//   -> [train] d llk / d out as an fp16 operand tile in shared memory -> two more tcgen05 GEMMs:
+//        dD    += G . W_out          (gradient wrt the decoder activations, TMEM-resident across gene tiles)
+//        dW_out = G^T . [d | 1]      (weight and bias gradient of the gene tile, flushed with vector reds)
+// Forward products are error-compensated 3xFP16 (d = d1 + d2, w = w1 + w2; d1w1 + d1w2 + d2w1 accumulated in
+// fp32), i.e. fp32-grade logits; the two gradient GEMMs use single fp16 operands (2^-11 relative).
+// One CTA owns a tile of 128 cells and walks a chunk of 32-gene tiles; roles: 8 epilogue warps (TMEM lane
+// quarter x gene half), 1 MMA-issuing thread, 1 bulk-copy (TMA) thread streaming pre-packed weight tiles.
+#pragma once
+#include "device_math.cuh"
+#include "tc_ptx.cuh"
+
+namespace sisua {
+namespace tc {
+
+constexpr int kCellTile = 128;
+constexpr int kGeneTile = 32;
+constexpr int kK = 64;                 // hidden width = contraction length
+constexpr int kEpiThreads = 256;
+constexpr int kOutThreads = 320;       // 8 epilogue warps + MMA warp + loader warp
+constexpr int kXPad = 36;              // floats per x-tile row (32 + 4: conflict-free float4 access)
+constexpr int kTmemCols = 512;
+constexpr int kTmemDD = 192, kTmemDWO = 256, kDwoCols = 80;
+
+__host__ __device__ constexpr int w_tile_bytes(int nh) { return nh * 32 * kK * 2; }                 // one fp16 copy
+__host__ __device__ constexpr int packed_tile_bytes(int nh) { return 2 * w_tile_bytes(nh) + nh * 32 * 4; }   // w1 | w2 | bias
+__host__ __device__ constexpr int packed_tile_stride(int nh) { return (packed_tile_bytes(nh) + 127) / 128 * 128; }
+
+// ---- weight pre-pack: W_out[nh*G, 64] fp32 -> per gene tile (w1 | w2 | bias) in the canonical UMMA layout ----
+__global__ void __launch_bounds__(256) pack_wout_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                        uint8_t* __restrict__ packed, int G, int nh, int n_tiles) {
+  const int tile = blockIdx.x;
+  const int rows = nh * 32;
+  const int RS = 128, CS = rows / 8 * 128;
+  uint8_t* base = packed + (size_t)tile * packed_tile_stride(nh);
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {     // (row, 8-column group)
+    int n = i % rows, cg = i / rows;
+    int h = n / 32, g = tile * kGeneTile + (n % 32);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v0 = 0.f, v1 = 0.f;
+      if (g < G) {
+        const float* src = W + ((size_t)h * G + g) * kK + cg * 8 + 2 * j;
+        v0 = src[0]; v1 = src[1];
+      }
+      __half h0, l0, h1, l1;
+      split_f16(v0, h0, l0); split_f16(v1, h1, l1);
+      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+    }
+    uint32_t off = (n >> 3) * RS + cg * CS + (n & 7) * 16;
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + w_tile_bytes(nh) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  float* bdst = reinterpret_cast<float*>(base + 2 * w_tile_bytes(nh));
+  for (int n = threadIdx.x; n < rows; n += blockDim.x) {
+    int h = n / 32, g = tile * kGeneTile + (n % 32);
+    bdst[n] = g < G ? bias[(size_t)h * G + g] : 0.f;
+  }
+}
+
+struct OutHeadsArgs {
+  const float* D;          // [R, 64] activated decoder output
+  const float* x;          // [B, G] counts
+  const uint8_t* packed;   // pre-packed weight tiles
+  float* llk_x;            // [R], zeroed by the caller (gene chunks add atomically)
+  // inference outputs (nullable)
+  float* out_mean; float* out_disp; float* out_pi;
+  // training outputs
+  float* dD;               // [R, 64] += d loss / d D
+  float* dW;               // [nh*G, 64] += d loss / d W_out
+  float* db;               // [nh*G]     += d loss / d b_out
+  int R, B, G, n_tiles, tiles_per_chunk;
+  int mean_act, disp_act;
+  float upstream;          // d loss / d llk_x = -1 / R
+};
+
+struct OutSmem {     // offsets into dynamic shared memory (bytes)
+  static constexpr int dA1 = 0;                          // [128][80] fp16 (cols 64.. = ones / zero pad, train)
+  static constexpr int dA2 = dA1 + 10 * 2048;            // [128][64] fp16
+  static constexpr int W0 = dA2 + 8 * 2048;              // 2 stages of packed tiles
+  __host__ __device__ static constexpr int Wstage(int nh) { return packed_tile_stride(nh); }
+  __host__ __device__ static constexpr int X0(int nh) { return W0 + 2 * Wstage(nh); }
+  __host__ __device__ static constexpr int Xstage() { return kCellTile * kXPad * 4; }
+  __host__ __device__ static constexpr int G0(int nh) { return X0(nh) + 2 * Xstage(); }      // [128][128] fp16 (train)
+  __host__ __device__ static constexpr int LLK(int nh, bool train) { return G0(nh) + (train ? 16 * 2048 : 0); }
+  __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + kCellTile * 4; }
+  __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
+};
+
+enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 9, DWO_FULL = 10, DWO_FREE = 12, DD_FULL = 14, NUM_BARS = 15 };
+
+template <int NH, bool TRAIN, bool VEC>
+__global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int N = NH * 32;
+  constexpr bool ZI = NH == 3;
+  constexpr int W_CS = NH * 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OutSmem::BAR(NH, TRAIN));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OutSmem::BAR(NH, TRAIN) + 32 * 8);
+  float* llk_s = reinterpret_cast<float*>(smem + OutSmem::LLK(NH, TRAIN));
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int row0 = blockIdx.x * kCellTile;
+  const int tile_begin = blockIdx.y * a.tiles_per_chunk;
+  const int tile_end = min(a.n_tiles, tile_begin + a.tiles_per_chunk);
+  const int nt = tile_end - tile_begin;
+  if (nt <= 0) return;
+
+  // ---------------- prologue: barriers, TMEM, decoder-activation tile (hi/lo fp16), pads ----------------
+  if (t == 0) {
+    mbar_init(&bars[W_FULL], 1); mbar_init(&bars[W_FULL + 1], 1);
+    mbar_init(&bars[W_FREE], 1); mbar_init(&bars[W_FREE + 1], 1);
+    mbar_init(&bars[ACC_FULL], 1); mbar_init(&bars[ACC_FULL + 1], 1);
+    mbar_init(&bars[ACC_FREE], 8); mbar_init(&bars[ACC_FREE + 1], 8);
+    mbar_init(&bars[G_FULL], 8); mbar_init(&bars[G_FREE], 1);
+    mbar_init(&bars[DWO_FULL], 1); mbar_init(&bars[DWO_FULL + 1], 1);
+    mbar_init(&bars[DWO_FREE], 8); mbar_init(&bars[DWO_FREE + 1], 8);
+    mbar_init(&bars[DD_FULL], 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  for (int item = t; item < kCellTile * 8; item += kOutThreads) {
+    int r = item % kCellTile, cg = item / kCellTile;
+    float v[8];
+    if (row0 + r < a.R) {
+      const float4* src = reinterpret_cast<const float4*>(a.D + (size_t)(row0 + r) * kK + cg * 8);
+      float4 p = src[0], q = src[1];
+      v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half h0, l0, h1, l1;
+      split_f16(v[2 * j], h0, l0); split_f16(v[2 * j + 1], h1, l1);
+      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+    }
+    uint32_t off = cg * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(smem + OutSmem::dA1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(smem + OutSmem::dA2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (TRAIN) {
+    for (int item = t; item < kCellTile * 2; item += kOutThreads) {      // column groups 8 (ones | 0..) and 9 (zeros)
+      int r = item % kCellTile, cg = 8 + item / kCellTile;
+      uint32_t off = cg * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+      uint32_t first = (cg == 8 && row0 + r < a.R) ? 0x00003C00u : 0u;  // fp16 1.0 in column 64
+      *reinterpret_cast<uint4*>(smem + OutSmem::dA1 + off) = make_uint4(first, 0u, 0u, 0u);
+    }
+    for (int item = t; item < 16 * 2048 / 16; item += kOutThreads)      // zero the whole G tile once (pad columns stay 0)
+      *reinterpret_cast<uint4*>(smem + OutSmem::G0(NH) + item * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (t < kCellTile) llk_s[t] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 9) {
+    // =========================== loader: pre-packed weight tiles via 1-D TMA bulk copies ===========================
+    if (lane == 0) {
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1;
+        if (i >= 2) mbar_wait(&bars[W_FREE + s], ((i >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[W_FULL + s], packed_tile_bytes(NH));
+        bulk_copy_g2s(smem + OutSmem::W0 + s * OutSmem::Wstage(NH),
+                      a.packed + (size_t)(tile_begin + i) * packed_tile_stride(NH), packed_tile_bytes(NH), &bars[W_FULL + s]);
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      const uint32_t idesc_fwd = make_idesc_f16(kCellTile, N, 0, 0);
+      const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
+      const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
+      const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
+      const uint32_t sG = smem_u32(smem + OutSmem::G0(NH));
+      auto fwd = [&](int i) {
+        const int s = i & 1;
+        const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
+        mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);
+        if (i >= 2) mbar_wait(&bars[ACC_FREE + s], ((i >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d_t = tmem + (uint32_t)(s * N);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t sa = (p == 2) ? sA2 : sA1, sb = (p == 1) ? sW2 : sW1;
+#pragma unroll
+          for (int ks = 0; ks < kK / 16; ++ks) {
+            umma_f16(d_t, make_smem_desc(sa + ks * 4096, 2048, 128), make_smem_desc(sb + ks * 2 * W_CS, W_CS, 128), idesc_fwd, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&bars[ACC_FULL + s]);
+        if (!TRAIN) umma_commit(&bars[W_FREE + s]);
+      };
+      fwd(0);
+      for (int i = 0; i < nt; ++i) {
+        if (i + 1 < nt) fwd(i + 1);
+        if (TRAIN) {
+          const int s = i & 1;
+          const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH));
+          mbar_wait(&bars[G_FULL], i & 1);
+          if (i >= 2) mbar_wait(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
+          tc_fence_after();
+          // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 MN-major)
+#pragma unroll
+          for (int ks = 0; ks < N / 16; ++ks)
+            umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128), make_smem_desc(sW1 + ks * 256, 128, W_CS),
+                     idesc_dd, (i > 0 || ks > 0) ? 1u : 0u);
+          // dW[n, k | 1] = G^T[n, cells] . [d | 1][cells, k]   (A: G MN-major, B: d1 MN-major)
+#pragma unroll
+          for (int ks = 0; ks < kCellTile / 16; ++ks)
+            umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
+                     make_smem_desc(sA1 + ks * 256, 128, 2048), idesc_dwo, ks > 0 ? 1u : 0u);
+          umma_commit(&bars[G_FREE]);
+          umma_commit(&bars[DWO_FULL + s]);
+          umma_commit(&bars[W_FREE + s]);
+          if (i == nt - 1) umma_commit(&bars[DD_FULL]);
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3, hh = warp >> 2;
+    const int cell = q * 32 + lane;
+    const int row = row0 + cell;
+    const bool row_ok = row < a.R;
+    const float* xrow = a.x + (size_t)((row_ok ? row : 0) % a.B) * a.G;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float llk_acc = 0.f;
+
+    auto load_x_tile = [&](int i) {          // cooperative, 256 threads
+      const int s = i & 1;
+      float* xs = reinterpret_cast<float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage());
+      const int g0 = (tile_begin + i) * kGeneTile;
+      if (VEC) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int idx = t + kEpiThreads * j;
+          int r = idx >> 3, c4 = idx & 7;
+          int rr = row0 + r, g = g0 + 4 * c4;
+          float* dst = xs + r * kXPad + 4 * c4;
+          if (rr < a.R && g < a.G) cp_async_16(dst, a.x + (size_t)(rr % a.B) * a.G + g);
+          else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        for (int idx = t; idx < kCellTile * kGeneTile; idx += kEpiThreads) {
+          int r = idx >> 5, c = idx & 31;
+          int rr = row0 + r, g = g0 + c;
+          xs[r * kXPad + c] = (rr < a.R && g < a.G) ? a.x[(size_t)(rr % a.B) * a.G + g] : 0.f;
+        }
+      }
+      cp_async_commit();
+    };
+    (void)xrow;
+
+    auto flush_dwo = [&](int i) {            // tile i's weight / bias gradient: TMEM -> vector reds
+      const int s = i & 1;
+      mbar_wait(&bars[DWO_FULL + s], (i >> 1) & 1);
+      tc_fence_after();
+      const int n = cell;                    // TMEM lane = output-unit row of the tile
+      const int h = n >> 5, g = (tile_begin + i) * kGeneTile + (n & 31);
+      const bool ok = n < N && g < a.G;
+      float v[32], vb[16];
+      const uint32_t base = tmem + lane_addr + kTmemDWO + s * kDwoCols + hh * 32;
+      tmem_ld16(base, v); tmem_ld16(base + 16, v + 16);
+      if (hh == 0) tmem_ld16(tmem + lane_addr + kTmemDWO + s * kDwoCols + 64, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[DWO_FREE + s]);
+      if (ok) {
+        float* dst = a.dW + ((size_t)h * a.G + g) * kK + hh * 32;
+        const float sc = a.upstream;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
+        if (hh == 0) atomicAdd(a.db + (size_t)h * a.G + g, sc * vb[0]);
+      }
+    };
+
+    load_x_tile(0);
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      const int g0 = (tile_begin + i) * kGeneTile;
+      if (i + 1 < nt) {
+        named_bar_sync(1, kEpiThreads);      // everyone is done reading stage s^1 (tile i-1)
+        load_x_tile(i + 1);
+      } else {
+        cp_async_commit();
+      }
+      cp_async_wait<1>();
+      named_bar_sync(1, kEpiThreads);        // tile i's counts are visible to all epilogue threads
+      mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
+      mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
+      tc_fence_after();
+      float va[16], vb[16], vl[16];
+      const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + hh * 16);
+      tmem_ld16(tb, va);
+      tmem_ld16(tb + 32, vb);
+      if (ZI) tmem_ld16(tb + 64, vl);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[ACC_FREE + s]);
+
+      const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH));
+      const float* xs = reinterpret_cast<const float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage()) + cell * kXPad + hh * 16;
+      float xv[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 p = *reinterpret_cast<const float4*>(xs + 4 * j);
+        xv[4 * j] = p.x; xv[4 * j + 1] = p.y; xv[4 * j + 2] = p.z; xv[4 * j + 3] = p.w;
+      }
+      float om[16], od[16];
+      uint32_t ga[8], gb[8], gl[8];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int g = g0 + hh * 16 + j;
+        const bool ok = row_ok && g < a.G;
+        float ra = va[j] + bias_s[hh * 16 + j];
+        float rb = vb[j] + bias_s[32 + hh * 16 + j];
+        float pi = ZI ? vl[j] + bias_s[64 + hh * 16 + j] : 0.f;
+        float mu, dmu, th, dth;
+        activation(a.mean_act, ra, mu, dmu);
+        activation(a.disp_act, rb, th, dth);
+        CountGrad cg;
+        float l = count_llk<ZI, TRAIN>(xv[j], mu, th, pi, cg);
+        llk_acc += ok ? l : 0.f;
+        if (!TRAIN) { om[j] = mu; od[j] = th; vl[j] = pi; }
+        if (TRAIN) {
+          float g_a = ok ? fminf(fmaxf(cg.dmu * dmu, -60000.f), 60000.f) : 0.f;
+          float g_b = ok ? fminf(fmaxf(cg.dth * dth, -60000.f), 60000.f) : 0.f;
+          float g_l = (ok && ZI) ? cg.dpi : 0.f;
+          // pack pairs of consecutive genes into one 32-bit word
+          uint32_t ha = (uint32_t)__half_as_ushort(__float2half_rn(g_a));
+          uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(g_b));
+          uint32_t hl = (uint32_t)__half_as_ushort(__float2half_rn(g_l));
+          if (j & 1) { ga[j >> 1] |= ha << 16; gb[j >> 1] |= hb << 16; gl[j >> 1] |= hl << 16; }
+          else { ga[j >> 1] = ha; gb[j >> 1] = hb; gl[j >> 1] = hl; }
+        }
+      }
+      if (!TRAIN && row_ok) {
+        const size_t o = (size_t)row * a.G + g0 + hh * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (g0 + hh * 16 + j < a.G) {
+            if (a.out_mean) a.out_mean[o + j] = om[j];
+            if (a.out_disp) a.out_disp[o + j] = od[j];
+            if (ZI && a.out_pi) a.out_pi[o + j] = vl[j];
+          }
+        }
+      }
+      if (TRAIN) {
+        if (i >= 1) mbar_wait(&bars[G_FREE], (i - 1) & 1);     // previous tile's gradient GEMMs have consumed G
+        uint8_t* gt = smem + OutSmem::G0(NH) + (cell >> 3) * 128 + (cell & 7) * 16;
+        // column groups of 8 output units: head h occupies groups 4h..4h+3; this thread owns 2hh, 2hh+1 of each head
+        *reinterpret_cast<uint4*>(gt + (0 * 4 + 2 * hh) * 2048) = make_uint4(ga[0], ga[1], ga[2], ga[3]);
+        *reinterpret_cast<uint4*>(gt + (0 * 4 + 2 * hh + 1) * 2048) = make_uint4(ga[4], ga[5], ga[6], ga[7]);
+        *reinterpret_cast<uint4*>(gt + (1 * 4 + 2 * hh) * 2048) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+        *reinterpret_cast<uint4*>(gt + (1 * 4 + 2 * hh + 1) * 2048) = make_uint4(gb[4], gb[5], gb[6], gb[7]);
+        if (ZI) {
+          *reinterpret_cast<uint4*>(gt + (2 * 4 + 2 * hh) * 2048) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
+          *reinterpret_cast<uint4*>(gt + (2 * 4 + 2 * hh + 1) * 2048) = make_uint4(gl[4], gl[5], gl[6], gl[7]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[G_FULL]);
+        if (i >= 1) flush_dwo(i - 1);
+      }
+    }
+    // per-cell log-likelihood: two gene halves per cell -> shared -> one atomic per cell and chunk
+    atomicAdd(&llk_s[cell], llk_acc);
+    named_bar_sync(1, kEpiThreads);
+    if (hh == 0 && row_ok) atomicAdd(a.llk_x + row, llk_s[cell]);
+    if (TRAIN) {
+      flush_dwo(nt - 1);
+      mbar_wait(&bars[DD_FULL], 0);
+      tc_fence_after();
+      float v[32];
+      const uint32_t base = tmem + lane_addr + kTmemDD + hh * 32;
+      tmem_ld16(base, v); tmem_ld16(base + 16, v + 16);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = a.dD + (size_t)row * kK + hh * 32;
+        const float sc = a.upstream;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace sisua

@@ -29,7 +29,7 @@ def _close(a, b, rtol=RTOL, atol=0.0, what=""):
 
 
 MODELS = [("vae", {}), ("scvi", {}), ("dca", {}), ("sisua", dict(n_proteins=10))]
-MODES = [C.GEMM_FP32_UNFUSED]
+MODES = [C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XTF32]
 
 
 def _setup(model, kw, G, B, mode, seed=0, trained_moving=True, **cfgkw):
@@ -81,7 +81,9 @@ def test_inference_mc_samples(mode):
   eng.close()
 
 
-def _grad_check(cfg, flat, mov, batch, eng, gtol=2e-3, drop=None, seed=0, step=-1):
+def _grad_check(cfg, flat, mov, batch, eng, gtol=None, drop=None, seed=0, step=-1):
+  # fused path: the two gradient GEMMs of the output heads run on single fp16 operands (2^-11 relative)
+  gtol = gtol or (2e-3 if cfg.gemm_mode == C.GEMM_FP32_UNFUSED else 6e-3)
   terms, loss = eng.train_step(seed=seed, step=step, **batch)
   torch.cuda.synchronize()
   P = Hh.oracle_params(cfg, flat)
@@ -147,7 +149,8 @@ def test_multi_step_training_matches_oracle(model, kw, mode):
   for name, p in P.items():
     # Adam's normalised update amplifies tiny gradient differences: compare against the step size
     err = np.abs(got[name] - p.numpy()).max()
-    assert err <= 2e-4, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
+    lim = 2e-4 if mode == C.GEMM_FP32_UNFUSED else 2e-3   # fp16-grade gradients can flip Adam's sign-like first steps
+    assert err <= lim, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
   eng.close()
 
 
@@ -180,3 +183,23 @@ def test_errors_are_loud():
     big = Hh.make_batch(cfg, 128)
     eng.infer(**big)                               # exceeds max_batch
   eng.close()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("N,K", [(96, 64), (64, 96), (80, 128)])
+def test_tcgen05_descriptor_selftest(a_mn, b_mn, N, K):
+  """Pins the shared-memory / instruction descriptor conventions (K-major and MN-major no-swizzle tiles, TMEM
+  lane = row) that the fused kernels rely on."""
+  import ctypes
+  from sisua_b200 import _lib
+  L = _lib.load()
+  g = torch.Generator(device="cuda"); g.manual_seed(N * 1000 + K + 2 * a_mn + b_mn)
+  A = torch.randn((128, K), device="cuda", generator=g)
+  Bm = torch.randn((N, K), device="cuda", generator=g)
+  D = torch.zeros((128, N), device="cuda")
+  rc = L.sisua_tc_selftest(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(Bm.data_ptr()), ctypes.c_void_p(D.data_ptr()),
+                           N, K, a_mn, b_mn, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+  assert rc == 0
+  torch.cuda.synchronize()
+  ref = A.half().float() @ Bm.half().float().T
+  assert torch.allclose(D, ref, rtol=1e-4, atol=1e-3), float((D - ref).abs().max())
