@@ -220,7 +220,9 @@ static bool tc_heads_enabled(const sisua_model* h) {
 
 template <int NH, bool TRAIN, bool VEC>
 static int tc_set_attr(sisua_model* h) {
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::OutSmem::total(NH, TRAIN)));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::OutSmem::total(NH, TRAIN)));
   return SISUA_OK;
 }
@@ -262,8 +264,12 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
   dim3 grid(cell_tiles, chunks);
   const bool vec = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   ++h->launches;
-#define TC_LAUNCH(NH, TRAIN, VEC) \
-  tc::out_heads_kernel<NH, TRAIN, VEC><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a)
+  const bool fast = c.mean_act == SISUA_ACT_SOFTPLUS && c.disp_act == SISUA_ACT_SOFTPLUS1;
+#define TC_LAUNCH(NH, TRAIN, VEC)                                                                                   \
+  do {                                                                                                              \
+    if (fast) tc::out_heads_kernel<NH, TRAIN, VEC, true><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);  \
+    else tc::out_heads_kernel<NH, TRAIN, VEC, false><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);      \
+  } while (0)
   if (nh == 3) {
     if (training) { if (vec) TC_LAUNCH(3, true, true); else TC_LAUNCH(3, true, false); }
     else { if (vec) TC_LAUNCH(3, false, true); else TC_LAUNCH(3, false, false); }

@@ -144,6 +144,120 @@ __device__ __forceinline__ float nb_tfp_llk(float y, float a, float b, float& da
   return llk;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lean evaluation for the fused epilogue with the default links (mean = softplus, dispersion =
+// softplus(. + log(e-1))): straight-line MUFU ex2 / lg2 / rcp code, no per-element branches except a
+// warp-uniform skip of the x > 0 terms.  Same mathematics as count_llk above (eps placement differs by
+// O(1e-8/theta), far below the 1e-4 parity tolerance).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// softplus(r) and sigmoid(r) (= its derivative)
+__device__ __forceinline__ void softplus_fast(float r, float& v, float& dv) {
+  float e = mufu_ex2(fminf(r, 30.f) * kLog2e);
+  float s = 1.f + e;
+  float big = kLn2 * mufu_lg2(s);
+  float small = e * (1.f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
+  v = e < 0.015625f ? small : big;
+  v = r > 30.f ? r : v;
+  dv = e * mufu_rcp(s);
+}
+
+// Stirling forms, z >= 8
+__device__ __forceinline__ float lgamma_stirling(float z, float lnz, float iz) {
+  float iz2 = iz * iz;
+  return (z - 0.5f) * lnz - z + 0.9189385332f + iz * (0.083333336f - iz2 * (0.0027777778f - iz2 * 0.00079365079f));
+}
+__device__ __forceinline__ float digamma_stirling(float lnz, float iz) {
+  float iz2 = iz * iz;
+  return lnz - 0.5f * iz - iz2 * (0.083333336f - iz2 * (0.008333334f - iz2 * 0.003968254f));
+}
+
+struct ElemResult { float llk, ga, gb, gl, mu, th; };   // ga, gb, gl = d llk / d raw head outputs
+
+template <bool kZeroInflated, bool kGrad>
+__device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float pi, float x) {
+  ElemResult o;
+  float mu, dmu, th, dth;
+  softplus_fast(ra, mu, dmu);
+  softplus_fast(rb + kSoftplus1Shift, th, dth);
+  o.mu = mu; o.th = th;
+  const float Rt = mufu_rcp(th + mu + kEps);
+  const float rho = th * Rt;
+  const float dlog = kLn2 * mufu_lg2(rho + 1e-30f);
+  const float n0 = th * dlog;
+  const float dn0_dmu = -rho, dn0_dth = dlog + 1.f - rho;
+  float Ep = 0.f, Rp = 1.f, pc = 0.f;
+  float llk, gmu, gth, gl = 0.f;
+  if (kZeroInflated) {
+    pc = fminf(fmaxf(pi, -60.f), 60.f);
+    Ep = mufu_ex2(-pc * kLog2e);            // exp(-pi)
+    Rp = mufu_rcp(1.f + Ep);                // sigmoid(pi)
+    float Eu = mufu_ex2((n0 - pc) * kLog2e);
+    float Su = 1.f + Eu;
+    float w = Eu * mufu_rcp(Su);            // sigmoid(n0 - pi)
+    llk = kLn2 * mufu_lg2(Su * Rp);         // softplus(n0 - pi) - softplus(-pi)
+    gl = Ep * Rp - w; gmu = w * dn0_dmu; gth = w * dn0_dth;
+  } else {
+    llk = n0; gmu = dn0_dmu; gth = dn0_dth;
+  }
+  const bool nz = x >= kEps;
+  if (__any_sync(0xffffffffu, nz)) {
+    // lg = lgamma(x+th) - lgamma(th) - lgamma(x+1), dg = psi(x+th) - psi(th)
+    float q = th, dq = 1.f, f = 1.f;          // q = prod_{k<min(x,8)} (th+k)
+    const bool small_x = (x == rintf(x)) && x <= 8.f;
+    const float lim = small_x ? x : 8.f;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      if ((float)k < lim) {
+        float tk = th + (float)k;
+        dq = fmaf(dq, tk, q);
+        q *= tk;
+        f *= (float)(k + 1);
+      }
+    }
+    float lnq = kLn2 * mufu_lg2(q);
+    float rq = mufu_rcp(q);
+    float lg = lnq - kLn2 * mufu_lg2(f);
+    float dg = dq * rq;
+    if (__any_sync(0xffffffffu, nz && !small_x)) {
+      // large or non-integer counts: Stirling at x+th, x+1 and th+8 (all >= 8); q = prod_{k<8}(th+k)
+      float z1 = x + th, z2 = x + 1.f, z3 = th + 8.f;
+      float l1 = kLn2 * mufu_lg2(z1), l2 = kLn2 * mufu_lg2(z2), l3 = kLn2 * mufu_lg2(z3);
+      float i1 = mufu_rcp(z1), i2 = mufu_rcp(z2), i3 = mufu_rcp(z3);
+      // for x < 7 (non-integer) shift x+th and x+1 up by 8 as well so Stirling stays accurate
+      float lg_big, dg_big;
+      if (x >= 7.f) {
+        lg_big = lgamma_stirling(z1, l1, i1) - lgamma_stirling(z2, l2, i2) - lgamma_stirling(z3, l3, i3) + lnq;
+        dg_big = digamma_stirling(l1, i1) - digamma_stirling(l3, i3) + dg;
+      } else {
+        lg_big = lgammaf(z1) - lgammaf(th) - lgammaf(z2);
+        dg_big = kGrad ? digamma_pos(z1) - digamma_pos(th) : 0.f;
+      }
+      lg = small_x ? lg : lg_big;
+      dg = small_x ? dg : dg_big;
+    }
+    float lnm = kLn2 * mufu_lg2((mu + kEps) * Rt);
+    float llk1 = n0 + x * lnm + lg;
+    float gmu1 = dn0_dmu + x * (mufu_rcp(mu + kEps) - Rt);
+    float gth1 = dn0_dth - x * Rt + dg;
+    float gl1 = 0.f;
+    if (kZeroInflated) {
+      llk1 += kLn2 * mufu_lg2(Ep * Rp) - fmaxf(pi - 60.f, 0.f);   // log sigmoid(-pi)
+      gl1 = -Rp;
+    }
+    llk = nz ? llk1 : llk; gmu = nz ? gmu1 : gmu; gth = nz ? gth1 : gth; gl = nz ? gl1 : gl;
+  }
+  o.llk = llk;
+  o.ga = gmu * dmu; o.gb = gth * dth; o.gl = gl;
+  return o;
+}
+
 // Counter-based dropout masks (Philox4x32-10): mask(seed, step, stream, row, col) is a pure function, so
 // forward and backward regenerate it instead of storing it, and the CPU oracle reproduces it exactly
 // (oracle/philox.py).  stream 0 = input dropout on log1p(x); stream 1+u = hidden unit u.

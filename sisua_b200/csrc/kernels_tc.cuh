@@ -6,8 +6,8 @@
 //        dW_out = G^T . [d | 1]      (weight and bias gradient of the gene tile, flushed with vector reds)
 // Forward products are error-compensated 3xFP16 (d = d1 + d2, w = w1 + w2; d1w1 + d1w2 + d2w1 accumulated in
 // fp32), i.e. fp32-grade logits; the two gradient GEMMs use single fp16 operands (2^-11 relative).
-// One CTA owns a tile of 128 cells and walks a chunk of 32-gene tiles; roles: 8 epilogue warps (TMEM lane
-// quarter x gene half), 1 MMA-issuing thread, 1 bulk-copy (TMA) thread streaming pre-packed weight tiles.
+// One CTA owns a tile of 128 cells and walks a chunk of 32-gene tiles; roles: 16 epilogue warps (TMEM lane
+// quarter x 8-gene slice), 1 MMA-issuing thread, 1 bulk-copy (TMA) thread streaming pre-packed weight tiles.
 #pragma once
 #include "device_math.cuh"
 #include "tc_ptx.cuh"
@@ -18,8 +18,10 @@ namespace tc {
 constexpr int kCellTile = 128;
 constexpr int kGeneTile = 32;
 constexpr int kK = 64;                 // hidden width = contraction length
-constexpr int kEpiThreads = 256;
-constexpr int kOutThreads = 320;       // 8 epilogue warps + MMA warp + loader warp
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kOutThreads = kEpiThreads + 64;   // 16 epilogue warps + MMA warp + loader warp
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1;
 constexpr int kXPad = 36;              // floats per x-tile row (32 + 4: conflict-free float4 access)
 constexpr int kTmemCols = 512;
 constexpr int kTmemDD = 192, kTmemDWO = 256, kDwoCols = 80;
@@ -92,7 +94,7 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
 
 enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 9, DWO_FULL = 10, DWO_FREE = 12, DD_FULL = 14, NUM_BARS = 15 };
 
-template <int NH, bool TRAIN, bool VEC>
+template <int NH, bool TRAIN, bool VEC, bool FAST>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int N = NH * 32;
@@ -113,14 +115,14 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     mbar_init(&bars[W_FULL], 1); mbar_init(&bars[W_FULL + 1], 1);
     mbar_init(&bars[W_FREE], 1); mbar_init(&bars[W_FREE + 1], 1);
     mbar_init(&bars[ACC_FULL], 1); mbar_init(&bars[ACC_FULL + 1], 1);
-    mbar_init(&bars[ACC_FREE], 8); mbar_init(&bars[ACC_FREE + 1], 8);
-    mbar_init(&bars[G_FULL], 8); mbar_init(&bars[G_FREE], 1);
+    mbar_init(&bars[ACC_FREE], kEpiWarps); mbar_init(&bars[ACC_FREE + 1], kEpiWarps);
+    mbar_init(&bars[G_FULL], kEpiWarps); mbar_init(&bars[G_FREE], 1);
     mbar_init(&bars[DWO_FULL], 1); mbar_init(&bars[DWO_FULL + 1], 1);
-    mbar_init(&bars[DWO_FREE], 8); mbar_init(&bars[DWO_FREE + 1], 8);
+    mbar_init(&bars[DWO_FREE], kEpiWarps); mbar_init(&bars[DWO_FREE + 1], kEpiWarps);
     mbar_init(&bars[DD_FULL], 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   for (int item = t; item < kCellTile * 8; item += kOutThreads) {
     int r = item % kCellTile, cg = item / kCellTile;
     float v[8];
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp == kLoadWarp) {
     // =========================== loader: pre-packed weight tiles via 1-D TMA bulk copies ===========================
     if (lane == 0) {
       for (int i = 0; i < nt; ++i) {
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
                       a.packed + (size_t)(tile_begin + i) * packed_tile_stride(NH), packed_tile_bytes(NH), &bars[W_FULL + s]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
       const uint32_t idesc_fwd = make_idesc_f16(kCellTile, N, 0, 0);
@@ -227,21 +229,20 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     }
   } else {
     // =========================== epilogue warps ===========================
-    const int q = warp & 3, hh = warp >> 2;
+    const int q = warp & 3, sub = warp >> 2;      // TMEM lane quarter, 8-gene slice of the 32-gene tile
     const int cell = q * 32 + lane;
     const int row = row0 + cell;
     const bool row_ok = row < a.R;
-    const float* xrow = a.x + (size_t)((row_ok ? row : 0) % a.B) * a.G;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float llk_acc = 0.f;
 
-    auto load_x_tile = [&](int i) {          // cooperative, 256 threads
+    auto load_x_tile = [&](int i) {          // cooperative, all epilogue threads
       const int s = i & 1;
       float* xs = reinterpret_cast<float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage());
       const int g0 = (tile_begin + i) * kGeneTile;
       if (VEC) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kCellTile * 8 / kEpiThreads; ++j) {
           int idx = t + kEpiThreads * j;
           int r = idx >> 3, c4 = idx & 7;
           int rr = row0 + r, g = g0 + 4 * c4;
@@ -258,7 +259,6 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       }
       cp_async_commit();
     };
-    (void)xrow;
 
     auto flush_dwo = [&](int i) {            // tile i's weight / bias gradient: TMEM -> vector reds
       const int s = i & 1;
@@ -267,27 +267,26 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       const int n = cell;                    // TMEM lane = output-unit row of the tile
       const int h = n >> 5, g = (tile_begin + i) * kGeneTile + (n & 31);
       const bool ok = n < N && g < a.G;
-      float v[32], vb[16];
-      const uint32_t base = tmem + lane_addr + kTmemDWO + s * kDwoCols + hh * 32;
-      tmem_ld16(base, v); tmem_ld16(base + 16, v + 16);
-      if (hh == 0) tmem_ld16(tmem + lane_addr + kTmemDWO + s * kDwoCols + 64, vb);
+      float v[16], vb[16];
+      tmem_ld16(tmem + lane_addr + kTmemDWO + s * kDwoCols + sub * 16, v);
+      if (sub == 0) tmem_ld16(tmem + lane_addr + kTmemDWO + s * kDwoCols + 64, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DWO_FREE + s]);
       if (ok) {
-        float* dst = a.dW + ((size_t)h * a.G + g) * kK + hh * 32;
+        float* dst = a.dW + ((size_t)h * a.G + g) * kK + sub * 16;
         const float sc = a.upstream;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
-        if (hh == 0) atomicAdd(a.db + (size_t)h * a.G + g, sc * vb[0]);
+        for (int j = 0; j < 4; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
+        if (sub == 0) atomicAdd(a.db + (size_t)h * a.G + g, sc * vb[0]);
       }
     };
 
     load_x_tile(0);
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
-      const int g0 = (tile_begin + i) * kGeneTile;
+      const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
       if (i + 1 < nt) {
         named_bar_sync(1, kEpiThreads);      // everyone is done reading stage s^1 (tile i-1)
         load_x_tile(i + 1);
@@ -299,45 +298,48 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
       mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
       tc_fence_after();
-      float va[16], vb[16], vl[16];
-      const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + hh * 16);
-      tmem_ld16(tb, va);
-      tmem_ld16(tb + 32, vb);
-      if (ZI) tmem_ld16(tb + 64, vl);
+      float va[8], vb[8], vl[8];
+      const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + sub * 8);
+      tmem_ld8(tb, va);
+      tmem_ld8(tb + 32, vb);
+      if (ZI) tmem_ld8(tb + 64, vl);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[ACC_FREE + s]);
 
-      const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH));
-      const float* xs = reinterpret_cast<const float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage()) + cell * kXPad + hh * 16;
-      float xv[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 p = *reinterpret_cast<const float4*>(xs + 4 * j);
-        xv[4 * j] = p.x; xv[4 * j + 1] = p.y; xv[4 * j + 2] = p.z; xv[4 * j + 3] = p.w;
+      const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
+      const float* xs = reinterpret_cast<const float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage()) + cell * kXPad + sub * 8;
+      float xv[8];
+      {
+        float4 p0 = *reinterpret_cast<const float4*>(xs), p1 = *reinterpret_cast<const float4*>(xs + 4);
+        xv[0] = p0.x; xv[1] = p0.y; xv[2] = p0.z; xv[3] = p0.w; xv[4] = p1.x; xv[5] = p1.y; xv[6] = p1.z; xv[7] = p1.w;
       }
-      float om[16], od[16];
-      uint32_t ga[8], gb[8], gl[8];
+      uint32_t ga[4], gb[4], gl[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int g = g0 + hh * 16 + j;
-        const bool ok = row_ok && g < a.G;
-        float ra = va[j] + bias_s[hh * 16 + j];
-        float rb = vb[j] + bias_s[32 + hh * 16 + j];
-        float pi = ZI ? vl[j] + bias_s[64 + hh * 16 + j] : 0.f;
-        float mu, dmu, th, dth;
-        activation(a.mean_act, ra, mu, dmu);
-        activation(a.disp_act, rb, th, dth);
-        CountGrad cg;
-        float l = count_llk<ZI, TRAIN>(xv[j], mu, th, pi, cg);
-        llk_acc += ok ? l : 0.f;
-        if (!TRAIN) { om[j] = mu; od[j] = th; vl[j] = pi; }
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = row_ok && (g0 + j) < a.G;
+        const float ra = va[j] + bias_s[j];
+        const float rb = vb[j] + bias_s[32 + j];
+        const float pi = ZI ? vl[j] + bias_s[64 + j] : 0.f;
+        ElemResult e;
+        if (FAST) {
+          e = count_elem_fast<ZI, TRAIN>(ra, rb, pi, xv[j]);
+        } else {
+          float dmu, dth;
+          activation(a.mean_act, ra, e.mu, dmu);
+          activation(a.disp_act, rb, e.th, dth);
+          CountGrad cg;
+          cg.dmu = cg.dth = cg.dpi = 0.f;
+          e.llk = count_llk<ZI, TRAIN>(xv[j], e.mu, e.th, pi, cg);
+          e.ga = cg.dmu * dmu; e.gb = cg.dth * dth; e.gl = cg.dpi;
+        }
+        llk_acc += ok ? e.llk : 0.f;
+        if (!TRAIN) { va[j] = e.mu; vb[j] = e.th; vl[j] = pi; }
         if (TRAIN) {
-          float g_a = ok ? fminf(fmaxf(cg.dmu * dmu, -60000.f), 60000.f) : 0.f;
-          float g_b = ok ? fminf(fmaxf(cg.dth * dth, -60000.f), 60000.f) : 0.f;
-          float g_l = (ok && ZI) ? cg.dpi : 0.f;
-          // pack pairs of consecutive genes into one 32-bit word
+          float g_a = ok ? fminf(fmaxf(e.ga, -60000.f), 60000.f) : 0.f;
+          float g_b = ok ? fminf(fmaxf(e.gb, -60000.f), 60000.f) : 0.f;
+          float g_l = (ok && ZI) ? e.gl : 0.f;
           uint32_t ha = (uint32_t)__half_as_ushort(__float2half_rn(g_a));
           uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(g_b));
           uint32_t hl = (uint32_t)__half_as_ushort(__float2half_rn(g_l));
@@ -346,57 +348,57 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         }
       }
       if (!TRAIN && row_ok) {
-        const size_t o = (size_t)row * a.G + g0 + hh * 16;
+        const size_t o = (size_t)row * a.G + g0;
+        if (VEC && g0 + 8 <= a.G) {
+          if (a.out_mean) { float4* d = reinterpret_cast<float4*>(a.out_mean + o); d[0] = make_float4(va[0], va[1], va[2], va[3]); d[1] = make_float4(va[4], va[5], va[6], va[7]); }
+          if (a.out_disp) { float4* d = reinterpret_cast<float4*>(a.out_disp + o); d[0] = make_float4(vb[0], vb[1], vb[2], vb[3]); d[1] = make_float4(vb[4], vb[5], vb[6], vb[7]); }
+          if (ZI && a.out_pi) { float4* d = reinterpret_cast<float4*>(a.out_pi + o); d[0] = make_float4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_float4(vl[4], vl[5], vl[6], vl[7]); }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (g0 + hh * 16 + j < a.G) {
-            if (a.out_mean) a.out_mean[o + j] = om[j];
-            if (a.out_disp) a.out_disp[o + j] = od[j];
-            if (ZI && a.out_pi) a.out_pi[o + j] = vl[j];
+          for (int j = 0; j < 8; ++j) {
+            if (g0 + j < a.G) {
+              if (a.out_mean) a.out_mean[o + j] = va[j];
+              if (a.out_disp) a.out_disp[o + j] = vb[j];
+              if (ZI && a.out_pi) a.out_pi[o + j] = vl[j];
+            }
           }
         }
       }
       if (TRAIN) {
         if (i >= 1) mbar_wait(&bars[G_FREE], (i - 1) & 1);     // previous tile's gradient GEMMs have consumed G
         uint8_t* gt = smem + OutSmem::G0(NH) + (cell >> 3) * 128 + (cell & 7) * 16;
-        // column groups of 8 output units: head h occupies groups 4h..4h+3; this thread owns 2hh, 2hh+1 of each head
-        *reinterpret_cast<uint4*>(gt + (0 * 4 + 2 * hh) * 2048) = make_uint4(ga[0], ga[1], ga[2], ga[3]);
-        *reinterpret_cast<uint4*>(gt + (0 * 4 + 2 * hh + 1) * 2048) = make_uint4(ga[4], ga[5], ga[6], ga[7]);
-        *reinterpret_cast<uint4*>(gt + (1 * 4 + 2 * hh) * 2048) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
-        *reinterpret_cast<uint4*>(gt + (1 * 4 + 2 * hh + 1) * 2048) = make_uint4(gb[4], gb[5], gb[6], gb[7]);
-        if (ZI) {
-          *reinterpret_cast<uint4*>(gt + (2 * 4 + 2 * hh) * 2048) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
-          *reinterpret_cast<uint4*>(gt + (2 * 4 + 2 * hh + 1) * 2048) = make_uint4(gl[4], gl[5], gl[6], gl[7]);
-        }
+        // column groups of 8 output units: head h occupies groups 4h..4h+3; this thread owns group `sub` of each head
+        *reinterpret_cast<uint4*>(gt + (0 * 4 + sub) * 2048) = make_uint4(ga[0], ga[1], ga[2], ga[3]);
+        *reinterpret_cast<uint4*>(gt + (1 * 4 + sub) * 2048) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+        if (ZI) *reinterpret_cast<uint4*>(gt + (2 * 4 + sub) * 2048) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[G_FULL]);
         if (i >= 1) flush_dwo(i - 1);
       }
     }
-    // per-cell log-likelihood: two gene halves per cell -> shared -> one atomic per cell and chunk
+    // per-cell log-likelihood: four gene slices per cell -> shared -> one atomic per cell and chunk
     atomicAdd(&llk_s[cell], llk_acc);
     named_bar_sync(1, kEpiThreads);
-    if (hh == 0 && row_ok) atomicAdd(a.llk_x + row, llk_s[cell]);
+    if (sub == 0 && row_ok) atomicAdd(a.llk_x + row, llk_s[cell]);
     if (TRAIN) {
       flush_dwo(nt - 1);
       mbar_wait(&bars[DD_FULL], 0);
       tc_fence_after();
-      float v[32];
-      const uint32_t base = tmem + lane_addr + kTmemDD + hh * 32;
-      tmem_ld16(base, v); tmem_ld16(base + 16, v + 16);
+      float v[16];
+      tmem_ld16(tmem + lane_addr + kTmemDD + sub * 16, v);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = a.dD + (size_t)row * kK + hh * 32;
+        float* dst = a.dD + (size_t)row * kK + sub * 16;
         const float sc = a.upstream;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace tc
