@@ -15,6 +15,7 @@
 #include "kernels_unfused.cuh"
 #ifdef SISUA_WITH_TC
 #include "kernels_tc.cuh"
+#include "kernels_tc_enc.cuh"
 #include "kernels_tc_selftest.cuh"
 #endif
 
@@ -67,9 +68,12 @@ struct sisua_model {
   double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
   double* sq = nullptr;        // [kMaxSegments]
   long long* d_step = nullptr;
+  float* d_lr_t = nullptr;
   SegTable seg;
   uint8_t* packed_wout = nullptr;   // pre-packed fp16 (hi | lo | bias) output-head weight tiles (tcgen05 path)
   int n_gene_tiles = 0;
+  uint8_t* packed_w1 = nullptr;     // pre-packed fp16 (hi | lo) first-layer weight k-blocks
+  int n_kblocks = 0;
   int num_sms = 148;
   int last_train_B = 0;
   // dropout stream of the current training step
@@ -213,6 +217,17 @@ static int ws_alloc(sisua_model* h, T** p, size_t count) {
   return SISUA_OK;
 }
 
+static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool training) {
+  DropSpec d;
+  memset(&d, 0, sizeof(d));
+  if (training && rate > 0.f) {
+    d.rate = rate; d.scale = 1.0f / (1.0f - rate);
+    d.seed_lo = (uint32_t)(h->drop_seed & 0xffffffffu); d.seed_hi = (uint32_t)(h->drop_seed >> 32);
+    d.step = h->drop_step; d.stream = stream;
+  }
+  return d;
+}
+
 #ifdef SISUA_WITH_TC
 static bool tc_heads_enabled(const sisua_model* h) {
   return h->cfg.gemm_mode != SISUA_GEMM_FP32_UNFUSED && h->cfg.model_kind != SISUA_MODEL_SCVI;
@@ -227,7 +242,78 @@ static int tc_set_attr(sisua_model* h) {
   return SISUA_OK;
 }
 
+template <int N0>
+static int tc_enc_attr(sisua_model* h) {
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
+  return SISUA_OK;
+}
+
+static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int B, int N0, bool training) {
+  const sisua_step_config& c = h->cfg;
+  ++h->launches;
+  tc::pack_w1_kernel<<<h->n_kblocks, 256, 0, st>>>(h->P + h->enc[0].w_off, h->Gp, h->packed_w1, c.n_genes, N0);
+  tc::EncFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
+  a.log_norm = c.log_norm; a.drop = make_drop(h, c.input_dropout, 0u, training);
+  const int cell_tiles = (B + 127) / 128;
+  int chunks = std::max(1, std::min(h->n_kblocks, h->num_sms / cell_tiles));
+  a.kblocks_per_chunk = (h->n_kblocks + chunks - 1) / chunks;
+  chunks = (h->n_kblocks + a.kblocks_per_chunk - 1) / a.kblocks_per_chunk;
+  a.atomic_out = chunks > 1 ? 1 : 0;
+  if (a.atomic_out) CUDA_OK(h, cudaMemsetAsync(h->A0, 0, (size_t)B * h->ld0 * sizeof(float), st));
+  const bool vec = (c.n_genes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  dim3 grid(cell_tiles, chunks);
+  ++h->launches;
+  if (N0 == 64) {
+    if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncThreads, tc::EncFwdSmem<64>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncThreads, tc::EncFwdSmem<64>::total, st>>>(a);
+  } else {
+    if (vec) tc::enc_first_fwd_kernel<128, true><<<grid, tc::kEncThreads, tc::EncFwdSmem<128>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<128, false><<<grid, tc::kEncThreads, tc::EncFwdSmem<128>::total, st>>>(a);
+  }
+  LAUNCH_OK(h, "enc_first_fwd_kernel (tcgen05)");
+  return SISUA_OK;
+}
+
+static int tc_encoder_first_bwd(sisua_model* h, cudaStream_t st, const float* x, int B, int N0) {
+  const sisua_step_config& c = h->cfg;
+  tc::EncBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.delta = h->delta1; a.dW = h->Gd + h->enc[0].w_off; a.B = B; a.G = c.n_genes; a.Gp = h->Gp; a.ld0 = h->ld0;
+  a.n_cell_tiles = (B + 127) / 128; a.log_norm = c.log_norm;
+  a.in_scale = (float)B; a.out_scale = 1.0f / (float)B;
+  a.drop = make_drop(h, c.input_dropout, 0u, true);
+  const int gene_tiles = (c.n_genes + 127) / 128;
+  int chunks = std::max(1, std::min(a.n_cell_tiles, h->num_sms / gene_tiles));
+  a.tiles_per_chunk = (a.n_cell_tiles + chunks - 1) / chunks;
+  chunks = (a.n_cell_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  const bool vec = (c.n_genes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  dim3 grid(gene_tiles, chunks);
+  ++h->launches;
+  if (N0 == 64) {
+    if (vec) tc::enc_first_bwd_kernel<64, true><<<grid, tc::kEncThreads, tc::EncBwdSmem<64>::total, st>>>(a);
+    else tc::enc_first_bwd_kernel<64, false><<<grid, tc::kEncThreads, tc::EncBwdSmem<64>::total, st>>>(a);
+  } else {
+    if (vec) tc::enc_first_bwd_kernel<128, true><<<grid, tc::kEncThreads, tc::EncBwdSmem<128>::total, st>>>(a);
+    else tc::enc_first_bwd_kernel<128, false><<<grid, tc::kEncThreads, tc::EncBwdSmem<128>::total, st>>>(a);
+  }
+  LAUNCH_OK(h, "enc_first_bwd_kernel (tcgen05)");
+  return SISUA_OK;
+}
+
 static int tc_create(sisua_model* h) {
+  {
+    const int n0 = h->cfg.model_kind == SISUA_MODEL_SCVI ? 128 : 64;
+    h->n_kblocks = (h->cfg.n_genes + 63) / 64;
+    int rc0 = ws_alloc(h, &h->packed_w1, (size_t)h->n_kblocks * tc::w1_block_bytes(n0));
+    if (rc0 != SISUA_OK) return rc0;
+    rc0 = n0 == 64 ? tc_enc_attr<64>(h) : tc_enc_attr<128>(h);
+    if (rc0 != SISUA_OK) return rc0;
+  }
   if (!tc_heads_enabled(h)) return SISUA_OK;
   const int nh = h->cfg.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
   h->n_gene_tiles = (h->cfg.n_genes + tc::kGeneTile - 1) / tc::kGeneTile;
@@ -346,6 +432,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   WS(h->stats, (size_t)h->n_units * 4 * H);
   WS(h->sq, kMaxSegments);
   WS(h->d_step, 1);
+  WS(h->d_lr_t, 1);
 #undef WS
   CUDA_OK(h, cudaMemset(h->d_step, 0, sizeof(long long)));
   CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
@@ -418,17 +505,6 @@ extern "C" int sisua_debug_copy(sisua_handle h, const char* name, float* dst, in
 }
 
 // ---- helpers ------------------------------------------------------------------------------------
-static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool training) {
-  DropSpec d;
-  memset(&d, 0, sizeof(d));
-  if (training && rate > 0.f) {
-    d.rate = rate; d.scale = 1.0f / (1.0f - rate);
-    d.seed_lo = (uint32_t)(h->drop_seed & 0xffffffffu); d.seed_hi = (uint32_t)(h->drop_seed >> 32);
-    d.step = h->drop_step; d.stream = stream;
-  }
-  return d;
-}
-
 static NormSpec make_norm(sisua_model* h, const Layer& L, bool training, int rows) {
   NormSpec ns;
   memset(&ns, 0, sizeof(ns));
@@ -537,6 +613,13 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   const int N0 = scvi ? 2 * H : H;
   bool first_done = false;
   sec_begin(h, st, SEC_ENC_FIRST);
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    int rc = tc_encoder_first(h, st, x, B, N0, training);
+    if (rc != SISUA_OK) return rc;
+    first_done = true;
+  }
+#endif
   if (!first_done) {
     DropSpec din = make_drop(h, c.input_dropout, 0u, training);
     if (c.log_norm)
@@ -783,6 +866,13 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   const int N0 = scvi ? 2 * H : H;
   bool w1_done = false;
   sec_begin(h, st, SEC_ENC_FIRST_BWD);
+#ifdef SISUA_WITH_TC
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    rc = tc_encoder_first_bwd(h, st, x, B, N0);
+    if (rc != SISUA_OK) return rc;
+    w1_done = true;
+  }
+#endif
   if (!w1_done) {
     DropSpec din = make_drop(h, c.input_dropout, 0u, true);
     if (c.log_norm)
@@ -822,11 +912,13 @@ extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta
   if (!h->P || !h->Gd || !h->M || !h->V) SET_ERR(h, SISUA_ERR_STATE, "adam_step needs params, grads, m and v bound");
   sec_begin(h, st, SEC_ADAM);
   CUDA_OK(h, cudaMemsetAsync(h->sq, 0, kMaxSegments * sizeof(double), st));
-  dim3 grid(std::max(1, std::min(64, (int)((h->total_floats / h->seg.n + 2047) / 2048))), h->seg.n);
+  long long max_seg = 1;
+  for (int i = 0; i < h->seg.n; ++i) max_seg = std::max(max_seg, h->seg.size[i]);
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(1024, (max_seg + 1023) / 1024)), h->seg.n);
   ++h->launches;
-  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->sq, h->d_step, (long long)t);
+  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->sq, h->d_step, (long long)t, lr, beta1, beta2, h->d_lr_t);
   ++h->launches;
-  adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->sq, h->d_step, lr, beta1, beta2, eps_hat,
+  adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->sq, h->d_lr_t, beta1, beta2, eps_hat,
                                      clipnorm, h->cfg.clip_mode, grad_scale);
   LAUNCH_OK(h, "adam");
   sec_end(h, st, SEC_ADAM);

@@ -15,7 +15,8 @@ struct SegTable {
 // per-variable sum of squared gradients (double); block (0,0) also advances the device step counter
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, SegTable st,
                                                           double* __restrict__ sq, long long* step,
-                                                          long long step_override) {
+                                                          long long step_override, float lr, float b1, float b2,
+                                                          float* __restrict__ lr_t_out) {
   __shared__ double scratch[33];
   int s = blockIdx.y;
   const float* p = g + st.off[s];
@@ -28,14 +29,19 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) {
     atomicAdd(&sq[s], acc);
-    if (blockIdx.x == 0 && blockIdx.y == 0) *step = step_override > 0 ? step_override : (*step + 1);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      long long t = step_override > 0 ? step_override : (*step + 1);
+      *step = t;
+      // Keras / TF formulation: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)   (one thread; read by adam_kernel)
+      *lr_t_out = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, SegTable st,
-                                                   const double* __restrict__ sq, const long long* __restrict__ step,
-                                                   float lr, float b1, float b2, float eps_hat, float clipnorm,
+                                                   const double* __restrict__ sq, const float* __restrict__ lr_t_in,
+                                                   float b1, float b2, float eps_hat, float clipnorm,
                                                    int clip_mode, float grad_scale) {
   int s = blockIdx.y;
   float scale = grad_scale;
@@ -45,8 +51,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     double nrm = sqrt(n2) * (double)fabsf(grad_scale);
     if (nrm > (double)clipnorm) scale *= (float)((double)clipnorm / nrm);
   }
-  double t = (double)(*step);
-  float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  const float lr_t = *lr_t_in;
   long long off = st.off[s], n = st.size[s];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long j = off + i;

@@ -1,0 +1,349 @@
+// tcgen05 kernels for the genes x hidden contraction of the first encoder layer:
+//   forward   A0[cells, N0] = dropout(log1p(x))[cells, G] . W1[N0, G]^T        (N0 = 64, or 128 for scVI's two encoders)
+//   backward  dW1[N0, G]   = delta1[cells, N0]^T . dropout(log1p(x))[cells, G]
+// Both stream the count matrix once from HBM (they are HBM-bound: 4 G bytes per cell against 2*G*N0 flops):
+// converter warps load coalesced fp32 rows, apply log1p (+ Philox input dropout), split to fp16 (hi, lo) and
+// write canonical no-swizzle UMMA tiles; one thread issues the MMAs, accumulators stay in TMEM for the whole
+// K (forward) or cell (backward) range.  Forward products are 3xFP16 compensated (fp32-grade pre-activations);
+// the weight gradient uses single fp16 operands with delta1 pre-scaled by the batch size to stay in range.
+#pragma once
+#include "device_math.cuh"
+#include "tc_ptx.cuh"
+
+namespace sisua {
+namespace tc {
+
+constexpr int kEncThreads = 320;        // 8 converter/epilogue warps + MMA warp + loader warp
+constexpr int kEncConv = 256;
+constexpr int kEncStages = 3;
+constexpr int kPadCS = 2064;            // column-group stride of thread-written tiles: 128 rows * 16 B + 16 B (bank spread)
+
+__host__ __device__ constexpr int w1_tile_bytes(int n0) { return n0 * 64 * 2; }          // one fp16 copy of a 64-gene k-block
+__host__ __device__ constexpr int w1_block_bytes(int n0) { return 2 * w1_tile_bytes(n0); }   // hi | lo
+
+// W1[N0, Gp] fp32 -> per 64-gene k-block (hi | lo) fp16 tiles T[n][k], RS = 128, CS = N0/8*128
+__global__ void __launch_bounds__(256) pack_w1_kernel(const float* __restrict__ W, int ldw, uint8_t* __restrict__ packed, int G,
+                                                      int n0) {
+  const int kb = blockIdx.x;
+  const int CS = n0 / 8 * 128;
+  uint8_t* base = packed + (size_t)kb * w1_block_bytes(n0);
+  for (int i = threadIdx.x; i < n0 * 8; i += blockDim.x) {
+    int n = i % n0, cg = i / n0;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int g = kb * 64 + cg * 8 + 2 * j;
+      float v0 = g < G ? W[(size_t)n * ldw + g] : 0.f;
+      float v1 = g + 1 < G ? W[(size_t)n * ldw + g + 1] : 0.f;
+      __half h0, l0, h1, l1;
+      split_f16(v0, h0, l0); split_f16(v1, h1, l1);
+      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+    }
+    uint32_t off = (n >> 3) * 128 + cg * CS + (n & 7) * 16;
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + w1_tile_bytes(n0) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__device__ __forceinline__ float log1p_count(float x) {
+  float big = kLn2 * mufu_lg2(1.f + x);
+  float small = x * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
+  return x < 0.015625f ? small : big;
+}
+
+// 8 consecutive columns c0..c0+7 of row r of X[rows, ld]; zero outside [0,rows) x [0,cols)
+template <bool VEC>
+__device__ __forceinline__ void load8(const float* __restrict__ X, int ld, int rows, int cols, int r, int c0, float* v) {
+  if (VEC) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r < rows) {
+      const float* p = X + (size_t)r * ld + c0;
+      if (c0 < cols) a = __ldg(reinterpret_cast<const float4*>(p));
+      if (c0 + 4 < cols) b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (r < rows && c0 + j < cols) ? __ldg(X + (size_t)r * ld + c0 + j) : 0.f;
+  }
+}
+
+// log1p + dropout on 8 count values of (row, c0..c0+7), in place
+__device__ __forceinline__ void normalise8(float* v, int log_norm, const DropSpec& drop, int row, int c0) {
+  if (log_norm) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = log1p_count(v[j]);
+  }
+  if (drop.rate > 0.f) {
+    float4 m0 = dropout_mult4(drop, (uint32_t)row, (uint32_t)(c0 >> 2));
+    float4 m1 = dropout_mult4(drop, (uint32_t)row, (uint32_t)(c0 >> 2) + 1u);
+    v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+  }
+}
+
+__device__ __forceinline__ void store8_hi_lo(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * j], h0, l0); split_f16(v[2 * j + 1], h1, l1);
+    hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void store8_hi(uint8_t* tile, uint32_t off, const float* v, float scale) {
+  uint32_t hi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    hi[j] = pack_h2(__float2half_rn(fminf(fmaxf(v[2 * j] * scale, -60000.f), 60000.f)),
+                    __float2half_rn(fminf(fmaxf(v[2 * j + 1] * scale, -60000.f), 60000.f)));
+  *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+
+struct EncFwdArgs {
+  const float* x;           // [B, G]
+  const uint8_t* packed;    // packed W1 k-blocks
+  float* A0;                // [B, ld0] pre-activations (zeroed by the caller when k_chunks > 1)
+  int B, G, ld0, n_kblocks, kblocks_per_chunk, atomic_out, log_norm;
+  DropSpec drop;
+};
+
+template <int N0>
+struct EncFwdSmem {
+  static constexpr int A = 8 * kPadCS;                       // one fp16 tile [128][64]
+  static constexpr int stage = 2 * A + w1_block_bytes(N0);
+  static constexpr int bar = kEncStages * stage;
+  static constexpr int total = bar + 16 * 8 + 16;
+};
+
+template <int N0, bool VEC>
+__global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = EncFwdSmem<N0>;
+  constexpr int W_CS = N0 / 8 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);   // [0..2] a_full, [3..5] w_full, [6..8] stage_free, [9] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bar + 16 * 8);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int row0 = blockIdx.x * 128;
+  const int kb_begin = blockIdx.y * a.kblocks_per_chunk;
+  const int nkb = min(a.n_kblocks, kb_begin + a.kblocks_per_chunk) - kb_begin;
+  if (nkb <= 0) return;
+  if (t == 0) {
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], 1); }
+    mbar_init(&bars[9], 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, N0 < 32 ? 32 : N0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kEncStages;
+        if (i >= kEncStages) mbar_wait(&bars[6 + s], ((i / kEncStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[3 + s], w1_block_bytes(N0));
+        bulk_copy_g2s(smem + s * S::stage + 2 * S::A, a.packed + (size_t)(kb_begin + i) * w1_block_bytes(N0), w1_block_bytes(N0),
+                      &bars[3 + s]);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, N0, 0, 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kEncStages;
+        const uint32_t ph = (i / kEncStages) & 1;
+        mbar_wait(&bars[s], ph);
+        mbar_wait(&bars[3 + s], ph);
+        tc_fence_after();
+        const uint32_t sA1 = smem_u32(smem + s * S::stage), sA2 = sA1 + S::A;
+        const uint32_t sW1 = sA1 + 2 * S::A, sW2 = sW1 + w1_tile_bytes(N0);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t sa = (p == 2) ? sA2 : sA1, sb = (p == 1) ? sW2 : sW1;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem, make_smem_desc(sa + ks * 2 * kPadCS, kPadCS, 128), make_smem_desc(sb + ks * 2 * W_CS, W_CS, 128), idesc,
+                     (i > 0 || p > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars[6 + s]);
+      }
+      umma_commit(&bars[9]);
+    }
+  } else {
+    // ---- converter warps: rows r = (t >> 3) + 32 j, column group cg = t & 7 ----
+    const int cg = t & 7, rbase = t >> 3;
+    float cur[4][8];
+    auto fetch = [&](int i, float (*dst)[8]) {
+      const int c0 = (kb_begin + i) * 64 + cg * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rbase + 32 * j, c0, dst[j]);
+    };
+    fetch(0, cur);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % kEncStages;
+      float nxt[4][8];
+      if (i + 1 < nkb) fetch(i + 1, nxt);
+      if (i >= kEncStages) mbar_wait(&bars[6 + s], ((i / kEncStages) - 1) & 1);
+      uint8_t* A1 = smem + s * S::stage;
+      const int c0 = (kb_begin + i) * 64 + cg * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rbase + 32 * j;
+        normalise8(cur[j], a.log_norm, a.drop, row0 + r, c0);
+        store8_hi_lo(A1, A1 + S::A, cg * kPadCS + (r >> 3) * 128 + (r & 7) * 16, cur[j]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[s]);
+      if (i + 1 < nkb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cur[j][k] = nxt[j][k];
+      }
+    }
+    // ---- epilogue: TMEM -> A0 ----
+    mbar_wait(&bars[9], 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int row = row0 + q * 32 + lane;
+    constexpr int CPT = N0 / 2;     // columns per thread
+#pragma unroll
+    for (int c = 0; c < CPT; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * CPT + c), v);
+      tmem_ld_wait();
+      if (row < a.B) {
+        float* dst = a.A0 + (size_t)row * a.ld0 + half * CPT + c;
+        if (a.atomic_out) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, N0 < 32 ? 32 : N0);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct EncBwdArgs {
+  const float* x;           // [B, G]
+  const float* delta;       // [B, ld0] d loss / d pre-activation of the first layer
+  float* dW;                // [N0, Gp] += delta^T . x~
+  int B, G, Gp, ld0, n_cell_tiles, tiles_per_chunk, log_norm;
+  float in_scale, out_scale;   // delta is multiplied by in_scale before fp16, the result by out_scale = 1/in_scale
+  DropSpec drop;
+};
+
+template <int N0>
+struct EncBwdSmem {
+  static constexpr int A = 16 * kPadCS;                      // x~ tile [128 cells][128 genes] fp16
+  static constexpr int Bt = (N0 / 8) * kPadCS;               // delta tile [128 cells][N0] fp16
+  static constexpr int stage = A + Bt;
+  static constexpr int bar = kEncStages * stage;
+  static constexpr int total = bar + 16 * 8 + 16;
+};
+
+template <int N0, bool VEC>
+__global__ void __launch_bounds__(kEncThreads, 1) enc_first_bwd_kernel(EncBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = EncBwdSmem<N0>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);   // [0..2] full, [3..5] free, [6] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bar + 16 * 8);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g0 = blockIdx.x * 128;
+  const int ct_begin = blockIdx.y * a.tiles_per_chunk;
+  const int nct = min(a.n_cell_tiles, ct_begin + a.tiles_per_chunk) - ct_begin;
+  if (nct <= 0) return;
+  if (t == 0) {
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); }
+    mbar_init(&bars[6], 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, N0 < 32 ? 32 : N0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, N0, 1, 1);
+      for (int i = 0; i < nct; ++i) {
+        const int s = i % kEncStages;
+        mbar_wait(&bars[s], (i / kEncStages) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + s * S::stage), sB = sA + S::A;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // 16 cells per step: two 8-row groups
+          umma_f16(tmem, make_smem_desc(sA + ks * 256, 128, kPadCS), make_smem_desc(sB + ks * 256, 128, kPadCS), idesc,
+                   (i > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&bars[3 + s]);
+      }
+      umma_commit(&bars[6]);
+    }
+  } else if (warp < 8) {
+    const int cgx = t & 15, rx = t >> 4;          // x~ tile: 16 column groups, rows rx + 16 j (j < 8)
+    const int cgd = t & 7, rd = t >> 3;           // delta tile (per 64 columns): 8 column groups, rows rd + 32 j (j < 4)
+    for (int i = 0; i < nct; ++i) {
+      const int s = i % kEncStages;
+      const int row0 = (ct_begin + i) * 128;
+      float xv[8][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rx + 16 * j, g0 + cgx * 8, xv[j]);
+      if (i >= kEncStages) mbar_wait(&bars[3 + s], ((i / kEncStages) - 1) & 1);
+      uint8_t* At = smem + s * S::stage;
+      uint8_t* Bt = At + S::A;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rx + 16 * j;
+        normalise8(xv[j], a.log_norm, a.drop, row0 + r, g0 + cgx * 8);
+        store8_hi_lo(At, nullptr, cgx * kPadCS + (r >> 3) * 128 + (r & 7) * 16, xv[j]);
+      }
+#pragma unroll
+      for (int blk = 0; blk < N0 / 64; ++blk) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rd + 32 * j;
+          float dv[8];
+          load8<true>(a.delta, a.ld0, a.B, a.ld0, row0 + r, blk * 64 + cgd * 8, dv);
+          store8_hi(Bt, (blk * 8 + cgd) * kPadCS + (r >> 3) * 128 + (r & 7) * 16, dv, a.in_scale);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[s]);
+    }
+    // ---- epilogue: TMEM lane = gene, column = output unit n ----
+    mbar_wait(&bars[6], 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int g = g0 + q * 32 + lane;
+    constexpr int CPT = N0 / 2;
+#pragma unroll
+    for (int c = 0; c < CPT; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * CPT + c), v);
+      tmem_ld_wait();
+      if (g < a.G) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(a.dW + (size_t)(half * CPT + c + j) * a.Gp + g, v[j] * a.out_scale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, N0 < 32 ? 32 : N0);
+}
+
+}  // namespace tc
+}  // namespace sisua

@@ -149,7 +149,7 @@ def test_multi_step_training_matches_oracle(model, kw, mode):
   for name, p in P.items():
     # Adam's normalised update amplifies tiny gradient differences: compare against the step size
     err = np.abs(got[name] - p.numpy()).max()
-    lim = 2e-4 if mode == C.GEMM_FP32_UNFUSED else 2e-3   # fp16-grade gradients can flip Adam's sign-like first steps
+    lim = 2e-4 if mode == C.GEMM_FP32_UNFUSED else 5e-3   # fp16-grade gradients can flip Adam's sign-like first steps
     assert err <= lim, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
   eng.close()
 
