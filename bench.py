@@ -23,7 +23,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GENES, LATENT, SHARD_CELLS, TOTAL_CELLS = 2000, 10, 131072, 1_000_000
+GENES, LATENT, SHARD_CELLS, TOTAL_CELLS = 2000, 10, 132608, 1_000_000
 
 
 def parse():
@@ -32,7 +32,7 @@ def parse():
   ap.add_argument("--steps", type=int, default=60)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--batch", type=int, default=8192, help="cells per GPU per step")
+  ap.add_argument("--batch", type=int, default=9472, help="cells per GPU per step (74 tiles of 128 cells: 2 gene chunks x 74 = 148 CTAs, one per SM)")
   ap.add_argument("--genes", type=int, default=GENES)
   ap.add_argument("--shard-cells", type=int, default=SHARD_CELLS)
   ap.add_argument("--gemm-mode", type=int, default=-1, help="-1: best available (tcgen05 3xTF32 if built)")

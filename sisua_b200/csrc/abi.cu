@@ -436,6 +436,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
 #undef WS
   CUDA_OK(h, cudaMemset(h->d_step, 0, sizeof(long long)));
   CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
+  CUDA_OK(h, cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseFwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (scvi && c.n_genes * sizeof(float) > 200 * 1024)
@@ -548,9 +549,11 @@ static void launch_sgemm(sisua_model* h, cudaStream_t st, const float* A, long l
 }
 
 static void launch_dense_fwd(sisua_model* h, cudaStream_t st, const float* A_in, int lda, int Kin, const NormSpec& ns,
-                             const float* W, int ldw, const float* bias, int Nout, float* A_out, int ldo, int R) {
+                             const float* W, int ldw, const float* bias, int Nout, float* A_out, int ldo, int R,
+                             double* out_sum = nullptr) {
   ++h->launches;
-  dense_fwd_kernel<<<mid_grid(h, R), kMidThreads, 0, st>>>(A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R);
+  dense_fwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseFwdSmem, st>>>(A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R, out_sum,
+                                                                   out_sum ? out_sum + kH : nullptr);
 }
 
 static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, int R) {
@@ -562,13 +565,15 @@ static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, in
 
 // hidden stack forward: layer 0's pre-activation is already in L[0].A; leaves the last layer's
 // pre-activation (plus statistics when training with BN) ready for the consumer.
-static void stack_forward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, bool training, int R) {
+static void stack_forward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, bool training, int R,
+                          bool first_has_stats = false) {
   for (size_t i = 0; i < Ls.size(); ++i) {
-    if (training && Ls[i].bn_index >= 0) launch_col_stats(h, st, Ls[i], R);
+    if (i == 0 && !first_has_stats && training && Ls[i].bn_index >= 0) launch_col_stats(h, st, Ls[i], R);
     if (i + 1 < Ls.size()) {
       NormSpec ns = make_norm(h, Ls[i], training, R);
+      double* next_stats = (training && Ls[i + 1].bn_index >= 0) ? h->stats + (size_t)Ls[i + 1].stat_index * 4 * kH : nullptr;
       launch_dense_fwd(h, st, Ls[i].A, Ls[i].lda, kH, ns, h->P + Ls[i + 1].w_off, Ls[i + 1].ldw, nullptr, kH,
-                       Ls[i + 1].A, Ls[i + 1].lda, R);
+                       Ls[i + 1].A, Ls[i + 1].lda, R, next_stats);
     }
   }
 }
@@ -659,9 +664,12 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     LAUNCH_OK(h, "latent_fwd_kernel");
   }
   // ---- decoder
-  launch_dense_fwd(h, st, h->Zs, Z, Z, raw_norm(), h->P + h->dec[0].w_off, h->dec[0].ldw, nullptr, H, h->dec[0].A,
-                   h->dec[0].lda, R);
-  stack_forward(h, st, h->dec, training, R);
+  {
+    double* st0 = (training && h->dec[0].bn_index >= 0) ? h->stats + (size_t)h->dec[0].stat_index * 4 * kH : nullptr;
+    launch_dense_fwd(h, st, h->Zs, Z, Z, raw_norm(), h->P + h->dec[0].w_off, h->dec[0].ldw, nullptr, H, h->dec[0].A,
+                     h->dec[0].lda, R, st0);
+  }
+  stack_forward(h, st, h->dec, training, R, true);
   NormSpec ns_d = make_norm(h, h->dec.back(), training, R);
   ++h->launches;
   norm_relu_kernel<<<std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms)), 256, 0, st>>>(
@@ -747,18 +755,21 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
 // dIn0: where the gradient wrt layer 0's input goes (null -> not needed), dA0: pre-activation
 // gradient of layer 0 (delta1) when requested.
 static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, int R, float* dH_top,
-                          const float* in0, int ld_in0, int Kin0, float* dIn0, int ld_dIn0, float* dA0, int ld_dA0) {
+                          const float* in0, int ld_in0, int Kin0, float* dIn0, int ld_dIn0, float* dA0, int ld_dA0,
+                          bool top_reduced = false) {
   float* dH = dH_top;
   for (int i = (int)Ls.size() - 1; i >= 0; --i) {
     Layer& L = Ls[i];
     NormSpec ns = make_norm(h, L, true, R);
     double* sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH;
     double* sdyx = sdy + kH;
-    float* dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr;
-    float* dbeta = h->Gd + L.b_off;
-    int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
-    ++h->launches;
-    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
+    if (i == (int)Ls.size() - 1 && !top_reduced) {   // top unit: no consumer kernel produced its reductions
+      float* dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr;
+      float* dbeta = h->Gd + L.b_off;
+      int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+      ++h->launches;
+      bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
+    }
     DenseBwdArgs a;
     memset(&a, 0, sizeof(a));
     a.out_mode = 1; a.dOut = dH; a.ldd = kH; a.A_out = L.A; a.lda_out = L.lda; a.ns_out = ns; a.sdy = sdy; a.sdyx = sdyx;
@@ -768,6 +779,10 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
       a.A_in = Ls[i - 1].A; a.lda_in = Ls[i - 1].lda; a.Kin = kH; a.ns_in = make_norm(h, Ls[i - 1], true, R);
       a.W = h->P + L.w_off; a.ldw = L.ldw; a.dW = h->Gd + L.w_off;
       a.dIn = dH_next; a.ldi = kH; a.accumulate_dIn = 0;
+      // the unit below gets its norm-backward reductions from this kernel
+      Layer& Lp = Ls[i - 1];
+      a.prev_sdy = h->stats + (size_t)Lp.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
+      a.prev_dgamma = Lp.g_off >= 0 ? h->Gd + Lp.g_off : nullptr; a.prev_dbeta = h->Gd + Lp.b_off;
     } else {
       a.A_in = in0; a.lda_in = ld_in0; a.Kin = in0 ? Kin0 : kH; a.ns_in = raw_norm();
       a.W = in0 ? h->P + L.w_off : nullptr; a.ldw = L.ldw; a.dW = in0 ? h->Gd + L.w_off : nullptr;
@@ -842,10 +857,12 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.out_mode = 0; a.dOut = h->dPL; a.ldd = ZP; a.Nout = ZP; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
     a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lat_w; a.ldw = H; a.dW = h->Gd + h->lat_w; a.db = h->Gd + h->lat_b;
     a.dIn = h->dHa; a.ldi = H; a.R = B;
+    a.prev_sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
+    a.prev_dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr; a.prev_dbeta = h->Gd + L.b_off;
     ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "latent projection backward");
-    rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0);
+    rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0, true);
     if (rc != SISUA_OK) return rc;
   }
   if (scvi) {
@@ -855,10 +872,12 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.out_mode = 0; a.dOut = h->dPLIB; a.ldd = 2; a.Nout = 2; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
     a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lib_w; a.ldw = H; a.dW = h->Gd + h->lib_w; a.db = h->Gd + h->lib_b;
     a.dIn = h->dHa; a.ldi = H; a.R = B;
+    a.prev_sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
+    a.prev_dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr; a.prev_dbeta = h->Gd + L.b_off;
     ++h->launches;
     dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
     LAUNCH_OK(h, "library projection backward");
-    rc = stack_backward(h, st, h->encl, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1 + H, h->ld0);
+    rc = stack_backward(h, st, h->encl, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1 + H, h->ld0, true);
     if (rc != SISUA_OK) return rc;
   }
   sec_end(h, st, SEC_MID_BWD);

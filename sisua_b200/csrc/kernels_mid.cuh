@@ -103,53 +103,88 @@ __global__ void __launch_bounds__(256) norm_relu_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// A_out[R, Nout] = act_in(A_in)[R, Kin] . W[Nout, Kin]^T (+ bias);  Kin, Nout <= 64
+// A_out[R, Nout] = act_in(A_in)[R, Kin] . W[Nout, Kin]^T (+ bias);  Kin, Nout <= 64.
+// 64-row tiles, 4x4 register blocking (operands k-major in shared memory, two LDS.128 per 16 FMA).
+// Optionally accumulates the column sums / sums of squares of A_out (next layer's BN statistics).
 // ------------------------------------------------------------------------------------------
+constexpr int kTS = 68;   // padded tile stride in floats (16-byte aligned rows)
+constexpr size_t kDenseFwdSmem = (size_t)(2 * kH * kTS + 2 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
+
 __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
     const float* __restrict__ A_in, int lda, int Kin, NormSpec ns, const float* __restrict__ W, int ldw,
-    const float* __restrict__ bias, int Nout, float* __restrict__ A_out, int ldo, int R) {
-  __shared__ float Ws[kH][kH + 1];
-  __shared__ float Hs[kTileR][kH + 1];
-  __shared__ float sc[kH], sh[kH];
-  int t = threadIdx.x;
+    const float* __restrict__ bias, int Nout, float* __restrict__ A_out, int ldo, int R, double* __restrict__ out_sum,
+    double* __restrict__ out_sumsq) {
+  extern __shared__ __align__(16) float dsm[];
+  float* WT = dsm;                       // [k][n]
+  float* HT = WT + kH * kTS;             // [k][r]
+  float* sc = HT + kH * kTS;
+  float* sh = sc + kH;
+  float* red1 = sh + kH;                 // [16][64] per-thread-row partial column sums
+  float* red2 = red1 + 16 * kH;
+  double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);   // [2][64] running sums of this CTA
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   for (int i = t; i < kH * kH; i += kMidThreads) {
     int n = i / kH, k = i % kH;
-    Ws[n][k] = (n < Nout && k < Kin) ? W[(size_t)n * ldw + k] : 0.f;
+    WT[k * kTS + n] = (n < Nout && k < Kin) ? W[(size_t)n * ldw + k] : 0.f;
   }
   if (t < kH) {
     float m, r;
     if (t < Kin) norm_coeffs(ns, t, sc[t], sh[t], m, r); else { sc[t] = 0.f; sh[t] = 0.f; }
+    dacc[t] = 0.0; dacc[kH + t] = 0.0;
   }
   __syncthreads();
-  int rl = t >> 2, cq = t & 3;
   for (int r0 = blockIdx.x * kTileR; r0 < R; r0 += gridDim.x * kTileR) {
-    for (int i = t; i < kTileR * Kin; i += kMidThreads) {
-      int r = i / Kin, k = i % Kin;
+    for (int i = t; i < kTileR * kH; i += kMidThreads) {
+      int r = i / kH, k = i % kH;
       float v = 0.f;
-      if (r0 + r < R) {
+      if (r0 + r < R && k < Kin) {
         v = A_in[(size_t)(r0 + r) * lda + k] * sc[k] + sh[k];
         if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(ns.drop, (uint32_t)(r0 + r), (uint32_t)k);
       }
-      Hs[r][k] = v;
+      HT[k * kTS + r] = v;
     }
     __syncthreads();
-    float acc[16];
+    float acc[4][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int k = 0; k < Kin; ++k) {
-      float h = Hs[rl][k];
+      float4 a4 = *reinterpret_cast<const float4*>(HT + k * kTS + 4 * ty);
+      float4 b4 = *reinterpret_cast<const float4*>(WT + k * kTS + 4 * tx);
+      float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(h, Ws[cq + 4 * j][k], acc[j]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    if (r0 + rl < R) {
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        int n = cq + 4 * j;
-        if (n < Nout) A_out[(size_t)(r0 + rl) * ldo + n] = acc[j] + (bias ? bias[n] : 0.f);
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 4 * ty + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * tx + j;
+        float v = acc[i][j] + ((bias && n < Nout) ? bias[n] : 0.f);
+        if (r < R && n < Nout) {
+          A_out[(size_t)r * ldo + n] = v;
+          cs[j] += v; cq[j] += v * v;
+        }
+      }
+    }
+    if (out_sum) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { red1[ty * kH + 4 * tx + j] = cs[j]; red2[ty * kH + 4 * tx + j] = cq[j]; }
+      __syncthreads();
+      if (t < kH) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int y = 0; y < 16; ++y) { s1 += (double)red1[y * kH + t]; s2 += (double)red2[y * kH + t]; }
+        dacc[t] += s1; dacc[kH + t] += s2;
       }
     }
     __syncthreads();
   }
+  if (out_sum && t < Nout) { atomicAdd(&out_sum[t], dacc[t]); atomicAdd(&out_sumsq[t], dacc[kH + t]); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -362,8 +397,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
 // the gradient wrt its input activations, and optionally the gradient wrt its pre-activation.
 //   out_mode 0: dOut[R, Nout] is given directly (heads with bias, no norm)
 //   out_mode 1: dOut = BN/bias backward of dH[R,64] applied on load (needs A_out, ns_out, sdy, sdyx)
+// When `prev_*` is set the kernel also reduces, for the unit feeding this one, the column sums of
+// dY and dY*xhat that ITS BatchNorm backward needs (plus its d gamma / d beta), so no separate pass
+// over dIn is required.  64-row tiles, 4x4 register blocking.
 // ------------------------------------------------------------------------------------------
-constexpr size_t kDenseBwdSmem = (size_t)(kH + 2 * kTileR) * (kH + 1) * sizeof(float) + 9 * kH * sizeof(float);
+constexpr size_t kDenseBwdSmem =
+    (size_t)(5 * kH * kTS + 11 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
 struct DenseBwdArgs {
   int out_mode;
   const float* dOut; int ldd;          // dOut (mode 0) or dH (mode 1)
@@ -378,45 +417,54 @@ struct DenseBwdArgs {
   float* dIn; int ldi; int accumulate_dIn;   // [R, Kin] (nullable)
   float* dA; int ldda;                 // [R, Nout] d loss / d pre-activation (nullable)
   int R;
+  // fused reduction for the producing unit's norm backward (nullable)
+  double* prev_sdy; double* prev_sdyx; float* prev_dgamma; float* prev_dbeta;
 };
 __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) {
-  extern __shared__ float dyn_smem[];
-  typedef float Row[kH + 1];
-  Row* Ws = reinterpret_cast<Row*>(dyn_smem);
-  Row* Hs = Ws + kH;
-  Row* Gs = Hs + kTileR;
-  float* sc_i = reinterpret_cast<float*>(Gs + kTileR);
-  float *sh_i = sc_i + kH, *sc_o = sh_i + kH, *sh_o = sc_o + kH, *mean_o = sh_o + kH, *rstd_o = mean_o + kH,
-        *m1 = rstd_o + kH, *m2 = m1 + kH, *gsc = m2 + kH;
-  int t = threadIdx.x;
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* Wn = dyn_smem;                 // [n][k]
+  float* Hn = Wn + kH * kTS;            // [r][k]   activated input
+  float* Gn = Hn + kH * kTS;            // [r][n]   gradient wrt this unit's pre-activation
+  float* GT = Gn + kH * kTS;            // [n][r]
+  float* An = GT + kH * kTS;            // [r][k]   raw pre-activation of the producing unit (fused reduction)
+  float* sc_i = An + kH * kTS;
+  float *sh_i = sc_i + kH, *mean_i = sh_i + kH, *rstd_i = mean_i + kH, *sc_o = rstd_i + kH, *sh_o = sc_o + kH,
+        *mean_o = sh_o + kH, *rstd_o = mean_o + kH, *m1 = rstd_o + kH, *m2 = m1 + kH, *gsc = m2 + kH;
+  float* red1 = gsc + kH;
+  float* red2 = red1 + 16 * kH;
+  double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int Nout = a.Nout, Kin = a.Kin;
   const bool has_in = a.A_in != nullptr;
+  const bool fuse_prev = a.prev_sdy != nullptr;
   for (int i = t; i < kH * kH; i += kMidThreads) {
     int n = i / kH, k = i % kH;
-    Ws[n][k] = (n < Nout && k < Kin && a.W) ? a.W[(size_t)n * a.ldw + k] : 0.f;
+    Wn[n * kTS + k] = (n < Nout && k < Kin && a.W) ? a.W[(size_t)n * a.ldw + k] : 0.f;
   }
   if (t < kH) {
-    float m, r;
-    if (has_in && t < Kin) norm_coeffs(a.ns_in, t, sc_i[t], sh_i[t], m, r); else { sc_i[t] = 0.f; sh_i[t] = 0.f; }
+    if (has_in && t < Kin) norm_coeffs(a.ns_in, t, sc_i[t], sh_i[t], mean_i[t], rstd_i[t]);
+    else { sc_i[t] = 0.f; sh_i[t] = 0.f; mean_i[t] = 0.f; rstd_i[t] = 0.f; }
     if (a.out_mode == 1) {
       norm_coeffs(a.ns_out, t, sc_o[t], sh_o[t], mean_o[t], rstd_o[t]);
       if (a.ns_out.mode == NORM_BN_BATCH) {
         m1[t] = (float)(a.sdy[t] * (double)a.ns_out.inv_count);
         m2[t] = (float)(a.sdyx[t] * (double)a.ns_out.inv_count);
-        gsc[t] = sc_o[t];           // gamma * rstd
       } else {                      // bias (or moving-stat BN): no batch coupling
-        m1[t] = 0.f; m2[t] = 0.f; gsc[t] = sc_o[t];
+        m1[t] = 0.f; m2[t] = 0.f;
       }
+      gsc[t] = sc_o[t];             // gamma * rstd
     }
+    dacc[t] = 0.0; dacc[kH + t] = 0.0;
   }
   __syncthreads();
-  const int rl = t >> 2, cq = t & 3;
-  float accW[16];
+  float accW[4][4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) accW[j] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accW[i][j] = 0.f;
   float accb = 0.f;
+  const float in_drop_scale = a.ns_in.drop.rate > 0.f ? a.ns_in.drop.scale : 1.f;
   for (int r0 = blockIdx.x * kTileR; r0 < a.R; r0 += gridDim.x * kTileR) {
-    // gradient wrt pre-activation of this unit -> Gs[r][n]
     for (int i = t; i < kTileR * kH; i += kMidThreads) {
       int r = i / kH, n = i % kH;
       float g = 0.f;
@@ -433,60 +481,105 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
         }
         if (a.dA) a.dA[(size_t)(r0 + r) * a.ldda + n] = g;
       }
-      Gs[r][n] = g;
+      Gn[r * kTS + n] = g;
+      GT[n * kTS + r] = g;
     }
     if (has_in) {
       for (int i = t; i < kTileR * kH; i += kMidThreads) {
         int r = i / kH, k = i % kH;
-        float v = 0.f;
+        float v = 0.f, raw = 0.f;
         if (r0 + r < a.R && k < Kin) {
-          v = a.A_in[(size_t)(r0 + r) * a.lda_in + k] * sc_i[k] + sh_i[k];
+          raw = a.A_in[(size_t)(r0 + r) * a.lda_in + k];
+          v = raw * sc_i[k] + sh_i[k];
           if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_in.drop, (uint32_t)(r0 + r), (uint32_t)k);
         }
-        Hs[r][k] = v;
+        Hn[r * kTS + k] = v;
+        if (fuse_prev) An[r * kTS + k] = raw;
       }
     }
     __syncthreads();
-    if (has_in && a.dW) {   // dW[n][k] += sum_r Gs[r][n] * Hs[r][k];  n = rl, k = cq + 4j
+    if (has_in && a.dW) {   // dW[n][k] += sum_r G[r][n] * H[r][k];  n = 4ty.., k = 4tx..
       for (int r = 0; r < kTileR; ++r) {
-        float g = Gs[r][rl];
+        float4 a4 = *reinterpret_cast<const float4*>(Gn + r * kTS + 4 * ty);
+        float4 b4 = *reinterpret_cast<const float4*>(Hn + r * kTS + 4 * tx);
+        float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) accW[j] = fmaf(g, Hs[r][cq + 4 * j], accW[j]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accW[i][j] = fmaf(av[i], bv[j], accW[i][j]);
       }
     }
     if (a.db && t < Nout) {
-      for (int r = 0; r < kTileR; ++r) accb += Gs[r][t];
+      for (int r = 0; r < kTileR; ++r) accb += Gn[r * kTS + t];
     }
-    if (a.dIn) {            // dIn[r][k] = sum_n Gs[r][n] * W[n][k];  r = rl, k = cq + 4j
-      float acc[16];
+    if (a.dIn) {            // dIn[r][k] = sum_n G[r][n] * W[n][k];  r = 4ty.., k = 4tx..
+      float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
       for (int n = 0; n < Nout; ++n) {
-        float g = Gs[rl][n];
+        float4 a4 = *reinterpret_cast<const float4*>(GT + n * kTS + 4 * ty);
+        float4 b4 = *reinterpret_cast<const float4*>(Wn + n * kTS + 4 * tx);
+        float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(g, Ws[n][cq + 4 * j], acc[j]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
-      if (r0 + rl < a.R) {
+      float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int k = cq + 4 * j;
-          if (k < Kin) {
-            float* p = a.dIn + (size_t)(r0 + rl) * a.ldi + k;
-            *p = a.accumulate_dIn ? (*p + acc[j]) : acc[j];
+      for (int i = 0; i < 4; ++i) {
+        const int rl = 4 * ty + i, r = r0 + rl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = 4 * tx + j;
+          if (r < a.R && k < Kin) {
+            float* p = a.dIn + (size_t)r * a.ldi + k;
+            float v = a.accumulate_dIn ? (*p + acc[i][j]) : acc[i][j];
+            *p = v;
+            if (fuse_prev) {
+              // gradient wrt the producing unit's norm output: relu mask (and dropout scale) of h = Hn
+              float dy = Hn[rl * kTS + k] > 0.f ? v * in_drop_scale : 0.f;
+              float xh = (An[rl * kTS + k] - mean_i[k]) * rstd_i[k];
+              cs[j] += dy; cq[j] += dy * xh;
+            }
           }
+        }
+      }
+      if (fuse_prev) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { red1[ty * kH + 4 * tx + j] = cs[j]; red2[ty * kH + 4 * tx + j] = cq[j]; }
+        __syncthreads();
+        if (t < kH) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int y = 0; y < 16; ++y) { s1 += (double)red1[y * kH + t]; s2 += (double)red2[y * kH + t]; }
+          dacc[t] += s1; dacc[kH + t] += s2;
         }
       }
     }
     __syncthreads();
   }
-  if (has_in && a.dW && rl < Nout) {
+  if (has_in && a.dW) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      int k = cq + 4 * j;
-      if (k < Kin) atomicAdd(&a.dW[(size_t)rl * a.ldw + k], accW[j]);
-    }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * ty + i, k = 4 * tx + j;
+        if (n < Nout && k < Kin) atomicAdd(&a.dW[(size_t)n * a.ldw + k], accW[i][j]);
+      }
   }
   if (a.db && t < Nout) atomicAdd(&a.db[t], accb);
+  if (fuse_prev && t < Kin) {
+    atomicAdd(&a.prev_sdy[t], dacc[t]);
+    atomicAdd(&a.prev_sdyx[t], dacc[kH + t]);
+    if (a.ns_in.mode == NORM_BIAS) {
+      atomicAdd(&a.prev_dbeta[t], (float)dacc[t]);
+    } else {
+      atomicAdd(&a.prev_dgamma[t], (float)dacc[kH + t]);
+      atomicAdd(&a.prev_dbeta[t], (float)dacc[t]);
+    }
+  }
 }
 
 }  // namespace sisua

@@ -86,7 +86,7 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
   __host__ __device__ static constexpr int Wstage(int nh) { return packed_tile_stride(nh); }
   __host__ __device__ static constexpr int X0(int nh) { return W0 + 2 * Wstage(nh); }
   __host__ __device__ static constexpr int Xstage() { return kCellTile * kXPad * 4; }
-  __host__ __device__ static constexpr int G0(int nh) { return X0(nh) + 2 * Xstage(); }      // [128][128] fp16 (train)
+  __host__ __device__ static constexpr int G0(int nh) { return X0(nh); }                     // [128][128] fp16 (train)
   __host__ __device__ static constexpr int LLK(int nh, bool train) { return G0(nh) + (train ? 16 * 2048 : 0); }
   __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + kCellTile * 4; }
   __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
@@ -236,28 +236,20 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float llk_acc = 0.f;
 
-    auto load_x_tile = [&](int i) {          // cooperative, all epilogue threads
-      const int s = i & 1;
-      float* xs = reinterpret_cast<float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage());
-      const int g0 = (tile_begin + i) * kGeneTile;
+    // this thread's 8 counts of tile i straight from global memory (one 32-byte sector per lane; prefetched a
+    // tile ahead into registers, so no shared-memory staging and no CTA-wide barriers in the tile loop)
+    const float* xrow = a.x + (size_t)((row_ok ? row : 0) % a.B) * a.G;
+    auto load_x = [&](int i, float* xv) {
+      const int g = (tile_begin + i) * kGeneTile + sub * 8;
       if (VEC) {
-#pragma unroll
-        for (int j = 0; j < kCellTile * 8 / kEpiThreads; ++j) {
-          int idx = t + kEpiThreads * j;
-          int r = idx >> 3, c4 = idx & 7;
-          int rr = row0 + r, g = g0 + 4 * c4;
-          float* dst = xs + r * kXPad + 4 * c4;
-          if (rr < a.R && g < a.G) cp_async_16(dst, a.x + (size_t)(rr % a.B) * a.G + g);
-          else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (row_ok && g < a.G) p0 = __ldg(reinterpret_cast<const float4*>(xrow + g));
+        if (row_ok && g + 4 < a.G) p1 = __ldg(reinterpret_cast<const float4*>(xrow + g + 4));
+        xv[0] = p0.x; xv[1] = p0.y; xv[2] = p0.z; xv[3] = p0.w; xv[4] = p1.x; xv[5] = p1.y; xv[6] = p1.z; xv[7] = p1.w;
       } else {
-        for (int idx = t; idx < kCellTile * kGeneTile; idx += kEpiThreads) {
-          int r = idx >> 5, c = idx & 31;
-          int rr = row0 + r, g = g0 + c;
-          xs[r * kXPad + c] = (rr < a.R && g < a.G) ? a.x[(size_t)(rr % a.B) * a.G + g] : 0.f;
-        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = (row_ok && g + j < a.G) ? __ldg(xrow + g + j) : 0.f;
       }
-      cp_async_commit();
     };
 
     auto flush_dwo = [&](int i) {            // tile i's weight / bias gradient: TMEM -> vector reds
@@ -283,18 +275,15 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       }
     };
 
-    load_x_tile(0);
+    float xnext[8];
+    load_x(0, xnext);
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
-      if (i + 1 < nt) {
-        named_bar_sync(1, kEpiThreads);      // everyone is done reading stage s^1 (tile i-1)
-        load_x_tile(i + 1);
-      } else {
-        cp_async_commit();
-      }
-      cp_async_wait<1>();
-      named_bar_sync(1, kEpiThreads);        // tile i's counts are visible to all epilogue threads
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = xnext[j];
+      if (i + 1 < nt) load_x(i + 1, xnext);
       mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
       mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
       tc_fence_after();
@@ -309,12 +298,6 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       if (lane == 0) mbar_arrive(&bars[ACC_FREE + s]);
 
       const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
-      const float* xs = reinterpret_cast<const float*>(smem + OutSmem::X0(NH) + s * OutSmem::Xstage()) + cell * kXPad + sub * 8;
-      float xv[8];
-      {
-        float4 p0 = *reinterpret_cast<const float4*>(xs), p1 = *reinterpret_cast<const float4*>(xs + 4);
-        xv[0] = p0.x; xv[1] = p0.y; xv[2] = p0.z; xv[3] = p0.w; xv[4] = p1.x; xv[5] = p1.y; xv[6] = p1.z; xv[7] = p1.w;
-      }
       uint32_t ga[4], gb[4], gl[4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
