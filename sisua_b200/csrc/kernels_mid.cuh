@@ -123,9 +123,18 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
   float* red2 = red1 + 16 * kH;
   double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);   // [2][64] running sums of this CTA
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  for (int i = t; i < kH * kH; i += kMidThreads) {
-    int n = i / kH, k = i % kH;
-    WT[k * kTS + n] = (n < Nout && k < Kin) ? W[(size_t)n * ldw + k] : 0.f;
+  {   // all 16 loads of a thread are issued before any is used (the kernels are latency-, not bandwidth-bound)
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      w[j] = (n < Nout && k < Kin) ? __ldg(W + (size_t)n * ldw + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      WT[k * kTS + n] = w[j];
+    }
   }
   if (t < kH) {
     float m, r;
@@ -134,14 +143,23 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
   }
   __syncthreads();
   for (int r0 = blockIdx.x * kTileR; r0 < R; r0 += gridDim.x * kTileR) {
-    for (int i = t; i < kTileR * kH; i += kMidThreads) {
-      int r = i / kH, k = i % kH;
-      float v = 0.f;
-      if (r0 + r < R && k < Kin) {
-        v = A_in[(size_t)(r0 + r) * lda + k] * sc[k] + sh[k];
-        if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(ns.drop, (uint32_t)(r0 + r), (uint32_t)k);
+    {
+      float hv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, k = i & 63;
+        hv[j] = (r0 + r < R && k < Kin) ? A_in[(size_t)(r0 + r) * lda + k] : 0.f;
       }
-      HT[k * kTS + r] = v;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, k = i & 63;
+        float v = 0.f;
+        if (r0 + r < R && k < Kin) {
+          v = hv[j] * sc[k] + sh[k];
+          if (ns.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(ns.drop, (uint32_t)(r0 + r), (uint32_t)k);
+        }
+        HT[k * kTS + r] = v;
+      }
     }
     __syncthreads();
     float acc[4][4];
@@ -437,9 +455,18 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
   const int Nout = a.Nout, Kin = a.Kin;
   const bool has_in = a.A_in != nullptr;
   const bool fuse_prev = a.prev_sdy != nullptr;
-  for (int i = t; i < kH * kH; i += kMidThreads) {
-    int n = i / kH, k = i % kH;
-    Wn[n * kTS + k] = (n < Nout && k < Kin && a.W) ? a.W[(size_t)n * a.ldw + k] : 0.f;
+  {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      w[j] = (n < Nout && k < Kin && a.W) ? __ldg(a.W + (size_t)n * a.ldw + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      Wn[n * kTS + k] = w[j];
+    }
   }
   if (t < kH) {
     if (has_in && t < Kin) norm_coeffs(a.ns_in, t, sc_i[t], sh_i[t], mean_i[t], rstd_i[t]);
@@ -465,36 +492,44 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
   float accb = 0.f;
   const float in_drop_scale = a.ns_in.drop.rate > 0.f ? a.ns_in.drop.scale : 1.f;
   for (int r0 = blockIdx.x * kTileR; r0 < a.R; r0 += gridDim.x * kTileR) {
-    for (int i = t; i < kTileR * kH; i += kMidThreads) {
-      int r = i / kH, n = i % kH;
-      float g = 0.f;
-      if (r0 + r < a.R && n < Nout) {
-        if (a.out_mode == 0) {
-          g = a.dOut[(size_t)(r0 + r) * a.ldd + n];
-        } else {
-          float av = a.A_out[(size_t)(r0 + r) * a.lda_out + n];
-          float dy = (av * sc_o[n] + sh_o[n] > 0.f)
-                         ? a.dOut[(size_t)(r0 + r) * a.ldd + n] * dropout_mult(a.ns_out.drop, (uint32_t)(r0 + r), (uint32_t)n)
-                         : 0.f;
-          float xh = (av - mean_o[n]) * rstd_o[n];
-          g = gsc[n] * (dy - m1[n] - xh * m2[n]);
-        }
-        if (a.dA) a.dA[(size_t)(r0 + r) * a.ldda + n] = g;
+    {
+      float go[16], ao[16], hi[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, n = i & 63;
+        const bool ok = r0 + r < a.R && n < Nout;
+        go[j] = ok ? a.dOut[(size_t)(r0 + r) * a.ldd + n] : 0.f;
+        ao[j] = (ok && a.out_mode == 1) ? a.A_out[(size_t)(r0 + r) * a.lda_out + n] : 0.f;
+        hi[j] = (has_in && r0 + r < a.R && n < Kin) ? a.A_in[(size_t)(r0 + r) * a.lda_in + n] : 0.f;
       }
-      Gn[r * kTS + n] = g;
-      GT[n * kTS + r] = g;
-    }
-    if (has_in) {
-      for (int i = t; i < kTileR * kH; i += kMidThreads) {
-        int r = i / kH, k = i % kH;
-        float v = 0.f, raw = 0.f;
-        if (r0 + r < a.R && k < Kin) {
-          raw = a.A_in[(size_t)(r0 + r) * a.lda_in + k];
-          v = raw * sc_i[k] + sh_i[k];
-          if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_in.drop, (uint32_t)(r0 + r), (uint32_t)k);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, n = i & 63;
+        float g = 0.f;
+        if (r0 + r < a.R && n < Nout) {
+          if (a.out_mode == 0) {
+            g = go[j];
+          } else {
+            float av = ao[j];
+            float dy = (av * sc_o[n] + sh_o[n] > 0.f) ? go[j] * dropout_mult(a.ns_out.drop, (uint32_t)(r0 + r), (uint32_t)n) : 0.f;
+            float xh = (av - mean_o[n]) * rstd_o[n];
+            g = gsc[n] * (dy - m1[n] - xh * m2[n]);
+          }
+          if (a.dA) a.dA[(size_t)(r0 + r) * a.ldda + n] = g;
         }
-        Hn[r * kTS + k] = v;
-        if (fuse_prev) An[r * kTS + k] = raw;
+        Gn[r * kTS + n] = g;
+        GT[n * kTS + r] = g;
+        if (has_in) {
+          const int k = n;
+          float v = 0.f, raw = 0.f;
+          if (r0 + r < a.R && k < Kin) {
+            raw = hi[j];
+            v = raw * sc_i[k] + sh_i[k];
+            if (a.ns_in.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_in.drop, (uint32_t)(r0 + r), (uint32_t)k);
+          }
+          Hn[r * kTS + k] = v;
+          if (fuse_prev) An[r * kTS + k] = raw;
+        }
       }
     }
     __syncthreads();
