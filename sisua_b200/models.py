@@ -409,8 +409,8 @@ class SingleCellModel:
         idx = perm[s * B:(s + 1) * B]
         b = self._batch_tensors(train, idx, cache)
         eps = self._eps(B, None, gen)
-        eng.train_step(terms=terms, loss=loss, **b, **eps)
         self.step += 1
+        eng.train_step(terms=terms, loss=loss, seed=self._seed, step=self.step, **b, **eps)
         eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), t=self.step)
         done += 1
         if logging_interval and done % int(logging_interval) == 0:
