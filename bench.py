@@ -29,7 +29,7 @@ GENES, LATENT, SHARD_CELLS, TOTAL_CELLS = 2000, 10, 132608, 1_000_000
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=60)
+  ap.add_argument("--steps", type=int, default=600)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--batch", type=int, default=9472, help="cells per GPU per step (74 tiles of 128 cells: 2 gene chunks x 74 = 148 CTAs, one per SM)")
@@ -92,7 +92,7 @@ class ClockSampler:
   def __init__(self, index):
     self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
     try:
-      self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+      self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                  "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
     except Exception:
       self.p = None
@@ -122,6 +122,20 @@ class ClockSampler:
     os.unlink(self.f.name)
     return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
             "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel, B, G):
+  """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
+  (profiles/r1_traffic.json), if it was taken at this batch / gene count."""
+  p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+  if not os.path.exists(p):
+    return None
+  with open(p) as f:
+    d = json.load(f)
+  e = d.get(kernel)
+  if e and e.get("batch") == B and e.get("genes") == G:
+    return e["dram_bytes_per_launch"]
+  return None
 
 
 def measured_peaks():
@@ -228,37 +242,60 @@ def main():
   final_loss = float(loss.item())
 
   # ---- end-to-end arm: host-resident minibatches through the host-buffer entry point
-  from sisua_b200.pipeline import HostTrainPipeline
+  from sisua_b200.pipeline import HostTrainPipeline, quantize_counts
   pipe = HostTrainPipeline(eng, B)
   n_host = 6
-  host_batches = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
-  for i, hb in enumerate(host_batches):
+  host_f32 = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
+  for i, hb in enumerate(host_f32):
     hb.copy_(X[i * B:(i + 1) * B])
+  # what the public host pipeline ships for integer count matrices (done once per dataset, outside the step)
+  host_u16 = [quantize_counts(hb.numpy()) for hb in host_f32]
   host_eps = [torch.randn((B, LATENT)).pin_memory() for _ in range(n_host)]
-  e2e_steps = max(10, a.steps // 2)
+  e2e_steps = max(10, min(200, a.steps // 3))
 
-  def e2e_run(n):
-    losses = []
+  def e2e_measure(host_batches):
+    def run(n):
+      losses = []
+      for i in range(n):
+        step_no[0] += 1
+        losses.append(pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
+                                allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None))
+      return pipe.flush(losses)
+    run(3)
+    sync_all()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run(e2e_steps)
+    ev1.record()
+    sync_all()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+    tt = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return world * B * e2e_steps / (float(tt.item()) * 1e-3)
+
+  e2e_val = e2e_measure(host_u16)
+  e2e_f32 = e2e_measure(host_f32)
+  x_bytes = host_u16[0].numel() * host_u16[0].element_size()
+
+  # ---- inference: predict-style step (ELBO terms, latent mean/scale, imputed means written to HBM)
+  inf_steps = max(10, min(100, a.steps // 6))
+  def infer_run(n):
     for i in range(n):
-      step_no[0] += 1
-      l = pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
-                    allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None)
-      losses.append(l)
-    return pipe.flush(losses)
-
-  e2e_run(3)
+      j = i % n_batches
+      eng.infer(X[j * B:(j + 1) * B], eps_z=eps_pool[i % 16], want_mean=True)
+  infer_run(3)
   sync_all()
-  t0 = time.perf_counter()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
-  e2e_losses = e2e_run(e2e_steps)
+  infer_run(inf_steps)
   ev1.record()
   sync_all()
-  e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-  t = torch.tensor([e2e_ms], device=dev)
+  tt = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
   if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e_val = world * B * e2e_steps / (float(t.item()) * 1e-3)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  infer_val = world * B * inf_steps / (float(tt.item()) * 1e-3)
 
   if rank == 0:
     hbm_peak, peak_src = measured_peaks()
@@ -276,11 +313,15 @@ def main():
         "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss,
         "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 3xTF32 fused", 2: "tcgen05 TF32 fused"}[mode],
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4),
+        "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(x_bytes + B * LATENT * 4),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "HostTrainPipeline.step (pinned host minibatch -> H2D -> sisua_train_step -> sisua_adam_step -> D2H loss)"},
+                "api": "HostTrainPipeline.step (pinned host minibatch, integer counts shipped as uint16 -> H2D -> unpack -> "
+                       "sisua_train_step -> sisua_adam_step -> D2H loss)",
+                "fp32_host_value": e2e_f32, "fp32_host_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
+        "inference": {"value": infer_val, "unit": "cells/s", "steps": inf_steps,
+                      "what": "sisua_infer per minibatch: ELBO terms, latent mean/scale, imputed means [B,G] written to HBM"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": ncu_traffic(dom, B, G), "peak_source": peak_src,
                      "ms_per_launch": per_step[dom], "share_of_step": per_step[dom] / (ms / a.steps),
                      "sections_ms_per_step": per_step},
     })

@@ -107,6 +107,10 @@ const float* sisua_debug_buffer(sisua_handle h, const char* name);
 
 int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
 
+/* Host pipelines ship integer count matrices over PCIe as uint16 (half the bytes of the reference's float32
+ * storage, sisua/data/utils.py:427-431); this widens n values to the fp32 layout the step consumes. */
+int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, float* dst, int64_t n, void* stream);
+
 /* Measurement hooks for bench.py: kernels launched so far through this handle; per-section device time
  * (CUDA events on the caller's stream). Sections: 0 first encoder layer, 1 mid forward, 2 output heads +
  * count likelihood (fused: one kernel), 3 mid backward, 4 first-layer weight gradient, 5 Adam. */

@@ -959,6 +959,31 @@ extern "C" int sisua_tc_selftest(const float* A, const float* B, float* D, int N
 #endif
 }
 
+// widen uint16 counts (what the host pipeline ships over PCIe for integer count matrices) to the fp32 layout
+__global__ void __launch_bounds__(256) unpack_u16_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    uint4 v = *reinterpret_cast<const uint4*>(src + i);
+    float4 a = make_float4((float)(v.x & 0xffffu), (float)(v.x >> 16), (float)(v.y & 0xffffu), (float)(v.y >> 16));
+    float4 b = make_float4((float)(v.z & 0xffffu), (float)(v.z >> 16), (float)(v.w & 0xffffu), (float)(v.w >> 16));
+    *reinterpret_cast<float4*>(dst + i) = a;
+    *reinterpret_cast<float4*>(dst + i + 4) = b;
+  } else {
+    for (; i < n; ++i) dst[i] = (float)src[i];
+  }
+}
+
+extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, float* dst, int64_t n, void* stream) {
+  if (!h || !src || !dst || n < 0) return SISUA_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    SET_ERR(h, SISUA_ERR_INVALID, "unpack_counts_u16: pointers must be 16-byte aligned");
+  long long blocks = (n / 8 + 255) / 256 + 1;
+  ++h->launches;
+  unpack_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, (long long)n);
+  LAUNCH_OK(h, "unpack_u16_kernel");
+  return SISUA_OK;
+}
+
 extern "C" int64_t sisua_launch_count(sisua_handle h) { return h ? h->launches : -1; }
 
 extern "C" int sisua_profile_enable(sisua_handle h, int on) {

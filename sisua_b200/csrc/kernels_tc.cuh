@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
   // ---------------- prologue: barriers, TMEM, decoder-activation tile (hi/lo fp16), pads ----------------
   if (t == 0) {
     mbar_init(&bars[W_FULL], 1); mbar_init(&bars[W_FULL + 1], 1);
-    mbar_init(&bars[W_FREE], 1); mbar_init(&bars[W_FREE + 1], 1);
+    // a weight stage is released by the MMA commit and, when there is no backward (whose commit already follows the
+    // epilogue), by every epilogue warp once it has read the stage's bias values
+    mbar_init(&bars[W_FREE], TRAIN ? 1 : 1 + kEpiWarps); mbar_init(&bars[W_FREE + 1], TRAIN ? 1 : 1 + kEpiWarps);
     mbar_init(&bars[ACC_FULL], 1); mbar_init(&bars[ACC_FULL + 1], 1);
     mbar_init(&bars[ACC_FREE], kEpiWarps); mbar_init(&bars[ACC_FREE + 1], kEpiWarps);
     mbar_init(&bars[G_FULL], kEpiWarps); mbar_init(&bars[G_FREE], 1);
@@ -329,6 +331,10 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           if (j & 1) { ga[j >> 1] |= ha << 16; gb[j >> 1] |= hb << 16; gl[j >> 1] |= hl << 16; }
           else { ga[j >> 1] = ha; gb[j >> 1] = hb; gl[j >> 1] = hl; }
         }
+      }
+      if (!TRAIN) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[W_FREE + s]);   // bias of this stage consumed
       }
       if (!TRAIN && row_ok) {
         const size_t o = (size_t)row * a.G + g0;

@@ -137,6 +137,13 @@ class Engine:
     return out
 
   # -------------------------------------------------------------------------------------------
+  def unpack_counts_u16(self, src_u16: torch.Tensor, dst_f32: torch.Tensor):
+    """device uint16 counts -> device fp32 counts (same shape), on the current stream."""
+    if src_u16.dtype not in (torch.uint16, torch.int16) or dst_f32.dtype != torch.float32 or src_u16.numel() != dst_f32.numel():
+      raise ValueError("unpack_counts_u16: need uint16 source and fp32 destination of equal size")
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_unpack_counts_u16(self.handle, _ptr(src_u16), _ptr(dst_f32), src_u16.numel(), self._stream()))
+
   SECTIONS = ("enc_first", "mid_fwd", "out_heads", "mid_bwd", "enc_first_bwd", "adam")
 
   def launch_count(self) -> int:

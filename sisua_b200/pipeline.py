@@ -10,6 +10,16 @@ import torch
 from .engine import Engine
 
 
+def quantize_counts(X):
+  """float32 count matrix -> pinned uint16 host tensor when every value is an integer below 65536 (done once per
+  dataset, like the reference's cached tf.data pipeline); otherwise the pinned float32 tensor."""
+  import numpy as np
+  X = np.ascontiguousarray(X)
+  if X.dtype != np.uint16 and (X.min() < 0 or X.max() >= 65536 or not np.array_equal(X, np.rint(X))):
+    return torch.from_numpy(X.astype(np.float32, copy=False)).pin_memory()
+  return torch.from_numpy(X.astype(np.uint16).view(np.int16)).pin_memory()
+
+
 class HostTrainPipeline:
   def __init__(self, eng: Engine, batch: int, depth: int = 2):
     self.eng = eng
@@ -18,6 +28,7 @@ class HostTrainPipeline:
     self.copy_stream = torch.cuda.Stream(device=dev)
     self.depth = depth
     self.x = [torch.empty((batch, cfg.n_genes), device=dev) for _ in range(depth)]
+    self.x16 = [torch.empty((batch, cfg.n_genes), device=dev, dtype=torch.int16) for _ in range(depth)]
     self.eps = [torch.empty((batch, cfg.n_latent), device=dev) for _ in range(depth)]
     self.ready = [torch.cuda.Event() for _ in range(depth)]
     self.consumed = [torch.cuda.Event() for _ in range(depth)]
@@ -38,10 +49,16 @@ class HostTrainPipeline:
     main = torch.cuda.current_stream(eng.device)
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.consumed[s])
-      self.x[s].copy_(x_host, non_blocking=True)
+      packed = x_host.dtype in (torch.int16, torch.uint16)   # integer counts shipped as 16-bit (see quantize_counts)
+      if packed:
+        self.x16[s].copy_(x_host.view(torch.int16), non_blocking=True)
+      else:
+        self.x[s].copy_(x_host, non_blocking=True)
       self.eps[s].copy_(eps_host, non_blocking=True)
       self.ready[s].record(self.copy_stream)
     main.wait_event(self.ready[s])
+    if packed:
+      eng.unpack_counts_u16(self.x16[s], self.x[s])
     eng.train_step(self.x[s], eps_z=self.eps[s], terms=self.terms, loss=self.loss, seed=0, step=step)
     self.consumed[s].record(main)
     if allreduce is not None:

@@ -203,3 +203,20 @@ def test_tcgen05_descriptor_selftest(a_mn, b_mn, N, K):
   torch.cuda.synchronize()
   ref = A.half().float() @ Bm.half().float().T
   assert torch.allclose(D, ref, rtol=1e-4, atol=1e-3), float((D - ref).abs().max())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_deep_gene_pipeline(mode):
+  """Many 32-gene tiles per CTA (weight / TMEM stages are recycled dozens of times) in inference and training."""
+  cfg, flat, mov, batch = _setup("vae", {}, 2000, 300, mode, trained_moving=True)
+  eng = _engine(cfg, flat, mov)
+  out = eng.infer(want_mean=True, **batch)
+  torch.cuda.synchronize()
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo")
+  _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="imputed mean")
+  terms, loss = eng.train_step(**batch)
+  torch.cuda.synchronize()
+  reft = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, **batch)
+  _close(terms[0].cpu().numpy(), reft["elbo"].numpy(), what="train elbo")
+  eng.close()
