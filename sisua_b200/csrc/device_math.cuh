@@ -178,6 +178,21 @@ __device__ __forceinline__ float digamma_stirling(float lnz, float iz) {
   return lnz - 0.5f * iz - iz2 * (0.083333336f - iz2 * (0.008333334f - iz2 * 0.003968254f));
 }
 
+// Large (> 8) or non-integer counts: Stirling at x+th, x+1 and th+8 (all >= 8) with
+// lgamma(th) = lgamma(th+8) - log prod_{k<8}(th+k)  (lnq, dgq = log and log-derivative of that product).
+__device__ __noinline__ void gamma_terms_large(float x, float th, float lnq, float dgq, bool grad, float* lg, float* dg) {
+  if (x >= 7.f) {
+    float z1 = x + th, z2 = x + 1.f, z3 = th + 8.f;
+    float l1 = kLn2 * mufu_lg2(z1), l2 = kLn2 * mufu_lg2(z2), l3 = kLn2 * mufu_lg2(z3);
+    float i1 = mufu_rcp(z1), i2 = mufu_rcp(z2), i3 = mufu_rcp(z3);
+    *lg = lgamma_stirling(z1, l1, i1) - lgamma_stirling(z2, l2, i2) - lgamma_stirling(z3, l3, i3) + lnq;
+    *dg = digamma_stirling(l1, i1) - digamma_stirling(l3, i3) + dgq;
+  } else {
+    *lg = lgammaf(x + th) - lgammaf(th) - lgammaf(x + 1.f);
+    *dg = grad ? digamma_pos(x + th) - digamma_pos(th) : 0.f;
+  }
+}
+
 struct ElemResult { float llk, ga, gb, gl, mu, th; };   // ga, gb, gl = d llk / d raw head outputs
 
 template <bool kZeroInflated, bool kGrad>
@@ -226,19 +241,8 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
     float lg = lnq - kLn2 * mufu_lg2(f);
     float dg = dq * rq;
     if (__any_sync(0xffffffffu, nz && !small_x)) {
-      // large or non-integer counts: Stirling at x+th, x+1 and th+8 (all >= 8); q = prod_{k<8}(th+k)
-      float z1 = x + th, z2 = x + 1.f, z3 = th + 8.f;
-      float l1 = kLn2 * mufu_lg2(z1), l2 = kLn2 * mufu_lg2(z2), l3 = kLn2 * mufu_lg2(z3);
-      float i1 = mufu_rcp(z1), i2 = mufu_rcp(z2), i3 = mufu_rcp(z3);
-      // for x < 7 (non-integer) shift x+th and x+1 up by 8 as well so Stirling stays accurate
       float lg_big, dg_big;
-      if (x >= 7.f) {
-        lg_big = lgamma_stirling(z1, l1, i1) - lgamma_stirling(z2, l2, i2) - lgamma_stirling(z3, l3, i3) + lnq;
-        dg_big = digamma_stirling(l1, i1) - digamma_stirling(l3, i3) + dg;
-      } else {
-        lg_big = lgammaf(z1) - lgammaf(th) - lgammaf(z2);
-        dg_big = kGrad ? digamma_pos(z1) - digamma_pos(th) : 0.f;
-      }
+      gamma_terms_large(x, th, lnq, dg, kGrad, &lg_big, &dg_big);   // out of line: rare, keeps the hot loop small
       lg = small_x ? lg : lg_big;
       dg = small_x ? dg : dg_big;
     }

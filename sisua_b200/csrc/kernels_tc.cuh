@@ -87,12 +87,14 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
   __host__ __device__ static constexpr int X0(int nh) { return W0 + 2 * Wstage(nh); }
   __host__ __device__ static constexpr int Xstage() { return kCellTile * kXPad * 4; }
   __host__ __device__ static constexpr int G0(int nh) { return X0(nh); }                     // [128][128] fp16 (train)
-  __host__ __device__ static constexpr int LLK(int nh, bool train) { return G0(nh) + (train ? 16 * 2048 : 0); }
+  static constexpr int Gstage = 16 * 2048;                                                 // two G stages when training
+  __host__ __device__ static constexpr int XS(int nh, bool train) { return G0(nh) + (train ? 2 * Gstage : 0); }   // [8][512] count stash
+  __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 8 * kEpiThreads * 4; }
   __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + kCellTile * 4; }
   __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
 };
 
-enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 9, DWO_FULL = 10, DWO_FREE = 12, DD_FULL = 14, NUM_BARS = 15 };
+enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12, DWO_FREE = 14, DD_FULL = 16, NUM_BARS = 17 };
 
 template <int NH, bool TRAIN, bool VEC, bool FAST>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     mbar_init(&bars[W_FREE], TRAIN ? 1 : 1 + kEpiWarps); mbar_init(&bars[W_FREE + 1], TRAIN ? 1 : 1 + kEpiWarps);
     mbar_init(&bars[ACC_FULL], 1); mbar_init(&bars[ACC_FULL + 1], 1);
     mbar_init(&bars[ACC_FREE], kEpiWarps); mbar_init(&bars[ACC_FREE + 1], kEpiWarps);
-    mbar_init(&bars[G_FULL], kEpiWarps); mbar_init(&bars[G_FREE], 1);
+    mbar_init(&bars[G_FULL], kEpiWarps); mbar_init(&bars[G_FULL + 1], kEpiWarps);
+    mbar_init(&bars[G_FREE], 1); mbar_init(&bars[G_FREE + 1], 1);
     mbar_init(&bars[DWO_FULL], 1); mbar_init(&bars[DWO_FULL + 1], 1);
     mbar_init(&bars[DWO_FREE], kEpiWarps); mbar_init(&bars[DWO_FREE + 1], kEpiWarps);
     mbar_init(&bars[DD_FULL], 1);
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       uint32_t first = (cg == 8 && row0 + r < a.R) ? 0x00003C00u : 0u;  // fp16 1.0 in column 64
       *reinterpret_cast<uint4*>(smem + OutSmem::dA1 + off) = make_uint4(first, 0u, 0u, 0u);
     }
-    for (int item = t; item < 16 * 2048 / 16; item += kOutThreads)      // zero the whole G tile once (pad columns stay 0)
+    for (int item = t; item < 2 * OutSmem::Gstage / 16; item += kOutThreads)      // zero both G stages once (pad columns stay 0)
       *reinterpret_cast<uint4*>(smem + OutSmem::G0(NH) + item * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (t < kCellTile) llk_s[t] = 0.f;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
       const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
       const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
-      const uint32_t sG = smem_u32(smem + OutSmem::G0(NH));
+      const uint32_t sG0 = smem_u32(smem + OutSmem::G0(NH));
       auto fwd = [&](int i) {
         const int s = i & 1;
         const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         if (TRAIN) {
           const int s = i & 1;
           const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH));
-          mbar_wait(&bars[G_FULL], i & 1);
+          const uint32_t sG = sG0 + s * OutSmem::Gstage;
+          mbar_wait(&bars[G_FULL + s], (i >> 1) & 1);
           if (i >= 2) mbar_wait(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
           tc_fence_after();
           // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 MN-major)
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           for (int ks = 0; ks < kCellTile / 16; ++ks)
             umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
                      make_smem_desc(sA1 + ks * 256, 128, 2048), idesc_dwo, ks > 0 ? 1u : 0u);
-          umma_commit(&bars[G_FREE]);
+          umma_commit(&bars[G_FREE + s]);
           umma_commit(&bars[DWO_FULL + s]);
           umma_commit(&bars[W_FREE + s]);
           if (i == nt - 1) umma_commit(&bars[DD_FULL]);
@@ -279,90 +283,80 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 
     float xnext[8];
     load_x(0, xnext);
+    float* xs = reinterpret_cast<float*>(smem + OutSmem::XS(NH, TRAIN)) + t;     // this thread's column of the [8][512] stash
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
-      float xv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = xnext[j];
+      for (int j = 0; j < 8; ++j) xs[j * kEpiThreads] = xnext[j];
       if (i + 1 < nt) load_x(i + 1, xnext);
       mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
       mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
+      if (TRAIN && i >= 2) mbar_wait(&bars[G_FREE + s], ((i >> 1) - 1) & 1);   // gradient GEMMs of tile i-2 consumed this G stage
       tc_fence_after();
-      float va[8], vb[8], vl[8];
       const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + sub * 8);
-      tmem_ld8(tb, va);
-      tmem_ld8(tb + 32, vb);
-      if (ZI) tmem_ld8(tb + 64, vl);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[ACC_FREE + s]);
-
       const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
-      uint32_t ga[4], gb[4], gl[4];
+      // this thread's 16-byte slot in column group `sub` of each head of the G stage
+      uint8_t* gt = smem + OutSmem::G0(NH) + s * OutSmem::Gstage + sub * 2048 + (cell >> 3) * 128 + (cell & 7) * 16;
+      const size_t o = (size_t)row * a.G + g0;
+      // rolled on purpose: two genes per trip keep the hot loop inside the instruction cache
+#pragma unroll 1
+      for (int j = 0; j < 8; j += 2) {
+        float va[2], vb[2], vl[2] = {0.f, 0.f};
+        tmem_ld2(tb + j, va);
+        tmem_ld2(tb + 32 + j, vb);
+        if (ZI) tmem_ld2(tb + 64 + j, vl);
+        tmem_ld_wait();
+        const float x2[2] = {xs[j * kEpiThreads], xs[(j + 1) * kEpiThreads]};
+        uint32_t pa = 0, pb = 0, pl = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = row_ok && (g0 + j) < a.G;
-        const float ra = va[j] + bias_s[j];
-        const float rb = vb[j] + bias_s[32 + j];
-        const float pi = ZI ? vl[j] + bias_s[64 + j] : 0.f;
-        ElemResult e;
-        if (FAST) {
-          e = count_elem_fast<ZI, TRAIN>(ra, rb, pi, xv[j]);
-        } else {
-          float dmu, dth;
-          activation(a.mean_act, ra, e.mu, dmu);
-          activation(a.disp_act, rb, e.th, dth);
-          CountGrad cg;
-          cg.dmu = cg.dth = cg.dpi = 0.f;
-          e.llk = count_llk<ZI, TRAIN>(xv[j], e.mu, e.th, pi, cg);
-          e.ga = cg.dmu * dmu; e.gb = cg.dth * dth; e.gl = cg.dpi;
-        }
-        llk_acc += ok ? e.llk : 0.f;
-        if (!TRAIN) { va[j] = e.mu; vb[j] = e.th; vl[j] = pi; }
-        if (TRAIN) {
-          float g_a = ok ? fminf(fmaxf(e.ga, -60000.f), 60000.f) : 0.f;
-          float g_b = ok ? fminf(fmaxf(e.gb, -60000.f), 60000.f) : 0.f;
-          float g_l = (ok && ZI) ? e.gl : 0.f;
-          uint32_t ha = (uint32_t)__half_as_ushort(__float2half_rn(g_a));
-          uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(g_b));
-          uint32_t hl = (uint32_t)__half_as_ushort(__float2half_rn(g_l));
-          if (j & 1) { ga[j >> 1] |= ha << 16; gb[j >> 1] |= hb << 16; gl[j >> 1] |= hl << 16; }
-          else { ga[j >> 1] = ha; gb[j >> 1] = hb; gl[j >> 1] = hl; }
-        }
-      }
-      if (!TRAIN) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[W_FREE + s]);   // bias of this stage consumed
-      }
-      if (!TRAIN && row_ok) {
-        const size_t o = (size_t)row * a.G + g0;
-        if (VEC && g0 + 8 <= a.G) {
-          if (a.out_mean) { float4* d = reinterpret_cast<float4*>(a.out_mean + o); d[0] = make_float4(va[0], va[1], va[2], va[3]); d[1] = make_float4(va[4], va[5], va[6], va[7]); }
-          if (a.out_disp) { float4* d = reinterpret_cast<float4*>(a.out_disp + o); d[0] = make_float4(vb[0], vb[1], vb[2], vb[3]); d[1] = make_float4(vb[4], vb[5], vb[6], vb[7]); }
-          if (ZI && a.out_pi) { float4* d = reinterpret_cast<float4*>(a.out_pi + o); d[0] = make_float4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_float4(vl[4], vl[5], vl[6], vl[7]); }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (g0 + j < a.G) {
-              if (a.out_mean) a.out_mean[o + j] = va[j];
-              if (a.out_disp) a.out_disp[o + j] = vb[j];
-              if (ZI && a.out_pi) a.out_pi[o + j] = vl[j];
-            }
+        for (int u = 0; u < 2; ++u) {
+          const bool ok = row_ok && (g0 + j + u) < a.G;
+          const float ra = va[u] + bias_s[j + u];
+          const float rb = vb[u] + bias_s[32 + j + u];
+          const float pi = ZI ? vl[u] + bias_s[64 + j + u] : 0.f;
+          ElemResult e;
+          if (FAST) {
+            e = count_elem_fast<ZI, TRAIN>(ra, rb, pi, x2[u]);
+          } else {
+            float dmu, dth;
+            activation(a.mean_act, ra, e.mu, dmu);
+            activation(a.disp_act, rb, e.th, dth);
+            CountGrad cg;
+            cg.dmu = cg.dth = cg.dpi = 0.f;
+            e.llk = count_llk<ZI, TRAIN>(x2[u], e.mu, e.th, pi, cg);
+            e.ga = cg.dmu * dmu; e.gb = cg.dth * dth; e.gl = cg.dpi;
+          }
+          llk_acc += ok ? e.llk : 0.f;
+          if (TRAIN) {
+            float g_a = ok ? fminf(fmaxf(e.ga, -60000.f), 60000.f) : 0.f;
+            float g_b = ok ? fminf(fmaxf(e.gb, -60000.f), 60000.f) : 0.f;
+            float g_l = (ok && ZI) ? e.gl : 0.f;
+            pa |= (uint32_t)__half_as_ushort(__float2half_rn(g_a)) << (16 * u);
+            pb |= (uint32_t)__half_as_ushort(__float2half_rn(g_b)) << (16 * u);
+            pl |= (uint32_t)__half_as_ushort(__float2half_rn(g_l)) << (16 * u);
+          } else if (ok) {
+            if (a.out_mean) a.out_mean[o + j + u] = e.mu;
+            if (a.out_disp) a.out_disp[o + j + u] = e.th;
+            if (ZI && a.out_pi) a.out_pi[o + j + u] = pi;
           }
         }
+        if (TRAIN) {
+          *reinterpret_cast<uint32_t*>(gt + 0 * 4 * 2048 + j * 2) = pa;
+          *reinterpret_cast<uint32_t*>(gt + 1 * 4 * 2048 + j * 2) = pb;
+          if (ZI) *reinterpret_cast<uint32_t*>(gt + 2 * 4 * 2048 + j * 2) = pl;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars[ACC_FREE + s]);
+        if (!TRAIN) mbar_arrive(&bars[W_FREE + s]);   // bias of this stage consumed
       }
       if (TRAIN) {
-        if (i >= 1) mbar_wait(&bars[G_FREE], (i - 1) & 1);     // previous tile's gradient GEMMs have consumed G
-        uint8_t* gt = smem + OutSmem::G0(NH) + (cell >> 3) * 128 + (cell & 7) * 16;
-        // column groups of 8 output units: head h occupies groups 4h..4h+3; this thread owns group `sub` of each head
-        *reinterpret_cast<uint4*>(gt + (0 * 4 + sub) * 2048) = make_uint4(ga[0], ga[1], ga[2], ga[3]);
-        *reinterpret_cast<uint4*>(gt + (1 * 4 + sub) * 2048) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
-        if (ZI) *reinterpret_cast<uint4*>(gt + (2 * 4 + sub) * 2048) = make_uint4(gl[0], gl[1], gl[2], gl[3]);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[G_FULL]);
+        if (lane == 0) mbar_arrive(&bars[G_FULL + s]);
         if (i >= 1) flush_dwo(i - 1);
       }
     }
