@@ -226,10 +226,13 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
     // lg = lgamma(x+th) - lgamma(th) - lgamma(x+1), dg = psi(x+th) - psi(th)
     float q = th, dq = 1.f, f = 1.f;          // q = prod_{k<min(x,8)} (th+k)
     const bool small_x = (x == rintf(x)) && x <= 8.f;
-    const float lim = small_x ? x : 8.f;
-#pragma unroll
+    const float lim = nz ? (small_x ? x : 8.f) : 0.f;
+    // the 32 cells of a warp rarely hold more than a few counts at one gene: stop as soon as every lane is done
+#pragma unroll 1
     for (int k = 1; k < 8; ++k) {
-      if ((float)k < lim) {
+      const bool more = (float)k < lim;
+      if (!__any_sync(0xffffffffu, more)) break;
+      if (more) {
         float tk = th + (float)k;
         dq = fmaf(dq, tk, q);
         q *= tk;

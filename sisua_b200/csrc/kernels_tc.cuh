@@ -299,18 +299,21 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       // this thread's 16-byte slot in column group `sub` of each head of the G stage
       uint8_t* gt = smem + OutSmem::G0(NH) + s * OutSmem::Gstage + sub * 2048 + (cell >> 3) * 128 + (cell & 7) * 16;
       const size_t o = (size_t)row * a.G + g0;
-      // rolled on purpose: two genes per trip keep the hot loop inside the instruction cache
+      // rolled on purpose: kU genes per trip keep the hot loop inside the instruction cache
+      constexpr int kU = 2;
 #pragma unroll 1
-      for (int j = 0; j < 8; j += 2) {
-        float va[2], vb[2], vl[2] = {0.f, 0.f};
-        tmem_ld2(tb + j, va);
-        tmem_ld2(tb + 32 + j, vb);
-        if (ZI) tmem_ld2(tb + 64 + j, vl);
+      for (int j = 0; j < 8; j += kU) {
+        float va[kU], vb[kU], vl[kU];
+        tmem_ldn<kU>(tb + j, va);
+        tmem_ldn<kU>(tb + 32 + j, vb);
+        if (ZI) tmem_ldn<kU>(tb + 64 + j, vl);
         tmem_ld_wait();
-        const float x2[2] = {xs[j * kEpiThreads], xs[(j + 1) * kEpiThreads]};
-        uint32_t pa = 0, pb = 0, pl = 0;
+        float x2[kU];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kU; ++u) x2[u] = xs[(j + u) * kEpiThreads];
+        float ga2[kU], gb2[kU], gl2[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
           const bool ok = row_ok && (g0 + j + u) < a.G;
           const float ra = va[u] + bias_s[j + u];
           const float rb = vb[u] + bias_s[32 + j + u];
@@ -329,22 +332,23 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           }
           llk_acc += ok ? e.llk : 0.f;
           if (TRAIN) {
-            float g_a = ok ? fminf(fmaxf(e.ga, -60000.f), 60000.f) : 0.f;
-            float g_b = ok ? fminf(fmaxf(e.gb, -60000.f), 60000.f) : 0.f;
-            float g_l = (ok && ZI) ? e.gl : 0.f;
-            pa |= (uint32_t)__half_as_ushort(__float2half_rn(g_a)) << (16 * u);
-            pb |= (uint32_t)__half_as_ushort(__float2half_rn(g_b)) << (16 * u);
-            pl |= (uint32_t)__half_as_ushort(__float2half_rn(g_l)) << (16 * u);
+            ga2[u] = ok ? e.ga : 0.f; gb2[u] = ok ? e.gb : 0.f; gl2[u] = (ok && ZI) ? e.gl : 0.f;
           } else if (ok) {
             if (a.out_mean) a.out_mean[o + j + u] = e.mu;
             if (a.out_disp) a.out_disp[o + j + u] = e.th;
             if (ZI && a.out_pi) a.out_pi[o + j + u] = pi;
           }
         }
-        if (TRAIN) {
-          *reinterpret_cast<uint32_t*>(gt + 0 * 4 * 2048 + j * 2) = pa;
-          *reinterpret_cast<uint32_t*>(gt + 1 * 4 * 2048 + j * 2) = pb;
-          if (ZI) *reinterpret_cast<uint32_t*>(gt + 2 * 4 * 2048 + j * 2) = pl;
+        if (TRAIN) {   // two genes -> one packed fp16x2 word per head (|g| is clamped into fp16 range; sigmoids need no clamp)
+          const float lim16 = 60000.f;
+#pragma unroll
+          for (int u = 0; u < kU; u += 2) {
+            __half2 ha = __floats2half2_rn(fminf(fmaxf(ga2[u], -lim16), lim16), fminf(fmaxf(ga2[u + 1], -lim16), lim16));
+            __half2 hb = __floats2half2_rn(fminf(fmaxf(gb2[u], -lim16), lim16), fminf(fmaxf(gb2[u + 1], -lim16), lim16));
+            *reinterpret_cast<__half2*>(gt + 0 * 4 * 2048 + (j + u) * 2) = ha;
+            *reinterpret_cast<__half2*>(gt + 1 * 4 * 2048 + (j + u) * 2) = hb;
+            if (ZI) *reinterpret_cast<__half2*>(gt + 2 * 4 * 2048 + (j + u) * 2) = __floats2half2_rn(gl2[u], gl2[u + 1]);
+          }
         }
       }
       tc_fence_before();
