@@ -156,7 +156,7 @@ def main():
 
   from sisua_b200 import config as C
   have_tc = os.path.exists(os.path.join(ROOT, "sisua_b200", "csrc", "kernels_tc.cuh"))
-  mode = a.gemm_mode if a.gemm_mode >= 0 else (C.GEMM_TC_3XTF32 if have_tc else C.GEMM_FP32_UNFUSED)
+  mode = a.gemm_mode if a.gemm_mode >= 0 else (C.GEMM_TC_3XFP16 if have_tc else C.GEMM_FP32_UNFUSED)
   cfg = C.make_step_config("vae", n_genes=a.genes, n_latent=LATENT, gemm_mode=mode, max_batch=a.batch)
   base = {"metric": "train cells/sec (ZINB-VAE step)", "unit": "cells/s", "n_gpus": a.gpus, "steps": a.steps,
           "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -204,12 +204,14 @@ def main():
   loss = torch.empty((1,), device=dev)
   step_no = [0]
 
+  from sisua_b200.distributed import OverlappedAllReduce
+  reducer = OverlappedAllReduce(eng)
+
   def one_step(xb):
     step_no[0] += 1
     eng.train_step(xb, eps_z=eps_pool[step_no[0] % 16], terms=terms, loss=loss, seed=rank, step=step_no[0])
-    if world > 1:
-      dist.all_reduce(eng.grads)
-    eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=1.0 / world, t=step_no[0])
+    scale = reducer()        # output-head gradients are reduced under the rest of the backward pass
+    eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=scale, t=step_no[0])
 
   def sync_all():
     if world > 1:
@@ -259,7 +261,7 @@ def main():
       for i in range(n):
         step_no[0] += 1
         losses.append(pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
-                                allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None))
+                                allreduce=(lambda g: reducer()) if world > 1 else None))
       return pipe.flush(losses)
     run(3)
     sync_all()
@@ -311,7 +313,7 @@ def main():
     out = dict(base)
     out.update({
         "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss,
-        "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 3xTF32 fused", 2: "tcgen05 TF32 fused"}[mode],
+        "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 fused (3xFP16 compensated forward, fp16 gradient GEMMs)"}[mode],
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(x_bytes + B * LATENT * 4),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,

@@ -25,7 +25,8 @@ enum { SISUA_XDIST_ZINBD = 0, SISUA_XDIST_NBD = 1 };
 enum { SISUA_YDIST_NB = 0, SISUA_YDIST_NBD = 1 };
 enum { SISUA_ACT_SOFTPLUS = 0, SISUA_ACT_SOFTPLUS1 = 1, SISUA_ACT_SOFTPLUS_P1 = 2, SISUA_ACT_EXP = 3,
        SISUA_ACT_IDENTITY = 4 };
-enum { SISUA_GEMM_FP32_UNFUSED = 0, SISUA_GEMM_TC_3XTF32 = 1, SISUA_GEMM_TC_TF32 = 2 };
+enum { SISUA_GEMM_FP32_UNFUSED = 0,   /* CUDA-core fp32 GEMMs, decoder output materialised (cross-check path) */
+       SISUA_GEMM_TC_3XFP16 = 1 };    /* fused tcgen05 kernels: 3xFP16 compensated forward, fp16 gradient GEMMs */
 
 /* Everything the step needs to know; built on the host from RVmeta / NetConf / configs/base.yaml
  * (sisua/train.py:71-106).  Field-for-field identical to sisua_b200.config.StepConfig. */
@@ -106,6 +107,11 @@ int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float ep
 const float* sisua_debug_buffer(sisua_handle h, const char* name);
 
 int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
+
+/* Multi-GPU overlap hook: the caller's cudaEvent_t (NULL clears) is recorded on the step's stream as soon as the
+ * gradients of the output heads (out.W, out.b — about 3/4 of the gradient bytes) are final, so their all-reduce can
+ * run on another stream under the remaining backward pass. */
+int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event);
 
 /* Host pipelines ship integer count matrices over PCIe as uint16 (half the bytes of the reference's float32
  * storage, sisua/data/utils.py:427-431); this widens n values to the fp32 layout the step consumes. */

@@ -80,6 +80,7 @@ struct sisua_model {
   uint64_t drop_seed = 0;
   uint32_t drop_step = 0;
   long long train_calls = 0;
+  cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
   // optional per-section device timing (CUDA events on the caller's stream)
   bool profiling = false;
@@ -183,12 +184,12 @@ static void build_layout(sisua_model* h) {
     h->dec[i].w_off = add(p + ".W", H, H, H, 0); h->dec[i].ldw = H; h->dec[i].Kin = H;
     add_norm(p, h->dec[i]);
   }
-  const int nheads = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
-  h->NO = nheads * G;
-  h->out_w = add("out.W", h->NO, H, H, 0);
-  h->out_b = add("out.b", h->NO, 0, h->NO, 1);
   h->y_w = h->y_b = -1;
   if (P > 0) { h->y_w = add("y.W", 2 * P, H, H, 0); h->y_b = add("y.b", 2 * P, 0, 2 * P, 1); }
+  const int nheads = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  h->NO = nheads * G;
+  h->out_w = add("out.W", h->NO, H, H, 0);     // last: one contiguous early-ready all-reduce bucket
+  h->out_b = add("out.b", h->NO, 0, h->NO, 1);
   h->total_floats = off;
   // BN indices follow config.py:bn_layer_names (enc, encl, dec)
   for (auto& L : h->enc) L.bn_index = bn ? bn_counter++ : -1;
@@ -396,6 +397,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   if (c.max_batch < 1) SET_ERR(h, SISUA_ERR_INVALID, "max_batch must be positive");
   for (float r : {c.input_dropout, c.enc_dropout, c.dec_dropout, c.encl_dropout})
     if (r < 0.f || r >= 1.f) SET_ERR(h, SISUA_ERR_INVALID, "dropout rates must be in [0, 1)");
+  if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED && c.gemm_mode != SISUA_GEMM_TC_3XFP16) SET_ERR(h, SISUA_ERR_INVALID, "unknown gemm_mode %d", c.gemm_mode);
 #ifndef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "library built without the tcgen05 kernels");
 #endif
@@ -703,6 +705,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     }
     int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi);
     if (rc != SISUA_OK) return rc;
+    if (training && h->ev_out_grads) CUDA_OK(h, cudaEventRecord(h->ev_out_grads, st));
     out_done = true;
   }
 #endif
@@ -830,6 +833,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     col_sum_kernel<<<g, 256, 0, st>>>(h->OUT, h->NO, R, h->NO, rows_per_block, h->Gd + h->out_b);
     launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->OUT, h->NO, 1, h->P + h->out_w, H, 1, h->dD, H, nullptr, R, H, h->NO, true);
     LAUNCH_OK(h, "output-layer backward");
+    if (h->ev_out_grads) CUDA_OK(h, cudaEventRecord(h->ev_out_grads, st));
     sec_end(h, st, SEC_OUT_HEADS);
   }
   // ---- decoder stack, latent, encoder stack(s)
@@ -981,6 +985,15 @@ extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, floa
   ++h->launches;
   unpack_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, (long long)n);
   LAUNCH_OK(h, "unpack_u16_kernel");
+  return SISUA_OK;
+}
+
+// Multi-GPU overlap hook: `cuda_event` (a cudaEvent_t owned by the caller, or NULL to clear) is recorded on the
+// step's stream as soon as the gradients of the output heads (out.W, out.b: ~3/4 of all gradient bytes) are final,
+// so the host can start their all-reduce on another stream while the rest of the backward pass runs.
+extern "C" int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event) {
+  if (!h) return SISUA_ERR_INVALID;
+  h->ev_out_grads = (cudaEvent_t)cuda_event;
   return SISUA_OK;
 }
 

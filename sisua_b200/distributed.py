@@ -44,3 +44,33 @@ def broadcast_parameters(*tensors: torch.Tensor, src: int = 0) -> None:
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
     for t in tensors:
       dist.broadcast(t, src=src)
+
+
+class OverlappedAllReduce:
+  """Two-bucket gradient all-reduce: bucket 0 (output heads, ~3/4 of the bytes) starts on a side stream as soon as
+  the step signals it is final and runs under the rest of the backward pass; bucket 1 (everything else) follows
+  the step.  Same collective order on every rank (bucket 0 then bucket 1)."""
+
+  def __init__(self, engine):
+    self.eng = engine
+    self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if self.enabled:
+      self.event, (self.b0, self.e0) = engine.enable_grad_overlap()
+      self.side = torch.cuda.Stream(device=engine.device)
+
+  def __call__(self) -> float:
+    """Call right after train_step has been enqueued. Returns the gradient scale for adam_step."""
+    if not self.enabled:
+      return 1.0
+    g = self.eng.grads
+    main = torch.cuda.current_stream(self.eng.device)
+    self.side.wait_event(self.event)
+    with torch.cuda.stream(self.side):
+      w0 = dist.all_reduce(g[self.b0:self.e0], async_op=True)
+    w1 = dist.all_reduce(g[:self.b0], async_op=True)
+    w2 = dist.all_reduce(g[self.e0:], async_op=True) if self.e0 < g.numel() else None   # empty: the heads are laid out last
+    w0.wait(); w1.wait()
+    if w2 is not None:
+      w2.wait()
+    main.wait_stream(self.side)
+    return 1.0 / dist.get_world_size()

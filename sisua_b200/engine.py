@@ -144,6 +144,18 @@ class Engine:
     with torch.cuda.device(self.device):
       self._check(self.lib.sisua_unpack_counts_u16(self.handle, _ptr(src_u16), _ptr(dst_f32), src_u16.numel(), self._stream()))
 
+  def enable_grad_overlap(self):
+    """Returns (event, (begin, end)): `event` fires inside train_step once grads[begin:end] (the output heads) are
+    final; see distributed.OverlappedAllReduce."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(self.device))      # forces creation of the underlying cudaEvent_t
+    self._check(self.lib.sisua_set_grad_ready_event(self.handle, ctypes.c_void_p(ev.cuda_event)))
+    self._grad_event = ev
+    ents = {e.name: e for e in self.entries}
+    begin = ents["out.W"].offset
+    end = self.total if self.entries[-1].name == "out.b" else ents["out.b"].offset + ents["out.b"].size
+    return ev, (begin, end)
+
   SECTIONS = ("enc_first", "mid_fwd", "out_heads", "mid_bwd", "enc_first_bwd", "adam")
 
   def launch_count(self) -> int:

@@ -120,7 +120,7 @@ class SingleCellModel:
     self.alpha = float(kwargs.pop("alpha", 10.0))
     self.name = name or type(self).__name__
     self._device_index = int(kwargs.pop("device", torch.cuda.current_device() if torch.cuda.is_available() else 0))
-    self._gemm_mode = int(kwargs.pop("gemm_mode", C.GEMM_FP32_UNFUSED))
+    self._gemm_mode = int(kwargs.pop("gemm_mode", C.GEMM_TC_3XFP16))
     self._seed = int(kwargs.pop("seed", 8))
     self._max_batch = int(kwargs.pop("max_batch", 8192))
     self._cfg_overrides = {k: kwargs.pop(k) for k in list(kwargs) if k in (

@@ -16,7 +16,7 @@ def _header():
 def test_library_exports_every_declared_symbol():
   build.build()
   L = _lib.load()
-  names = set(re.findall(r"\b(sisua_[a-z_]+)\s*\(", _header()))
+  names = set(re.findall(r"\b(sisua_[a-z0-9_]+)\s*\(", _header()))
   assert {"sisua_create", "sisua_train_step", "sisua_infer", "sisua_adam_step"} <= names
   for n in names:
     assert hasattr(L, n), n

@@ -32,7 +32,7 @@ def test_oracle_reproduces_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XTF32])
+@pytest.mark.parametrize("mode", [C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XFP16])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_matches_golden(name, mode):
   from sisua_b200.engine import Engine

@@ -29,7 +29,7 @@ def _close(a, b, rtol=RTOL, atol=0.0, what=""):
 
 
 MODELS = [("vae", {}), ("scvi", {}), ("dca", {}), ("sisua", dict(n_proteins=10))]
-MODES = [C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XTF32]
+MODES = [C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XFP16]
 
 
 def _setup(model, kw, G, B, mode, seed=0, trained_moving=True, **cfgkw):
