@@ -126,6 +126,22 @@ static void sec_end(sisua_model* h, cudaStream_t st, int id) {
     if (_e != cudaSuccess) SET_ERR(h, SISUA_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
   } while (0)
 
+
+// Launch with Programmatic Dependent Launch: the kernel may be scheduled while its predecessor on the stream is
+// still running; every kernel launched this way executes `griddepcontrol.wait` (pdl_wait()) before it touches
+// anything a predecessor produced, so only its launch latency and parameter-only prologue overlap.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static long long align64(long long n) { return (n + 63) / 64 * 64; }
 
 // ---- parameter table: must agree with sisua_b200/config.py:param_layout -------------------------
@@ -554,7 +570,7 @@ static void launch_dense_fwd(sisua_model* h, cudaStream_t st, const float* A_in,
                              const float* W, int ldw, const float* bias, int Nout, float* A_out, int ldo, int R,
                              double* out_sum = nullptr) {
   ++h->launches;
-  dense_fwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseFwdSmem, st>>>(A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R, out_sum,
+  launch_pdl(dense_fwd_kernel, dim3(mid_grid(h, R)), dim3(kMidThreads), kDenseFwdSmem, st, A_in, lda, Kin, ns, W, ldw, bias, Nout, A_out, ldo, R, out_sum,
                                                                    out_sum ? out_sum + kH : nullptr);
 }
 
@@ -562,7 +578,7 @@ static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, in
   double* s = h->stats + (size_t)L.stat_index * 4 * kH;
   int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
   ++h->launches;
-  col_stats_kernel<<<grid, 256, 0, st>>>(L.A, L.lda, R, kH, s, s + kH);
+  launch_pdl(col_stats_kernel, dim3(grid), dim3(256), 0, st, L.A, L.lda, R, kH, s, s + kH);
 }
 
 // hidden stack forward: layer 0's pre-activation is already in L[0].A; leaves the last layer's
@@ -590,7 +606,7 @@ static int init_dD(sisua_model* h, cudaStream_t st, int R) {
     a.ns_in = raw_norm(); a.W = h->P + h->y_w; a.ldw = H; a.dW = h->Gd + h->y_w; a.db = h->Gd + h->y_b;
     a.dIn = h->dD; a.ldi = H; a.accumulate_dIn = 0; a.R = R;
     ++h->launches;
-    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
+    launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, R)), dim3(kMidThreads), kDenseBwdSmem, st, a);
     LAUNCH_OK(h, "protein head backward");
   } else {
     CUDA_OK(h, cudaMemsetAsync(h->dD, 0, (size_t)R * H * sizeof(float), st));
@@ -662,7 +678,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     }
     a.B = B; a.S = S; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
     ++h->launches;
-    latent_fwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    launch_pdl(latent_fwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, a);
     LAUNCH_OK(h, "latent_fwd_kernel");
   }
   // ---- decoder
@@ -674,7 +690,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   stack_forward(h, st, h->dec, training, R, true);
   NormSpec ns_d = make_norm(h, h->dec.back(), training, R);
   ++h->launches;
-  norm_relu_kernel<<<std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms)), 256, 0, st>>>(
+  launch_pdl(norm_relu_kernel, dim3(std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms))), dim3(256), 0, st, 
       h->dec.back().A, h->dec.back().lda, ns_d, h->D, R);
   LAUNCH_OK(h, "decoder stack");
   // ---- protein head (before the output layer so dD can be initialised by its backward)
@@ -688,7 +704,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     a.upstream = -c.alpha / (float)R;
     a.mask_scale = c.mask_norm == 1 ? h->mask_scale : nullptr;
     ++h->launches;
-    yhead_kernel<<<(R + 127) / 128, 128, 0, st>>>(a);
+    launch_pdl(yhead_kernel, dim3((R + 127) / 128), dim3(128), 0, st, a);
     LAUNCH_OK(h, "yhead_kernel");
   } else {
     CUDA_OK(h, cudaMemsetAsync(terms + (size_t)2 * R, 0, (size_t)R * sizeof(float), st));
@@ -732,7 +748,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     a.terms = terms; a.mask = P > 0 ? mask : nullptr; a.mask_scale = (P > 0 && c.mask_norm == 1) ? h->mask_scale : nullptr;
     a.R = R; a.B = B; a.alpha = c.alpha; a.beta = c.beta; a.loss = loss;
     ++h->launches;
-    elbo_kernel<<<std::max(1, std::min((R + 255) / 256, h->num_sms)), 256, 0, st>>>(a);
+    launch_pdl(elbo_kernel, dim3(std::max(1, std::min((R + 255) / 256, h->num_sms))), dim3(256), 0, st, a);
     LAUNCH_OK(h, "elbo_kernel");
   }
   if (training && c.batchnorm) {
@@ -747,7 +763,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     for (auto& L : h->encl) reg(L, B);
     for (auto& L : h->dec) reg(L, R);
     ++h->launches;
-    bn_moving_update_kernel<<<h->n_bn, kH, 0, st>>>(mu, h->moving, c.bn_momentum);
+    launch_pdl(bn_moving_update_kernel, dim3(h->n_bn), dim3(kH), 0, st, mu, h->moving, c.bn_momentum);
     LAUNCH_OK(h, "bn_moving_update_kernel");
   }
   return SISUA_OK;
@@ -771,7 +787,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
       float* dbeta = h->Gd + L.b_off;
       int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
       ++h->launches;
-      bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
+      launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
     }
     DenseBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -793,7 +809,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
       a.dA = dA0; a.ldda = ld_dA0;
     }
     ++h->launches;
-    dense_bwd_kernel<<<mid_grid(h, R), kMidThreads, kDenseBwdSmem, st>>>(a);
+    launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, R)), dim3(kMidThreads), kDenseBwdSmem, st, a);
     LAUNCH_OK(h, "hidden backward");
     dH = dH_next;
   }
@@ -850,7 +866,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     }
     a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
     ++h->launches;
-    latent_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(a);
+    launch_pdl(latent_bwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, a);
     LAUNCH_OK(h, "latent_bwd_kernel");
   }
   {
@@ -864,7 +880,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.prev_sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
     a.prev_dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr; a.prev_dbeta = h->Gd + L.b_off;
     ++h->launches;
-    dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
+    launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kDenseBwdSmem, st, a);
     LAUNCH_OK(h, "latent projection backward");
     rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0, true);
     if (rc != SISUA_OK) return rc;
@@ -879,7 +895,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.prev_sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
     a.prev_dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr; a.prev_dbeta = h->Gd + L.b_off;
     ++h->launches;
-    dense_bwd_kernel<<<mid_grid(h, B), kMidThreads, kDenseBwdSmem, st>>>(a);
+    launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kDenseBwdSmem, st, a);
     LAUNCH_OK(h, "library projection backward");
     rc = stack_backward(h, st, h->encl, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1 + H, h->ld0, true);
     if (rc != SISUA_OK) return rc;

@@ -307,6 +307,11 @@ __device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, u
   return j == 0 ? m.x : (j == 1 ? m.y : (j == 2 ? m.z : m.w));
 }
 
+// Programmatic dependent launch (sm_90+): let the next kernel on the stream be scheduled early / wait until every
+// predecessor grid has completed and flushed.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // warp / block reductions -------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

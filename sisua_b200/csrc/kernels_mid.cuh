@@ -55,6 +55,8 @@ __device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc
 __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ A, int lda, int R, int ncols,
                                                         double* __restrict__ sum, double* __restrict__ sumsq) {
   __shared__ double s1[256], s2[256];
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int groups = 256 / ncols;                    // ncols in {64,128}
   int c = threadIdx.x % ncols, grp = threadIdx.x / ncols;
   double a1 = 0.0, a2 = 0.0;
@@ -78,6 +80,8 @@ struct MovingUpdateArgs {
   float inv_count[16];
 };
 __global__ void bn_moving_update_kernel(MovingUpdateArgs a, float* __restrict__ moving, float momentum) {
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int l = blockIdx.x, c = threadIdx.x;
   double m = a.sum[l][c] * (double)a.inv_count[l];
   double v = a.sumsq[l][c] * (double)a.inv_count[l] - m * m;
@@ -91,6 +95,8 @@ __global__ void bn_moving_update_kernel(MovingUpdateArgs a, float* __restrict__ 
 __global__ void __launch_bounds__(256) norm_relu_kernel(const float* __restrict__ A, int lda, NormSpec ns,
                                                         float* __restrict__ D, int R) {
   __shared__ float sc[kH], sh[kH];
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   if (threadIdx.x < kH) { float m, r; norm_coeffs(ns, threadIdx.x, sc[threadIdx.x], sh[threadIdx.x], m, r); }
   __syncthreads();
   size_t n = (size_t)R * kH;
@@ -123,6 +129,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
   float* red2 = red1 + 16 * kH;
   double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);   // [2][64] running sums of this CTA
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
   {   // all 16 loads of a thread are issued before any is used (the kernels are latency-, not bandwidth-bound)
     float w[16];
 #pragma unroll
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
       WT[k * kTS + n] = w[j];
     }
   }
+  pdl_wait();   // weights are step-constant; everything below reads what earlier kernels of this step wrote
   if (t < kH) {
     float m, r;
     if (t < Kin) norm_coeffs(ns, t, sc[t], sh[t], m, r); else { sc[t] = 0.f; sh[t] = 0.f; }
@@ -225,6 +233,8 @@ struct LatentArgs {
   int B, S, Z, deterministic, scale_act;
 };
 __global__ void latent_fwd_kernel(LatentArgs a) {
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   int Z = a.Z;
@@ -271,6 +281,8 @@ struct LatentBwdArgs {
   float kl_weight;     // beta / B : d loss / d KL_b
 };
 __global__ void latent_bwd_kernel(LatentBwdArgs a) {
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   int Z = a.Z;
@@ -315,6 +327,8 @@ struct YHeadArgs {
   const float* mask_scale;  // device scalar: 1 (Q3 default) or B / n_labelled
 };
 __global__ void yhead_kernel(YHeadArgs a) {
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.R) return;
   int b = r % a.B, P = a.P;
@@ -363,6 +377,8 @@ struct ElboArgs {
   int R, B; float alpha, beta; float* loss;  // loss: device scalar, pre-zeroed
 };
 __global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   __shared__ float scratch[33];
   float local = 0.f;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.R; r += gridDim.x * blockDim.x) {
@@ -385,6 +401,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
     const float* __restrict__ dH, int ldd, const float* __restrict__ A, int lda, NormSpec ns, int R,
     double* __restrict__ sdy, double* __restrict__ sdyx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ double s1[256], s2[256];
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+  pdl_wait();
   int c = threadIdx.x % kH, grp = threadIdx.x / kH;  // 4 row groups
   float sc, sh, mean, rstd;
   norm_coeffs(ns, c, sc, sh, mean, rstd);
@@ -455,6 +473,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
   const int Nout = a.Nout, Kin = a.Kin;
   const bool has_in = a.A_in != nullptr;
   const bool fuse_prev = a.prev_sdy != nullptr;
+  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
   {
     float w[16];
 #pragma unroll
@@ -468,6 +487,7 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
       Wn[n * kTS + k] = w[j];
     }
   }
+  pdl_wait();
   if (t < kH) {
     if (has_in && t < Kin) norm_coeffs(a.ns_in, t, sc_i[t], sh_i[t], mean_i[t], rstd_i[t]);
     else { sc_i[t] = 0.f; sh_i[t] = 0.f; mean_i[t] = 0.f; rstd_i[t] = 0.f; }
