@@ -299,6 +299,29 @@ def main():
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
   infer_val = world * B * inf_steps / (float(tt.item()) * 1e-3)
 
+  # ---- latency regime: the reference's own minibatch sizes (configs/base.yaml:23 -> 64, tests/test_scalability.py:27 -> 128)
+  small = {}
+  if rank == 0:
+    for sb in (64, 128):
+      cfg_s = cfg.clone(max_batch=sb)
+      eng_s = Engine(cfg_s, local_rank, seed=8)
+      tm, ls = torch.empty((5, sb), device=dev), torch.empty((1,), device=dev)
+      def small_step(i):
+        eng_s.train_step(X[i * sb:(i + 1) * sb], eps_z=eps_pool[i % 16, :sb], terms=tm, loss=ls, seed=0, step=i + 1)
+        eng_s.adam_step(lr=1e-3, clipnorm=100.0, t=i + 1)
+      for i in range(10):
+        small_step(i)
+      torch.cuda.synchronize()
+      ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      n_small = 200
+      ev0.record()
+      for i in range(n_small):
+        small_step(10 + i)
+      ev1.record()
+      torch.cuda.synchronize()
+      small[str(sb)] = {"ms_per_step": ev0.elapsed_time(ev1) / n_small, "cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)}
+      eng_s.close()
+
   if rank == 0:
     hbm_peak, peak_src = measured_peaks()
     # dominant kernel / section from the live CUDA-event profile of the timed region
@@ -320,6 +343,7 @@ def main():
                 "api": "HostTrainPipeline.step (pinned host minibatch, integer counts shipped as uint16 -> H2D -> unpack -> "
                        "sisua_train_step -> sisua_adam_step -> D2H loss)",
                 "fp32_host_value": e2e_f32, "fp32_host_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
+        "latency_regime": {"what": "same train step at the reference's default minibatch sizes (launch-bound)", **small},
         "inference": {"value": infer_val, "unit": "cells/s", "steps": inf_steps,
                       "what": "sisua_infer per minibatch: ELBO terms, latent mean/scale, imputed means [B,G] written to HBM"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
