@@ -196,6 +196,7 @@ def main():
   from sisua_b200.engine import Engine
   eng = Engine(cfg, local_rank, seed=8)
   B, G = a.batch, a.genes
+  a.shard_cells = max(a.shard_cells // B, 4) * B      # whole batches, at least four (each > L2 together)
   X = synth_on_device(a.shard_cells, G, dev, seed=87654321 + rank)
   n_batches = a.shard_cells // B
   gen = torch.Generator(device=dev); gen.manual_seed(8 + rank)
