@@ -245,7 +245,7 @@ def main():
   final_loss = float(loss.item())
 
   # ---- end-to-end arm: host-resident minibatches through the host-buffer entry point
-  from sisua_b200.pipeline import HostTrainPipeline, quantize_counts
+  from sisua_b200.pipeline import CsrBatch, HostTrainPipeline, quantize_counts
   pipe = HostTrainPipeline(eng, B)
   n_host = 6
   host_f32 = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
@@ -278,9 +278,11 @@ def main():
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     return world * B * e2e_steps / (float(tt.item()) * 1e-3)
 
-  e2e_val = e2e_measure(host_u16)
+  host_csr = [CsrBatch(hb.numpy()) for hb in host_f32]
+  e2e_val = e2e_measure(host_csr)
+  e2e_u16 = e2e_measure(host_u16)
   e2e_f32 = e2e_measure(host_f32)
-  x_bytes = host_u16[0].numel() * host_u16[0].element_size()
+  x_bytes = int(np.mean([c.nbytes for c in host_csr]))
 
   # ---- inference: predict-style step (ELBO terms, latent mean/scale, imputed means written to HBM)
   inf_steps = max(10, min(100, a.steps // 6))
@@ -341,9 +343,10 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(x_bytes + B * LATENT * 4),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "HostTrainPipeline.step (pinned host minibatch, integer counts shipped as uint16 -> H2D -> unpack -> "
-                       "sisua_train_step -> sisua_adam_step -> D2H loss)",
-                "fp32_host_value": e2e_f32, "fp32_host_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
+                "api": "HostTrainPipeline.step (pinned host minibatch in CSR form: int32 row pointers + uint16 column ids and "
+                       "counts -> H2D -> sisua_unpack_counts_csr -> sisua_train_step -> sisua_adam_step -> D2H loss)",
+                "dense_u16_host_value": e2e_u16, "dense_u16_h2d_bytes_per_step": int(B * G * 2 + B * LATENT * 4),
+                "dense_fp32_host_value": e2e_f32, "dense_fp32_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
         "latency_regime": {"what": "same train step at the reference's default minibatch sizes (launch-bound)", **small},
         "inference": {"value": infer_val, "unit": "cells/s", "steps": inf_steps,
                       "what": "sisua_infer per minibatch: ELBO terms, latent mean/scale, imputed means [B,G] written to HBM"},

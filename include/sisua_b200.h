@@ -116,6 +116,10 @@ int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event);
 /* Host pipelines ship integer count matrices over PCIe as uint16 (half the bytes of the reference's float32
  * storage, sisua/data/utils.py:427-431); this widens n values to the fp32 layout the step consumes. */
 int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, float* dst, int64_t n, void* stream);
+/* Same for a CSR minibatch: indptr [rows+1] (offsets into cols/vals, starting at 0), uint16 column ids and counts;
+ * dst [rows, n_genes] is fully overwritten. */
+int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals, float* dst,
+                            int rows, void* stream);
 
 /* Measurement hooks for bench.py: kernels launched so far through this handle; per-section device time
  * (CUDA events on the caller's stream). Sections: 0 first encoder layer, 1 mid forward, 2 output heads +

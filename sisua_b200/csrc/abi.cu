@@ -993,6 +993,36 @@ __global__ void __launch_bounds__(256) unpack_u16_kernel(const uint16_t* __restr
   }
 }
 
+// CSR minibatch (row pointers, uint16 column ids, uint16 counts) -> dense fp32 [rows, G]: one warp per row zeroes the
+// row with 16-byte stores, then scatters its non-zeros.  Single-cell count matrices are 70-96 % zeros
+// (description/dataset.html:32,158,188), so this is what the host pipeline ships over PCIe.
+__global__ void __launch_bounds__(256) unpack_csr_kernel(const int* __restrict__ indptr, const uint16_t* __restrict__ cols,
+                                                         const uint16_t* __restrict__ vals, float* __restrict__ dst, int rows, int G) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float* row = dst + (size_t)warp * G;
+  if ((G & 3) == 0) {
+    float4* r4 = reinterpret_cast<float4*>(row);
+    for (int i = lane; i < G / 4; i += 32) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int i = lane; i < G; i += 32) row[i] = 0.f;
+  }
+  __syncwarp();
+  const int b = indptr[warp], e = indptr[warp + 1];
+  for (int i = b + lane; i < e; i += 32) row[cols[i]] = (float)vals[i];
+}
+
+extern "C" int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals,
+                                       float* dst, int rows, void* stream) {
+  if (!h || !indptr || !dst || rows < 0) return SISUA_ERR_INVALID;
+  if (h->cfg.n_genes > 65536) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "unpack_counts_csr: uint16 column ids need n_genes <= 65536");
+  if (reinterpret_cast<uintptr_t>(dst) & 15) SET_ERR(h, SISUA_ERR_INVALID, "unpack_counts_csr: dst must be 16-byte aligned");
+  ++h->launches;
+  unpack_csr_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(indptr, cols, vals, dst, rows, h->cfg.n_genes);
+  LAUNCH_OK(h, "unpack_csr_kernel");
+  return SISUA_OK;
+}
+
 extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, float* dst, int64_t n, void* stream) {
   if (!h || !src || !dst || n < 0) return SISUA_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))

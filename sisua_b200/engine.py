@@ -156,6 +156,15 @@ class Engine:
     end = self.total if self.entries[-1].name == "out.b" else ents["out.b"].offset + ents["out.b"].size
     return ev, (begin, end)
 
+  def unpack_counts_csr(self, indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, dst_f32: torch.Tensor):
+    """device CSR minibatch (int32 indptr [rows+1], 16-bit cols / vals) -> dense fp32 [rows, G] on the current stream."""
+    rows = indptr.numel() - 1
+    if dst_f32.shape != (rows, self.cfg.n_genes) or dst_f32.dtype != torch.float32 or indptr.dtype != torch.int32:
+      raise ValueError("unpack_counts_csr: bad shapes / dtypes")
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_unpack_counts_csr(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst_f32), rows,
+                                                   self._stream()))
+
   SECTIONS = ("enc_first", "mid_fwd", "out_heads", "mid_bwd", "enc_first_bwd", "adam")
 
   def launch_count(self) -> int:

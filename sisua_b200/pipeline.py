@@ -20,6 +20,25 @@ def quantize_counts(X):
   return torch.from_numpy(X.astype(np.uint16).view(np.int16)).pin_memory()
 
 
+class CsrBatch:
+  """Pinned host CSR form of one minibatch of integer counts (built once per dataset / epoch cache)."""
+
+  def __init__(self, X):
+    import numpy as np
+    X = np.ascontiguousarray(X)
+    if X.shape[1] > 65536 or X.min() < 0 or X.max() >= 65536 or not np.array_equal(X, np.rint(X)):
+      raise ValueError("CsrBatch needs non-negative integer counts below 65536 and at most 65536 genes")
+    r, c = np.nonzero(X)
+    self.rows, self.genes = X.shape
+    self.indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(r, minlength=X.shape[0]))]).astype(np.int32)).pin_memory()
+    self.cols = torch.from_numpy(c.astype(np.uint16).view(np.int16)).pin_memory()
+    self.vals = torch.from_numpy(X[r, c].astype(np.uint16).view(np.int16)).pin_memory()
+
+  @property
+  def nbytes(self) -> int:
+    return self.indptr.numel() * 4 + self.cols.numel() * 2 + self.vals.numel() * 2
+
+
 class HostTrainPipeline:
   def __init__(self, eng: Engine, batch: int, depth: int = 2):
     self.eng = eng
@@ -29,6 +48,7 @@ class HostTrainPipeline:
     self.depth = depth
     self.x = [torch.empty((batch, cfg.n_genes), device=dev) for _ in range(depth)]
     self.x16 = [torch.empty((batch, cfg.n_genes), device=dev, dtype=torch.int16) for _ in range(depth)]
+    self.csr = [None] * depth   # (indptr, cols, vals) device buffers, grown on demand
     self.eps = [torch.empty((batch, cfg.n_latent), device=dev) for _ in range(depth)]
     self.ready = [torch.cuda.Event() for _ in range(depth)]
     self.consumed = [torch.cuda.Event() for _ in range(depth)]
@@ -49,15 +69,28 @@ class HostTrainPipeline:
     main = torch.cuda.current_stream(eng.device)
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.consumed[s])
-      packed = x_host.dtype in (torch.int16, torch.uint16)   # integer counts shipped as 16-bit (see quantize_counts)
-      if packed:
+      is_csr = isinstance(x_host, CsrBatch)
+      packed = (not is_csr) and x_host.dtype in (torch.int16, torch.uint16)   # integer counts shipped as 16-bit (see quantize_counts)
+      if is_csr:
+        nnz = x_host.cols.numel()
+        if self.csr[s] is None or self.csr[s][1].numel() < nnz:
+          cap = int(nnz * 1.25) + 1024
+          self.csr[s] = (torch.empty(self.x[s].shape[0] + 1, device=eng.device, dtype=torch.int32),
+                         torch.empty(cap, device=eng.device, dtype=torch.int16), torch.empty(cap, device=eng.device, dtype=torch.int16))
+        ip, cc, vv = self.csr[s]
+        ip.copy_(x_host.indptr, non_blocking=True)
+        cc[:nnz].copy_(x_host.cols, non_blocking=True)
+        vv[:nnz].copy_(x_host.vals, non_blocking=True)
+      elif packed:
         self.x16[s].copy_(x_host.view(torch.int16), non_blocking=True)
       else:
         self.x[s].copy_(x_host, non_blocking=True)
       self.eps[s].copy_(eps_host, non_blocking=True)
       self.ready[s].record(self.copy_stream)
     main.wait_event(self.ready[s])
-    if packed:
+    if is_csr:
+      eng.unpack_counts_csr(self.csr[s][0], self.csr[s][1], self.csr[s][2], self.x[s])
+    elif packed:
       eng.unpack_counts_u16(self.x16[s], self.x[s])
     eng.train_step(self.x[s], eps_z=self.eps[s], terms=self.terms, loss=self.loss, seed=0, step=step)
     self.consumed[s].record(main)

@@ -220,3 +220,24 @@ def test_deep_gene_pipeline(mode):
   reft = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, **batch)
   _close(terms[0].cpu().numpy(), reft["elbo"].numpy(), what="train elbo")
   eng.close()
+
+
+def test_host_count_formats_roundtrip():
+  """uint16 and CSR host formats unpack to exactly the fp32 matrix the step consumes."""
+  from sisua_b200.engine import Engine
+  from sisua_b200.pipeline import CsrBatch, quantize_counts
+  cfg = C.make_step_config("vae", n_genes=558, max_batch=128)
+  eng = Engine(cfg, 0)
+  X = Hh.make_batch(cfg, 100)["x"]
+  dst = torch.full((100, 558), -1.0, device="cuda")
+  q = quantize_counts(X)
+  assert q.dtype == torch.int16
+  eng.unpack_counts_u16(q.cuda(), dst)
+  assert torch.equal(dst.cpu(), torch.from_numpy(X))
+  dst.fill_(-1.0)
+  c = CsrBatch(X)
+  eng.unpack_counts_csr(c.indptr.cuda(), c.cols.cuda(), c.vals.cuda(), dst)
+  assert torch.equal(dst.cpu(), torch.from_numpy(X))
+  assert c.nbytes < X.nbytes
+  assert quantize_counts(X + 0.5).dtype == torch.float32     # non-integer data stays fp32
+  eng.close()
