@@ -74,6 +74,8 @@ struct sisua_model {
   int n_gene_tiles = 0;
   uint8_t* packed_w1 = nullptr;     // pre-packed fp16 (hi | lo) first-layer weight k-blocks
   int n_kblocks = 0;
+  uint8_t* xt_tiles = nullptr;      // fp16 tiles of dropout(log1p(x)) written by the forward first-layer kernel for its backward
+  int xt_kblocks = 0;
   int num_sms = 148;
   int last_train_B = 0;
   // dropout stream of the current training step
@@ -276,6 +278,7 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   memset(&a, 0, sizeof(a));
   a.x = x; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
   a.log_norm = c.log_norm; a.drop = make_drop(h, c.input_dropout, 0u, training);
+  a.xt = training ? h->xt_tiles : nullptr; a.xt_kblocks = h->xt_kblocks;
   const int cell_tiles = (B + 127) / 128;
   int chunks = std::max(1, std::min(h->n_kblocks, h->num_sms / cell_tiles));
   a.kblocks_per_chunk = (h->n_kblocks + chunks - 1) / chunks;
@@ -300,6 +303,7 @@ static int tc_encoder_first_bwd(sisua_model* h, cudaStream_t st, const float* x,
   const sisua_step_config& c = h->cfg;
   tc::EncBwdArgs a;
   memset(&a, 0, sizeof(a));
+  a.xt = h->xt_tiles; a.xt_kblocks = h->xt_kblocks;
   a.x = x; a.delta = h->delta1; a.dW = h->Gd + h->enc[0].w_off; a.B = B; a.G = c.n_genes; a.Gp = h->Gp; a.ld0 = h->ld0;
   a.n_cell_tiles = (B + 127) / 128; a.log_norm = c.log_norm;
   a.in_scale = (float)B; a.out_scale = 1.0f / (float)B;
@@ -328,6 +332,11 @@ static int tc_create(sisua_model* h) {
     h->n_kblocks = (h->cfg.n_genes + 63) / 64;
     int rc0 = ws_alloc(h, &h->packed_w1, (size_t)h->n_kblocks * tc::w1_block_bytes(n0));
     if (rc0 != SISUA_OK) return rc0;
+    h->xt_kblocks = (h->n_kblocks + 1) / 2 * 2;
+    const size_t xt_bytes = (size_t)((h->cfg.max_batch + 127) / 128) * h->xt_kblocks * tc::kXtTile;
+    rc0 = ws_alloc(h, &h->xt_tiles, xt_bytes);
+    if (rc0 != SISUA_OK) return rc0;
+    CUDA_OK(h, cudaMemset(h->xt_tiles, 0, xt_bytes));   // the padding k-block of an odd gene count is never written
     rc0 = n0 == 64 ? tc_enc_attr<64>(h) : tc_enc_attr<128>(h);
     if (rc0 != SISUA_OK) return rc0;
   }
@@ -951,13 +960,11 @@ extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta
   if (!h->P || !h->Gd || !h->M || !h->V) SET_ERR(h, SISUA_ERR_STATE, "adam_step needs params, grads, m and v bound");
   sec_begin(h, st, SEC_ADAM);
   CUDA_OK(h, cudaMemsetAsync(h->sq, 0, kMaxSegments * sizeof(double), st));
-  long long max_seg = 1;
-  for (int i = 0; i < h->seg.n; ++i) max_seg = std::max(max_seg, h->seg.size[i]);
-  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(1024, (max_seg + 1023) / 1024)), h->seg.n);
+  dim3 grid((unsigned)((h->total_floats + kAdamChunk - 1) / kAdamChunk));
   ++h->launches;
-  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->sq, h->d_step, (long long)t, lr, beta1, beta2, h->d_lr_t);
+  grad_sqnorm_kernel<<<grid, 256, 0, st>>>(h->Gd, h->seg, h->total_floats, h->sq, h->d_step, (long long)t, lr, beta1, beta2, h->d_lr_t);
   ++h->launches;
-  adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->sq, h->d_lr_t, beta1, beta2, eps_hat,
+  adam_kernel<<<grid, 256, 0, st>>>(h->P, h->Gd, h->M, h->V, h->seg, h->total_floats, h->sq, h->d_lr_t, beta1, beta2, eps_hat,
                                      clipnorm, h->cfg.clip_mode, grad_scale);
   LAUNCH_OK(h, "adam");
   sec_end(h, st, SEC_ADAM);

@@ -13,10 +13,11 @@
 namespace sisua {
 namespace tc {
 
-constexpr int kEncThreads = 320;        // 8 converter/epilogue warps + MMA warp + loader warp
+constexpr int kEncThreads = 352;        // 8 converter/epilogue warps + MMA warp + weight-loader warp + tile-store warp
 constexpr int kEncConv = 256;
 constexpr int kEncStages = 3;
 constexpr int kPadCS = 2064;            // column-group stride of thread-written tiles: 128 rows * 16 B + 16 B (bank spread)
+constexpr int kXtTile = 8 * kPadCS;     // bytes of one normalised fp16 count tile [128 cells][64 genes] as kept for the backward
 
 __host__ __device__ constexpr int w1_tile_bytes(int n0) { return n0 * 64 * 2; }          // one fp16 copy of a 64-gene k-block
 __host__ __device__ constexpr int w1_block_bytes(int n0) { return 2 * w1_tile_bytes(n0); }   // hi | lo
@@ -107,6 +108,8 @@ struct EncFwdArgs {
   float* A0;                // [B, ld0] pre-activations (zeroed by the caller when k_chunks > 1)
   int B, G, ld0, n_kblocks, kblocks_per_chunk, atomic_out, log_norm;
   DropSpec drop;
+  uint8_t* xt;              // [cell_tiles][xt_kblocks] tiles of dropout(log1p(x)) in fp16, exactly as the MMA consumed them
+  int xt_kblocks;           // (training) kept for the weight-gradient kernel so the counts are not converted twice
 };
 
 template <int N0>
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
   const int nkb = min(a.n_kblocks, kb_begin + a.kblocks_per_chunk) - kb_begin;
   if (nkb <= 0) return;
   if (t == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], 1); }
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], a.xt ? 2 : 1); }
     mbar_init(&bars[9], 1);
     fence_barrier_init();
   }
@@ -149,6 +152,18 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
         bulk_copy_g2s(smem + s * S::stage + 2 * S::A, a.packed + (size_t)(kb_begin + i) * w1_block_bytes(N0), w1_block_bytes(N0),
                       &bars[3 + s]);
       }
+    }
+  } else if (warp == 10) {
+    // ---- tile store: the hi tile of every stage goes to HBM once (TMA bulk store) for enc_first_bwd_kernel ----
+    if (lane == 0 && a.xt) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kEncStages;
+        mbar_wait(&bars[s], (i / kEncStages) & 1);
+        bulk_store_s2g(a.xt + ((size_t)blockIdx.x * a.xt_kblocks + kb_begin + i) * kXtTile, smem + s * S::stage, kXtTile);
+        bulk_store_wait_read();
+        mbar_arrive(&bars[6 + s]);
+      }
+      bulk_store_wait_all();
     }
   } else if (warp == 8) {
     if (lane == 0) {
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
       }
       umma_commit(&bars[9]);
     }
-  } else {
+  } else if (warp < 8) {
     // ---- converter warps: rows r = (t >> 3) + 32 j, column group cg = t & 7 ----
     const int cg = t & 7, rbase = t >> 3;
     float cur[4][8];
@@ -236,7 +251,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
 
 // ------------------------------------------------------------------------------------------------
 struct EncBwdArgs {
-  const float* x;           // [B, G]
+  const uint8_t* xt;        // fp16 tiles written by enc_first_fwd_kernel: [cell_tiles][xt_kblocks][kXtTile]
+  int xt_kblocks;           // even; gene tile g of this kernel = k-blocks 2g, 2g+1 (adjacent in memory)
+  const float* x;           // [B, G] (unused: the normalised counts come from xt)
   const float* delta;       // [B, ld0] d loss / d pre-activation of the first layer
   float* dW;                // [N0, Gp] += delta^T . x~
   int B, G, Gp, ld0, n_cell_tiles, tiles_per_chunk, log_norm;
@@ -265,7 +282,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_bwd_kernel(EncBwdArg
   const int nct = min(a.n_cell_tiles, ct_begin + a.tiles_per_chunk) - ct_begin;
   if (nct <= 0) return;
   if (t == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); }
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8 + 1); mbar_init(&bars[3 + s], 1); }   // 8 converter warps + the TMA arrival
     mbar_init(&bars[6], 1);
     fence_barrier_init();
   }
@@ -291,34 +308,36 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_bwd_kernel(EncBwdArg
       }
       umma_commit(&bars[6]);
     }
+  } else if (warp == 9) {
+    // ---- TMA: two adjacent 64-gene tiles of normalised counts per 128-cell tile = one 33 KB bulk copy ----
+    if (lane == 0) {
+      for (int i = 0; i < nct; ++i) {
+        const int s = i % kEncStages;
+        if (i >= kEncStages) mbar_wait(&bars[3 + s], ((i / kEncStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[s], 2 * kXtTile);
+        bulk_copy_g2s(smem + s * S::stage, a.xt + ((size_t)(ct_begin + i) * a.xt_kblocks + 2 * blockIdx.x) * kXtTile, 2 * kXtTile,
+                      &bars[s]);
+      }
+    }
   } else if (warp < 8) {
-    const int cgx = t & 15, rx = t >> 4;          // x~ tile: 16 column groups, rows rx + 16 j (j < 8)
     const int cgd = t & 7, rd = t >> 3;           // delta tile (per 64 columns): 8 column groups, rows rd + 32 j (j < 4)
     for (int i = 0; i < nct; ++i) {
       const int s = i % kEncStages;
       const int row0 = (ct_begin + i) * 128;
-      float xv[8][8];
+      float dv[N0 / 64][4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rx + 16 * j, g0 + cgx * 8, xv[j]);
+      for (int blk = 0; blk < N0 / 64; ++blk)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load8<true>(a.delta, a.ld0, a.B, a.ld0, row0 + rd + 32 * j, blk * 64 + cgd * 8, dv[blk][j]);
       if (i >= kEncStages) mbar_wait(&bars[3 + s], ((i / kEncStages) - 1) & 1);
-      uint8_t* At = smem + s * S::stage;
-      uint8_t* Bt = At + S::A;
+      uint8_t* Bt = smem + s * S::stage + S::A;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = rx + 16 * j;
-        normalise8(xv[j], a.log_norm, a.drop, row0 + r, g0 + cgx * 8);
-        store8_hi_lo(At, nullptr, cgx * kPadCS + (r >> 3) * 128 + (r & 7) * 16, xv[j]);
-      }
-#pragma unroll
-      for (int blk = 0; blk < N0 / 64; ++blk) {
+      for (int blk = 0; blk < N0 / 64; ++blk)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = rd + 32 * j;
-          float dv[8];
-          load8<true>(a.delta, a.ld0, a.B, a.ld0, row0 + r, blk * 64 + cgd * 8, dv);
-          store8_hi(Bt, (blk * 8 + cgd) * kPadCS + (r >> 3) * 128 + (r & 7) * 16, dv, a.in_scale);
+          store8_hi(Bt, (blk * 8 + cgd) * kPadCS + (r >> 3) * 128 + (r & 7) * 16, dv[blk][j], a.in_scale);
         }
-      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[s]);
