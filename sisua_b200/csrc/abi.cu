@@ -289,11 +289,11 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   dim3 grid(cell_tiles, chunks);
   ++h->launches;
   if (N0 == 64) {
-    if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncThreads, tc::EncFwdSmem<64>::total, st>>>(a);
-    else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncThreads, tc::EncFwdSmem<64>::total, st>>>(a);
+    if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64>::total, st>>>(a);
   } else {
-    if (vec) tc::enc_first_fwd_kernel<128, true><<<grid, tc::kEncThreads, tc::EncFwdSmem<128>::total, st>>>(a);
-    else tc::enc_first_fwd_kernel<128, false><<<grid, tc::kEncThreads, tc::EncFwdSmem<128>::total, st>>>(a);
+    if (vec) tc::enc_first_fwd_kernel<128, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<128, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128>::total, st>>>(a);
   }
   LAUNCH_OK(h, "enc_first_fwd_kernel (tcgen05)");
   return SISUA_OK;

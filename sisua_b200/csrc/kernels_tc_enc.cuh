@@ -13,7 +13,9 @@
 namespace sisua {
 namespace tc {
 
-constexpr int kEncThreads = 352;        // 8 converter/epilogue warps + MMA warp + weight-loader warp + tile-store warp
+constexpr int kEncFwdConvWarps = 16;    // forward: converter / epilogue warps (the conversion, not HBM, is what limits it)
+constexpr int kEncFwdThreads = (kEncFwdConvWarps + 3) * 32;   // + MMA warp + weight-loader warp + tile-store warp
+constexpr int kEncThreads = 320;        // backward: 8 delta-converter / epilogue warps + MMA warp + TMA warp
 constexpr int kEncConv = 256;
 constexpr int kEncStages = 3;
 constexpr int kPadCS = 2064;            // column-group stride of thread-written tiles: 128 rows * 16 B + 16 B (bank spread)
@@ -58,9 +60,11 @@ __device__ __forceinline__ void load8(const float* __restrict__ X, int ld, int r
   if (VEC) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (r < rows) {
+      // volatile asm keeps the loads where they are written: the software prefetch one block ahead must not be
+      // sunk next to the first use by the compiler
       const float* p = X + (size_t)r * ld + c0;
-      if (c0 < cols) a = __ldg(reinterpret_cast<const float4*>(p));
-      if (c0 + 4 < cols) b = __ldg(reinterpret_cast<const float4*>(p + 4));
+      if (c0 < cols) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+      if (c0 + 4 < cols) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
     }
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
@@ -121,7 +125,8 @@ struct EncFwdSmem {
 };
 
 template <int N0, bool VEC>
-__global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArgs a) {
+__global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwdArgs a) {
+  constexpr int CW = kEncFwdConvWarps, kMma = CW, kLoad = CW + 1, kStore = CW + 2;
   extern __shared__ __align__(128) uint8_t smem[];
   using S = EncFwdSmem<N0>;
   constexpr int W_CS = N0 / 8 * 128;
@@ -133,17 +138,17 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
   const int nkb = min(a.n_kblocks, kb_begin + a.kblocks_per_chunk) - kb_begin;
   if (nkb <= 0) return;
   if (t == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], 8); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], a.xt ? 2 : 1); }
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], CW); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], a.xt ? 2 : 1); }
     mbar_init(&bars[9], 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, N0 < 32 ? 32 : N0);
+  if (warp == kMma) tmem_alloc(tmem_slot, N0 < 32 ? 32 : N0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp == kLoad) {
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
         const int s = i % kEncStages;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
                       &bars[3 + s]);
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kStore) {
     // ---- tile store: the hi tile of every stage goes to HBM once (TMA bulk store) for enc_first_bwd_kernel ----
     if (lane == 0 && a.xt) {
       for (int i = 0; i < nkb; ++i) {
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
       }
       bulk_store_wait_all();
     }
-  } else if (warp == 8) {
+  } else if (warp == kMma) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, N0, 0, 0);
       for (int i = 0; i < nkb; ++i) {
@@ -188,26 +193,28 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
       }
       umma_commit(&bars[9]);
     }
-  } else if (warp < 8) {
-    // ---- converter warps: rows r = (t >> 3) + 32 j, column group cg = t & 7 ----
+  } else if (warp < CW) {
+    // ---- converter warps: rows r = (t >> 3) + 64 j, column group cg = t & 7 ----
+    constexpr int RPT = 128 * 8 / (CW * 32);   // (row, column-group) items per thread
+    constexpr int RSTEP = CW * 32 / 8;
     const int cg = t & 7, rbase = t >> 3;
-    float cur[4][8];
+    float cur[RPT][8];
     auto fetch = [&](int i, float (*dst)[8]) {
       const int c0 = (kb_begin + i) * 64 + cg * 8;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rbase + 32 * j, c0, dst[j]);
+      for (int j = 0; j < RPT; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rbase + RSTEP * j, c0, dst[j]);
     };
     fetch(0, cur);
     for (int i = 0; i < nkb; ++i) {
       const int s = i % kEncStages;
-      float nxt[4][8];
+      float nxt[RPT][8];
       if (i + 1 < nkb) fetch(i + 1, nxt);
       if (i >= kEncStages) mbar_wait(&bars[6 + s], ((i / kEncStages) - 1) & 1);
       uint8_t* A1 = smem + s * S::stage;
       const int c0 = (kb_begin + i) * 64 + cg * 8;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = rbase + 32 * j;
+      for (int j = 0; j < RPT; ++j) {
+        const int r = rbase + RSTEP * j;
         normalise8(cur[j], a.log_norm, a.drop, row0 + r, c0);
         store8_hi_lo(A1, A1 + S::A, cg * kPadCS + (r >> 3) * 128 + (r & 7) * 16, cur[j]);
       }
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
       if (lane == 0) mbar_arrive(&bars[s]);
       if (i + 1 < nkb) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < RPT; ++j)
 #pragma unroll
           for (int k = 0; k < 8; ++k) cur[j][k] = nxt[j][k];
       }
@@ -224,9 +231,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
     // ---- epilogue: TMEM -> A0 ----
     mbar_wait(&bars[9], 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter, column slice
     const int row = row0 + q * 32 + lane;
-    constexpr int CPT = N0 / 2;     // columns per thread
+    constexpr int CPT = N0 / (CW / 4);     // columns per thread
 #pragma unroll
     for (int c = 0; c < CPT; c += 16) {
       float v[16];
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) enc_first_fwd_kernel(EncFwdArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, N0 < 32 ? 32 : N0);
+  if (warp == kMma) tmem_dealloc(tmem, N0 < 32 ? 32 : N0);
 }
 
 // ------------------------------------------------------------------------------------------------
