@@ -124,6 +124,15 @@ class ClockSampler:
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_entry(kernel, B, G):
+  p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+  if not os.path.exists(p):
+    return None
+  with open(p) as f:
+    e = json.load(f).get(kernel)
+  return e if e and e.get("batch") == B and e.get("genes") == G else None
+
+
 def ncu_traffic(kernel, B, G):
   """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
   (profiles/r1_traffic.json), if it was taken at this batch / gene count."""
@@ -353,6 +362,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": ncu_traffic(dom, B, G), "peak_source": peak_src,
                      "ms_per_launch": per_step[dom], "share_of_step": per_step[dom] / (ms / a.steps),
+                     "relevant_bound": "special-function (MUFU) and issue rate of the fused likelihood epilogue, not HBM: "
+                                       "see ncu counters (profiles/r1_ncu_out_heads_details.txt)" if dom == "out_heads" else None,
+                     "ncu": ncu_entry(dom, B, G),
                      "sections_ms_per_step": per_step},
     })
     if not a.no_cpu_baseline:

@@ -377,6 +377,18 @@ class SingleCellModel:
     train = _to_data(train)
     valid = _to_data(valid) if valid is not None else None
     eng = self.engine
+    # data parallel over cells when torch.distributed is initialised (one process per GPU): every rank trains on its
+    # contiguous shard, gradients are all-reduced (sisua_b200/distributed.py), replicas stay bit-identical
+    from . import distributed as DP
+    import torch.distributed as dist
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if world > 1:
+      b0, e0 = DP.shard_range(len(train), rank, world)
+      n_common = len(train) // world                      # every rank takes the same number of steps
+      train = train._take(np.arange(b0, b0 + n_common), train.name)
+      DP.broadcast_parameters(eng.params, eng.bn_moving)
+    reducer = DP.OverlappedAllReduce(eng)
     B = int(batch_size)
     if B > eng.cfg.max_batch:
       raise ValueError(f"batch_size {B} > max_batch {eng.cfg.max_batch}")
@@ -389,7 +401,7 @@ class SingleCellModel:
     total = epochs * steps_per_epoch if (max_iter is None or max_iter <= 0) else min(int(max_iter), epochs * steps_per_epoch)
     cache = self._upload(train)
     vcache = self._upload(valid) if valid is not None else None
-    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed if seed is None else int(seed))
+    gen = torch.Generator(device=eng.device); gen.manual_seed((self._seed if seed is None else int(seed)) + 7919 * rank)
     terms = torch.empty((5, B), device=eng.device)
     loss = torch.empty((1,), device=eng.device)
     names = ["loss", "llk_" + self.posteriors[0].name] + (["llk_" + self.posteriors[1].name] if self.labels else []) + \
@@ -410,8 +422,9 @@ class SingleCellModel:
         b = self._batch_tensors(train, idx, cache)
         eps = self._eps(B, None, gen)
         self.step += 1
-        eng.train_step(terms=terms, loss=loss, seed=self._seed, step=self.step, **b, **eps)
-        eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), t=self.step)
+        eng.train_step(terms=terms, loss=loss, seed=self._seed + 7919 * rank, step=self.step, **b, **eps)
+        gscale = reducer()
+        eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), grad_scale=gscale, t=self.step)
         done += 1
         if logging_interval and done % int(logging_interval) == 0:
           log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
@@ -440,6 +453,8 @@ class SingleCellModel:
           print(f"epoch {ep + 1}/{epochs} loss {vals[-1, 0]:.3f}")
       if stop:
         break
+    if world > 1:
+      DP.average_moving_statistics(eng.bn_moving)
     torch.cuda.current_stream(eng.device).synchronize()
     self.is_fitted = True
     return self
