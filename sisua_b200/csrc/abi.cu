@@ -464,6 +464,8 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   CUDA_OK(h, cudaMemset(h->d_step, 0, sizeof(long long)));
   CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseFwdSmem));
+  CUDA_OK(h, cudaFuncSetAttribute(latent_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatentFwdSmem));
+  CUDA_OK(h, cudaFuncSetAttribute(latent_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatentBwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (scvi && c.n_genes * sizeof(float) > 200 * 1024)
@@ -663,7 +665,22 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   sec_end(h, st, SEC_ENC_FIRST);
   sec_begin(h, st, SEC_MID_FWD);
   stack_forward(h, st, h->enc, training, B);
-  {
+  const bool fused_latent = (S == 1);    // one kernel: latent projection -> reparameterisation / KL -> first decoder layer
+  if (fused_latent) {
+    Layer& L = h->enc.back();
+    LatentBlockFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A_enc = L.A; a.lda = L.lda; a.ns_enc = make_norm(h, L, training, B);
+    a.W_lat = h->P + h->lat_w; a.b_lat = h->P + h->lat_b; a.ZP = dca ? Z : 2 * Z;
+    a.eps_z = eps_z; a.W_d0 = h->P + h->dec[0].w_off;
+    a.PL = h->PL; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs; a.kl_z = terms + (size_t)3 * R;
+    a.A_d0 = h->dec[0].A; a.ldd0 = h->dec[0].lda;
+    if (training && h->dec[0].bn_index >= 0) { a.out_sum = h->stats + (size_t)h->dec[0].stat_index * 4 * kH; a.out_sumsq = a.out_sum + kH; }
+    a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
+    ++h->launches;
+    launch_pdl(latent_block_fwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kLatentFwdSmem, st, a);
+    LAUNCH_OK(h, "latent_block_fwd_kernel");
+  } else {
     Layer& L = h->enc.back();
     NormSpec ns = make_norm(h, L, training, B);
     const int ZP = dca ? Z : 2 * Z;
@@ -676,10 +693,10 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     launch_dense_fwd(h, st, L.A, L.lda, H, ns, h->P + h->lib_w, H, h->P + h->lib_b, 2, h->PLIB, 2, B);
   }
   LAUNCH_OK(h, "encoder stack");
-  {
+  if (!fused_latent || scvi) {
     LatentArgs a;
     memset(&a, 0, sizeof(a));
-    a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
+    a.PL = fused_latent ? nullptr : h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
     a.kl_z = terms + (size_t)3 * R; a.kl_l = terms + (size_t)4 * R;
     if (scvi) {
       a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc; a.lib_scale = h->lib_scale;
@@ -689,9 +706,11 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     ++h->launches;
     launch_pdl(latent_fwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, a);
     LAUNCH_OK(h, "latent_fwd_kernel");
+  } else {
+    CUDA_OK(h, cudaMemsetAsync(terms + (size_t)4 * R, 0, (size_t)R * sizeof(float), st));   // kl_l = 0
   }
   // ---- decoder
-  {
+  if (!fused_latent) {
     double* st0 = (training && h->dec[0].bn_index >= 0) ? h->stats + (size_t)h->dec[0].stat_index * 4 * kH : nullptr;
     launch_dense_fwd(h, st, h->Zs, Z, Z, raw_norm(), h->P + h->dec[0].w_off, h->dec[0].ldw, nullptr, H, h->dec[0].A,
                      h->dec[0].lda, R, st0);
@@ -784,9 +803,10 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
 // gradient of layer 0 (delta1) when requested.
 static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& Ls, int R, float* dH_top,
                           const float* in0, int ld_in0, int Kin0, float* dIn0, int ld_dIn0, float* dA0, int ld_dA0,
-                          bool top_reduced = false) {
+                          bool top_reduced = false, int stop_at = 0, float** dH_out = nullptr) {
   float* dH = dH_top;
-  for (int i = (int)Ls.size() - 1; i >= 0; --i) {
+  if (dH_out) *dH_out = dH_top;
+  for (int i = (int)Ls.size() - 1; i >= stop_at; --i) {
     Layer& L = Ls[i];
     NormSpec ns = make_norm(h, L, true, R);
     double* sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH;
@@ -821,6 +841,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
     launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, R)), dim3(kMidThreads), kDenseBwdSmem, st, a);
     LAUNCH_OK(h, "hidden backward");
     dH = dH_next;
+    if (dH_out) *dH_out = dH;
   }
   return SISUA_OK;
 }
@@ -863,35 +884,48 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   }
   // ---- decoder stack, latent, encoder stack(s)
   sec_begin(h, st, SEC_MID_BWD);
-  rc = stack_backward(h, st, h->dec, R, h->dD, h->Zs, Z, Z, h->dZ, Z, nullptr, 0);
+  // decoder units 1.. (unit 0 is handled by the fused latent block below)
+  float* dH_d0 = h->dD;
+  rc = stack_backward(h, st, h->dec, R, h->dD, nullptr, 0, 0, nullptr, 0, nullptr, 0, false, 1, &dH_d0);
   if (rc != SISUA_OK) return rc;
   {
-    LatentBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.dZ = h->dZ; a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.dPL = h->dPL;
-    if (scvi) {
-      a.dLib = h->dLib; a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc;
-      a.lib_scale = h->lib_scale; a.dPLIB = h->dPLIB;
+    Layer& L0 = h->dec[0];
+    Layer& Le = h->enc.back();
+    NormSpec ns0 = make_norm(h, L0, true, R);
+    double* sdy0 = h->stats + (size_t)L0.stat_index * 4 * kH + 2 * kH;
+    if (h->dec.size() == 1) {     // no decoder unit above produced unit 0's norm-backward reductions
+      int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+      ++h->launches;
+      launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, (const float*)dH_d0, kH, (const float*)L0.A, L0.lda, ns0, R, sdy0,
+                 sdy0 + kH, L0.g_off >= 0 ? h->Gd + L0.g_off : (float*)nullptr, h->Gd + L0.b_off);
     }
+    // the staging buffer for dH_enc must differ from dH_d0 (both ping-pong buffers may be in use)
+    float* dH_enc = (dH_d0 == h->dHa) ? h->dHb : h->dHa;
+    LatentBlockBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dH_d0 = dH_d0; a.A_d0 = L0.A; a.ldd0 = L0.lda; a.ns_d0 = ns0; a.sdy = sdy0; a.sdyx = sdy0 + kH;
+    a.W_d0 = h->P + L0.w_off; a.dW_d0 = h->Gd + L0.w_off;
+    a.z = h->Zs; a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale;
+    a.W_lat = h->P + h->lat_w; a.dW_lat = h->Gd + h->lat_w; a.db_lat = h->Gd + h->lat_b; a.ZP = dca ? Z : 2 * Z;
+    a.A_enc = Le.A; a.lda = Le.lda; a.ns_enc = make_norm(h, Le, true, B);
+    a.dH_enc = dH_enc;
+    a.prev_sdy = h->stats + (size_t)Le.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
+    a.prev_dgamma = Le.g_off >= 0 ? h->Gd + Le.g_off : nullptr; a.prev_dbeta = h->Gd + Le.b_off;
     a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
     ++h->launches;
-    launch_pdl(latent_bwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, a);
-    LAUNCH_OK(h, "latent_bwd_kernel");
-  }
-  {
-    const int ZP = dca ? Z : 2 * Z;
-    Layer& L = h->enc.back();
-    DenseBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.out_mode = 0; a.dOut = h->dPL; a.ldd = ZP; a.Nout = ZP; a.A_in = L.A; a.lda_in = L.lda; a.Kin = H;
-    a.ns_in = make_norm(h, L, true, B); a.W = h->P + h->lat_w; a.ldw = H; a.dW = h->Gd + h->lat_w; a.db = h->Gd + h->lat_b;
-    a.dIn = h->dHa; a.ldi = H; a.R = B;
-    a.prev_sdy = h->stats + (size_t)L.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
-    a.prev_dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr; a.prev_dbeta = h->Gd + L.b_off;
-    ++h->launches;
-    launch_pdl(dense_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kDenseBwdSmem, st, a);
-    LAUNCH_OK(h, "latent projection backward");
-    rc = stack_backward(h, st, h->enc, B, h->dHa, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0, true);
+    launch_pdl(latent_block_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kLatentBwdSmem, st, a);
+    LAUNCH_OK(h, "latent_block_bwd_kernel");
+    if (scvi) {     // library latent: d lib -> d(raw loc, raw scale)
+      LatentBwdArgs lb;
+      memset(&lb, 0, sizeof(lb));
+      lb.dLib = h->dLib; lb.PLIB = h->PLIB; lb.eps_l = eps_l; lb.library = library; lb.lib_loc = h->lib_loc;
+      lb.lib_scale = h->lib_scale; lb.dPLIB = h->dPLIB;
+      lb.B = B; lb.Z = Z; lb.deterministic = dca ? 1 : 0; lb.scale_act = c.scale_act; lb.kl_weight = c.beta / (float)B;
+      ++h->launches;
+      launch_pdl(latent_bwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, lb);
+      LAUNCH_OK(h, "latent_bwd_kernel");
+    }
+    rc = stack_backward(h, st, h->enc, B, dH_enc, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0, true);
     if (rc != SISUA_OK) return rc;
   }
   if (scvi) {

@@ -238,7 +238,9 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   int Z = a.Z;
-  if (a.deterministic) {
+  if (!a.PL) {
+    // library-only call (the z path ran in latent_block_fwd_kernel)
+  } else if (a.deterministic) {
     for (int j = 0; j < Z; ++j) {
       float v = fmaxf(a.PL[(size_t)b * Z + j], 0.f);
       a.loc[(size_t)b * Z + j] = v; a.scale[(size_t)b * Z + j] = 0.f; a.z[(size_t)b * Z + j] = v;
@@ -286,7 +288,9 @@ __global__ void latent_bwd_kernel(LatentBwdArgs a) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   int Z = a.Z;
-  if (a.deterministic) {
+  if (!a.dPL) {
+    // library-only call (the z path ran in latent_block_bwd_kernel)
+  } else if (a.deterministic) {
     for (int j = 0; j < Z; ++j)
       a.dPL[(size_t)b * Z + j] = a.PL[(size_t)b * Z + j] > 0.f ? a.dZ[(size_t)b * Z + j] : 0.f;
   } else {
@@ -629,6 +633,345 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
     atomicAdd(&a.prev_sdy[t], dacc[t]);
     atomicAdd(&a.prev_sdyx[t], dacc[kH + t]);
     if (a.ns_in.mode == NORM_BIAS) {
+      atomicAdd(&a.prev_dbeta[t], (float)dacc[t]);
+    } else {
+      atomicAdd(&a.prev_dgamma[t], (float)dacc[kH + t]);
+      atomicAdd(&a.prev_dbeta[t], (float)dacc[t]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused "latent block": the three row-local steps around the reparameterisation in one kernel.
+//   forward : PL = act(A_enc_last) . W_lat^T + b  ->  loc / scale / z = loc + scale*eps / KL  ->  A_dec0 = z . W_dec0^T
+//   backward: BN-bwd(dH_dec0) -> dW_dec0, dz -> d(loc, scale) (+ KL gradient) -> dW_lat, db_lat, dH_enc_last
+// (no BatchNorm sits between them, so nothing but launch latency separated the former three kernels).
+// Same 64-row tiles / 4x4 register blocking as dense_fwd_kernel / dense_bwd_kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_mma(const float* __restrict__ At, const float* __restrict__ Bt, int K, int ty, int tx,
+                                         float (&acc)[4][4]) {
+  for (int k = 0; k < K; ++k) {
+    float4 a4 = *reinterpret_cast<const float4*>(At + k * kTS + 4 * ty);
+    float4 b4 = *reinterpret_cast<const float4*>(Bt + k * kTS + 4 * tx);
+    float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+__device__ __forceinline__ void zero16(float (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+struct LatentBlockFwdArgs {
+  const float* A_enc; int lda; NormSpec ns_enc;     // last encoder unit (pre-activation + norm)
+  const float* W_lat; const float* b_lat; int ZP;   // [ZP, 64]
+  const float* eps_z;                               // [B, Z]
+  const float* W_d0;                                // [64, Z]
+  float* PL; float* loc; float* scale; float* z; float* kl_z;
+  float* A_d0; int ldd0;                            // [B, 64]
+  double* out_sum; double* out_sumsq;               // BN statistics of A_d0 (nullable)
+  int B, Z, deterministic, scale_act;
+};
+constexpr size_t kLatentFwdSmem = (size_t)(5 * kH * kTS + 2 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
+
+__global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlockFwdArgs a) {
+  extern __shared__ __align__(16) float lsm[];
+  float* HT = lsm;                    // [k][r]
+  float* W1T = HT + kH * kTS;         // [k][m]   W_lat transposed
+  float* PLs = W1T + kH * kTS;        // [r][m]
+  float* ZT = PLs + kH * kTS;         // [j][r]
+  float* W2T = ZT + kH * kTS;         // [j][n]   W_dec0 transposed
+  float* sc = W2T + kH * kTS;
+  float* sh = sc + kH;
+  float* red1 = sh + kH;
+  float* red2 = red1 + 16 * kH;
+  double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int Z = a.Z, ZP = a.ZP;
+  {
+    float w1[16], w2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, m = i >> 6, k = i & 63;
+      w1[j] = m < ZP ? __ldg(a.W_lat + (size_t)m * kH + k) : 0.f;       // (m, k)
+      w2[j] = k < Z ? __ldg(a.W_d0 + (size_t)m * Z + k) : 0.f;          // (n = m, j = k)
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, m = i >> 6, k = i & 63;
+      W1T[k * kTS + m] = w1[j];
+      W2T[k * kTS + m] = w2[j];
+    }
+  }
+  pdl_wait();
+  if (t < kH) {
+    float m, r;
+    norm_coeffs(a.ns_enc, t, sc[t], sh[t], m, r);
+    dacc[t] = 0.0; dacc[kH + t] = 0.0;
+  }
+  __syncthreads();
+  for (int r0 = blockIdx.x * kTileR; r0 < a.B; r0 += gridDim.x * kTileR) {
+    {
+      float hv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, k = i & 63;
+        hv[j] = r0 + r < a.B ? a.A_enc[(size_t)(r0 + r) * a.lda + k] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, k = i & 63;
+        float v = 0.f;
+        if (r0 + r < a.B) {
+          v = hv[j] * sc[k] + sh[k];
+          if (a.ns_enc.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_enc.drop, (uint32_t)(r0 + r), (uint32_t)k);
+        }
+        HT[k * kTS + r] = v;
+      }
+    }
+    __syncthreads();
+    float acc[4][4];
+    zero16(acc);
+    tile_mma(HT, W1T, kH, ty, tx, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = 4 * ty + i, m = 4 * tx + j;
+        float v = m < ZP ? acc[i][j] + a.b_lat[m] : 0.f;
+        PLs[r * kTS + m] = v;
+        if (r0 + r < a.B && m < ZP) a.PL[(size_t)(r0 + r) * ZP + m] = v;
+      }
+    __syncthreads();
+    if (t < kTileR) {      // one thread per row: loc / scale / sample / KL
+      const int r = t, b = r0 + r;
+      float kl = 0.f;
+      for (int j = 0; j < Z; ++j) {
+        float mu, sg, zz;
+        if (a.deterministic) {
+          mu = fmaxf(PLs[r * kTS + j], 0.f); sg = 0.f; zz = mu;
+        } else {
+          float dsg;
+          mu = PLs[r * kTS + j];
+          activation(a.scale_act, PLs[r * kTS + Z + j], sg, dsg);
+          zz = b < a.B ? fmaf(sg, a.eps_z[(size_t)b * Z + j], mu) : 0.f;
+          kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
+        }
+        ZT[j * kTS + r] = b < a.B ? zz : 0.f;
+        if (b < a.B) { a.loc[(size_t)b * Z + j] = mu; a.scale[(size_t)b * Z + j] = sg; a.z[(size_t)b * Z + j] = zz; }
+      }
+      if (b < a.B) a.kl_z[b] = a.deterministic ? 0.f : 0.5f * kl;
+    }
+    __syncthreads();
+    zero16(acc);
+    tile_mma(ZT, W2T, Z, ty, tx, acc);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 4 * ty + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r < a.B) {
+          float v = acc[i][j];
+          a.A_d0[(size_t)r * a.ldd0 + 4 * tx + j] = v;
+          cs[j] += v; cq[j] += v * v;
+        }
+      }
+    }
+    if (a.out_sum) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { red1[ty * kH + 4 * tx + j] = cs[j]; red2[ty * kH + 4 * tx + j] = cq[j]; }
+      __syncthreads();
+      if (t < kH) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int y = 0; y < 16; ++y) { s1 += (double)red1[y * kH + t]; s2 += (double)red2[y * kH + t]; }
+        dacc[t] += s1; dacc[kH + t] += s2;
+      }
+    }
+    __syncthreads();
+  }
+  if (a.out_sum && t < kH) { atomicAdd(&a.out_sum[t], dacc[t]); atomicAdd(&a.out_sumsq[t], dacc[kH + t]); }
+}
+
+struct LatentBlockBwdArgs {
+  const float* dH_d0;                       // [B, 64] gradient wrt the activated output of decoder unit 0
+  const float* A_d0; int ldd0; NormSpec ns_d0; const double* sdy; const double* sdyx;
+  const float* W_d0; float* dW_d0;          // [64, Z]
+  const float* z; const float* PL; const float* eps_z; const float* loc; const float* scale;
+  const float* W_lat; float* dW_lat; float* db_lat; int ZP;     // [ZP, 64]
+  const float* A_enc; int lda; NormSpec ns_enc;
+  float* dH_enc;                            // [B, 64] gradient wrt the activated output of the last encoder unit
+  double* prev_sdy; double* prev_sdyx; float* prev_dgamma; float* prev_dbeta;   // its norm-backward reductions
+  int B, Z, deterministic, scale_act;
+  float kl_weight;
+};
+constexpr size_t kLatentBwdSmem = (size_t)(7 * kH * kTS + 11 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
+
+__global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlockBwdArgs a) {
+  extern __shared__ __align__(16) float lsm[];
+  float* Gn = lsm;                    // [r][n]  (stage 1: decoder-0 pre-activation gradient; stage 2: dPL)
+  float* GT = Gn + kH * kTS;          // [n][r]
+  float* Zn = GT + kH * kTS;          // [r][j]  z, later dz
+  float* Wd0n = Zn + kH * kTS;        // [n][j]
+  float* Hn = Wd0n + kH * kTS;        // [r][k]  activated encoder output
+  float* An = Hn + kH * kTS;          // [r][k]  its raw pre-activation
+  float* Wln = An + kH * kTS;         // [m][k]  W_lat
+  float* sc_i = Wln + kH * kTS;
+  float *sh_i = sc_i + kH, *mean_i = sh_i + kH, *rstd_i = mean_i + kH, *sc_o = rstd_i + kH, *sh_o = sc_o + kH,
+        *mean_o = sh_o + kH, *rstd_o = mean_o + kH, *m1 = rstd_o + kH, *m2 = m1 + kH, *gsc = m2 + kH;
+  float* red1 = gsc + kH;
+  float* red2 = red1 + 16 * kH;
+  double* dacc = reinterpret_cast<double*>(red2 + 16 * kH);
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int Z = a.Z, ZP = a.ZP;
+  {
+    float w1[16], w2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      w1[j] = k < Z ? __ldg(a.W_d0 + (size_t)n * Z + k) : 0.f;
+      w2[j] = n < ZP ? __ldg(a.W_lat + (size_t)n * kH + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
+      Wd0n[n * kTS + k] = w1[j];
+      Wln[n * kTS + k] = w2[j];
+    }
+  }
+  pdl_wait();
+  if (t < kH) {
+    norm_coeffs(a.ns_enc, t, sc_i[t], sh_i[t], mean_i[t], rstd_i[t]);
+    norm_coeffs(a.ns_d0, t, sc_o[t], sh_o[t], mean_o[t], rstd_o[t]);
+    if (a.ns_d0.mode == NORM_BN_BATCH) {
+      m1[t] = (float)(a.sdy[t] * (double)a.ns_d0.inv_count);
+      m2[t] = (float)(a.sdyx[t] * (double)a.ns_d0.inv_count);
+    } else { m1[t] = 0.f; m2[t] = 0.f; }
+    gsc[t] = sc_o[t];
+    dacc[t] = 0.0; dacc[kH + t] = 0.0;
+  }
+  __syncthreads();
+  float accW0[4][4], accW1[4][4];
+  zero16(accW0); zero16(accW1);
+  float accb = 0.f;
+  const float in_drop_scale = a.ns_enc.drop.rate > 0.f ? a.ns_enc.drop.scale : 1.f;
+  for (int r0 = blockIdx.x * kTileR; r0 < a.B; r0 += gridDim.x * kTileR) {
+    {
+      float go[16], ao[16], hi[16], zv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, n = i & 63;
+        const bool ok = r0 + r < a.B;
+        go[j] = ok ? a.dH_d0[(size_t)(r0 + r) * kH + n] : 0.f;
+        ao[j] = ok ? a.A_d0[(size_t)(r0 + r) * a.ldd0 + n] : 0.f;
+        hi[j] = ok ? a.A_enc[(size_t)(r0 + r) * a.lda + n] : 0.f;
+        zv[j] = (ok && n < Z) ? a.z[(size_t)(r0 + r) * Z + n] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int i = t + kMidThreads * j, r = i >> 6, n = i & 63;
+        float g = 0.f, v = 0.f;
+        if (r0 + r < a.B) {
+          float av = ao[j];
+          float dy = (av * sc_o[n] + sh_o[n] > 0.f) ? go[j] * dropout_mult(a.ns_d0.drop, (uint32_t)(r0 + r), (uint32_t)n) : 0.f;
+          float xh = (av - mean_o[n]) * rstd_o[n];
+          g = gsc[n] * (dy - m1[n] - xh * m2[n]);
+          v = hi[j] * sc_i[n] + sh_i[n];
+          if (a.ns_enc.mode != NORM_RAW) v = fmaxf(v, 0.f) * dropout_mult(a.ns_enc.drop, (uint32_t)(r0 + r), (uint32_t)n);
+        }
+        Gn[r * kTS + n] = g; GT[n * kTS + r] = g;
+        Hn[r * kTS + n] = v; An[r * kTS + n] = hi[j];
+        Zn[r * kTS + n] = zv[j];
+      }
+    }
+    __syncthreads();
+    // dW_dec0[n][j] += sum_r G[r][n] z[r][j] ;  dz[r][j] = sum_n G[r][n] W_dec0[n][j]
+    tile_mma(Gn, Zn, kTileR, ty, tx, accW0);
+    float dz[4][4];
+    zero16(dz);
+    tile_mma(GT, Wd0n, kH, ty, tx, dz);
+    __syncthreads();                       // everyone is done reading z and G
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Zn[(4 * ty + i) * kTS + 4 * tx + j] = dz[i][j];
+    __syncthreads();
+    // latent backward, one thread per row: dz -> dPL = (d loc | d scale_raw); overwrites G with dPL
+    for (int i = t; i < kTileR * kH; i += kMidThreads) { Gn[(i >> 6) * kTS + (i & 63)] = 0.f; GT[(i & 63) * kTS + (i >> 6)] = 0.f; }
+    __syncthreads();
+    if (t < kTileR) {
+      const int r = t, b = r0 + r;
+      if (b < a.B) {
+        for (int j = 0; j < Z; ++j) {
+          const float dzz = Zn[r * kTS + j];
+          if (a.deterministic) {
+            float g = a.PL[(size_t)b * Z + j] > 0.f ? dzz : 0.f;
+            Gn[r * kTS + j] = g; GT[j * kTS + r] = g;
+          } else {
+            float mu = a.loc[(size_t)b * Z + j], sg = a.scale[(size_t)b * Z + j];
+            float v, dv;
+            activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], v, dv);
+            float dmu = dzz + a.kl_weight * mu;
+            float dsr = (dzz * a.eps_z[(size_t)b * Z + j] + a.kl_weight * (sg - 1.f / sg)) * dv;
+            Gn[r * kTS + j] = dmu; GT[j * kTS + r] = dmu;
+            Gn[r * kTS + Z + j] = dsr; GT[(Z + j) * kTS + r] = dsr;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // dW_lat[m][k] += sum_r dPL[r][m] h[r][k] ; db_lat[m] += sum_r dPL[r][m] ; dH_enc[r][k] = sum_m dPL[r][m] W_lat[m][k]
+    tile_mma(Gn, Hn, kTileR, ty, tx, accW1);
+    if (t < ZP) {
+      for (int r = 0; r < kTileR; ++r) accb += Gn[r * kTS + t];
+    }
+    float dh[4][4];
+    zero16(dh);
+    tile_mma(GT, Wln, ZP, ty, tx, dh);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = 4 * ty + i, r = r0 + rl;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * tx + j;
+        if (r < a.B) {
+          const float v = dh[i][j];
+          a.dH_enc[(size_t)r * kH + k] = v;
+          float dy = Hn[rl * kTS + k] > 0.f ? v * in_drop_scale : 0.f;
+          float xh = (An[rl * kTS + k] - mean_i[k]) * rstd_i[k];
+          cs[j] += dy; cq[j] += dy * xh;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red1[ty * kH + 4 * tx + j] = cs[j]; red2[ty * kH + 4 * tx + j] = cq[j]; }
+    __syncthreads();
+    if (t < kH) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int y = 0; y < 16; ++y) { s1 += (double)red1[y * kH + t]; s2 += (double)red2[y * kH + t]; }
+      dacc[t] += s1; dacc[kH + t] += s2;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = 4 * ty + i, k = 4 * tx + j;
+      if (k < Z) atomicAdd(&a.dW_d0[(size_t)n * Z + k], accW0[i][j]);
+      if (n < ZP) atomicAdd(&a.dW_lat[(size_t)n * kH + k], accW1[i][j]);
+    }
+  if (t < ZP) atomicAdd(&a.db_lat[t], accb);
+  if (t < kH) {
+    atomicAdd(&a.prev_sdy[t], dacc[t]);
+    atomicAdd(&a.prev_sdyx[t], dacc[kH + t]);
+    if (a.ns_enc.mode == NORM_BIAS) {
       atomicAdd(&a.prev_dbeta[t], (float)dacc[t]);
     } else {
       atomicAdd(&a.prev_dgamma[t], (float)dacc[kH + t]);
