@@ -290,7 +290,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // out of line on purpose: it sits behind a `rate > 0` test at every use, and inlining ten Philox rounds into the
 // unrolled tile loaders of the small kernels multiplied their code size (they run once per CTA, so instruction
 // fetch, not arithmetic, is what they wait for)
-__device__ __noinline__ float4 dropout_mult4(const DropSpec& d, uint32_t row, uint32_t col4) {
+__device__ __noinline__ float4 dropout_mult4(DropSpec d, uint32_t row, uint32_t col4) {   // by value: a reference would force the caller's argument struct into local memory
   uint4 r = philox4x32_10(make_uint4(row, col4, d.step, d.stream), make_uint2(d.seed_lo, d.seed_hi));
   const float u = 1.0f / 16777216.0f;
   float4 m;

@@ -12,6 +12,10 @@ constexpr int kH = 64;          // hidden width (single_cell_model.py:78-81)
 constexpr int kTileR = 64;      // rows per CTA tile in the mid kernels
 constexpr int kMidThreads = 256;
 
+// Pointers that arrive inside by-value argument structs are compiled as generic addresses (LD/ST + address-space
+// checks around every atomic); telling the compiler they are global shrinks the code of the once-through kernels.
+#define SISUA_GLOBAL(p) __builtin_assume((p) == nullptr || __isGlobal(p))
+
 enum NormMode : int { NORM_RAW = 0, NORM_BN_BATCH = 1, NORM_BN_MOVING = 2, NORM_BIAS = 3 };
 
 struct NormSpec {
@@ -27,8 +31,11 @@ struct NormSpec {
 };
 
 // per-column affine (h = relu(a*sc + sh)) and the standardisation (xhat = (a - mean)*rstd)
-__device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc, float& sh, float& mean,
-                                            float& rstd) {
+// out of line: double-precision divide / sqrt expand to long instruction sequences, and the small kernels that call
+// this once per CTA are bound by instruction fetch.  Everything by value: handing out references to a kernel's
+// by-value argument struct would force the whole struct into local memory.
+__device__ __noinline__ float4 norm_coeffs4(NormSpec ns, int c) {     // (sc, sh, mean, rstd)
+  float sc, sh, mean, rstd;
   if (ns.mode == NORM_BN_BATCH) {
     double m = ns.sum[c] * (double)ns.inv_count;
     double v = ns.sumsq[c] * (double)ns.inv_count - m * m;
@@ -47,6 +54,11 @@ __device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc
   } else {
     mean = 0.f; rstd = 1.f; sc = 1.f; sh = 0.f;
   }
+  return make_float4(sc, sh, mean, rstd);
+}
+__device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc, float& sh, float& mean, float& rstd) {
+  float4 q = norm_coeffs4(ns, c);
+  sc = q.x; sh = q.y; mean = q.z; rstd = q.w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,6 +473,11 @@ struct DenseBwdArgs {
   double* prev_sdy; double* prev_sdyx; float* prev_dgamma; float* prev_dbeta;
 };
 __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) {
+  SISUA_GLOBAL(a.dOut); SISUA_GLOBAL(a.A_out); SISUA_GLOBAL(a.sdy); SISUA_GLOBAL(a.sdyx); SISUA_GLOBAL(a.A_in); SISUA_GLOBAL(a.W);
+  SISUA_GLOBAL(a.dW); SISUA_GLOBAL(a.db); SISUA_GLOBAL(a.dIn); SISUA_GLOBAL(a.dA); SISUA_GLOBAL(a.prev_sdy); SISUA_GLOBAL(a.prev_sdyx);
+  SISUA_GLOBAL(a.prev_dgamma); SISUA_GLOBAL(a.prev_dbeta);
+  SISUA_GLOBAL(a.ns_out.sum); SISUA_GLOBAL(a.ns_out.sumsq); SISUA_GLOBAL(a.ns_out.gamma); SISUA_GLOBAL(a.ns_out.beta); SISUA_GLOBAL(a.ns_out.moving);
+  SISUA_GLOBAL(a.ns_in.sum); SISUA_GLOBAL(a.ns_in.sumsq); SISUA_GLOBAL(a.ns_in.gamma); SISUA_GLOBAL(a.ns_in.beta); SISUA_GLOBAL(a.ns_in.moving);
   extern __shared__ __align__(16) float dyn_smem[];
   float* Wn = dyn_smem;                 // [n][k]
   float* Hn = Wn + kH * kTS;            // [r][k]   activated input
@@ -680,6 +697,9 @@ struct LatentBlockFwdArgs {
 constexpr size_t kLatentFwdSmem = (size_t)(5 * kH * kTS + 2 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
 
 __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlockFwdArgs a) {
+  SISUA_GLOBAL(a.A_enc); SISUA_GLOBAL(a.W_lat); SISUA_GLOBAL(a.b_lat); SISUA_GLOBAL(a.eps_z); SISUA_GLOBAL(a.W_d0); SISUA_GLOBAL(a.PL);
+  SISUA_GLOBAL(a.loc); SISUA_GLOBAL(a.scale); SISUA_GLOBAL(a.z); SISUA_GLOBAL(a.kl_z); SISUA_GLOBAL(a.A_d0); SISUA_GLOBAL(a.out_sum);
+  SISUA_GLOBAL(a.out_sumsq);
   extern __shared__ __align__(16) float lsm[];
   float* HT = lsm;                    // [k][r]
   float* W1T = HT + kH * kTS;         // [k][m]   W_lat transposed
@@ -813,6 +833,10 @@ struct LatentBlockBwdArgs {
 constexpr size_t kLatentBwdSmem = (size_t)(7 * kH * kTS + 11 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
 
 __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlockBwdArgs a) {
+  SISUA_GLOBAL(a.dH_d0); SISUA_GLOBAL(a.A_d0); SISUA_GLOBAL(a.sdy); SISUA_GLOBAL(a.sdyx); SISUA_GLOBAL(a.W_d0); SISUA_GLOBAL(a.dW_d0);
+  SISUA_GLOBAL(a.z); SISUA_GLOBAL(a.PL); SISUA_GLOBAL(a.eps_z); SISUA_GLOBAL(a.loc); SISUA_GLOBAL(a.scale); SISUA_GLOBAL(a.W_lat);
+  SISUA_GLOBAL(a.dW_lat); SISUA_GLOBAL(a.db_lat); SISUA_GLOBAL(a.A_enc); SISUA_GLOBAL(a.dH_enc); SISUA_GLOBAL(a.prev_sdy);
+  SISUA_GLOBAL(a.prev_sdyx); SISUA_GLOBAL(a.prev_dgamma); SISUA_GLOBAL(a.prev_dbeta);
   extern __shared__ __align__(16) float lsm[];
   float* Gn = lsm;                    // [r][n]  (stage 1: decoder-0 pre-activation gradient; stage 2: dPL)
   float* GT = Gn + kH * kTS;          // [n][r]
