@@ -36,6 +36,8 @@ def parse():
   ap.add_argument("--genes", type=int, default=GENES)
   ap.add_argument("--shard-cells", type=int, default=SHARD_CELLS)
   ap.add_argument("--gemm-mode", type=int, default=-1, help="-1: best available (tcgen05 3xTF32 if built)")
+  ap.add_argument("--input-dropout", type=float, default=0.3,
+                  help="encoder input dropout; 0.3 is the reference class default (single_cell_model.py:78-81)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--cpu-steps", type=int, default=6)
   return ap.parse_args()
@@ -166,12 +168,13 @@ def main():
   from sisua_b200 import config as C
   have_tc = os.path.exists(os.path.join(ROOT, "sisua_b200", "csrc", "kernels_tc.cuh"))
   mode = a.gemm_mode if a.gemm_mode >= 0 else (C.GEMM_TC_3XFP16 if have_tc else C.GEMM_FP32_UNFUSED)
-  cfg = C.make_step_config("vae", n_genes=a.genes, n_latent=LATENT, gemm_mode=mode, max_batch=a.batch)
+  cfg = C.make_step_config("vae", n_genes=a.genes, n_latent=LATENT, gemm_mode=mode, max_batch=a.batch,
+                           input_dropout=a.input_dropout)
   base = {"metric": "train cells/sec (ZINB-VAE step)", "unit": "cells/s", "n_gpus": a.gpus, "steps": a.steps,
           "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
           "data": "synthetic",
           "config": {"workload": workload_name(a), "model": "vae/zinbd", "genes": a.genes, "latent": LATENT,
-                     "hidden": [64, 64], "batch_per_gpu": a.batch, "global_batch": a.batch * a.gpus,
+                     "hidden": [64, 64], "batchnorm": True, "input_dropout": a.input_dropout, "batch_per_gpu": a.batch, "global_batch": a.batch * a.gpus,
                      "parallelism": f"dp{a.gpus} (cells sharded, grads all-reduced)",
                      "l2": "inputs larger than L2: each step streams a fresh minibatch of a >= 1 GB resident shard"}}
 

@@ -31,7 +31,19 @@ def time_train_steps(cfg, params_np, moving_np, batches, steps: int, warmup: int
   for t in range(1, warmup + steps + 1):
     b = batches[(t - 1) % len(batches)]
     t0 = time.perf_counter()
-    O.train_step(cfg, P, mov, m, v, t, b, lr=lr, clipnorm=100.0)
+    drop = None
+    if cfg.input_dropout > 0 or cfg.enc_dropout > 0 or cfg.dec_dropout > 0:   # fresh Bernoulli masks, drawn inside the timed step
+      B = b["x"].shape[0]
+      drop = {}
+      if cfg.input_dropout > 0:
+        drop["input"] = (torch.rand((B, cfg.n_genes)) >= cfg.input_dropout).float()
+      for i in range(cfg.n_enc_layers):
+        if cfg.enc_dropout > 0:
+          drop[f"enc.{i}"] = (torch.rand((B, cfg.n_hidden)) >= cfg.enc_dropout).float()
+      for i in range(cfg.n_dec_layers):
+        if cfg.dec_dropout > 0:
+          drop[f"dec.{i}"] = (torch.rand((B, cfg.n_hidden)) >= cfg.dec_dropout).float()
+    O.train_step(cfg, P, mov, m, v, t, b, lr=lr, clipnorm=100.0, drop=drop)
     dt = time.perf_counter() - t0
     if t > warmup:
       times.append(dt)

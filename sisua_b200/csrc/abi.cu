@@ -818,6 +818,14 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
       ++h->launches;
       launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
     }
+    if (i == 0 && !in0 && !dIn0 && dA0) {   // only the pre-activation gradient is wanted: light element-wise kernel
+      ++h->launches;
+      launch_pdl(bn_bwd_apply_kernel, dim3(std::max(1, std::min((R * (kH / 4) + 255) / 256, 2 * h->num_sms))), dim3(256), 0, st,
+                 (const float*)dH, kH, (const float*)L.A, L.lda, ns, (const double*)sdy, (const double*)sdyx, dA0, ld_dA0, R);
+      LAUNCH_OK(h, "bn_bwd_apply_kernel");
+      if (dH_out) *dH_out = dH;
+      break;
+    }
     DenseBwdArgs a;
     memset(&a, 0, sizeof(a));
     a.out_mode = 1; a.dOut = dH; a.ldd = kH; a.A_out = L.A; a.lda_out = L.lda; a.ns_out = ns; a.sdy = sdy; a.sdyx = sdyx;

@@ -659,6 +659,41 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// norm + ReLU backward only: dA[r][c] = gamma*rstd * (dy - mean(dy) - xhat * mean(dy*xhat)), dy = dH * relu' * dropout.
+// Used for the first encoder unit, whose weight gradient is the big genes x hidden GEMM (enc_first_bwd_kernel).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dH, int ldd, const float* __restrict__ A, int lda,
+                                                           NormSpec ns, const double* __restrict__ sdy,
+                                                           const double* __restrict__ sdyx, float* __restrict__ dA, int ldda, int R) {
+  __shared__ float sc[kH], sh[kH], mean[kH], rstd[kH], m1[kH], m2[kH];
+  pdl_wait();
+  if (threadIdx.x < kH) {
+    const int c = threadIdx.x;
+    float4 q = norm_coeffs4(ns, c);
+    sc[c] = q.x; sh[c] = q.y; mean[c] = q.z; rstd[c] = q.w;
+    const bool bn = ns.mode == NORM_BN_BATCH;
+    m1[c] = bn ? (float)(sdy[c] * (double)ns.inv_count) : 0.f;
+    m2[c] = bn ? (float)(sdyx[c] * (double)ns.inv_count) : 0.f;
+  }
+  __syncthreads();
+  const int n4 = R * (kH / 4);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int r = i / (kH / 4), c0 = (i % (kH / 4)) * 4;
+    const float4 g4 = *reinterpret_cast<const float4*>(dH + (size_t)r * ldd + c0);
+    const float4 a4 = *reinterpret_cast<const float4*>(A + (size_t)r * lda + c0);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      float dy = (av[j] * sc[c] + sh[c] > 0.f) ? gv[j] * dropout_mult(ns.drop, (uint32_t)r, (uint32_t)c) : 0.f;
+      o[j] = sc[c] * (dy - m1[c] - (av[j] - mean[c]) * rstd[c] * m2[c]);
+    }
+    *reinterpret_cast<float4*>(dA + (size_t)r * ldda + c0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused "latent block": the three row-local steps around the reparameterisation in one kernel.
 //   forward : PL = act(A_enc_last) . W_lat^T + b  ->  loc / scale / z = loc + scale*eps / KL  ->  A_dec0 = z . W_dec0^T
 //   backward: BN-bwd(dH_dec0) -> dW_dec0, dz -> d(loc, scale) (+ KL gradient) -> dW_lat, db_lat, dH_enc_last
