@@ -335,6 +335,19 @@ def main():
       ev1.record()
       torch.cuda.synchronize()
       small[str(sb)] = {"ms_per_step": ev0.elapsed_time(ev1) / n_small, "cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)}
+      # the same step replayed as one CUDA graph (what fit() does for batch <= 2048)
+      from sisua_b200.pipeline import GraphedTrainStep
+      gts = GraphedTrainStep(eng_s, sb, lr=1e-3, clipnorm=100.0, seed=0)
+      for i in range(10):
+        gts.step(X[i * sb:(i + 1) * sb], eps_z=eps_pool[i % 16, :sb])
+      torch.cuda.synchronize()
+      ev0.record()
+      for i in range(n_small):
+        gts.step(X[(10 + i) * sb:(11 + i) * sb], eps_z=eps_pool[i % 16, :sb])
+      ev1.record()
+      torch.cuda.synchronize()
+      small[str(sb)].update({"graph_ms_per_step": ev0.elapsed_time(ev1) / n_small,
+                             "graph_cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)})
       eng_s.close()
 
   if rank == 0:

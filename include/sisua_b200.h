@@ -79,8 +79,8 @@ int sisua_bind_buffers(sisua_handle h, float* params, float* grads, float* adam_
  * mask [B] bytes or NULL; eps_z [B,z]; eps_l [B] (scVI).  Outputs: terms [5,B] =
  * (elbo | llk_x | llk_y | kl_z | kl_l), loss [1].  Gradients land in the bound `grads` buffer and
  * BN moving statistics are updated.  Dropout masks (NetConf input_dropout / dropout) are the pure function
- * Philox4x32-10(seed; row, col/4, step, stream) regenerated in forward and backward; step < 0 uses an
- * internal call counter.  The optimiser is a separate call so the host can all-reduce
+ * Philox4x32-10(seed; row, col/8, step, stream), 16 bits per column, regenerated in forward and backward; step < 0 makes the kernels
+ * read the device-side optimiser step counter (+1), so a captured CUDA graph of train_step + adam_step can be replayed.  The optimiser is a separate call so the host can all-reduce
  * `grads` across GPUs in between. */
 int sisua_train_step(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
                      const float* eps_z, const float* eps_l, int B, uint64_t seed, int64_t step, float* terms,
@@ -107,6 +107,9 @@ int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float ep
 const float* sisua_debug_buffer(sisua_handle h, const char* name);
 
 int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
+
+/* Sets the device-side optimiser step counter (t = Adam steps applied so far); synchronises the stream. */
+int sisua_set_step(sisua_handle h, int64_t t, void* stream);
 
 /* Multi-GPU overlap hook: the caller's cudaEvent_t (NULL clears) is recorded on the step's stream as soon as the
  * gradients of the output heads (out.W, out.b — about 3/4 of the gradient bytes) are final, so their all-reduce can

@@ -1,7 +1,7 @@
 """NumPy replica of the product's counter-based dropout masks.  TEST INFRASTRUCTURE ONLY.
 
-The CUDA step draws its dropout masks as Philox4x32-10(key = seed; counter = (row, col // 4, step,
-stream))[col % 4] (sisua_b200/csrc/device_math.cuh: philox4x32_10 / dropout_mult).  Philox is the
+The CUDA step draws its dropout masks from Philox4x32-10(key = seed; counter = (row, col // 8, step,
+stream)), 16 bits per column (sisua_b200/csrc/device_math.cuh: philox4x32_10 / dropout_mult).  Philox is the
 published counter-based generator of Salmon et al. (SC'11); this file restates it so the oracle can
 be fed the very same masks.  Known-answer vectors from the Random123 distribution pin it
 (tests/test_oracle_kat.py)."""
@@ -27,12 +27,16 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def dropout_mask(rows: int, cols: int, rate: float, seed: int, step: int, stream: int) -> np.ndarray:
-  """[rows, cols] array of {0, 1}: 1 = kept."""
-  c4 = (cols + 3) // 4
-  r = np.repeat(np.arange(rows, dtype=np.uint64)[:, None], c4, axis=1)
-  c = np.repeat(np.arange(c4, dtype=np.uint64)[None, :], rows, axis=0)
+  """[rows, cols] array of {0, 1}: 1 = kept.  One Philox call covers 8 consecutive columns: column j of the group
+  takes the (low if j even else high) 16 bits of output word j // 2 and is kept when that is >= floor(rate * 65536)."""
+  c8 = (cols + 7) // 8
+  r = np.repeat(np.arange(rows, dtype=np.uint64)[:, None], c8, axis=1)
+  c = np.repeat(np.arange(c8, dtype=np.uint64)[None, :], rows, axis=0)
   out = philox4x32_10(r, c, np.full_like(r, step & 0xFFFFFFFF), np.full_like(r, stream),
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-  u = np.stack(out, axis=-1).reshape(rows, c4 * 4)[:, :cols]
-  uf = (u >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-  return (uf >= np.float32(rate)).astype(np.float64)
+  w = np.stack(out, axis=-1)                                    # [rows, c8, 4]
+  lo = w & np.uint64(0xFFFF)
+  hi = (w >> np.uint64(16)) & np.uint64(0xFFFF)
+  u = np.stack([lo, hi], axis=-1).reshape(rows, c8 * 8)[:, :cols]   # word-major, low half first
+  thr = np.uint64(int(np.float32(rate) * np.float32(65536.0)))
+  return (u >= thr).astype(np.float64)

@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
-           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_set_step", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -67,6 +67,8 @@ def load():
   L.sisua_set_grad_ready_event.restype = ci
   L.sisua_unpack_counts_csr.argtypes = [vp, vp, vp, vp, vp, ci, vp]
   L.sisua_unpack_counts_csr.restype = ci
+  L.sisua_set_step.argtypes = [vp, ctypes.c_int64, vp]
+  L.sisua_set_step.restype = ci
   L.sisua_last_error.argtypes = [vp]
   L.sisua_last_error.restype = ctypes.c_char_p
   L.sisua_version.argtypes = []

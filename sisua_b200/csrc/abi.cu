@@ -81,6 +81,7 @@ struct sisua_model {
   // dropout stream of the current training step
   uint64_t drop_seed = 0;
   uint32_t drop_step = 0;
+  bool drop_step_on_device = false;   // step < 0: kernels read the device-side optimiser counter (graph replays)
   long long train_calls = 0;
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
@@ -243,6 +244,7 @@ static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool trai
     d.rate = rate; d.scale = 1.0f / (1.0f - rate);
     d.seed_lo = (uint32_t)(h->drop_seed & 0xffffffffu); d.seed_hi = (uint32_t)(h->drop_seed >> 32);
     d.step = h->drop_step; d.stream = stream;
+    d.step_ptr = h->drop_step_on_device ? h->d_step : nullptr;
   }
   return d;
 }
@@ -564,7 +566,7 @@ static int mid_grid(sisua_model* h, int rows) { return std::max(1, std::min((row
 template <int AOP, int BOP>
 static void launch_sgemm(sisua_model* h, cudaStream_t st, const float* A, long long a_rs, long long a_cs, const float* B,
                          long long b_rs, long long b_cs, float* C, long long ldc, const float* bias, int M, int N, int K,
-                         bool accumulate, DropSpec drop = DropSpec{0.f, 1.f, 0u, 0u, 0u, 0u}) {
+                         bool accumulate, DropSpec drop = DropSpec{0.f, 1.f, 0u, 0u, 0u, 0u, nullptr}) {
   int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
   int want = (2 * h->num_sms + tiles - 1) / tiles;
   int max_splits = std::max(1, K / 256);
@@ -862,7 +864,8 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   const sisua_step_config& c = h->cfg;
   h->train_calls += 1;
   h->drop_seed = seed;
-  h->drop_step = (uint32_t)(step >= 0 ? step : h->train_calls);
+  h->drop_step = (uint32_t)(step >= 0 ? step : 0);
+  h->drop_step_on_device = step < 0;
   if (!h->Gd) SET_ERR(h, SISUA_ERR_STATE, "train_step needs a bound grads buffer");
   if (c.batchnorm && B < 2) SET_ERR(h, SISUA_ERR_INVALID, "training-mode batch norm needs B >= 2");
   const int H = kH, G = c.n_genes, Z = c.n_latent, P = c.n_proteins, R = B;
@@ -1089,6 +1092,15 @@ extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, floa
 extern "C" int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event) {
   if (!h) return SISUA_ERR_INVALID;
   h->ev_out_grads = (cudaEvent_t)cuda_event;
+  return SISUA_OK;
+}
+
+// device-side optimiser step counter (number of Adam steps applied so far)
+extern "C" int sisua_set_step(sisua_handle h, int64_t t, void* stream) {
+  if (!h || t < 0) return SISUA_ERR_INVALID;
+  long long v = (long long)t;
+  CUDA_OK(h, cudaMemcpyAsync(h->d_step, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CUDA_OK(h, cudaStreamSynchronize((cudaStream_t)stream));     // `v` lives on this stack frame
   return SISUA_OK;
 }
 

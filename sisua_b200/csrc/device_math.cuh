@@ -265,13 +265,14 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
   return o;
 }
 
-// Counter-based dropout masks (Philox4x32-10): mask(seed, step, stream, row, col) is a pure function, so
+// Counter-based dropout masks (Philox4x32-10, counter = (row, col/8, step, stream)): a pure function, so
 // forward and backward regenerate it instead of storing it, and the CPU oracle reproduces it exactly
 // (oracle/philox.py).  stream 0 = input dropout on log1p(x); stream 1+u = hidden unit u.
 struct DropSpec {
   float rate;      // 0 -> disabled
   float scale;     // 1 / (1 - rate)
   uint32_t seed_lo, seed_hi, step, stream;
+  const long long* step_ptr;   // non-null: step = *step_ptr + 1 (device-side optimiser step counter; CUDA-graph replays)
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -286,25 +287,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// four consecutive columns (col4*4 .. col4*4+3) of one row: multiplier is 0 or 1/(1-rate)
-// out of line on purpose: it sits behind a `rate > 0` test at every use, and inlining ten Philox rounds into the
-// unrolled tile loaders of the small kernels multiplied their code size (they run once per CTA, so instruction
-// fetch, not arithmetic, is what they wait for)
-__device__ __noinline__ float4 dropout_mult4(DropSpec d, uint32_t row, uint32_t col4) {   // by value: a reference would force the caller's argument struct into local memory
-  uint4 r = philox4x32_10(make_uint4(row, col4, d.step, d.stream), make_uint2(d.seed_lo, d.seed_hi));
-  const float u = 1.0f / 16777216.0f;
-  float4 m;
-  m.x = ((r.x >> 8) * u >= d.rate) ? d.scale : 0.f;
-  m.y = ((r.y >> 8) * u >= d.rate) ? d.scale : 0.f;
-  m.z = ((r.z >> 8) * u >= d.rate) ? d.scale : 0.f;
-  m.w = ((r.w >> 8) * u >= d.rate) ? d.scale : 0.f;
-  return m;
+// EIGHT consecutive columns (col8*8 .. col8*8+7) of one row from ONE Philox call: column j of the group uses the
+// (j&1 ? high : low) 16 bits of output word j>>1 as a uniform in [0, 65536); kept when it is >= floor(rate * 65536).
+// multiplier is 0 or 1/(1-rate).  Out of line on purpose: it sits behind a `rate > 0` test at every use, and inlining
+// ten Philox rounds into the unrolled tile loaders of the small kernels multiplied their code size.  The spec is
+// passed by value: a reference would force the caller's by-value argument struct into local memory.
+struct DropMult8 { float m[8]; };
+__device__ __noinline__ DropMult8 dropout_mult8(DropSpec d, uint32_t row, uint32_t col8) {
+  const uint32_t step = d.step_ptr ? (uint32_t)(*d.step_ptr + 1) : d.step;
+  uint4 r = philox4x32_10(make_uint4(row, col8, step, d.stream), make_uint2(d.seed_lo, d.seed_hi));
+  const uint32_t thr = (uint32_t)(d.rate * 65536.0f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  DropMult8 o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t u = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+    o.m[j] = u >= thr ? d.scale : 0.f;
+  }
+  return o;
 }
 __device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, uint32_t col) {
   if (d.rate <= 0.f) return 1.f;
-  float4 m = dropout_mult4(d, row, col >> 2);
-  uint32_t j = col & 3u;
-  return j == 0 ? m.x : (j == 1 ? m.y : (j == 2 ? m.z : m.w));
+  DropMult8 m = dropout_mult8(d, row, col >> 3);
+  return m.m[col & 7u];
 }
 
 // Programmatic dependent launch (sm_90+): let the next kernel on the stream be scheduled early / wait until every

@@ -79,10 +79,10 @@ __device__ __forceinline__ void normalise8(float* v, int log_norm, const DropSpe
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = log1p_count(v[j]);
   }
-  if (drop.rate > 0.f) {
-    float4 m0 = dropout_mult4(drop, (uint32_t)row, (uint32_t)(c0 >> 2));
-    float4 m1 = dropout_mult4(drop, (uint32_t)row, (uint32_t)(c0 >> 2) + 1u);
-    v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+  if (drop.rate > 0.f) {     // c0 is a multiple of 8: one Philox call masks the whole group
+    DropMult8 m = dropout_mult8(drop, (uint32_t)row, (uint32_t)(c0 >> 3));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= m.m[j];
   }
 }
 

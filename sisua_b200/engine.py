@@ -165,6 +165,12 @@ class Engine:
       self._check(self.lib.sisua_unpack_counts_csr(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst_f32), rows,
                                                    self._stream()))
 
+  def reset_step_counter(self, t: int):
+    """Sets the device-side optimiser step counter (what `adam_step(t=0)` and `train_step(step=-1)` follow)."""
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_set_step(self.handle, int(t), self._stream()))
+    self.step_count = int(t)
+
   SECTIONS = ("enc_first", "mid_fwd", "out_heads", "mid_bwd", "enc_first_bwd", "adam")
 
   def launch_count(self) -> int:

@@ -357,6 +357,7 @@ class SingleCellModel:
           shuffle=True,
           seed=None,
           verbose=False,
+          cuda_graph='auto',
           **kwargs):
     r""" `Model.compile` + `Model.fit` of the reference in one call
     (single_cell_model.py:213-236; keys of configs/base.yaml:45-62). """
@@ -409,6 +410,14 @@ class SingleCellModel:
     for n in names:
       self.train_history.setdefault(n, [])
       self.valid_history.setdefault(n, [])
+    # launch-bound regime (the reference's minibatch sizes): replay the whole step as one CUDA graph
+    use_graph = (cuda_graph is True) or (cuda_graph == 'auto' and B <= 2048 and world == 1)
+    graphed = None
+    if use_graph:
+      from .pipeline import GraphedTrainStep
+      eng.reset_step_counter(self.step)
+      graphed = GraphedTrainStep(eng, B, lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), seed=self._seed)
+      terms, loss = graphed.terms, graphed.loss
     best, patience, done = float("inf"), 0, 0
     log_buf: List[torch.Tensor] = []
     stop = False
@@ -422,9 +431,13 @@ class SingleCellModel:
         b = self._batch_tensors(train, idx, cache)
         eps = self._eps(B, None, gen)
         self.step += 1
-        eng.train_step(terms=terms, loss=loss, seed=self._seed + 7919 * rank, step=self.step, **b, **eps)
-        gscale = reducer()
-        eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), grad_scale=gscale, t=self.step)
+        if graphed is not None:
+          graphed.step(b["x"], eps_z=eps.get("eps_z"), eps_l=eps.get("eps_l"), library=b.get("library"), y=b.get("y"),
+                       mask=b.get("mask"))
+        else:
+          eng.train_step(terms=terms, loss=loss, seed=self._seed + 7919 * rank, step=self.step, **b, **eps)
+          gscale = reducer()
+          eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), grad_scale=gscale, t=self.step)
         done += 1
         if logging_interval and done % int(logging_interval) == 0:
           log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))

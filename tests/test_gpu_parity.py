@@ -241,3 +241,30 @@ def test_host_count_formats_roundtrip():
   assert c.nbytes < X.nbytes
   assert quantize_counts(X + 0.5).dtype == torch.float32     # non-integer data stays fp32
   eng.close()
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+  """train_step + adam_step captured as a CUDA graph and replayed == the same steps launched eagerly (dropout on:
+  masks and Adam's bias correction must follow the device-side step counter, not values baked into the graph)."""
+  from sisua_b200.engine import Engine
+  from sisua_b200.pipeline import GraphedTrainStep
+  cfg = C.make_step_config("vae", n_genes=200, max_batch=64, input_dropout=0.3, enc_dropout=0.1)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  g = GraphedTrainStep(a, 64, lr=1e-3, clipnorm=100.0, seed=5)
+  losses_a, losses_b = [], []
+  for t in range(1, 5):
+    batch = Hh.make_batch(cfg, 64, seed=t)
+    x = torch.from_numpy(batch["x"]).cuda(); e = torch.from_numpy(batch["eps_z"]).cuda()
+    _, la = g.step(x, eps_z=e)
+    losses_a.append(float(la))
+    _, lb = b.train_step(x, eps_z=e, seed=5, step=t)
+    b.adam_step(lr=1e-3, clipnorm=100.0, t=t)
+    losses_b.append(float(lb))
+  np.testing.assert_allclose(losses_a, losses_b, rtol=1e-6)
+  # float atomics make gradient sums order-dependent at 1e-7; Adam's normalised first steps amplify that up to ~lr
+  assert float((a.params - b.params).abs().max()) <= 4e-3 and float((a.params - b.params).abs().mean()) <= 1e-5
+  assert losses_a[0] != losses_a[1]
+  a.close(); b.close()
