@@ -61,7 +61,7 @@ struct sisua_model {
   // workspace
   std::vector<void*> allocs;
   float *A0 = nullptr, *PL = nullptr, *loc = nullptr, *scale = nullptr, *Zs = nullptr, *PLIB = nullptr,
-        *lib_loc = nullptr, *lib_scale = nullptr, *lib = nullptr, *dZ = nullptr, *dPL = nullptr, *dPLIB = nullptr,
+        *lib_loc = nullptr, *lib_scale = nullptr, *lib = nullptr, *dPLIB = nullptr,
         *dLib = nullptr, *D = nullptr, *dD = nullptr, *dHa = nullptr, *dHb = nullptr, *delta1 = nullptr,
         *PY = nullptr, *dPY = nullptr, *OUT = nullptr, *mask_scale = nullptr, *scratch_terms = nullptr;
   int n_units = 0;             // hidden units (layers) that own a statistics slot
@@ -77,12 +77,10 @@ struct sisua_model {
   uint8_t* xt_tiles = nullptr;      // fp16 tiles of dropout(log1p(x)) written by the forward first-layer kernel for its backward
   int xt_kblocks = 0;
   int num_sms = 148;
-  int last_train_B = 0;
   // dropout stream of the current training step
   uint64_t drop_seed = 0;
   uint32_t drop_step = 0;
   bool drop_step_on_device = false;   // step < 0: kernels read the device-side optimiser counter (graph replays)
-  long long train_calls = 0;
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
   // optional per-section device timing (CUDA events on the caller's stream)
@@ -306,7 +304,7 @@ static int tc_encoder_first_bwd(sisua_model* h, cudaStream_t st, const float* x,
   tc::EncBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.xt = h->xt_tiles; a.xt_kblocks = h->xt_kblocks;
-  a.x = x; a.delta = h->delta1; a.dW = h->Gd + h->enc[0].w_off; a.B = B; a.G = c.n_genes; a.Gp = h->Gp; a.ld0 = h->ld0;
+  a.delta = h->delta1; a.dW = h->Gd + h->enc[0].w_off; a.B = B; a.G = c.n_genes; a.Gp = h->Gp; a.ld0 = h->ld0;
   a.n_cell_tiles = (B + 127) / 128; a.log_norm = c.log_norm;
   a.in_scale = (float)B; a.out_scale = 1.0f / (float)B;
   a.drop = make_drop(h, c.input_dropout, 0u, true);
@@ -449,7 +447,6 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   }
   for (int i = 0; i < c.n_dec_layers; ++i) { WS(h->dec[i].A, R * H); h->dec[i].lda = H; }
   WS(h->PL, R * 2 * Z); WS(h->loc, R * Z); WS(h->scale, R * Z); WS(h->Zs, R * Z);
-  WS(h->dZ, R * Z); WS(h->dPL, R * 2 * Z);
   if (scvi) {
     WS(h->PLIB, R * 2); WS(h->lib_loc, R); WS(h->lib_scale, R); WS(h->lib, R); WS(h->dPLIB, R * 2); WS(h->dLib, R);
   }
@@ -862,7 +859,6 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   if (!h) return SISUA_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const sisua_step_config& c = h->cfg;
-  h->train_calls += 1;
   h->drop_seed = seed;
   h->drop_step = (uint32_t)(step >= 0 ? step : 0);
   h->drop_step_on_device = step < 0;
@@ -873,7 +869,6 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   CUDA_OK(h, cudaMemsetAsync(h->Gd, 0, (size_t)h->total_floats * sizeof(float), st));
   int rc = forward_common(h, st, true, x, y, library, mask, eps_z, eps_l, B, 1, terms, loss, nullptr, nullptr, nullptr, nullptr);
   if (rc != SISUA_OK) return rc;
-  h->last_train_B = B;
   bool out_done = false;
 #ifdef SISUA_WITH_TC
   if (tc_heads_enabled(h)) out_done = true;   // fused kernel already produced dW_out, db_out, dD
@@ -927,14 +922,14 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     launch_pdl(latent_block_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kLatentBwdSmem, st, a);
     LAUNCH_OK(h, "latent_block_bwd_kernel");
     if (scvi) {     // library latent: d lib -> d(raw loc, raw scale)
-      LatentBwdArgs lb;
+      LibraryBwdArgs lb;
       memset(&lb, 0, sizeof(lb));
       lb.dLib = h->dLib; lb.PLIB = h->PLIB; lb.eps_l = eps_l; lb.library = library; lb.lib_loc = h->lib_loc;
       lb.lib_scale = h->lib_scale; lb.dPLIB = h->dPLIB;
-      lb.B = B; lb.Z = Z; lb.deterministic = dca ? 1 : 0; lb.scale_act = c.scale_act; lb.kl_weight = c.beta / (float)B;
+      lb.B = B; lb.scale_act = c.scale_act; lb.kl_weight = c.beta / (float)B;
       ++h->launches;
-      launch_pdl(latent_bwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, lb);
-      LAUNCH_OK(h, "latent_bwd_kernel");
+      launch_pdl(library_bwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, lb);
+      LAUNCH_OK(h, "library_bwd_kernel");
     }
     rc = stack_backward(h, st, h->enc, B, dH_enc, nullptr, 0, 0, nullptr, 0, h->delta1, h->ld0, true);
     if (rc != SISUA_OK) return rc;

@@ -284,48 +284,26 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
   }
 }
 
-struct LatentBwdArgs {
-  const float* dZ;     // [B, Z] d loss / d z
-  const float* PL; const float* eps_z; const float* loc; const float* scale;
-  float* dPL;          // [B, ZP]
-  const float* dLib;   // [B] d loss / d sampled log-library (scVI) or null
+// backward of the scVI library latent (row a10): d loss / d sampled log-library -> d(raw loc, raw scale), KL included.
+// (The z latent's backward lives in latent_block_bwd_kernel.)
+struct LibraryBwdArgs {
+  const float* dLib;   // [B] d loss / d sampled log-library
   const float* PLIB; const float* eps_l; const float* library; const float* lib_loc; const float* lib_scale;
   float* dPLIB;        // [B, 2]
-  int B, Z, deterministic, scale_act;
+  int B, scale_act;
   float kl_weight;     // beta / B : d loss / d KL_b
 };
-__global__ void latent_bwd_kernel(LatentBwdArgs a) {
-  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
+__global__ void library_bwd_kernel(LibraryBwdArgs a) {
   pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
-  int Z = a.Z;
-  if (!a.dPL) {
-    // library-only call (the z path ran in latent_block_bwd_kernel)
-  } else if (a.deterministic) {
-    for (int j = 0; j < Z; ++j)
-      a.dPL[(size_t)b * Z + j] = a.PL[(size_t)b * Z + j] > 0.f ? a.dZ[(size_t)b * Z + j] : 0.f;
-  } else {
-    for (int j = 0; j < Z; ++j) {
-      float dz = a.dZ[(size_t)b * Z + j];
-      float mu = a.loc[(size_t)b * Z + j], sg = a.scale[(size_t)b * Z + j];
-      float v, dv;
-      activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], v, dv);
-      float dmu = dz + a.kl_weight * mu;
-      float dsg = dz * a.eps_z[(size_t)b * Z + j] + a.kl_weight * (sg - 1.f / sg);
-      a.dPL[(size_t)b * 2 * Z + j] = dmu;
-      a.dPL[(size_t)b * 2 * Z + Z + j] = dsg * dv;
-    }
-  }
-  if (a.dPLIB) {
-    float dl = a.dLib[b];
-    float mu = a.lib_loc[b], sg = a.lib_scale[b];
-    float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
-    float v, dv;
-    activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], v, dv);
-    a.dPLIB[(size_t)b * 2] = dl + a.kl_weight * (mu - pm) / pv;
-    a.dPLIB[(size_t)b * 2 + 1] = (dl * a.eps_l[b] + a.kl_weight * (sg / pv - 1.f / sg)) * dv;
-  }
+  float dl = a.dLib[b];
+  float mu = a.lib_loc[b], sg = a.lib_scale[b];
+  float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
+  float v, dv;
+  activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], v, dv);
+  a.dPLIB[(size_t)b * 2] = dl + a.kl_weight * (mu - pm) / pv;
+  a.dPLIB[(size_t)b * 2 + 1] = (dl * a.eps_l[b] + a.kl_weight * (sg / pv - 1.f / sg)) * dv;
 }
 
 // ------------------------------------------------------------------------------------------

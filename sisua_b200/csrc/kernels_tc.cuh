@@ -22,7 +22,6 @@ constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kOutThreads = kEpiThreads + 64;   // 16 epilogue warps + MMA warp + loader warp
 constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1;
-constexpr int kXPad = 36;              // floats per x-tile row (32 + 4: conflict-free float4 access)
 constexpr int kTmemCols = 512;
 constexpr int kTmemDD = 192, kTmemDWO = 256, kDwoCols = 80;
 
@@ -84,9 +83,7 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
   static constexpr int dA2 = dA1 + 10 * 2048;            // [128][64] fp16
   static constexpr int W0 = dA2 + 8 * 2048;              // 2 stages of packed tiles
   __host__ __device__ static constexpr int Wstage(int nh) { return packed_tile_stride(nh); }
-  __host__ __device__ static constexpr int X0(int nh) { return W0 + 2 * Wstage(nh); }
-  __host__ __device__ static constexpr int Xstage() { return kCellTile * kXPad * 4; }
-  __host__ __device__ static constexpr int G0(int nh) { return X0(nh); }                     // [128][128] fp16 (train)
+  __host__ __device__ static constexpr int G0(int nh) { return W0 + 2 * Wstage(nh); }       // [128][128] fp16 x 2 stages (train)
   static constexpr int Gstage = 16 * 2048;                                                 // two G stages when training
   __host__ __device__ static constexpr int XS(int nh, bool train) { return G0(nh) + (train ? 2 * Gstage : 0); }   // [8][512] count stash
   __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 8 * kEpiThreads * 4; }

@@ -1,10 +1,11 @@
 // tcgen05 kernels for the genes x hidden contraction of the first encoder layer:
 //   forward   A0[cells, N0] = dropout(log1p(x))[cells, G] . W1[N0, G]^T        (N0 = 64, or 128 for scVI's two encoders)
 //   backward  dW1[N0, G]   = delta1[cells, N0]^T . dropout(log1p(x))[cells, G]
-// Both stream the count matrix once from HBM (they are HBM-bound: 4 G bytes per cell against 2*G*N0 flops):
-// converter warps load coalesced fp32 rows, apply log1p (+ Philox input dropout), split to fp16 (hi, lo) and
-// write canonical no-swizzle UMMA tiles; one thread issues the MMAs, accumulators stay in TMEM for the whole
-// K (forward) or cell (backward) range.  Forward products are 3xFP16 compensated (fp32-grade pre-activations);
+// The forward streams the count matrix once from HBM (4 G bytes per cell against 2*G*N0 flops): converter warps load
+// coalesced fp32 rows, apply log1p (+ Philox input dropout), split to fp16 (hi, lo) and write canonical no-swizzle UMMA
+// tiles; one thread issues the MMAs, accumulators stay in TMEM for the whole K range; the hi tiles are also written
+// back to HBM with TMA bulk stores, and the backward re-loads them with TMA (read MN-major) instead of converting the
+// counts a second time.  Forward products are 3xFP16 compensated (fp32-grade pre-activations);
 // the weight gradient uses single fp16 operands with delta1 pre-scaled by the batch size to stay in range.
 #pragma once
 #include "device_math.cuh"
@@ -16,7 +17,6 @@ namespace tc {
 constexpr int kEncFwdConvWarps = 16;    // forward: converter / epilogue warps (the conversion, not HBM, is what limits it)
 constexpr int kEncFwdThreads = (kEncFwdConvWarps + 3) * 32;   // + MMA warp + weight-loader warp + tile-store warp
 constexpr int kEncThreads = 320;        // backward: 8 delta-converter / epilogue warps + MMA warp + TMA warp
-constexpr int kEncConv = 256;
 constexpr int kEncStages = 3;
 constexpr int kPadCS = 2064;            // column-group stride of thread-written tiles: 128 rows * 16 B + 16 B (bank spread)
 constexpr int kXtTile = 8 * kPadCS;     // bytes of one normalised fp16 count tile [128 cells][64 genes] as kept for the backward
@@ -260,7 +260,6 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
 struct EncBwdArgs {
   const uint8_t* xt;        // fp16 tiles written by enc_first_fwd_kernel: [cell_tiles][xt_kblocks][kXtTile]
   int xt_kblocks;           // even; gene tile g of this kernel = k-blocks 2g, 2g+1 (adjacent in memory)
-  const float* x;           // [B, G] (unused: the normalised counts come from xt)
   const float* delta;       // [B, ld0] d loss / d pre-activation of the first layer
   float* dW;                // [N0, Gp] += delta^T . x~
   int B, G, Gp, ld0, n_cell_tiles, tiles_per_chunk, log_norm;
