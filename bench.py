@@ -262,7 +262,7 @@ def main():
   n_host = 6
   host_f32 = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
   for i, hb in enumerate(host_f32):
-    hb.copy_(X[i * B:(i + 1) * B])
+    hb.copy_(X[(i % n_batches) * B:(i % n_batches + 1) * B])
   # what the public host pipeline ships for integer count matrices (done once per dataset, outside the step)
   host_u16 = [quantize_counts(hb.numpy()) for hb in host_f32]
   host_eps = [torch.randn((B, LATENT)).pin_memory() for _ in range(n_host)]
@@ -322,7 +322,8 @@ def main():
       eng_s = Engine(cfg_s, local_rank, seed=8)
       tm, ls = torch.empty((5, sb), device=dev), torch.empty((1,), device=dev)
       def small_step(i):
-        eng_s.train_step(X[i * sb:(i + 1) * sb], eps_z=eps_pool[i % 16, :sb], terms=tm, loss=ls, seed=0, step=i + 1)
+        k = i % (a.shard_cells // sb)
+        eng_s.train_step(X[k * sb:(k + 1) * sb], eps_z=eps_pool[i % 16, :sb], terms=tm, loss=ls, seed=0, step=i + 1)
         eng_s.adam_step(lr=1e-3, clipnorm=100.0, t=i + 1)
       for i in range(10):
         small_step(i)
@@ -339,11 +340,12 @@ def main():
       from sisua_b200.pipeline import GraphedTrainStep
       gts = GraphedTrainStep(eng_s, sb, lr=1e-3, clipnorm=100.0, seed=0)
       for i in range(10):
-        gts.step(X[i * sb:(i + 1) * sb], eps_z=eps_pool[i % 16, :sb])
+        gts.step(X[(i % (a.shard_cells // sb)) * sb:(i % (a.shard_cells // sb) + 1) * sb], eps_z=eps_pool[i % 16, :sb])
       torch.cuda.synchronize()
       ev0.record()
       for i in range(n_small):
-        gts.step(X[(10 + i) * sb:(11 + i) * sb], eps_z=eps_pool[i % 16, :sb])
+        k = (10 + i) % (a.shard_cells // sb)
+        gts.step(X[k * sb:(k + 1) * sb], eps_z=eps_pool[i % 16, :sb])
       ev1.record()
       torch.cuda.synchronize()
       small[str(sb)].update({"graph_ms_per_step": ev0.elapsed_time(ev1) / n_small,

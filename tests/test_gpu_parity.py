@@ -268,3 +268,28 @@ def test_cuda_graph_replay_equals_eager_steps():
   assert float((a.params - b.params).abs().max()) <= 4e-3 and float((a.params - b.params).abs().mean()) <= 1e-5
   assert losses_a[0] != losses_a[1]
   a.close(); b.close()
+
+
+@pytest.mark.parametrize("model,kw,G,B", [("vae", {}, 1, 2), ("vae", {}, 7, 3), ("sisua", dict(n_proteins=1), 33, 5),
+                                          ("dca", {}, 65, 129), ("scvi", {}, 31, 130)])
+def test_edge_shapes(model, kw, G, B):
+  """Ragged shapes: fewer genes than one tile / vector, batches that are not multiples of any tile, B = 2."""
+  cfg, flat, mov, batch = _setup(model, kw, G, B, C.GEMM_TC_3XFP16, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng, gtol=8e-3)
+  out = eng.infer(**batch)
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, eng.bn_moving.cpu().numpy()), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo")
+  _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="mean")
+  eng.close()
+
+
+def test_wide_gene_panel_20000():
+  """The 20000-gene variant of the scalability config (BASELINE.json configs[4]) at a small batch."""
+  cfg, flat, mov, batch = _setup("vae", {}, 20000, 130, C.GEMM_TC_3XFP16, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  terms, loss = eng.train_step(**batch)
+  torch.cuda.synchronize()
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, **batch)
+  _close(terms[0].cpu().numpy(), ref["elbo"].detach().numpy(), what="train elbo (20000 genes)")
+  eng.close()
