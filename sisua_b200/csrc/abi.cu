@@ -62,7 +62,7 @@ struct sisua_model {
   std::vector<void*> allocs;
   float *A0 = nullptr, *PL = nullptr, *loc = nullptr, *scale = nullptr, *Zs = nullptr, *PLIB = nullptr,
         *lib_loc = nullptr, *lib_scale = nullptr, *lib = nullptr, *dPLIB = nullptr,
-        *dLib = nullptr, *D = nullptr, *dD = nullptr, *dHa = nullptr, *dHb = nullptr, *delta1 = nullptr,
+        *dLib = nullptr, *lse_part = nullptr, *Trow = nullptr, *dlibsum = nullptr, *D = nullptr, *dD = nullptr, *dHa = nullptr, *dHb = nullptr, *delta1 = nullptr,
         *PY = nullptr, *dPY = nullptr, *OUT = nullptr, *mask_scale = nullptr, *scratch_terms = nullptr;
   int n_units = 0;             // hidden units (layers) that own a statistics slot
   double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
@@ -249,7 +249,24 @@ static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool trai
 
 #ifdef SISUA_WITH_TC
 static bool tc_heads_enabled(const sisua_model* h) {
-  return h->cfg.gemm_mode != SISUA_GEMM_FP32_UNFUSED && h->cfg.model_kind != SISUA_MODEL_SCVI;
+  // the literal reading of Q2 (activations applied again on scVI's positive parameters) keeps the un-fused row kernel
+  return h->cfg.gemm_mode != SISUA_GEMM_FP32_UNFUSED &&
+         !(h->cfg.model_kind == SISUA_MODEL_SCVI && h->cfg.scvi_reapply_act);
+}
+
+constexpr int kLseChunks = 16;   // gene chunks of the scVI logsumexp pass (x 4 slices = partials per row)
+
+template <int NH, bool VEC>
+static int tc_set_attr_scvi(sisua_model* h) {
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, true, true, tc::MODE_SCVI_LSE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_EVAL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_SUMS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, VEC, true, tc::MODE_SCVI_TRAIN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, true)));
+  return SISUA_OK;
 }
 
 template <int NH, bool TRAIN, bool VEC>
@@ -345,11 +362,48 @@ static int tc_create(sisua_model* h) {
   h->n_gene_tiles = (h->cfg.n_genes + tc::kGeneTile - 1) / tc::kGeneTile;
   int rc = ws_alloc(h, &h->packed_wout, (size_t)h->n_gene_tiles * tc::packed_tile_stride(nh));
   if (rc != SISUA_OK) return rc;
+  if (h->cfg.model_kind == SISUA_MODEL_SCVI) {
+    const size_t R = h->cfg.max_batch;
+    if ((rc = ws_alloc(h, &h->lse_part, R * kLseChunks * 4 * 2)) || (rc = ws_alloc(h, &h->Trow, R)) ||
+        (rc = ws_alloc(h, &h->dlibsum, R))) return rc;
+    if (nh == 3) { if ((rc = tc_set_attr_scvi<3, true>(h)) || (rc = tc_set_attr_scvi<3, false>(h))) return rc; }
+    else { if ((rc = tc_set_attr_scvi<2, true>(h)) || (rc = tc_set_attr_scvi<2, false>(h))) return rc; }
+    return SISUA_OK;
+  }
 #define TC_ATTR(NH) \
   if ((rc = tc_set_attr<NH, true, true>(h)) || (rc = tc_set_attr<NH, true, false>(h)) || \
       (rc = tc_set_attr<NH, false, true>(h)) || (rc = tc_set_attr<NH, false, false>(h))) return rc
   if (nh == 3) { TC_ATTR(3); } else { TC_ATTR(2); }
 #undef TC_ATTR
+  return SISUA_OK;
+}
+
+// scVI heads on the same fused kernel (gene softmax needs row sums before the Jacobian can be applied):
+//   logsumexp pass -> [inference] evaluation pass
+//                  -> [training] row-sum pass (llk, T = sum s t, d llk / d library) -> gradient pass
+template <int NH, bool VEC>
+static int tc_scvi_passes(sisua_model* h, cudaStream_t st, bool training, tc::OutHeadsArgs a, dim3 grid) {
+  dim3 grid_lse(grid.x, std::min<int>(grid.y, kLseChunks));
+  tc::OutHeadsArgs l = a;
+  l.tiles_per_chunk = (a.n_tiles + (int)grid_lse.y - 1) / (int)grid_lse.y;
+  grid_lse.y = (a.n_tiles + l.tiles_per_chunk - 1) / l.tiles_per_chunk;
+  l.n_lse_parts = a.n_lse_parts = (int)grid_lse.y * 4;
+  ++h->launches;
+  tc::out_heads_kernel<NH, false, true, true, tc::MODE_SCVI_LSE><<<grid_lse, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(l);
+  LAUNCH_OK(h, "out_heads_kernel (scVI logsumexp)");
+  ++h->launches;
+  if (!training) {
+    tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_EVAL><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
+    LAUNCH_OK(h, "out_heads_kernel (scVI evaluation)");
+    return SISUA_OK;
+  }
+  CUDA_OK(h, cudaMemsetAsync(a.Trow, 0, (size_t)a.R * sizeof(float), st));
+  CUDA_OK(h, cudaMemsetAsync(a.dlibsum, 0, (size_t)a.R * sizeof(float), st));
+  tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_SUMS><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
+  LAUNCH_OK(h, "out_heads_kernel (scVI row sums)");
+  ++h->launches;
+  tc::out_heads_kernel<NH, true, VEC, true, tc::MODE_SCVI_TRAIN><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);
+  LAUNCH_OK(h, "out_heads_kernel (scVI gradients)");
   return SISUA_OK;
 }
 
@@ -375,6 +429,12 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
   chunks = (h->n_gene_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
   dim3 grid(cell_tiles, chunks);
   const bool vec = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (c.model_kind == SISUA_MODEL_SCVI) {
+    a.lse_part = reinterpret_cast<float2*>(h->lse_part); a.lib = h->lib; a.clip_library = c.clip_library;
+    a.Trow = h->Trow; a.dlibsum = h->dlibsum; a.dLib = h->dLib;
+    if (nh == 3) return vec ? tc_scvi_passes<3, true>(h, st, training, a, grid) : tc_scvi_passes<3, false>(h, st, training, a, grid);
+    return vec ? tc_scvi_passes<2, true>(h, st, training, a, grid) : tc_scvi_passes<2, false>(h, st, training, a, grid);
+  }
   ++h->launches;
   const bool fast = c.mean_act == SISUA_ACT_SOFTPLUS && c.disp_act == SISUA_ACT_SOFTPLUS1;
 #define TC_LAUNCH(NH, TRAIN, VEC)                                                                                   \
@@ -452,7 +512,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   }
   WS(h->D, R * H); WS(h->dD, R * H); WS(h->dHa, R * H); WS(h->dHb, R * H); WS(h->delta1, R * h->ld0);
   if (P > 0) { WS(h->PY, R * 2 * P); WS(h->dPY, R * 2 * P); }
-  if (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED || scvi) WS(h->OUT, R * (size_t)h->NO);   // scVI heads (gene softmax) stay un-fused
+  if (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED || (scvi && c.scvi_reapply_act)) WS(h->OUT, R * (size_t)h->NO);
   WS(h->mask_scale, 1);
   WS(h->scratch_terms, 5 * R);
   WS(h->stats, (size_t)h->n_units * 4 * H);
@@ -467,7 +527,7 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   CUDA_OK(h, cudaFuncSetAttribute(latent_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatentBwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_OK(h, cudaFuncSetAttribute(count_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  if (scvi && c.n_genes * sizeof(float) > 200 * 1024)
+  if (scvi && (c.gemm_mode == SISUA_GEMM_FP32_UNFUSED || c.scvi_reapply_act) && c.n_genes * sizeof(float) > 200 * 1024)
     SET_ERR(h, SISUA_ERR_UNSUPPORTED, "un-fused scVI row kernel caches one softmax row in shared memory: n_genes <= 51200");
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {

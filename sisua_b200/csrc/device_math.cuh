@@ -181,7 +181,7 @@ __device__ __forceinline__ float digamma_stirling(float lnz, float iz) {
 // Large (> 8) or non-integer counts: Stirling at x+th, x+1 and th+8 (all >= 8) with
 // lgamma(th) = lgamma(th+8) - log prod_{k<8}(th+k)  (lnq, dgq = log and log-derivative of that product).
 __device__ __noinline__ void gamma_terms_large(float x, float th, float lnq, float dgq, bool grad, float* lg, float* dg) {
-  if (x >= 7.f) {
+  if (x >= 7.f && th < 1e4f) {
     float z1 = x + th, z2 = x + 1.f, z3 = th + 8.f;
     float l1 = kLn2 * mufu_lg2(z1), l2 = kLn2 * mufu_lg2(z2), l3 = kLn2 * mufu_lg2(z3);
     float i1 = mufu_rcp(z1), i2 = mufu_rcp(z2), i3 = mufu_rcp(z3);
@@ -194,14 +194,11 @@ __device__ __noinline__ void gamma_terms_large(float x, float th, float lnq, flo
 }
 
 struct ElemResult { float llk, ga, gb, gl, mu, th; };   // ga, gb, gl = d llk / d raw head outputs
+struct CoreResult { float llk, gmu, gth, gl; };         // d llk / d (mean, dispersion, dropout logit)
 
+// (ZI)NB log-likelihood of one count given the positive parameters, and its partial derivatives
 template <bool kZeroInflated, bool kGrad>
-__device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float pi, float x) {
-  ElemResult o;
-  float mu, dmu, th, dth;
-  softplus_fast(ra, mu, dmu);
-  softplus_fast(rb + kSoftplus1Shift, th, dth);
-  o.mu = mu; o.th = th;
+__device__ __forceinline__ CoreResult count_core_fast(float mu, float th, float pi, float x) {
   const float Rt = mufu_rcp(th + mu + kEps);
   const float rho = th * Rt;
   const float dlog = kLn2 * mufu_lg2(rho + 1e-30f);
@@ -225,7 +222,8 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
   if (__any_sync(0xffffffffu, nz)) {
     // lg = lgamma(x+th) - lgamma(th) - lgamma(x+1), dg = psi(x+th) - psi(th)
     float q = th, dq = 1.f, f = 1.f;          // q = prod_{k<min(x,8)} (th+k)
-    const bool small_x = (x == rintf(x)) && x <= 8.f;
+    // the product form needs (th+7)^8 inside fp32 range; beyond that the rare out-of-line path takes over
+    const bool small_x = (x == rintf(x)) && x <= 8.f && th < 1e4f;
     const float lim = nz ? (small_x ? x : 8.f) : 0.f;
     // the 32 cells of a warp rarely hold more than a few counts at one gene: stop as soon as every lane is done
 #pragma unroll 1
@@ -260,8 +258,47 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
     }
     llk = nz ? llk1 : llk; gmu = nz ? gmu1 : gmu; gth = nz ? gth1 : gth; gl = nz ? gl1 : gl;
   }
-  o.llk = llk;
-  o.ga = gmu * dmu; o.gb = gth * dth; o.gl = gl;
+  CoreResult o;
+  o.llk = llk; o.gmu = gmu; o.gth = gth; o.gl = gl;
+  return o;
+}
+
+// default links of the VAE / DCA / SISUA heads: mean = softplus(ra), dispersion = softplus(rb + log(e-1))
+template <bool kZeroInflated, bool kGrad>
+__device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float pi, float x) {
+  ElemResult o;
+  float mu, dmu, th, dth;
+  softplus_fast(ra, mu, dmu);
+  softplus_fast(rb + kSoftplus1Shift, th, dth);
+  o.mu = mu; o.th = th;
+  CoreResult c = count_core_fast<kZeroInflated, kGrad>(mu, th, pi, x);
+  o.llk = c.llk;
+  o.ga = c.gmu * dmu; o.gb = c.gth * dth; o.gl = c.gl;
+  return o;
+}
+
+// scVI links (scvi.py:64-86): mean = exp(clip(library)) * clamp(softmax_g(u)), dispersion = exp(rb).
+//   u_lse = u_g - logsumexp_g(u), eL = exp(clipped library).
+//   t = d llk / d s_raw_g (softmax output before the clamp); the softmax Jacobian s_raw (t - sum_j s_raw_j t_j)
+//   is finished by the caller once the row sum is known.  gmu_mu = (d llk / d mean) * mean -> d llk / d library.
+struct ScviElem { float llk, mu, th, s_raw, t, gmu_mu, gb, gl; };
+
+template <bool kZeroInflated, bool kGrad>
+__device__ __forceinline__ ScviElem count_elem_scvi(float u_lse, float rb, float pi, float x, float eL) {
+  ScviElem o;
+  const float s_raw = mufu_ex2(u_lse * kLog2e);
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  const bool inside = s_raw >= lo && s_raw <= hi;
+  const float s = fminf(fmaxf(s_raw, lo), hi);
+  o.s_raw = s_raw;
+  o.mu = eL * s;
+  o.th = mufu_ex2(rb * kLog2e);
+  CoreResult c = count_core_fast<kZeroInflated, kGrad>(o.mu, o.th, pi, x);
+  o.llk = c.llk;
+  o.t = inside ? c.gmu * eL : 0.f;
+  o.gmu_mu = c.gmu * o.mu;
+  o.gb = c.gth * o.th;
+  o.gl = c.gl;
   return o;
 }
 

@@ -76,7 +76,20 @@ struct OutHeadsArgs {
   int R, B, G, n_tiles, tiles_per_chunk;
   int mean_act, disp_act;
   float upstream;          // d loss / d llk_x = -1 / R
+  // scVI (gene softmax over head 0, library-scaled mean, exp dispersion): see the MODE table below
+  float2* lse_part;        // [R, n_lse_parts] running (max, sum exp) of the head-0 logits per gene chunk and slice
+  int n_lse_parts;
+  const float* lib;        // [R] sampled log library size
+  float clip_library;
+  float* Trow;             // [R] sum_g s_raw_g * d llk / d s_raw_g   (zeroed by the caller)
+  float* dlibsum;          // [R] sum_g (d llk / d mean_g) * mean_g     (zeroed by the caller)
+  float* dLib;             // [R] d loss / d library (written by the training pass)
 };
+
+// MODE: 0 = VAE / DCA / SISUA heads (elementwise links);  scVI passes over the same weight tiles:
+//   1 = logsumexp of the head-0 logits (per-row partials), 2 = evaluation (llk, parameters),
+//   3 = llk + the two row sums the softmax / library gradients need, 4 = training pass (G tiles + gradient GEMMs)
+enum OutMode { MODE_PLAIN = 0, MODE_SCVI_LSE = 1, MODE_SCVI_EVAL = 2, MODE_SCVI_SUMS = 3, MODE_SCVI_TRAIN = 4 };
 
 struct OutSmem {     // offsets into dynamic shared memory (bytes)
   static constexpr int dA1 = 0;                          // [128][80] fp16 (cols 64.. = ones / zero pad, train)
@@ -87,16 +100,19 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
   static constexpr int Gstage = 16 * 2048;                                                 // two G stages when training
   __host__ __device__ static constexpr int XS(int nh, bool train) { return G0(nh) + (train ? 2 * Gstage : 0); }   // [8][512] count stash
   __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 8 * kEpiThreads * 4; }
-  __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + kCellTile * 4; }
+  __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + 3 * kCellTile * 4; }   // llk | T | dlib
   __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
 };
 
 enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12, DWO_FREE = 14, DD_FULL = 16, NUM_BARS = 17 };
 
-template <int NH, bool TRAIN, bool VEC, bool FAST>
+template <int NH, bool TRAIN, bool VEC, bool FAST, int MODE = MODE_PLAIN>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
+  static_assert(TRAIN == (MODE == MODE_SCVI_TRAIN) || MODE == MODE_PLAIN, "only the plain and scVI-train modes run the gradient GEMMs");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int N = NH * 32;
+  constexpr int NF = MODE == MODE_SCVI_LSE ? 32 : N;     // the logsumexp pass only needs head 0 (rows 0..31 of a tile)
+  constexpr bool SCVI = MODE >= MODE_SCVI_EVAL;
   constexpr bool ZI = NH == 3;
   constexpr int W_CS = NH * 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OutSmem::BAR(NH, TRAIN));
@@ -157,7 +173,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     for (int item = t; item < 2 * OutSmem::Gstage / 16; item += kOutThreads)      // zero both G stages once (pad columns stay 0)
       *reinterpret_cast<uint4*>(smem + OutSmem::G0(NH) + item * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (t < kCellTile) llk_s[t] = 0.f;
+  if (t < 3 * kCellTile) llk_s[t] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
-      const uint32_t idesc_fwd = make_idesc_f16(kCellTile, N, 0, 0);
+      const uint32_t idesc_fwd = make_idesc_f16(kCellTile, NF, 0, 0);
       const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
       const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
       const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
@@ -238,6 +254,22 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     const bool row_ok = row < a.R;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float llk_acc = 0.f;
+    // scVI row state: logsumexp of the gene logits (merged from the MODE 1 partials), exp(clipped library)
+    float lse = 0.f, eL = 1.f, t_row = 0.f, t_acc = 0.f, dl_acc = 0.f;
+    float m_run = -1e30f, s_run = 0.f;
+    bool lib_open = false;
+    if (SCVI && row_ok) {
+      const float2* pp = a.lse_part + (size_t)row * a.n_lse_parts;
+      float m = -1e30f;
+      for (int i = 0; i < a.n_lse_parts; ++i) m = fmaxf(m, pp[i].x);
+      float ssum = 0.f;
+      for (int i = 0; i < a.n_lse_parts; ++i) { float2 v = pp[i]; ssum += v.y * __expf(v.x - m); }
+      lse = m + logf(ssum);
+      const float lr = a.lib[row];
+      lib_open = lr >= 0.f && lr <= a.clip_library;
+      eL = expf(fminf(fmaxf(lr, 0.f), a.clip_library));
+      if (MODE == MODE_SCVI_TRAIN) t_row = a.Trow[row];
+    }
 
     // this thread's 8 counts of tile i straight from global memory (one 32-byte sector per lane; prefetched a
     // tile ahead into registers, so no shared-memory staging and no CTA-wide barriers in the tile loop)
@@ -279,14 +311,16 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     };
 
     float xnext[8];
-    load_x(0, xnext);
+    if (MODE != MODE_SCVI_LSE) load_x(0, xnext);
     float* xs = reinterpret_cast<float*>(smem + OutSmem::XS(NH, TRAIN)) + t;     // this thread's column of the [8][512] stash
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
+      if (MODE != MODE_SCVI_LSE) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xs[j * kEpiThreads] = xnext[j];
-      if (i + 1 < nt) load_x(i + 1, xnext);
+        for (int j = 0; j < 8; ++j) xs[j * kEpiThreads] = xnext[j];
+        if (i + 1 < nt) load_x(i + 1, xnext);
+      }
       mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
       mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
       if (TRAIN && i >= 2) mbar_wait(&bars[G_FREE + s], ((i >> 1) - 1) & 1);   // gradient GEMMs of tile i-2 consumed this G stage
@@ -296,10 +330,25 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       // this thread's 16-byte slot in column group `sub` of each head of the G stage
       uint8_t* gt = smem + OutSmem::G0(NH) + s * OutSmem::Gstage + sub * 2048 + (cell >> 3) * 128 + (cell & 7) * 16;
       const size_t o = (size_t)row * a.G + g0;
+      if (MODE == MODE_SCVI_LSE) {
+        // running (max, sum exp) of this thread's slice of the head-0 logits; finite sentinels keep it NaN-free
+        float u[8];
+        tmem_ld8(tb, u);
+        tmem_ld_wait();
+        float tm = -3e38f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          u[j] = (g0 + j) < a.G ? u[j] + bias_s[j] : -3e38f;
+          tm = fmaxf(tm, u[j]);
+        }
+        if (tm > m_run) { s_run *= mufu_ex2((m_run - tm) * kLog2e); m_run = tm; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_run += mufu_ex2((u[j] - m_run) * kLog2e);
+      }
       // rolled on purpose: kU genes per trip keep the hot loop inside the instruction cache
       constexpr int kU = 2;
 #pragma unroll 1
-      for (int j = 0; j < 8; j += kU) {
+      for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += kU) {
         float va[kU], vb[kU], vl[kU];
         tmem_ldn<kU>(tb + j, va);
         tmem_ldn<kU>(tb + 32 + j, vb);
@@ -316,7 +365,13 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           const float rb = vb[u] + bias_s[32 + j + u];
           const float pi = ZI ? vl[u] + bias_s[64 + j + u] : 0.f;
           ElemResult e;
-          if (FAST) {
+          if (SCVI) {
+            ScviElem se = count_elem_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS)>(ra - lse, rb, pi, x2[u], eL);
+            e.llk = se.llk; e.mu = se.mu; e.th = se.th;
+            e.ga = se.s_raw * (se.t - t_row);          // softmax Jacobian (row sum from the MODE 3 pass)
+            e.gb = se.gb; e.gl = se.gl;
+            if (MODE == MODE_SCVI_SUMS && ok) { t_acc = fmaf(se.s_raw, se.t, t_acc); dl_acc += se.gmu_mu; }
+          } else if (FAST) {
             e = count_elem_fast<ZI, TRAIN>(ra, rb, pi, x2[u]);
           } else {
             float dmu, dth;
@@ -362,9 +417,25 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       }
     }
     // per-cell log-likelihood: four gene slices per cell -> shared -> one atomic per cell and chunk
-    atomicAdd(&llk_s[cell], llk_acc);
-    named_bar_sync(1, kEpiThreads);
-    if (sub == 0 && row_ok) atomicAdd(a.llk_x + row, llk_s[cell]);
+    if (MODE == MODE_SCVI_LSE) {
+      if (row_ok) a.lse_part[(size_t)row * a.n_lse_parts + blockIdx.y * 4 + sub] = make_float2(m_run, s_run);
+    } else if (MODE != MODE_SCVI_TRAIN) {      // the scVI training pass re-walks the tiles: llk came from MODE 3
+      atomicAdd(&llk_s[cell], llk_acc);
+      if (MODE == MODE_SCVI_SUMS) {
+        atomicAdd(&llk_s[kCellTile + cell], t_acc);
+        atomicAdd(&llk_s[2 * kCellTile + cell], dl_acc);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (sub == 0 && row_ok) {
+        atomicAdd(a.llk_x + row, llk_s[cell]);
+        if (MODE == MODE_SCVI_SUMS) {
+          atomicAdd(a.Trow + row, llk_s[kCellTile + cell]);
+          atomicAdd(a.dlibsum + row, llk_s[2 * kCellTile + cell]);
+        }
+      }
+    } else if (sub == 0 && row_ok && blockIdx.y == 0) {
+      a.dLib[row] = lib_open ? a.upstream * a.dlibsum[row] : 0.f;
+    }
     if (TRAIN) {
       flush_dwo(nt - 1);
       mbar_wait(&bars[DD_FULL], 0);

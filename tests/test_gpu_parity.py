@@ -293,3 +293,42 @@ def test_wide_gene_panel_20000():
   ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, **batch)
   _close(terms[0].cpu().numpy(), ref["elbo"].detach().numpy(), what="train elbo (20000 genes)")
   eng.close()
+
+
+@pytest.mark.parametrize("x_dist", ["zinbd", "nbd"])
+@pytest.mark.parametrize("G,B,clip", [(2100, 200, 12.0), (333, 64, 5.0)])
+def test_scvi_fused_softmax_heads(x_dist, G, B, clip):
+  """scVI heads on the fused kernel: gene softmax over many gene chunks (logsumexp partials), closed and open
+  library clip gates (clip 5 < log library of most cells -> d loss / d library gated off), both likelihoods."""
+  cfg, flat, mov, batch = _setup("scvi", dict(x_dist=x_dist, clip_library=clip), G, B, C.GEMM_TC_3XFP16, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng)
+  out = eng.infer(**batch, want_disp=True)
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, eng.bn_moving.cpu().numpy()), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo")
+  _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="mean")
+  _close(out["disp"].cpu().numpy(), ref["theta"].numpy(), atol=1e-7, what="disp")
+  eng.close()
+
+
+def test_scvi_fused_matches_unfused_with_samples():
+  """S = 3 Monte-Carlo samples through the fused scVI passes == the fp32 un-fused row kernel."""
+  outs = []
+  for mode in (C.GEMM_FP32_UNFUSED, C.GEMM_TC_3XFP16):
+    cfg, flat, mov, _ = _setup("scvi", {}, 700, 128, mode)
+    batch = Hh.make_batch(cfg, 100, S=3)
+    eng = _engine(cfg, flat, mov)
+    out = eng.infer(**batch, S=3, want_disp=True)
+    outs.append({k: out[k].cpu().numpy() for k in ("terms", "mean", "disp")})
+    eng.close()
+  _close(outs[1]["terms"][0], outs[0]["terms"][0], what="elbo fused vs un-fused")
+  _close(outs[1]["mean"], outs[0]["mean"], atol=1e-7, what="mean fused vs un-fused")
+  _close(outs[1]["disp"], outs[0]["disp"], atol=1e-7, what="disp fused vs un-fused")
+
+
+def test_scvi_reapply_activation_uses_row_kernel():
+  """The literal Q2 reading (activations applied again on scVI's positive parameters) stays on the un-fused row kernel."""
+  cfg, flat, mov, batch = _setup("scvi", dict(scvi_reapply_act=1), 150, 48, C.GEMM_TC_3XFP16, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng)
+  eng.close()
