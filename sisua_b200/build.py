@@ -34,6 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
   defs = []
   if os.path.exists(os.path.join(CSRC, "kernels_tc.cuh")):
     defs.append("-DSISUA_WITH_TC")
+  defs += os.environ.get("SISUA_NVCC_DEFS", "").split()      # tuning experiments, e.g. -DSISUA_OUT_KU=4
   cmd = [nvcc] + NVCC_FLAGS + defs + [os.path.join(CSRC, "abi.cu"), "-o", LIB_PATH, "-lcuda"]
   if verbose:
     cmd.insert(-4, "-Xptxas")

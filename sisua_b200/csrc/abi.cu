@@ -280,8 +280,8 @@ static int tc_set_attr(sisua_model* h) {
 
 template <int N0>
 static int tc_enc_attr(sisua_model* h) {
-  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0>::total));
-  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0, true>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0, false>::total));
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
   return SISUA_OK;
@@ -306,11 +306,11 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   dim3 grid(cell_tiles, chunks);
   ++h->launches;
   if (N0 == 64) {
-    if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64>::total, st>>>(a);
-    else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64>::total, st>>>(a);
+    if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64, true>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64, false>::total, st>>>(a);
   } else {
-    if (vec) tc::enc_first_fwd_kernel<128, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128>::total, st>>>(a);
-    else tc::enc_first_fwd_kernel<128, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128>::total, st>>>(a);
+    if (vec) tc::enc_first_fwd_kernel<128, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128, true>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<128, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128, false>::total, st>>>(a);
   }
   LAUNCH_OK(h, "enc_first_fwd_kernel (tcgen05)");
   return SISUA_OK;

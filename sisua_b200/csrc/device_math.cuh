@@ -196,85 +196,124 @@ __device__ __noinline__ void gamma_terms_large(float x, float th, float lnq, flo
 struct ElemResult { float llk, ga, gb, gl, mu, th; };   // ga, gb, gl = d llk / d raw head outputs
 struct CoreResult { float llk, gmu, gth, gl; };         // d llk / d (mean, dispersion, dropout logit)
 
-// (ZI)NB log-likelihood of one count given the positive parameters, and its partial derivatives
-template <bool kZeroInflated, bool kGrad>
-__device__ __forceinline__ CoreResult count_core_fast(float mu, float th, float pi, float x) {
-  const float Rt = mufu_rcp(th + mu + kEps);
-  const float rho = th * Rt;
-  const float dlog = kLn2 * mufu_lg2(rho + 1e-30f);
-  const float n0 = th * dlog;
-  const float dn0_dmu = -rho, dn0_dth = dlog + 1.f - rho;
-  float Ep = 0.f, Rp = 1.f, pc = 0.f;
-  float llk, gmu, gth, gl = 0.f;
-  if (kZeroInflated) {
-    pc = fminf(fmaxf(pi, -60.f), 60.f);
-    Ep = mufu_ex2(-pc * kLog2e);            // exp(-pi)
-    Rp = mufu_rcp(1.f + Ep);                // sigmoid(pi)
-    float Eu = mufu_ex2((n0 - pc) * kLog2e);
-    float Su = 1.f + Eu;
-    float w = Eu * mufu_rcp(Su);            // sigmoid(n0 - pi)
-    llk = kLn2 * mufu_lg2(Su * Rp);         // softplus(n0 - pi) - softplus(-pi)
-    gl = Ep * Rp - w; gmu = w * dn0_dmu; gth = w * dn0_dth;
-  } else {
-    llk = n0; gmu = dn0_dmu; gth = dn0_dth;
+__constant__ float c_inv_int[9] = {1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.f / 5.f, 1.f / 6.f, 1.f / 7.f, 1.f / 8.f, 1.f / 9.f};   // [k] = 1 / (k+1)
+
+// (ZI)NB log-likelihood of U counts given the positive parameters, and the partial derivatives.
+// The U elements advance in lock-step through every warp-uniform branch so that the scheduler can interleave
+// their dependent MUFU / FMA chains inside each basic block (one element at a time leaves the issue slots idle).
+template <bool kZeroInflated, bool kGrad, int U>
+__device__ __forceinline__ void count_core_fast(const float (&mu)[U], const float (&th)[U], const float (&pi)[U],
+                                                const float (&x)[U], CoreResult (&o)[U]) {
+  float Rt[U], n0[U], dn0_dmu[U], dn0_dth[U], Ep[U], Rp[U];
+  bool nz[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    Rt[u] = mufu_rcp(th[u] + mu[u] + kEps);
+    const float rho = th[u] * Rt[u];
+    const float dlog = kLn2 * mufu_lg2(rho + 1e-30f);
+    n0[u] = th[u] * dlog;
+    dn0_dmu[u] = -rho; dn0_dth[u] = dlog + 1.f - rho;
+    Ep[u] = 0.f; Rp[u] = 1.f;
+    if (kZeroInflated) {
+      const float pc = fminf(fmaxf(pi[u], -60.f), 60.f);
+      Ep[u] = mufu_ex2(-pc * kLog2e);            // exp(-pi)
+      Rp[u] = mufu_rcp(1.f + Ep[u]);             // sigmoid(pi)
+      float Eu = mufu_ex2((n0[u] - pc) * kLog2e);
+      float Su = 1.f + Eu;
+      float w = Eu * mufu_rcp(Su);               // sigmoid(n0 - pi)
+      o[u].llk = kLn2 * mufu_lg2(Su * Rp[u]);    // softplus(n0 - pi) - softplus(-pi)
+      o[u].gl = Ep[u] * Rp[u] - w; o[u].gmu = w * dn0_dmu[u]; o[u].gth = w * dn0_dth[u];
+    } else {
+      o[u].llk = n0[u]; o[u].gmu = dn0_dmu[u]; o[u].gth = dn0_dth[u]; o[u].gl = 0.f;
+    }
+    nz[u] = x[u] >= kEps;
   }
-  const bool nz = x >= kEps;
-  if (__any_sync(0xffffffffu, nz)) {
-    // lg = lgamma(x+th) - lgamma(th) - lgamma(x+1), dg = psi(x+th) - psi(th)
-    float q = th, dq = 1.f, f = 1.f;          // q = prod_{k<min(x,8)} (th+k)
+  // per-lane trip count of the rising-factorial product, as a float (no int<->float conversions: those run on the
+  // same quarter-rate unit as the transcendentals); non-negative floats order like their bit patterns
+  float lim[U];
+  bool small_x[U];
+  float lim_max = 0.f;
+  bool any_big = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float xr = (x[u] + 8388608.f) - 8388608.f;          // rint(x) for 0 <= x < 2^22
     // the product form needs (th+7)^8 inside fp32 range; beyond that the rare out-of-line path takes over
-    const bool small_x = (x == rintf(x)) && x <= 8.f && th < 1e4f;
-    const float lim = nz ? (small_x ? x : 8.f) : 0.f;
-    // the 32 cells of a warp rarely hold more than a few counts at one gene: stop as soon as every lane is done
+    small_x[u] = (x[u] == xr) && x[u] <= 8.f && th[u] < 1e4f;
+    lim[u] = nz[u] ? (small_x[u] ? x[u] : 8.f) : 0.f;
+    lim_max = fmaxf(lim_max, lim[u]);
+    any_big = any_big || (nz[u] && !small_x[u]);
+  }
+  const float kmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lim_max)));
+  if (kmax > 0.f) {            // some lane of the warp holds a non-zero count
+    // lg = lgamma(x+th) - lgamma(th) - lgamma(x+1), dg = psi(x+th) - psi(th)
+    float q[U], dq[U], finv[U];          // q = prod_{k<min(x,8)} (th+k), finv = 1 / min(x,8)!
+#pragma unroll
+    for (int u = 0; u < U; ++u) { q[u] = th[u]; dq[u] = 1.f; finv[u] = 1.f; }
+    // the 32 cells of a warp rarely hold more than a few counts at one gene: the loop stops at the warp's largest
+    float kf = 1.f;
 #pragma unroll 1
-    for (int k = 1; k < 8; ++k) {
-      const bool more = (float)k < lim;
-      if (!__any_sync(0xffffffffu, more)) break;
-      if (more) {
-        float tk = th + (float)k;
-        dq = fmaf(dq, tk, q);
-        q *= tk;
-        f *= (float)(k + 1);
+    for (int k = 1; kf < kmax; ++k, kf += 1.f) {
+      const float inv = c_inv_int[k];     // 1 / (k+1), uniform constant load
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (kf < lim[u]) {
+          float tk = th[u] + kf;
+          dq[u] = fmaf(dq[u], tk, q[u]);
+          q[u] *= tk;
+          finv[u] *= inv;
+        }
       }
     }
-    float lnq = kLn2 * mufu_lg2(q);
-    float rq = mufu_rcp(q);
-    float lg = lnq - kLn2 * mufu_lg2(f);
-    float dg = dq * rq;
-    if (__any_sync(0xffffffffu, nz && !small_x)) {
-      float lg_big, dg_big;
-      gamma_terms_large(x, th, lnq, dg, kGrad, &lg_big, &dg_big);   // out of line: rare, keeps the hot loop small
-      lg = small_x ? lg : lg_big;
-      dg = small_x ? dg : dg_big;
+    float lg[U], dg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      lg[u] = kLn2 * mufu_lg2(q[u] * finv[u]);
+      dg[u] = dq[u] * mufu_rcp(q[u]);
     }
-    float lnm = kLn2 * mufu_lg2((mu + kEps) * Rt);
-    float llk1 = n0 + x * lnm + lg;
-    float gmu1 = dn0_dmu + x * (mufu_rcp(mu + kEps) - Rt);
-    float gth1 = dn0_dth - x * Rt + dg;
-    float gl1 = 0.f;
-    if (kZeroInflated) {
-      llk1 += kLn2 * mufu_lg2(Ep * Rp) - fmaxf(pi - 60.f, 0.f);   // log sigmoid(-pi)
-      gl1 = -Rp;
+    if (__any_sync(0xffffffffu, any_big)) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {                                     // out of line: rare, keeps the hot loop small
+        float lg_big, dg_big;
+        gamma_terms_large(x[u], th[u], kLn2 * mufu_lg2(q[u]), dg[u], kGrad, &lg_big, &dg_big);
+        const bool take = nz[u] && !small_x[u];
+        lg[u] = take ? lg_big : lg[u];
+        dg[u] = take ? dg_big : dg[u];
+      }
     }
-    llk = nz ? llk1 : llk; gmu = nz ? gmu1 : gmu; gth = nz ? gth1 : gth; gl = nz ? gl1 : gl;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float lnm = kLn2 * mufu_lg2((mu[u] + kEps) * Rt[u]);
+      float llk1 = n0[u] + x[u] * lnm + lg[u];
+      float gmu1 = dn0_dmu[u] + x[u] * (mufu_rcp(mu[u] + kEps) - Rt[u]);
+      float gth1 = dn0_dth[u] - x[u] * Rt[u] + dg[u];
+      float gl1 = 0.f;
+      if (kZeroInflated) {
+        llk1 += kLn2 * mufu_lg2(Ep[u] * Rp[u]) - fmaxf(pi[u] - 60.f, 0.f);   // log sigmoid(-pi)
+        gl1 = -Rp[u];
+      }
+      o[u].llk = nz[u] ? llk1 : o[u].llk; o[u].gmu = nz[u] ? gmu1 : o[u].gmu;
+      o[u].gth = nz[u] ? gth1 : o[u].gth; o[u].gl = nz[u] ? gl1 : o[u].gl;
+    }
   }
-  CoreResult o;
-  o.llk = llk; o.gmu = gmu; o.gth = gth; o.gl = gl;
-  return o;
 }
 
 // default links of the VAE / DCA / SISUA heads: mean = softplus(ra), dispersion = softplus(rb + log(e-1))
-template <bool kZeroInflated, bool kGrad>
-__device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float pi, float x) {
-  ElemResult o;
-  float mu, dmu, th, dth;
-  softplus_fast(ra, mu, dmu);
-  softplus_fast(rb + kSoftplus1Shift, th, dth);
-  o.mu = mu; o.th = th;
-  CoreResult c = count_core_fast<kZeroInflated, kGrad>(mu, th, pi, x);
-  o.llk = c.llk;
-  o.ga = c.gmu * dmu; o.gb = c.gth * dth; o.gl = c.gl;
-  return o;
+template <bool kZeroInflated, bool kGrad, int U>
+__device__ __forceinline__ void count_elem_fast(const float (&ra)[U], const float (&rb)[U], const float (&pi)[U],
+                                                const float (&x)[U], ElemResult (&o)[U]) {
+  float mu[U], dmu[U], th[U], dth[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    softplus_fast(ra[u], mu[u], dmu[u]);
+    softplus_fast(rb[u] + kSoftplus1Shift, th[u], dth[u]);
+  }
+  CoreResult c[U];
+  count_core_fast<kZeroInflated, kGrad, U>(mu, th, pi, x, c);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    o[u].mu = mu[u]; o[u].th = th[u]; o[u].llk = c[u].llk;
+    o[u].ga = c[u].gmu * dmu[u]; o[u].gb = c[u].gth * dth[u]; o[u].gl = c[u].gl;
+  }
 }
 
 // scVI links (scvi.py:64-86): mean = exp(clip(library)) * clamp(softmax_g(u)), dispersion = exp(rb).
@@ -283,23 +322,30 @@ __device__ __forceinline__ ElemResult count_elem_fast(float ra, float rb, float 
 //   is finished by the caller once the row sum is known.  gmu_mu = (d llk / d mean) * mean -> d llk / d library.
 struct ScviElem { float llk, mu, th, s_raw, t, gmu_mu, gb, gl; };
 
-template <bool kZeroInflated, bool kGrad>
-__device__ __forceinline__ ScviElem count_elem_scvi(float u_lse, float rb, float pi, float x, float eL) {
-  ScviElem o;
-  const float s_raw = mufu_ex2(u_lse * kLog2e);
+template <bool kZeroInflated, bool kGrad, int U>
+__device__ __forceinline__ void count_elem_scvi(const float (&u_lse)[U], const float (&rb)[U], const float (&pi)[U],
+                                                const float (&x)[U], float eL, ScviElem (&o)[U]) {
   const float lo = 1e-7f, hi = 1.f - 1e-7f;
-  const bool inside = s_raw >= lo && s_raw <= hi;
-  const float s = fminf(fmaxf(s_raw, lo), hi);
-  o.s_raw = s_raw;
-  o.mu = eL * s;
-  o.th = mufu_ex2(rb * kLog2e);
-  CoreResult c = count_core_fast<kZeroInflated, kGrad>(o.mu, o.th, pi, x);
-  o.llk = c.llk;
-  o.t = inside ? c.gmu * eL : 0.f;
-  o.gmu_mu = c.gmu * o.mu;
-  o.gb = c.gth * o.th;
-  o.gl = c.gl;
-  return o;
+  float mu[U], th[U];
+  bool inside[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float s_raw = mufu_ex2(u_lse[u] * kLog2e);
+    inside[u] = s_raw >= lo && s_raw <= hi;
+    o[u].s_raw = s_raw;
+    mu[u] = eL * fminf(fmaxf(s_raw, lo), hi);
+    th[u] = mufu_ex2(rb[u] * kLog2e);
+  }
+  CoreResult c[U];
+  count_core_fast<kZeroInflated, kGrad, U>(mu, th, pi, x, c);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    o[u].mu = mu[u]; o[u].th = th[u]; o[u].llk = c[u].llk;
+    o[u].t = inside[u] ? c[u].gmu * eL : 0.f;
+    o[u].gmu_mu = c[u].gmu * mu[u];
+    o[u].gb = c[u].gth * th[u];
+    o[u].gl = c[u].gl;
+  }
 }
 
 // Counter-based dropout masks (Philox4x32-10, counter = (row, col/8, step, stream)): a pure function, so
@@ -330,17 +376,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // ten Philox rounds into the unrolled tile loaders of the small kernels multiplied their code size.  The spec is
 // passed by value: a reference would force the caller's by-value argument struct into local memory.
 struct DropMult8 { float m[8]; };
-__device__ __noinline__ DropMult8 dropout_mult8(DropSpec d, uint32_t row, uint32_t col8) {
-  const uint32_t step = d.step_ptr ? (uint32_t)(*d.step_ptr + 1) : d.step;
+__device__ __forceinline__ uint32_t dropout_step(const DropSpec& d) {
+  return d.step_ptr ? (uint32_t)(*d.step_ptr + 1) : d.step;
+}
+// inline form for the streaming first-layer kernel (step resolved once by the caller)
+__device__ __forceinline__ void dropout_mult8_inline(const DropSpec& d, uint32_t step, uint32_t row, uint32_t col8, float* m) {
   uint4 r = philox4x32_10(make_uint4(row, col8, step, d.stream), make_uint2(d.seed_lo, d.seed_hi));
-  const uint32_t thr = (uint32_t)(d.rate * 65536.0f);
+  const uint32_t thr = (uint32_t)(d.rate * 65536.0f), thr_hi = thr << 16;
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  DropMult8 o;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t u = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
-    o.m[j] = u >= thr ? d.scale : 0.f;
+  for (int j = 0; j < 4; ++j) {
+    m[2 * j] = (w[j] & 0xffffu) >= thr ? d.scale : 0.f;
+    m[2 * j + 1] = w[j] >= thr_hi ? d.scale : 0.f;        // (w >> 16) >= thr
   }
+}
+__device__ __noinline__ DropMult8 dropout_mult8(DropSpec d, uint32_t row, uint32_t col8) {
+  DropMult8 o;
+  dropout_mult8_inline(d, dropout_step(d), row, col8, o.m);
   return o;
 }
 __device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, uint32_t col) {

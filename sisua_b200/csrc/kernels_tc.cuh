@@ -47,9 +47,7 @@ __global__ void __launch_bounds__(256) pack_wout_kernel(const float* __restrict_
         const float* src = W + ((size_t)h * G + g) * kK + cg * 8 + 2 * j;
         v0 = src[0]; v1 = src[1];
       }
-      __half h0, l0, h1, l1;
-      split_f16(v0, h0, l0); split_f16(v1, h1, l1);
-      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+      split_f16x2(v0, v1, hi[j], lo[j]);
     }
     uint32_t off = (n >> 3) * RS + cg * CS + (n & 7) * 16;
     *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -154,11 +152,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __half h0, l0, h1, l1;
-      split_f16(v[2 * j], h0, l0); split_f16(v[2 * j + 1], h1, l1);
-      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
-    }
+    for (int j = 0; j < 4; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
     uint32_t off = cg * 2048 + (r >> 3) * 128 + (r & 7) * 16;
     *reinterpret_cast<uint4*>(smem + OutSmem::dA1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(smem + OutSmem::dA2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -346,49 +340,78 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         for (int j = 0; j < 8; ++j) s_run += mufu_ex2((u[j] - m_run) * kLog2e);
       }
       // rolled on purpose: kU genes per trip keep the hot loop inside the instruction cache
-      constexpr int kU = 2;
+#ifndef SISUA_OUT_KU
+#define SISUA_OUT_KU 2
+#endif
+      constexpr int kU = SISUA_OUT_KU;
+      // the TMEM reads of trip j+1 are in flight while trip j is evaluated
+      float pa[kU], pb[kU], pl[kU];
+      if (MODE != MODE_SCVI_LSE) {
+        tmem_ldn<kU>(tb, pa);
+        tmem_ldn<kU>(tb + 32, pb);
+        if (ZI) tmem_ldn<kU>(tb + 64, pl);
+      }
 #pragma unroll 1
       for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += kU) {
         float va[kU], vb[kU], vl[kU];
-        tmem_ldn<kU>(tb + j, va);
-        tmem_ldn<kU>(tb + 32 + j, vb);
-        if (ZI) tmem_ldn<kU>(tb + 64 + j, vl);
-        tmem_ld_wait();
+        tmem_ld_wait_tie<kU>(pa); tmem_ld_tie<kU>(pb);
+        if (ZI) tmem_ld_tie<kU>(pl);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { va[u] = pa[u]; vb[u] = pb[u]; vl[u] = ZI ? pl[u] : 0.f; }
+        if (j + kU < 8) {
+          tmem_ldn<kU>(tb + j + kU, pa);
+          tmem_ldn<kU>(tb + 32 + j + kU, pb);
+          if (ZI) tmem_ldn<kU>(tb + 64 + j + kU, pl);
+        }
         float x2[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) x2[u] = xs[(j + u) * kEpiThreads];
         float ga2[kU], gb2[kU], gl2[kU];
+        float ra[kU], rb[kU], pi[kU];
+        bool ok[kU];
+        ElemResult e[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-          const bool ok = row_ok && (g0 + j + u) < a.G;
-          const float ra = va[u] + bias_s[j + u];
-          const float rb = vb[u] + bias_s[32 + j + u];
-          const float pi = ZI ? vl[u] + bias_s[64 + j + u] : 0.f;
-          ElemResult e;
+          ok[u] = row_ok && (g0 + j + u) < a.G;
+          ra[u] = va[u] + bias_s[j + u];
+          rb[u] = vb[u] + bias_s[32 + j + u];
+          pi[u] = ZI ? vl[u] + bias_s[64 + j + u] : 0.f;
+        }
+        // one element at a time on purpose: evaluating the kU elements in lock-step (count_*<.., U = kU>) measured
+        // 12 % slower (longer live ranges, product loop runs to the larger count of the pair)
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const float ra1[1] = {ra[u] - lse}, rb1[1] = {rb[u]}, pi1[1] = {pi[u]}, x1[1] = {x2[u]};
           if (SCVI) {
-            ScviElem se = count_elem_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS)>(ra - lse, rb, pi, x2[u], eL);
-            e.llk = se.llk; e.mu = se.mu; e.th = se.th;
-            e.ga = se.s_raw * (se.t - t_row);          // softmax Jacobian (row sum from the MODE 3 pass)
-            e.gb = se.gb; e.gl = se.gl;
-            if (MODE == MODE_SCVI_SUMS && ok) { t_acc = fmaf(se.s_raw, se.t, t_acc); dl_acc += se.gmu_mu; }
+            ScviElem se[1];
+            count_elem_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS), 1>(ra1, rb1, pi1, x1, eL, se);
+            e[u].llk = se[0].llk; e[u].mu = se[0].mu; e[u].th = se[0].th;
+            e[u].ga = se[0].s_raw * (se[0].t - t_row);          // softmax Jacobian (row sum from the MODE 3 pass)
+            e[u].gb = se[0].gb; e[u].gl = se[0].gl;
+            if (MODE == MODE_SCVI_SUMS && ok[u]) { t_acc = fmaf(se[0].s_raw, se[0].t, t_acc); dl_acc += se[0].gmu_mu; }
           } else if (FAST) {
-            e = count_elem_fast<ZI, TRAIN>(ra, rb, pi, x2[u]);
+            ElemResult e1[1];
+            count_elem_fast<ZI, TRAIN, 1>(ra1, rb1, pi1, x1, e1);
+            e[u] = e1[0];
           } else {
             float dmu, dth;
-            activation(a.mean_act, ra, e.mu, dmu);
-            activation(a.disp_act, rb, e.th, dth);
+            activation(a.mean_act, ra[u], e[u].mu, dmu);
+            activation(a.disp_act, rb[u], e[u].th, dth);
             CountGrad cg;
             cg.dmu = cg.dth = cg.dpi = 0.f;
-            e.llk = count_llk<ZI, TRAIN>(x2[u], e.mu, e.th, pi, cg);
-            e.ga = cg.dmu * dmu; e.gb = cg.dth * dth; e.gl = cg.dpi;
+            e[u].llk = count_llk<ZI, TRAIN>(x2[u], e[u].mu, e[u].th, pi[u], cg);
+            e[u].ga = cg.dmu * dmu; e[u].gb = cg.dth * dth; e[u].gl = cg.dpi;
           }
-          llk_acc += ok ? e.llk : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          llk_acc += ok[u] ? e[u].llk : 0.f;
           if (TRAIN) {
-            ga2[u] = ok ? e.ga : 0.f; gb2[u] = ok ? e.gb : 0.f; gl2[u] = (ok && ZI) ? e.gl : 0.f;
-          } else if (ok) {
-            if (a.out_mean) a.out_mean[o + j + u] = e.mu;
-            if (a.out_disp) a.out_disp[o + j + u] = e.th;
-            if (ZI && a.out_pi) a.out_pi[o + j + u] = pi;
+            ga2[u] = ok[u] ? e[u].ga : 0.f; gb2[u] = ok[u] ? e[u].gb : 0.f; gl2[u] = (ok[u] && ZI) ? e[u].gl : 0.f;
+          } else if (ok[u]) {
+            if (a.out_mean) a.out_mean[o + j + u] = e[u].mu;
+            if (a.out_disp) a.out_disp[o + j + u] = e[u].th;
+            if (ZI && a.out_pi) a.out_pi[o + j + u] = pi[u];
           }
         }
         if (TRAIN) {   // two genes -> one packed fp16x2 word per head (|g| is clamped into fp16 range; sigmoids need no clamp)

@@ -38,9 +38,7 @@ __global__ void __launch_bounds__(256) pack_w1_kernel(const float* __restrict__ 
       int g = kb * 64 + cg * 8 + 2 * j;
       float v0 = g < G ? W[(size_t)n * ldw + g] : 0.f;
       float v1 = g + 1 < G ? W[(size_t)n * ldw + g + 1] : 0.f;
-      __half h0, l0, h1, l1;
-      split_f16(v0, h0, l0); split_f16(v1, h1, l1);
-      hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+      split_f16x2(v0, v1, hi[j], lo[j]);
     }
     uint32_t off = (n >> 3) * 128 + cg * CS + (n & 7) * 16;
     *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -48,11 +46,8 @@ __global__ void __launch_bounds__(256) pack_w1_kernel(const float* __restrict__ 
   }
 }
 
-__device__ __forceinline__ float log1p_count(float x) {
-  float big = kLn2 * mufu_lg2(1.f + x);
-  float small = x * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
-  return x < 0.015625f ? small : big;
-}
+// log(1 + x): |error| <= 1 ulp of (1 + x) in absolute terms, far below the 2^-22 of the hi/lo operand split
+__device__ __forceinline__ float log1p_count(float x) { return kLn2 * mufu_lg2(1.f + x); }
 
 // 8 consecutive columns c0..c0+7 of row r of X[rows, ld]; zero outside [0,rows) x [0,cols)
 template <bool VEC>
@@ -73,27 +68,24 @@ __device__ __forceinline__ void load8(const float* __restrict__ X, int ld, int r
   }
 }
 
-// log1p + dropout on 8 count values of (row, c0..c0+7), in place
-__device__ __forceinline__ void normalise8(float* v, int log_norm, const DropSpec& drop, int row, int c0) {
+// log1p + dropout on 8 count values of (row, c0..c0+7), in place (`step`: dropout_step(drop), read once per thread)
+__device__ __forceinline__ void normalise8(float* v, int log_norm, const DropSpec& drop, uint32_t step, int row, int c0) {
   if (log_norm) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = log1p_count(v[j]);
   }
   if (drop.rate > 0.f) {     // c0 is a multiple of 8: one Philox call masks the whole group
-    DropMult8 m = dropout_mult8(drop, (uint32_t)row, (uint32_t)(c0 >> 3));
+    float m[8];
+    dropout_mult8_inline(drop, step, (uint32_t)row, (uint32_t)(c0 >> 3), m);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= m.m[j];
+    for (int j = 0; j < 8; ++j) v[j] *= m[j];
   }
 }
 
 __device__ __forceinline__ void store8_hi_lo(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(v[2 * j], h0, l0); split_f16(v[2 * j + 1], h1, l1);
-    hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
-  }
+  for (int j = 0; j < 4; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
   *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
@@ -101,8 +93,11 @@ __device__ __forceinline__ void store8_hi(uint8_t* tile, uint32_t off, const flo
   uint32_t hi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    hi[j] = pack_h2(__float2half_rn(fminf(fmaxf(v[2 * j] * scale, -60000.f), 60000.f)),
-                    __float2half_rn(fminf(fmaxf(v[2 * j + 1] * scale, -60000.f), 60000.f)));
+  {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * j] * scale, -60000.f), 60000.f),
+                                        fminf(fmaxf(v[2 * j + 1] * scale, -60000.f), 60000.f));
+    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
   *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
 }
 
@@ -116,21 +111,33 @@ struct EncFwdArgs {
   int xt_kblocks;           // (training) kept for the weight-gradient kernel so the counts are not converted twice
 };
 
-template <int N0>
+constexpr int kRawTile = 128 * 64 * 4;   // one raw fp32 count tile [128 cells][64 genes] as the bulk copies land it
+
+// VEC (row pitch and base 16-byte aligned): the counts arrive by 16-byte async copies (cp.async) into raw fp32 stages,
+// issued by the loader warp several k-blocks ahead, so no converter warp ever waits on a global load (one bulk copy per
+// 256-byte row segment was tried first: the TMA unit's per-request cost made it 2x slower); otherwise the converter
+// warps load through registers.
+template <int N0, bool VEC>
 struct EncFwdSmem {
+  static constexpr int kStages = VEC ? 2 : 3;                // operand stages (hi | lo | weights)
+  static constexpr int kRaw = VEC ? (N0 == 64 ? 3 : 2) : 0;  // raw stages
   static constexpr int A = 8 * kPadCS;                       // one fp16 tile [128][64]
   static constexpr int stage = 2 * A + w1_block_bytes(N0);
-  static constexpr int bar = kEncStages * stage;
+  static constexpr int raw = kStages * stage;
+  static constexpr int bar = raw + kRaw * kRawTile;
   static constexpr int total = bar + 16 * 8 + 16;
 };
+
+enum EncBar { EB_A_FULL = 0, EB_W_FULL = 3, EB_STAGE_FREE = 6, EB_ACC_FULL = 9, EB_RAW_FULL = 10, EB_RAW_FREE = 13 };
 
 template <int N0, bool VEC>
 __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwdArgs a) {
   constexpr int CW = kEncFwdConvWarps, kMma = CW, kLoad = CW + 1, kStore = CW + 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  using S = EncFwdSmem<N0>;
+  using S = EncFwdSmem<N0, VEC>;
+  constexpr int NS = S::kStages, NR = S::kRaw > 0 ? S::kRaw : 1;
   constexpr int W_CS = N0 / 8 * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);   // [0..2] a_full, [3..5] w_full, [6..8] stage_free, [9] acc_full
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::bar + 16 * 8);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int row0 = blockIdx.x * 128;
@@ -138,8 +145,11 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
   const int nkb = min(a.n_kblocks, kb_begin + a.kblocks_per_chunk) - kb_begin;
   if (nkb <= 0) return;
   if (t == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(&bars[s], CW); mbar_init(&bars[3 + s], 1); mbar_init(&bars[6 + s], a.xt ? 2 : 1); }
-    mbar_init(&bars[9], 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&bars[EB_A_FULL + s], CW); mbar_init(&bars[EB_W_FULL + s], 1); mbar_init(&bars[EB_STAGE_FREE + s], a.xt ? 2 : 1);
+      mbar_init(&bars[EB_RAW_FULL + s], CW * 32); mbar_init(&bars[EB_RAW_FREE + s], CW);
+    }
+    mbar_init(&bars[EB_ACC_FULL], 1);
     fence_barrier_init();
   }
   if (warp == kMma) tmem_alloc(tmem_slot, N0 < 32 ? 32 : N0);
@@ -151,22 +161,22 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
   if (warp == kLoad) {
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kEncStages;
-        if (i >= kEncStages) mbar_wait(&bars[6 + s], ((i / kEncStages) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[3 + s], w1_block_bytes(N0));
+        const int s = i % NS;
+        if (i >= NS) mbar_wait(&bars[EB_STAGE_FREE + s], ((i / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[EB_W_FULL + s], w1_block_bytes(N0));
         bulk_copy_g2s(smem + s * S::stage + 2 * S::A, a.packed + (size_t)(kb_begin + i) * w1_block_bytes(N0), w1_block_bytes(N0),
-                      &bars[3 + s]);
+                      &bars[EB_W_FULL + s]);
       }
     }
   } else if (warp == kStore) {
     // ---- tile store: the hi tile of every stage goes to HBM once (TMA bulk store) for enc_first_bwd_kernel ----
     if (lane == 0 && a.xt) {
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kEncStages;
-        mbar_wait(&bars[s], (i / kEncStages) & 1);
+        const int s = i % NS;
+        mbar_wait(&bars[EB_A_FULL + s], (i / NS) & 1);
         bulk_store_s2g(a.xt + ((size_t)blockIdx.x * a.xt_kblocks + kb_begin + i) * kXtTile, smem + s * S::stage, kXtTile);
         bulk_store_wait_read();
-        mbar_arrive(&bars[6 + s]);
+        mbar_arrive(&bars[EB_STAGE_FREE + s]);
       }
       bulk_store_wait_all();
     }
@@ -174,10 +184,10 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, N0, 0, 0);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kEncStages;
-        const uint32_t ph = (i / kEncStages) & 1;
-        mbar_wait(&bars[s], ph);
-        mbar_wait(&bars[3 + s], ph);
+        const int s = i % NS;
+        const uint32_t ph = (i / NS) & 1;
+        mbar_wait(&bars[EB_A_FULL + s], ph);
+        mbar_wait(&bars[EB_W_FULL + s], ph);
         tc_fence_after();
         const uint32_t sA1 = smem_u32(smem + s * S::stage), sA2 = sA1 + S::A;
         const uint32_t sW1 = sA1 + 2 * S::A, sW2 = sW1 + w1_tile_bytes(N0);
@@ -189,39 +199,85 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
             umma_f16(tmem, make_smem_desc(sa + ks * 2 * kPadCS, kPadCS, 128), make_smem_desc(sb + ks * 2 * W_CS, W_CS, 128), idesc,
                      (i > 0 || p > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(&bars[6 + s]);
+        umma_commit(&bars[EB_STAGE_FREE + s]);
       }
-      umma_commit(&bars[9]);
+      umma_commit(&bars[EB_ACC_FULL]);
     }
   } else if (warp < CW) {
     // ---- converter warps: rows r = (t >> 3) + 64 j, column group cg = t & 7 ----
     constexpr int RPT = 128 * 8 / (CW * 32);   // (row, column-group) items per thread
     constexpr int RSTEP = CW * 32 / 8;
     const int cg = t & 7, rbase = t >> 3;
+    const uint32_t step = a.drop.rate > 0.f ? dropout_step(a.drop) : 0u;
     float cur[RPT][8];
     auto fetch = [&](int i, float (*dst)[8]) {
       const int c0 = (kb_begin + i) * 64 + cg * 8;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) load8<VEC>(a.x, a.G, a.B, a.G, row0 + rbase + RSTEP * j, c0, dst[j]);
+      for (int j = 0; j < RPT; ++j) load8<false>(a.x, a.G, a.B, a.G, row0 + rbase + RSTEP * j, c0, dst[j]);
     };
-    fetch(0, cur);
+    // VEC: every converter thread issues four 16-byte async copies per k-block (rows (t >> 4) + 32 j, chunk t & 15 of the
+    // 256-byte row segment), NR - 1 k-blocks ahead of the one it converts; cells / genes outside the matrix are zero-filled.
+    // (A single loader warp issuing all 2048 copies of a tile was issue-bound: 1.5 TB/s.)
+    const float* cp_src = a.x + (size_t)min(row0 + (t >> 4), a.B - 1) * a.G + kb_begin * 64 + (t & 15) * 4;
+    const size_t cp_row_step = (size_t)32 * a.G;
+    uint8_t* cp_dst = smem + S::raw + (t >> 4) * 256 + (t & 15) * 16;
+    auto issue = [&](int i) {
+      const int rs = i % NR;
+      const bool c_ok = (kb_begin + i) * 64 + (t & 15) * 4 < a.G;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = c_ok && row0 + (t >> 4) + 32 * j < a.B;
+        cp_async_16_zfill(cp_dst + rs * kRawTile + j * 32 * 256, ok ? (const void*)(cp_src + j * cp_row_step + (size_t)i * 64) : (const void*)a.x,
+                          ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(&bars[EB_RAW_FULL + rs]);
+    };
+    if (VEC) {
+      for (int i = 0; i < NR - 1 && i < nkb; ++i) issue(i);
+    } else {
+      fetch(0, cur);
+    }
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % kEncStages;
-      float nxt[RPT][8];
-      if (i + 1 < nkb) fetch(i + 1, nxt);
-      if (i >= kEncStages) mbar_wait(&bars[6 + s], ((i / kEncStages) - 1) & 1);
-      uint8_t* A1 = smem + s * S::stage;
+      const int s = i % NS;
       const int c0 = (kb_begin + i) * 64 + cg * 8;
+      float nxt[RPT][8];
+      if (VEC) {
+        const int rs = i % NR;
+        if (i + NR - 1 < nkb) {      // refill the stage every warp finished reading one k-block ago
+          if (i >= 1) mbar_wait(&bars[EB_RAW_FREE + (i - 1) % NR], ((i - 1) / NR) & 1);
+          issue(i + NR - 1);
+        }
+        mbar_wait(&bars[EB_RAW_FULL + rs], (i / NR) & 1);
+        // two 16-byte halves per item; column groups 4..7 read theirs in the opposite order, which spreads a quarter
+        // warp over all 32 banks
+        const bool swap = (cg >> 2) & 1;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = rbase + RSTEP * j;
+          const uint8_t* src = smem + S::raw + rs * kRawTile + r * 256 + cg * 32;
+          const float4 p = *reinterpret_cast<const float4*>(src + (swap ? 16 : 0));
+          const float4 q = *reinterpret_cast<const float4*>(src + (swap ? 0 : 16));
+          const float4 lo = swap ? q : p, hi = swap ? p : q;       // cells / genes outside the matrix were zero-filled
+          cur[j][0] = lo.x; cur[j][1] = lo.y; cur[j][2] = lo.z; cur[j][3] = lo.w;
+          cur[j][4] = hi.x; cur[j][5] = hi.y; cur[j][6] = hi.z; cur[j][7] = hi.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[EB_RAW_FREE + rs]);     // the raw stage can be refilled while this tile is converted
+      } else if (i + 1 < nkb) {
+        fetch(i + 1, nxt);
+      }
+      if (i >= NS) mbar_wait(&bars[EB_STAGE_FREE + s], ((i / NS) - 1) & 1);
+      uint8_t* A1 = smem + s * S::stage;
 #pragma unroll
       for (int j = 0; j < RPT; ++j) {
         const int r = rbase + RSTEP * j;
-        normalise8(cur[j], a.log_norm, a.drop, row0 + r, c0);
+        normalise8(cur[j], a.log_norm, a.drop, step, row0 + r, c0);
         store8_hi_lo(A1, A1 + S::A, cg * kPadCS + (r >> 3) * 128 + (r & 7) * 16, cur[j]);
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[s]);
-      if (i + 1 < nkb) {
+      if (lane == 0) mbar_arrive(&bars[EB_A_FULL + s]);
+      if (!VEC && i + 1 < nkb) {
 #pragma unroll
         for (int j = 0; j < RPT; ++j)
 #pragma unroll
@@ -229,7 +285,7 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
       }
     }
     // ---- epilogue: TMEM -> A0 ----
-    mbar_wait(&bars[9], 0);
+    mbar_wait(&bars[EB_ACC_FULL], 0);
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter, column slice
     const int row = row0 + q * 32 + lane;

@@ -63,6 +63,14 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+// 16-byte async copy that zero-fills when src_bytes == 0 (source outside the matrix; the address must still be valid)
+__device__ __forceinline__ void cp_async_16_zfill(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all of this thread's earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -115,6 +123,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding TMEM loads and make the compiler treat the destination registers as produced here, so that
+// a load issued well before its wait (software pipelining) cannot have its results consumed or moved early
+template <int N>
+__device__ __forceinline__ void tmem_ld_tie(float* v) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]) :: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_tie(float* v) {
+  tmem_ld_wait();
+  tmem_ld_tie<N>(v);
+}
 
 // ---- UMMA descriptors ---------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle (layout_type 0), Blackwell version field = 1
@@ -157,6 +177,14 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// two values at once through the packed converts (F2FP on the ALU pipe; the scalar cvt is a quarter-rate XU op)
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
