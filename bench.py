@@ -383,8 +383,9 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(x_bytes + B * LATENT * 4),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "HostTrainPipeline.step (pinned host minibatch in CSR form: int32 row pointers + uint16 column ids and "
-                       "counts -> H2D -> sisua_unpack_counts_csr -> sisua_train_step -> sisua_adam_step -> D2H loss)",
+                "api": "HostTrainPipeline.step: pinned host minibatch in CSR form (int32 row pointers + uint16 gene ids and counts) "
+                       "-> H2D on a copy stream into a double-buffered slot -> that slot's CUDA graph (sisua_unpack_counts_csr -> "
+                       "sisua_train_step -> sisua_adam_step -> loss D2H); N > 1: sisua_train_step_host + NCCL all-reduce + sisua_adam_step",
                 "dense_u16_host_value": e2e_u16, "dense_u16_h2d_bytes_per_step": int(B * G * 2 + B * LATENT * 4),
                 "dense_fp32_host_value": e2e_f32, "dense_fp32_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
         "latency_regime": {"what": "same train step at the reference's default minibatch sizes (launch-bound)", **small},

@@ -124,6 +124,35 @@ int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, float* dst, int
 int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals, float* dst,
                             int rows, void* stream);
 
+/* One train step from HOST buffers — the call a reference-side data pipeline makes per minibatch
+ * (the dict of sisua/data/_single_cell_base.py:582-591 as it comes out of tf.data, on the host).
+ * The library stages the batch on a private copy stream into double-buffered device memory (so the H2D copy of
+ * call i+1 overlaps the kernels of call i), widens 16-bit / CSR count formats to fp32, runs sisua_train_step on
+ * `stream`, and copies the scalar loss (and, if host_terms != NULL, the [5,B] terms) back to the host.
+ * Asynchronous: host buffers must stay valid and host_loss / host_terms are defined once `stream` has drained
+ * (pinned host memory keeps the copies asynchronous).  Follow with sisua_adam_step (after the gradient all-reduce
+ * when data-parallel).  format: 0 = float32 [B,G], 1 = uint16 [B,G], 2 = CSR (indptr int32 [B+1] from 0,
+ * uint16 gene ids, uint16 counts, nnz entries). */
+#define SISUA_HOST_F32 0
+#define SISUA_HOST_U16 1
+#define SISUA_HOST_CSR 2
+typedef struct sisua_host_batch {
+  int32_t format;
+  int32_t B;
+  const void* x;            /* F32 / U16 dense counts; unused for CSR */
+  const int32_t* indptr;    /* CSR */
+  const uint16_t* cols;     /* CSR */
+  const uint16_t* vals;     /* CSR */
+  int64_t nnz;              /* CSR */
+  const float* y;           /* [B,P] or NULL    (arguments as in sisua_train_step, host memory) */
+  const float* library;     /* [B,2] or NULL */
+  const uint8_t* mask;      /* [B] or NULL */
+  const float* eps_z;       /* [B,Z] or NULL */
+  const float* eps_l;       /* [B] or NULL */
+} sisua_host_batch;
+int sisua_train_step_host(sisua_handle h, const sisua_host_batch* batch, uint64_t seed, int64_t step, float* host_loss,
+                          float* host_terms, void* stream);
+
 /* Measurement hooks for bench.py: kernels launched so far through this handle; per-section device time
  * (CUDA events on the caller's stream). Sections: 0 first encoder layer, 1 mid forward, 2 output heads +
  * count likelihood (fused: one kernel), 3 mid backward, 4 first-layer weight gradient, 5 Adam. */

@@ -10,12 +10,22 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
-           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_set_step", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_set_step", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
   _fields_ = [("name", ctypes.c_char * 32), ("offset", ctypes.c_int64), ("rows", ctypes.c_int32),
               ("cols", ctypes.c_int32), ("ld", ctypes.c_int32), ("kind", ctypes.c_int32)]
+
+
+class HostBatch(ctypes.Structure):
+  """sisua_host_batch (include/sisua_b200.h): one minibatch in host memory."""
+  _fields_ = [("format", ctypes.c_int32), ("B", ctypes.c_int32), ("x", ctypes.c_void_p), ("indptr", ctypes.c_void_p),
+              ("cols", ctypes.c_void_p), ("vals", ctypes.c_void_p), ("nnz", ctypes.c_int64), ("y", ctypes.c_void_p),
+              ("library", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("eps_z", ctypes.c_void_p), ("eps_l", ctypes.c_void_p)]
+
+
+HOST_F32, HOST_U16, HOST_CSR = 0, 1, 2
 
 
 class SisuaError(RuntimeError):
@@ -67,6 +77,8 @@ def load():
   L.sisua_set_grad_ready_event.restype = ci
   L.sisua_unpack_counts_csr.argtypes = [vp, vp, vp, vp, vp, ci, vp]
   L.sisua_unpack_counts_csr.restype = ci
+  L.sisua_train_step_host.argtypes = [vp, ctypes.POINTER(HostBatch), ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
+  L.sisua_train_step_host.restype = ci
   L.sisua_set_step.argtypes = [vp, ctypes.c_int64, vp]
   L.sisua_set_step.restype = ci
   L.sisua_last_error.argtypes = [vp]

@@ -64,6 +64,22 @@ struct sisua_model {
         *lib_loc = nullptr, *lib_scale = nullptr, *lib = nullptr, *dPLIB = nullptr,
         *dLib = nullptr, *lse_part = nullptr, *Trow = nullptr, *dlibsum = nullptr, *D = nullptr, *dD = nullptr, *dHa = nullptr, *dHb = nullptr, *delta1 = nullptr,
         *PY = nullptr, *dPY = nullptr, *OUT = nullptr, *mask_scale = nullptr, *scratch_terms = nullptr;
+  // host-buffer entry point (sisua_train_step_host): double-buffered device staging filled on a private copy stream
+  struct HostStage {
+    bool ready = false;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t filled[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    float* x[2] = {nullptr, nullptr};
+    uint16_t* x16[2] = {nullptr, nullptr};
+    int32_t* indptr[2] = {nullptr, nullptr};
+    uint16_t* cols[2] = {nullptr, nullptr}; uint16_t* vals[2] = {nullptr, nullptr};
+    size_t csr_cap[2] = {0, 0};
+    float* y[2] = {nullptr, nullptr}; float* lib[2] = {nullptr, nullptr}; float* eps_z[2] = {nullptr, nullptr};
+    float* eps_l[2] = {nullptr, nullptr};
+    uint8_t* mask[2] = {nullptr, nullptr};
+    float* terms = nullptr; float* loss = nullptr;
+    long long calls = 0;
+  } hs;
   int n_units = 0;             // hidden units (layers) that own a statistics slot
   double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
   double* sq = nullptr;        // [kMaxSegments]
@@ -544,6 +560,15 @@ extern "C" int sisua_destroy(sisua_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& v : h->sec_events)
     for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (h->hs.copy) {
+    cudaStreamSynchronize(h->hs.copy);
+    for (int s = 0; s < 2; ++s) {
+      if (h->hs.filled[s]) cudaEventDestroy(h->hs.filled[s]);
+      if (h->hs.consumed[s]) cudaEventDestroy(h->hs.consumed[s]);
+      cudaFree(h->hs.indptr[s]); cudaFree(h->hs.cols[s]); cudaFree(h->hs.vals[s]);
+    }
+    cudaStreamDestroy(h->hs.copy);
+  }
   delete h;
   return SISUA_OK;
 }
@@ -1138,6 +1163,94 @@ extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, floa
   ++h->launches;
   unpack_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, (long long)n);
   LAUNCH_OK(h, "unpack_u16_kernel");
+  return SISUA_OK;
+}
+
+// ---- host-buffer train step ---------------------------------------------------------------------
+static int host_stage_init(sisua_model* h) {
+  auto& S = h->hs;
+  if (S.ready) return SISUA_OK;
+  const sisua_step_config& c = h->cfg;
+  const size_t R = c.max_batch;
+  CUDA_OK(h, cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+  int rc;
+  for (int s = 0; s < 2; ++s) {
+    CUDA_OK(h, cudaEventCreateWithFlags(&S.filled[s], cudaEventDisableTiming));
+    CUDA_OK(h, cudaEventCreateWithFlags(&S.consumed[s], cudaEventDisableTiming));
+    if ((rc = ws_alloc(h, &S.x[s], R * c.n_genes)) || (rc = ws_alloc(h, &S.x16[s], R * c.n_genes + 8)) ||
+        (rc = ws_alloc(h, &S.eps_z[s], R * c.n_latent)) || (rc = ws_alloc(h, &S.eps_l[s], R)) ||
+        (rc = ws_alloc(h, &S.lib[s], R * 2)) || (rc = ws_alloc(h, &S.mask[s], R)) ||
+        (rc = ws_alloc(h, &S.y[s], R * std::max(1, c.n_proteins)))) return rc;
+  }
+  if ((rc = ws_alloc(h, &S.terms, 5 * R)) || (rc = ws_alloc(h, &S.loss, 1))) return rc;
+  S.ready = true;
+  return SISUA_OK;
+}
+
+extern "C" int sisua_train_step_host(sisua_handle h, const sisua_host_batch* hb, uint64_t seed, int64_t step, float* host_loss,
+                                     float* host_terms, void* stream) {
+  if (!h || !hb) return SISUA_ERR_INVALID;
+  const sisua_step_config& c = h->cfg;
+  const int B = hb->B, G = c.n_genes;
+  if (B < 1 || B > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: B=%d outside [1, max_batch=%d]", B, c.max_batch);
+  if (hb->format < SISUA_HOST_F32 || hb->format > SISUA_HOST_CSR) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: unknown format %d", hb->format);
+  if (hb->format == SISUA_HOST_CSR) {
+    if (!hb->indptr || hb->nnz < 0 || (hb->nnz > 0 && (!hb->cols || !hb->vals))) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: incomplete CSR batch");
+    if (G > 65536) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "train_step_host: uint16 column ids need n_genes <= 65536");
+  } else if (!hb->x) {
+    SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: x is NULL");
+  }
+  int rc = host_stage_init(h);
+  if (rc != SISUA_OK) return rc;
+  auto& S = h->hs;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int s = (int)(S.calls++ & 1);
+  // ---- stage on the copy stream (after the kernels that last read this slot)
+  if (S.calls > 2) CUDA_OK(h, cudaStreamWaitEvent(S.copy, S.consumed[s], 0));
+  const size_t n = (size_t)B * G;
+  if (hb->format == SISUA_HOST_F32) {
+    CUDA_OK(h, cudaMemcpyAsync(S.x[s], hb->x, n * sizeof(float), cudaMemcpyHostToDevice, S.copy));
+  } else if (hb->format == SISUA_HOST_U16) {
+    CUDA_OK(h, cudaMemcpyAsync(S.x16[s], hb->x, n * sizeof(uint16_t), cudaMemcpyHostToDevice, S.copy));
+  } else {
+    if (S.csr_cap[s] < (size_t)hb->nnz || !S.indptr[s]) {      // grow (rare): nothing on the copy stream may still use the old buffers
+      CUDA_OK(h, cudaStreamSynchronize(S.copy));
+      CUDA_OK(h, cudaStreamSynchronize(st));
+      cudaFree(S.cols[s]); cudaFree(S.vals[s]);
+      S.cols[s] = S.vals[s] = nullptr;
+      const size_t cap = (size_t)hb->nnz + (size_t)hb->nnz / 4 + 1024;
+      CUDA_OK(h, cudaMalloc((void**)&S.cols[s], cap * sizeof(uint16_t)));
+      CUDA_OK(h, cudaMalloc((void**)&S.vals[s], cap * sizeof(uint16_t)));
+      if (!S.indptr[s]) CUDA_OK(h, cudaMalloc((void**)&S.indptr[s], ((size_t)c.max_batch + 1) * sizeof(int32_t)));
+      S.csr_cap[s] = cap;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(S.indptr[s], hb->indptr, ((size_t)B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, S.copy));
+    if (hb->nnz > 0) {
+      CUDA_OK(h, cudaMemcpyAsync(S.cols[s], hb->cols, (size_t)hb->nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, S.copy));
+      CUDA_OK(h, cudaMemcpyAsync(S.vals[s], hb->vals, (size_t)hb->nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, S.copy));
+    }
+  }
+  if (hb->eps_z) CUDA_OK(h, cudaMemcpyAsync(S.eps_z[s], hb->eps_z, (size_t)B * c.n_latent * sizeof(float), cudaMemcpyHostToDevice, S.copy));
+  if (hb->eps_l) CUDA_OK(h, cudaMemcpyAsync(S.eps_l[s], hb->eps_l, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, S.copy));
+  if (hb->library) CUDA_OK(h, cudaMemcpyAsync(S.lib[s], hb->library, (size_t)B * 2 * sizeof(float), cudaMemcpyHostToDevice, S.copy));
+  if (hb->mask) CUDA_OK(h, cudaMemcpyAsync(S.mask[s], hb->mask, (size_t)B, cudaMemcpyHostToDevice, S.copy));
+  if (hb->y && c.n_proteins > 0) CUDA_OK(h, cudaMemcpyAsync(S.y[s], hb->y, (size_t)B * c.n_proteins * sizeof(float), cudaMemcpyHostToDevice, S.copy));
+  CUDA_OK(h, cudaEventRecord(S.filled[s], S.copy));
+  // ---- compute stream: widen the counts, run the step, read the loss back
+  CUDA_OK(h, cudaStreamWaitEvent(st, S.filled[s], 0));
+  if (hb->format == SISUA_HOST_U16) {
+    rc = sisua_unpack_counts_u16(h, S.x16[s], S.x[s], (int64_t)n, stream);
+  } else if (hb->format == SISUA_HOST_CSR) {
+    rc = sisua_unpack_counts_csr(h, S.indptr[s], S.cols[s], S.vals[s], S.x[s], B, stream);
+  }
+  if (rc != SISUA_OK) return rc;
+  rc = sisua_train_step(h, S.x[s], (hb->y && c.n_proteins > 0) ? S.y[s] : nullptr, hb->library ? S.lib[s] : nullptr,
+                        hb->mask ? S.mask[s] : nullptr, hb->eps_z ? S.eps_z[s] : nullptr, hb->eps_l ? S.eps_l[s] : nullptr, B, seed,
+                        step, S.terms, S.loss, stream);
+  if (rc != SISUA_OK) return rc;
+  CUDA_OK(h, cudaEventRecord(S.consumed[s], st));
+  if (host_loss) CUDA_OK(h, cudaMemcpyAsync(host_loss, S.loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (host_terms) CUDA_OK(h, cudaMemcpyAsync(host_terms, S.terms, (size_t)5 * B * sizeof(float), cudaMemcpyDeviceToHost, st));
   return SISUA_OK;
 }
 

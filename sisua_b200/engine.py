@@ -165,6 +165,40 @@ class Engine:
       self._check(self.lib.sisua_unpack_counts_csr(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst_f32), rows,
                                                    self._stream()))
 
+  def train_step_host(self, x, *, y=None, library=None, mask=None, eps_z=None, eps_l=None, host_loss=None, host_terms=None,
+                      seed: int = 0, step: int = -1):
+    """One train step from HOST tensors (sisua_train_step_host): `x` is a pinned float32 / 16-bit [B,G] tensor or a
+    `pipeline.CsrBatch`; the other arguments are host tensors as in `train_step`.  The library stages them on its
+    own copy stream (double-buffered), so consecutive calls overlap H2D with compute.  Asynchronous: `host_loss`
+    (pinned, 1 float) / `host_terms` (pinned, [5,B]) are valid after the current stream has been synchronised, and
+    the host tensors must stay alive until then."""
+    hb = _lib.HostBatch()
+    hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    if hasattr(x, "indptr"):
+      hb.format, hb.B, hb.nnz = _lib.HOST_CSR, x.rows, x.cols.numel()
+      hb.indptr, hb.cols, hb.vals = hp(x.indptr), hp(x.cols), hp(x.vals)
+      if x.genes != self.cfg.n_genes:
+        raise ValueError("train_step_host: CSR batch has a different gene count")
+    else:
+      if x.is_cuda or x.dim() != 2 or x.shape[1] != self.cfg.n_genes or not x.is_contiguous():
+        raise ValueError("train_step_host: x must be a contiguous host [B, n_genes] tensor")
+      if x.dtype == torch.float32:
+        hb.format = _lib.HOST_F32
+      elif x.dtype in (torch.int16, torch.uint16):
+        hb.format = _lib.HOST_U16
+      else:
+        raise ValueError("train_step_host: x must be float32 or a 16-bit integer tensor")
+      hb.B, hb.x = x.shape[0], hp(x)
+    for name, t, dt in (("y", y, torch.float32), ("library", library, torch.float32), ("mask", mask, torch.uint8),
+                        ("eps_z", eps_z, torch.float32), ("eps_l", eps_l, torch.float32)):
+      if t is not None:
+        if t.is_cuda or t.dtype != dt or not t.is_contiguous():
+          raise ValueError(f"train_step_host: {name} must be a contiguous host tensor of dtype {dt}")
+        setattr(hb, name, hp(t))
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_train_step_host(self.handle, ctypes.byref(hb), int(seed), int(step), hp(host_loss),
+                                                 hp(host_terms), self._stream()))
+
   def reset_step_counter(self, t: int):
     """Sets the device-side optimiser step counter (what `adam_step(t=0)` and `train_step(step=-1)` follow)."""
     with torch.cuda.device(self.device):

@@ -1,6 +1,6 @@
-"""Host-buffer entry point of the train step: the caller hands pinned host minibatches (what a
-`tf.data`-style input pipeline yields, sisua/data/_single_cell_base.py:593-601); copies are
-double-buffered on a side stream so the H2D transfer of step i+1 overlaps the kernels of step i."""
+"""Host-side helpers around the train step: pinned host minibatch formats (what a `tf.data`-style input pipeline
+yields, sisua/data/_single_cell_base.py:593-601), the host-buffer training loop, and the CUDA-graph replay of the
+launch-bound small-batch step."""
 from __future__ import annotations
 
 from typing import Callable, List, Optional
@@ -39,67 +39,129 @@ class CsrBatch:
     return self.indptr.numel() * 4 + self.cols.numel() * 2 + self.vals.numel() * 2
 
 
-class HostTrainPipeline:
-  def __init__(self, eng: Engine, batch: int, depth: int = 2):
-    self.eng = eng
-    dev = eng.device
-    cfg = eng.cfg
-    self.copy_stream = torch.cuda.Stream(device=dev)
-    self.depth = depth
-    self.x = [torch.empty((batch, cfg.n_genes), device=dev) for _ in range(depth)]
-    self.x16 = [torch.empty((batch, cfg.n_genes), device=dev, dtype=torch.int16) for _ in range(depth)]
-    self.csr = [None] * depth   # (indptr, cols, vals) device buffers, grown on demand
-    self.eps = [torch.empty((batch, cfg.n_latent), device=dev) for _ in range(depth)]
-    self.ready = [torch.cuda.Event() for _ in range(depth)]
-    self.consumed = [torch.cuda.Event() for _ in range(depth)]
-    self.terms = torch.empty((5, batch), device=dev)
-    self.loss = torch.empty((1,), device=dev)
-    self.host_loss = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(depth)]
-    self.i = 0
-    for e in self.consumed:
-      e.record()
+def _capture_step(eng: Engine, run: Callable[[], None]) -> "torch.cuda.CUDAGraph":
+  """Warm `run` up once outside capture (restoring the optimiser state it touches), then capture it."""
+  dev = eng.device
+  side = torch.cuda.Stream(device=dev)
+  side.wait_stream(torch.cuda.current_stream(dev))
+  with torch.cuda.stream(side):
+    snap = [t.clone() for t in (eng.params, eng.adam_m, eng.adam_v, eng.bn_moving)]
+    step0 = eng.step_count
+    run()
+    side.synchronize()
+    for t, s_ in zip((eng.params, eng.adam_m, eng.adam_v, eng.bn_moving), snap):
+      t.copy_(s_)
+    eng.reset_step_counter(step0)
+  torch.cuda.current_stream(dev).wait_stream(side)
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    run()
+  eng.reset_step_counter(step0)            # capture does not execute, but keep host / device counters aligned
+  return graph
 
-  def step(self, x_host: torch.Tensor, eps_host: torch.Tensor, step: int, lr: float = 1e-3, clipnorm: float = 100.0,
-           world: int = 1, allreduce: Optional[Callable] = None):
-    """Enqueue one train step from pinned host buffers; returns the pinned host tensor that will hold
-    the loss once the stream has drained (read it after `flush`)."""
+
+class HostTrainPipeline:
+  """Train from pinned host minibatches (float32 / 16-bit dense or `CsrBatch`).
+
+  Single GPU: each of `depth` slots owns static device staging buffers and one CUDA graph
+  (widen counts -> train step -> Adam -> loss D2H); `step` enqueues the H2D copies on a side stream and replays the
+  slot's graph, so the transfer of step i+1 runs under the kernels of step i.  The graph matters here: with eager
+  launches the per-kernel command fetches queue behind the bulk H2D traffic on PCIe and the ~20 short kernels of a
+  step each start late (measured: 417 -> 700 us per step under a concurrent 11 MB copy; graph replay: 411 -> 423 us).
+  Data parallel (an `allreduce` callback between backward and Adam) or ragged batches go through the library's
+  host-buffer entry point `sisua_train_step_host`, which stages on its own copy stream."""
+
+  def __init__(self, eng: Engine, batch: int, depth: int = 2, use_graph: bool = True):
+    self.eng = eng
+    self.batch = batch
+    self.depth = depth
+    self.use_graph = use_graph
+    dev, cfg = eng.device, eng.cfg
+    self.copy_stream = torch.cuda.Stream(device=dev)
+    self.host_loss = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(max(depth, 4))]
+    self.slots = [None] * depth
+    self.graphs = {}
+    self.i = 0
+
+  def _slot(self, s: int):
+    if self.slots[s] is None:
+      eng, B = self.eng, self.batch
+      dev, G = eng.device, eng.cfg.n_genes
+      self.slots[s] = dict(
+          x=torch.empty((B, G), device=dev), x16=None, csr=None,
+          eps=torch.zeros((B, eng.cfg.n_latent), device=dev),
+          terms=torch.empty((5, B), device=dev), loss=torch.empty((1,), device=dev),
+          filled=torch.cuda.Event(), consumed=torch.cuda.Event())
+      self.slots[s]["consumed"].record()
+    return self.slots[s]
+
+  def _graph(self, s: int, fmt: str, lr: float, clipnorm: float):
+    key = (s, fmt, float(lr), float(clipnorm))
+    if key not in self.graphs:
+      eng, sl = self.eng, self._slot(s)
+      def run():
+        if fmt == "csr":
+          eng.unpack_counts_csr(*sl["csr"], sl["x"])
+        elif fmt == "u16":
+          eng.unpack_counts_u16(sl["x16"], sl["x"])
+        eng.train_step(sl["x"], eps_z=sl["eps"] if eng.cfg.model_kind != 2 else None, terms=sl["terms"], loss=sl["loss"],
+                       seed=0, step=-1)
+        eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0, t=0)
+        self.host_loss[s].copy_(sl["loss"], non_blocking=True)
+      self.graphs[key] = _capture_step(eng, run)
+    return self.graphs[key]
+
+  def step(self, x_host, eps_host: Optional[torch.Tensor], step: int, lr: float = 1e-3, clipnorm: float = 100.0,
+           world: int = 1, allreduce: Optional[Callable] = None, **host_extras):
+    """Enqueue one train step; returns the pinned host tensor that will hold the loss once the stream has drained
+    (read it after `flush`; it is reused `depth` steps later)."""
     eng = self.eng
+    is_csr = isinstance(x_host, CsrBatch)
+    rows = x_host.rows if is_csr else x_host.shape[0]
+    graphable = (self.use_graph and allreduce is None and not host_extras and rows == self.batch and
+                 eng.cfg.model_kind in (0, 2) and eng.cfg.n_proteins == 0)
+    if not graphable:
+      out = self.host_loss[self.i % len(self.host_loss)]
+      self.i += 1
+      eng.train_step_host(x_host, eps_z=eps_host, host_loss=out, seed=0, step=step, **host_extras)
+      if allreduce is not None:
+        allreduce(eng.grads)
+      eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=step)
+      return out
     s = self.i % self.depth
     self.i += 1
+    sl = self._slot(s)
+    fmt = "csr" if is_csr else ("u16" if x_host.dtype in (torch.int16, torch.uint16) else "f32")
+    if fmt == "csr" and sl["csr"] is None:      # worst-case capacity: the graph bakes the addresses in
+      cap = self.batch * eng.cfg.n_genes
+      sl["csr"] = (torch.zeros(self.batch + 1, device=eng.device, dtype=torch.int32),
+                   torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
+    if fmt == "u16" and sl["x16"] is None:
+      sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
+    graph = self._graph(s, fmt, lr, clipnorm)
+    if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
+      eng.reset_step_counter(step - 1)
     main = torch.cuda.current_stream(eng.device)
     with torch.cuda.stream(self.copy_stream):
-      self.copy_stream.wait_event(self.consumed[s])
-      is_csr = isinstance(x_host, CsrBatch)
-      packed = (not is_csr) and x_host.dtype in (torch.int16, torch.uint16)   # integer counts shipped as 16-bit (see quantize_counts)
-      if is_csr:
+      self.copy_stream.wait_event(sl["consumed"])
+      if fmt == "csr":
         nnz = x_host.cols.numel()
-        if self.csr[s] is None or self.csr[s][1].numel() < nnz:
-          cap = int(nnz * 1.25) + 1024
-          self.csr[s] = (torch.empty(self.x[s].shape[0] + 1, device=eng.device, dtype=torch.int32),
-                         torch.empty(cap, device=eng.device, dtype=torch.int16), torch.empty(cap, device=eng.device, dtype=torch.int16))
-        ip, cc, vv = self.csr[s]
+        ip, cc, vv = sl["csr"]
         ip.copy_(x_host.indptr, non_blocking=True)
         cc[:nnz].copy_(x_host.cols, non_blocking=True)
         vv[:nnz].copy_(x_host.vals, non_blocking=True)
-      elif packed:
-        self.x16[s].copy_(x_host.view(torch.int16), non_blocking=True)
+      elif fmt == "u16":
+        sl["x16"].copy_(x_host.view(torch.int16), non_blocking=True)
       else:
-        self.x[s].copy_(x_host, non_blocking=True)
-      self.eps[s].copy_(eps_host, non_blocking=True)
-      self.ready[s].record(self.copy_stream)
-    main.wait_event(self.ready[s])
-    if is_csr:
-      eng.unpack_counts_csr(self.csr[s][0], self.csr[s][1], self.csr[s][2], self.x[s])
-    elif packed:
-      eng.unpack_counts_u16(self.x16[s], self.x[s])
-    eng.train_step(self.x[s], eps_z=self.eps[s], terms=self.terms, loss=self.loss, seed=0, step=step)
-    self.consumed[s].record(main)
-    if allreduce is not None:
-      allreduce(eng.grads)
-    eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=step)
-    out = self.host_loss[s]
-    out.copy_(self.loss, non_blocking=True)
-    return out
+        sl["x"].copy_(x_host, non_blocking=True)
+      if eps_host is not None:
+        sl["eps"].copy_(eps_host, non_blocking=True)
+      sl["filled"].record(self.copy_stream)
+    main.wait_event(sl["filled"])
+    graph.replay()
+    sl["consumed"].record(main)
+    eng.step_count += 1
+    return self.host_loss[s]
 
   def flush(self, losses: List[torch.Tensor]):
     torch.cuda.current_stream(self.eng.device).synchronize()
@@ -125,21 +187,7 @@ class GraphedTrainStep:
     self.mask = torch.zeros((batch,), device=dev, dtype=torch.uint8) if cfg.n_proteins > 0 else None
     self.terms = torch.empty((5, batch), device=dev)
     self.loss = torch.empty((1,), device=dev)
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):            # warm-up outside capture, then restore the optimiser state it touched
-      snap = [t.clone() for t in (eng.params, eng.adam_m, eng.adam_v, eng.bn_moving)]
-      step0 = eng.step_count
-      self._run(lr, clipnorm, seed)
-      side.synchronize()
-      for t, s_ in zip((eng.params, eng.adam_m, eng.adam_v, eng.bn_moving), snap):
-        t.copy_(s_)
-      eng.reset_step_counter(step0)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    self.graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(self.graph):
-      self._run(lr, clipnorm, seed)
-    eng.reset_step_counter(step0)            # capture does not execute, but keep host / device counters aligned
+    self.graph = _capture_step(eng, lambda: self._run(lr, clipnorm, seed))
 
   def _run(self, lr, clipnorm, seed):
     self.eng.train_step(self.x, y=self.y, library=self.library, mask=self.mask, eps_z=self.eps_z, eps_l=self.eps_l,

@@ -332,3 +332,86 @@ def test_scvi_reapply_activation_uses_row_kernel():
   eng = _engine(cfg, flat, mov)
   _grad_check(cfg, flat, mov, batch, eng)
   eng.close()
+
+
+@pytest.mark.parametrize("model,kw", [("vae", {}), ("scvi", {}), ("sisua", dict(n_proteins=10))])
+@pytest.mark.parametrize("fmt", ["f32", "u16", "csr"])
+def test_host_buffer_train_step_equals_device_step(model, kw, fmt):
+  """sisua_train_step_host (host minibatches staged by the library, double-buffered) == sisua_train_step on the same
+  batches already in HBM, over several consecutive steps (slot reuse, CSR buffers growing)."""
+  from sisua_b200.engine import Engine
+  from sisua_b200.pipeline import CsrBatch, quantize_counts
+  cfg = C.make_step_config(model, n_genes=300, max_batch=96, input_dropout=0.2, **kw)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  host_loss = [torch.empty(1).pin_memory() for _ in range(6)]
+  host_terms = [torch.empty((5, 96)).pin_memory() for _ in range(6)]
+  dev_loss, dev_terms, keep = [], [], []
+  for t in range(1, 7):
+    Bt = 96 if t != 4 else 50                    # a ragged batch in the middle
+    batch = Hh.make_batch(cfg, Bt, seed=t, stress=(t % 2 == 0))      # dense stress batches make the CSR buffers grow
+    x = batch["x"]
+    xh = {"f32": lambda: torch.from_numpy(x).pin_memory(), "u16": lambda: quantize_counts(x), "csr": lambda: CsrBatch(x)}[fmt]()
+    extras = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items() if k != "x"}
+    keep.append((xh, extras))
+    a.train_step_host(xh, host_loss=host_loss[t - 1], host_terms=host_terms[t - 1][:, :Bt] if Bt == 96 else None,
+                      seed=3, step=t, **extras)
+    a.adam_step(lr=1e-3, clipnorm=100.0, t=t)
+    tm, ls = b.train_step(**batch, seed=3, step=t)
+    b.adam_step(lr=1e-3, clipnorm=100.0, t=t)
+    dev_loss.append(ls.clone()); dev_terms.append(tm.clone())
+  torch.cuda.synchronize()
+  for t in range(6):
+    # same kernels on the same data; only the order of float atomics (and, after a few Adam steps, 1e-5 parameter
+    # differences) separate the two runs -- a staging bug would show up at the 1e-2 level
+    np.testing.assert_allclose(float(host_loss[t]), float(dev_loss[t]), rtol=2e-4)
+    if t != 3:
+      np.testing.assert_allclose(host_terms[t].numpy(), dev_terms[t].cpu().numpy(), rtol=2e-3, atol=2e-3)
+  assert float((a.params - b.params).abs().max()) <= 4e-3 and float((a.params - b.params).abs().mean()) <= 1e-5
+  a.close(); b.close()
+
+
+def test_host_buffer_step_rejects_bad_input():
+  from sisua_b200 import _lib
+  from sisua_b200.engine import Engine
+  cfg = C.make_step_config("vae", n_genes=64, max_batch=32)
+  eng = Engine(cfg, 0)
+  with pytest.raises(ValueError):
+    eng.train_step_host(torch.zeros((8, 63)), eps_z=torch.zeros((8, cfg.n_latent)))        # wrong gene count
+  with pytest.raises(_lib.SisuaError):
+    eng.train_step_host(torch.zeros((64, 64)), eps_z=torch.zeros((64, cfg.n_latent)))      # exceeds max_batch
+  eng.close()
+
+
+@pytest.mark.parametrize("fmt", ["f32", "u16", "csr"])
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
+  """HostTrainPipeline (per-slot CUDA graphs fed by a copy stream, or the library's host-buffer entry point) trains
+  exactly like explicit device-side steps on the same minibatches."""
+  from sisua_b200.engine import Engine
+  from sisua_b200.pipeline import CsrBatch, HostTrainPipeline, quantize_counts
+  cfg = C.make_step_config("vae", n_genes=256, max_batch=64, input_dropout=0.3, enc_dropout=0.1)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  pipe = HostTrainPipeline(a, 64, use_graph=use_graph)
+  la, lb, keep = [], [], []
+  for t in range(1, 8):
+    batch = Hh.make_batch(cfg, 64, seed=t, stress=(t == 3))
+    x = batch["x"]
+    xh = {"f32": lambda: torch.from_numpy(x).pin_memory(), "u16": lambda: quantize_counts(x), "csr": lambda: CsrBatch(x)}[fmt]()
+    eh = torch.from_numpy(batch["eps_z"]).pin_memory()
+    keep.append((xh, eh))
+    out = pipe.step(xh, eh, step=t, lr=1e-3, clipnorm=100.0)
+    torch.cuda.synchronize()
+    la.append(float(out))
+    _, ls = b.train_step(**batch, seed=0, step=t)
+    b.adam_step(lr=1e-3, clipnorm=100.0, t=t)
+    lb.append(float(ls))
+  np.testing.assert_allclose(la, lb, rtol=2e-4)
+  assert float((a.params - b.params).abs().max()) <= 4e-3 and float((a.params - b.params).abs().mean()) <= 1e-5
+  assert la[0] != la[1]
+  a.close(); b.close()
