@@ -80,6 +80,7 @@ struct sisua_model {
     float* terms = nullptr; float* loss = nullptr;
     long long calls = 0;
   } hs;
+  bool wout_packed = false;    // output-head tiles already re-packed in this step (pack_weights_kernel)
   int n_units = 0;             // hidden units (layers) that own a statistics slot
   double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
   double* sq = nullptr;        // [kMaxSegments]
@@ -305,8 +306,16 @@ static int tc_enc_attr(sisua_model* h) {
 
 static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int B, int N0, bool training) {
   const sisua_step_config& c = h->cfg;
-  ++h->launches;
-  tc::pack_w1_kernel<<<h->n_kblocks, 256, 0, st>>>(h->P + h->enc[0].w_off, h->Gp, h->packed_w1, c.n_genes, N0);
+  {
+    // both packed operands in one launch (the output-head tiles are consumed later in the same step)
+    const bool heads = tc_heads_enabled(h);
+    const int nh = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+    ++h->launches;
+    tc::pack_weights_kernel<<<h->n_kblocks + (heads ? h->n_gene_tiles : 0), 256, 0, st>>>(
+        h->P + h->enc[0].w_off, h->Gp, h->packed_w1, c.n_genes, N0, h->n_kblocks, heads ? h->P + h->out_w : nullptr,
+        heads ? h->P + h->out_b : nullptr, h->packed_wout, nh);
+    h->wout_packed = heads;
+  }
   tc::EncFwdArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
@@ -425,16 +434,20 @@ static int tc_scvi_passes(sisua_model* h, cudaStream_t st, bool training, tc::Ou
 
 // fused output heads + count likelihood (+ backward of the heads when training)
 static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const float* x, int B, int S, float* llk_x,
-                           float* out_mean, float* out_disp, float* out_pi) {
+                           float* out_mean, float* out_disp, float* out_pi, const NormSpec* fused_norm) {
   const sisua_step_config& c = h->cfg;
   const int nh = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
   const int R = S * B, G = c.n_genes;
-  ++h->launches;
-  tc::pack_wout_kernel<<<h->n_gene_tiles, 256, 0, st>>>(h->P + h->out_w, h->P + h->out_b, h->packed_wout, G, nh, h->n_gene_tiles);
+  if (!h->wout_packed) {      // normally packed together with the first-layer operand at the start of the step
+    ++h->launches;
+    tc::pack_wout_kernel<<<h->n_gene_tiles, 256, 0, st>>>(h->P + h->out_w, h->P + h->out_b, h->packed_wout, G, nh, h->n_gene_tiles);
+  }
+  h->wout_packed = false;
   CUDA_OK(h, cudaMemsetAsync(llk_x, 0, (size_t)R * sizeof(float), st));
   tc::OutHeadsArgs a;
   memset(&a, 0, sizeof(a));
-  a.D = h->D; a.x = x; a.packed = h->packed_wout; a.llk_x = llk_x;
+  a.D = h->D; a.ldD = kH; a.x = x; a.packed = h->packed_wout; a.llk_x = llk_x;
+  if (fused_norm) { a.D = h->dec.back().A; a.ldD = h->dec.back().lda; a.fuse_norm = 1; a.ns = *fused_norm; }
   a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
   a.dD = h->dD; a.dW = h->Gd ? h->Gd + h->out_w : nullptr; a.db = h->Gd ? h->Gd + h->out_b : nullptr;
   a.R = R; a.B = B; a.G = G; a.n_tiles = h->n_gene_tiles;
@@ -801,10 +814,18 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   }
   stack_forward(h, st, h->dec, training, R, true);
   NormSpec ns_d = make_norm(h, h->dec.back(), training, R);
-  ++h->launches;
-  launch_pdl(norm_relu_kernel, dim3(std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms))), dim3(256), 0, st, 
-      h->dec.back().A, h->dec.back().lda, ns_d, h->D, R);
-  LAUNCH_OK(h, "decoder stack");
+  // the fused output-head kernel applies the last unit's norm + ReLU + dropout while it loads its cell tile; the
+  // activated matrix is only materialised for the protein head and the un-fused cross-check path
+  bool fuse_dec_norm = false;
+#ifdef SISUA_WITH_TC
+  fuse_dec_norm = tc_heads_enabled(h) && P == 0;
+#endif
+  if (!fuse_dec_norm) {
+    ++h->launches;
+    launch_pdl(norm_relu_kernel, dim3(std::max(1, std::min((R * H + 255) / 256, 4 * h->num_sms))), dim3(256), 0, st,
+        h->dec.back().A, h->dec.back().lda, ns_d, h->D, R);
+    LAUNCH_OK(h, "decoder stack");
+  }
   // ---- protein head (before the output layer so dD can be initialised by its backward)
   if (P > 0) {
     launch_dense_fwd(h, st, h->D, H, H, raw_norm(), h->P + h->y_w, H, h->P + h->y_b, 2 * P, h->PY, 2 * P, R);
@@ -831,7 +852,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
       int rc0 = init_dD(h, st, R);
       if (rc0 != SISUA_OK) return rc0;
     }
-    int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi);
+    int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi, fuse_dec_norm ? &ns_d : nullptr);
     if (rc != SISUA_OK) return rc;
     if (training && h->ev_out_grads) CUDA_OK(h, cudaEventRecord(h->ev_out_grads, st));
     out_done = true;
@@ -854,29 +875,26 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     LAUNCH_OK(h, "count_row_kernel");
   }
   sec_end(h, st, SEC_OUT_HEADS);
-  // ---- ELBO
+  // ---- ELBO (+ moving BatchNorm statistics, folded into the same launch)
   {
     ElboArgs a;
+    memset(&a, 0, sizeof(a));
     a.terms = terms; a.mask = P > 0 ? mask : nullptr; a.mask_scale = (P > 0 && c.mask_norm == 1) ? h->mask_scale : nullptr;
     a.R = R; a.B = B; a.alpha = c.alpha; a.beta = c.beta; a.loss = loss;
+    if (training && c.batchnorm) {
+      auto reg = [&](const Layer& L, int rows) {
+        a.mu.sum[L.bn_index] = h->stats + (size_t)L.stat_index * 4 * kH;
+        a.mu.sumsq[L.bn_index] = a.mu.sum[L.bn_index] + kH;
+        a.mu.inv_count[L.bn_index] = 1.0f / (float)rows;
+      };
+      for (auto& L : h->enc) reg(L, B);
+      for (auto& L : h->encl) reg(L, B);
+      for (auto& L : h->dec) reg(L, R);
+      a.n_bn = h->n_bn; a.moving = h->moving; a.momentum = c.bn_momentum;
+    }
     ++h->launches;
-    launch_pdl(elbo_kernel, dim3(std::max(1, std::min((R + 255) / 256, h->num_sms))), dim3(256), 0, st, a);
+    launch_pdl(elbo_kernel, dim3(std::max(1, std::min((R + 255) / 256, h->num_sms)) + a.n_bn), dim3(256), 0, st, a);
     LAUNCH_OK(h, "elbo_kernel");
-  }
-  if (training && c.batchnorm) {
-    MovingUpdateArgs mu;
-    memset(&mu, 0, sizeof(mu));
-    auto reg = [&](const Layer& L, int rows) {
-      mu.sum[L.bn_index] = h->stats + (size_t)L.stat_index * 4 * kH;
-      mu.sumsq[L.bn_index] = mu.sum[L.bn_index] + kH;
-      mu.inv_count[L.bn_index] = 1.0f / (float)rows;
-    };
-    for (auto& L : h->enc) reg(L, B);
-    for (auto& L : h->encl) reg(L, B);
-    for (auto& L : h->dec) reg(L, R);
-    ++h->launches;
-    launch_pdl(bn_moving_update_kernel, dim3(h->n_bn), dim3(kH), 0, st, mu, h->moving, c.bn_momentum);
-    LAUNCH_OK(h, "bn_moving_update_kernel");
   }
   return SISUA_OK;
 }

@@ -85,24 +85,12 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   }
 }
 
-// moving <- m * moving + (1-m) * batch   (one block of 64 threads per BN layer)
+// moving <- m * moving + (1-m) * batch   (one block per BN layer: the tail blocks of elbo_kernel)
 struct MovingUpdateArgs {
   const double* sum[16];
   const double* sumsq[16];
   float inv_count[16];
 };
-__global__ void bn_moving_update_kernel(MovingUpdateArgs a, float* __restrict__ moving, float momentum) {
-  // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
-  pdl_wait();
-  int l = blockIdx.x, c = threadIdx.x;
-  double m = a.sum[l][c] * (double)a.inv_count[l];
-  double v = a.sumsq[l][c] * (double)a.inv_count[l] - m * m;
-  if (v < 0.0) v = 0.0;
-  float* mv = moving + (size_t)l * 2 * kH;
-  mv[c] = momentum * mv[c] + (1.f - momentum) * (float)m;
-  mv[kH + c] = momentum * mv[kH + c] + (1.f - momentum) * (float)v;
-}
-
 // D = relu(norm(A))  (materialises the activated decoder output for the output heads)
 __global__ void __launch_bounds__(256) norm_relu_kernel(const float* __restrict__ A, int lda, NormSpec ns,
                                                         float* __restrict__ D, int R) {
@@ -369,13 +357,28 @@ __global__ void mask_scale_kernel(const uint8_t* mask, int B, float* out) {
 struct ElboArgs {
   float* terms; const uint8_t* mask; const float* mask_scale;
   int R, B; float alpha, beta; float* loss;  // loss: device scalar, pre-zeroed
+  // training: the last n_bn blocks of the grid fold the batch statistics into the moving ones (one block per BN layer)
+  int n_bn; float* moving; float momentum; MovingUpdateArgs mu;
 };
 __global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
   // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
   pdl_wait();
   __shared__ float scratch[33];
+  const int nblk = gridDim.x - a.n_bn;
+  if ((int)blockIdx.x >= nblk) {
+    const int l = blockIdx.x - nblk, c = threadIdx.x;
+    if (c < kH) {
+      double m = a.mu.sum[l][c] * (double)a.mu.inv_count[l];
+      double v = a.mu.sumsq[l][c] * (double)a.mu.inv_count[l] - m * m;
+      if (v < 0.0) v = 0.0;
+      float* mv = a.moving + (size_t)l * 2 * kH;
+      mv[c] = a.momentum * mv[c] + (1.f - a.momentum) * (float)m;
+      mv[kH + c] = a.momentum * mv[kH + c] + (1.f - a.momentum) * (float)v;
+    }
+    return;
+  }
   float local = 0.f;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.R; r += gridDim.x * blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.R; r += nblk * blockDim.x) {
     int b = r % a.B;
     float w = (a.mask && a.mask[b]) ? 1.f : 0.f;
     if (a.mask_scale) w *= *a.mask_scale;

@@ -10,6 +10,7 @@
 // quarter x 8-gene slice), 1 MMA-issuing thread, 1 bulk-copy (TMA) thread streaming pre-packed weight tiles.
 #pragma once
 #include "device_math.cuh"
+#include "kernels_mid.cuh"
 #include "tc_ptx.cuh"
 
 namespace sisua {
@@ -30,9 +31,8 @@ __host__ __device__ constexpr int packed_tile_bytes(int nh) { return 2 * w_tile_
 __host__ __device__ constexpr int packed_tile_stride(int nh) { return (packed_tile_bytes(nh) + 127) / 128 * 128; }
 
 // ---- weight pre-pack: W_out[nh*G, 64] fp32 -> per gene tile (w1 | w2 | bias) in the canonical UMMA layout ----
-__global__ void __launch_bounds__(256) pack_wout_kernel(const float* __restrict__ W, const float* __restrict__ bias,
-                                                        uint8_t* __restrict__ packed, int G, int nh, int n_tiles) {
-  const int tile = blockIdx.x;
+__device__ __forceinline__ void pack_wout_tile(const float* __restrict__ W, const float* __restrict__ bias,
+                                               uint8_t* __restrict__ packed, int G, int nh, int tile) {
   const int rows = nh * 32;
   const int RS = 128, CS = rows / 8 * 128;
   uint8_t* base = packed + (size_t)tile * packed_tile_stride(nh);
@@ -59,9 +59,15 @@ __global__ void __launch_bounds__(256) pack_wout_kernel(const float* __restrict_
     bdst[n] = g < G ? bias[(size_t)h * G + g] : 0.f;
   }
 }
+__global__ void __launch_bounds__(256) pack_wout_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                        uint8_t* __restrict__ packed, int G, int nh, int n_tiles) {
+  pack_wout_tile(W, bias, packed, G, nh, blockIdx.x);
+}
 
 struct OutHeadsArgs {
-  const float* D;          // [R, 64] activated decoder output
+  const float* D;          // [R, ldD] decoder output: activated (fuse_norm = 0) or the last unit's pre-activation
+  int ldD, fuse_norm;      //          whose norm / bias + ReLU + dropout is then applied on load (ns)
+  NormSpec ns;
   const float* x;          // [B, G] counts
   const uint8_t* packed;   // pre-packed weight tiles
   float* llk_x;            // [R], zeroed by the caller (gene chunks add atomically)
@@ -98,7 +104,7 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
   static constexpr int Gstage = 16 * 2048;                                                 // two G stages when training
   __host__ __device__ static constexpr int XS(int nh, bool train) { return G0(nh) + (train ? 2 * Gstage : 0); }   // [8][512] count stash
   __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 8 * kEpiThreads * 4; }
-  __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + 3 * kCellTile * 4; }   // llk | T | dlib
+  __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + (3 * kCellTile + 2 * kK) * 4; }   // llk | T | dlib | norm scale, shift
   __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
 };
 
@@ -139,13 +145,30 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  float* nsc = llk_s + 3 * kCellTile;      // [64] scale, [64] shift of the fused norm
+  if (a.fuse_norm) {
+    if (t < kK) { float4 q = norm_coeffs4(a.ns, t); nsc[t] = q.x; nsc[kK + t] = q.y; }
+    __syncthreads();
+  }
   for (int item = t; item < kCellTile * 8; item += kOutThreads) {
     int r = item % kCellTile, cg = item / kCellTile;
     float v[8];
     if (row0 + r < a.R) {
-      const float4* src = reinterpret_cast<const float4*>(a.D + (size_t)(row0 + r) * kK + cg * 8);
+      const float4* src = reinterpret_cast<const float4*>(a.D + (size_t)(row0 + r) * a.ldD + cg * 8);
       float4 p = src[0], q = src[1];
       v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+      if (a.fuse_norm) {            // h = dropout(relu(a * sc + sh)): what norm_relu_kernel would have written to HBM
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(v[j], nsc[cg * 8 + j], nsc[kK + cg * 8 + j]);
+          if (a.ns.mode != NORM_RAW) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.ns.mode != NORM_RAW && a.ns.drop.rate > 0.f) {
+          DropMult8 m = dropout_mult8(a.ns.drop, (uint32_t)(row0 + r), (uint32_t)cg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= m.m[j];
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;

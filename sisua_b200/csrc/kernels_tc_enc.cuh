@@ -25,9 +25,8 @@ __host__ __device__ constexpr int w1_tile_bytes(int n0) { return n0 * 64 * 2; } 
 __host__ __device__ constexpr int w1_block_bytes(int n0) { return 2 * w1_tile_bytes(n0); }   // hi | lo
 
 // W1[N0, Gp] fp32 -> per 64-gene k-block (hi | lo) fp16 tiles T[n][k], RS = 128, CS = N0/8*128
-__global__ void __launch_bounds__(256) pack_w1_kernel(const float* __restrict__ W, int ldw, uint8_t* __restrict__ packed, int G,
-                                                      int n0) {
-  const int kb = blockIdx.x;
+__device__ __forceinline__ void pack_w1_block(const float* __restrict__ W, int ldw, uint8_t* __restrict__ packed, int G, int n0,
+                                              int kb) {
   const int CS = n0 / 8 * 128;
   uint8_t* base = packed + (size_t)kb * w1_block_bytes(n0);
   for (int i = threadIdx.x; i < n0 * 8; i += blockDim.x) {
@@ -44,6 +43,15 @@ __global__ void __launch_bounds__(256) pack_w1_kernel(const float* __restrict__ 
     *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(base + w1_tile_bytes(n0) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+}
+// one launch per step re-packs both tensor-core weight operands after the optimiser moved them: blocks [0, n_kblocks)
+// the first-layer k-blocks, the rest the output-head gene tiles (W_out == nullptr: first layer only)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W1, int ldw, uint8_t* __restrict__ packed_w1,
+                                                           int G, int n0, int n_kblocks, const float* __restrict__ W_out,
+                                                           const float* __restrict__ b_out, uint8_t* __restrict__ packed_wout,
+                                                           int nh) {
+  if ((int)blockIdx.x < n_kblocks) pack_w1_block(W1, ldw, packed_w1, G, n0, blockIdx.x);
+  else pack_wout_tile(W_out, b_out, packed_wout, G, nh, blockIdx.x - n_kblocks);
 }
 
 // log(1 + x): |error| <= 1 ulp of (1 + x) in absolute terms, far below the 2^-22 of the hi/lo operand split
