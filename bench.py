@@ -424,5 +424,15 @@ def main():
     dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+  """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; print() then writes the JSON line
+  to the real stdout, so the driver reads exactly one line."""
+  real = os.dup(1)
+  sys.stdout.flush()
+  os.dup2(2, 1)
+  sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+  _only_json_on_stdout()
   main()
