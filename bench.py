@@ -299,7 +299,7 @@ def main():
       for i in range(n):
         step_no[0] += 1
         losses.append(pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
-                                allreduce=(lambda g: reducer()) if world > 1 else None))
+                                allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None))
       return pipe.flush(losses)
     run(3)
     sync_all()
@@ -397,7 +397,8 @@ def main():
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
                 "api": "HostTrainPipeline.step: pinned host minibatch in CSR form (int32 row pointers + uint16 gene ids and counts) "
                        "-> H2D on a copy stream into a double-buffered slot -> that slot's CUDA graph (sisua_unpack_counts_csr -> "
-                       "sisua_train_step -> sisua_adam_step -> loss D2H); N > 1: sisua_train_step_host + NCCL all-reduce + sisua_adam_step",
+                       "sisua_train_step -> sisua_adam_step -> loss D2H); N > 1: the slot has two graphs with the NCCL all-reduce of the "
+                       "gradient buffer launched between them",
                 "dense_u16_host_value": e2e_u16, "dense_u16_h2d_bytes_per_step": int(B * G * 2 + B * LATENT * 4),
                 "dense_fp32_host_value": e2e_f32, "dense_fp32_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
         "latency_regime": {"what": "same train step at the reference's default minibatch sizes (launch-bound)", **small},

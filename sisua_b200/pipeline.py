@@ -68,8 +68,10 @@ class HostTrainPipeline:
   slot's graph, so the transfer of step i+1 runs under the kernels of step i.  The graph matters here: with eager
   launches the per-kernel command fetches queue behind the bulk H2D traffic on PCIe and the ~20 short kernels of a
   step each start late (measured: 417 -> 700 us per step under a concurrent 11 MB copy; graph replay: 411 -> 423 us).
-  Data parallel (an `allreduce` callback between backward and Adam) or ragged batches go through the library's
-  host-buffer entry point `sisua_train_step_host`, which stages on its own copy stream."""
+  Data parallel: the slot owns two graphs (… -> train step | Adam -> loss D2H) and the `allreduce(grads)` callback is
+  launched eagerly between them, so only the collective's own launches see the busy PCIe link.  Ragged batches and
+  model families with extra host inputs go through the library's host-buffer entry point `sisua_train_step_host`,
+  which stages on its own copy stream."""
 
   def __init__(self, eng: Engine, batch: int, depth: int = 2, use_graph: bool = True):
     self.eng = eng
@@ -95,20 +97,27 @@ class HostTrainPipeline:
       self.slots[s]["consumed"].record()
     return self.slots[s]
 
-  def _graph(self, s: int, fmt: str, lr: float, clipnorm: float):
-    key = (s, fmt, float(lr), float(clipnorm))
+  def _graph(self, s: int, fmt: str, lr: float, clipnorm: float, world: int = 1, split: bool = False):
+    """(graph, None), or (backward graph, optimiser graph) when an all-reduce sits between them."""
+    key = (s, fmt, float(lr), float(clipnorm), int(world), bool(split))
     if key not in self.graphs:
       eng, sl = self.eng, self._slot(s)
-      def run():
+      def fwd_bwd():
         if fmt == "csr":
           eng.unpack_counts_csr(*sl["csr"], sl["x"])
         elif fmt == "u16":
           eng.unpack_counts_u16(sl["x16"], sl["x"])
         eng.train_step(sl["x"], eps_z=sl["eps"] if eng.cfg.model_kind != 2 else None, terms=sl["terms"], loss=sl["loss"],
                        seed=0, step=-1)
-        eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0, t=0)
+      def optimise():
+        eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=0)
         self.host_loss[s].copy_(sl["loss"], non_blocking=True)
-      self.graphs[key] = _capture_step(eng, run)
+      if not split:
+        self.graphs[key] = (_capture_step(eng, lambda: (fwd_bwd(), optimise())), None)
+      else:
+        # captured separately; the warm-up of the first one leaves gradients behind that the second one's warm-up
+        # consumes, and _capture_step restores parameters and optimiser state after each
+        self.graphs[key] = (_capture_step(eng, fwd_bwd), _capture_step(eng, optimise))
     return self.graphs[key]
 
   def step(self, x_host, eps_host: Optional[torch.Tensor], step: int, lr: float = 1e-3, clipnorm: float = 100.0,
@@ -118,7 +127,7 @@ class HostTrainPipeline:
     eng = self.eng
     is_csr = isinstance(x_host, CsrBatch)
     rows = x_host.rows if is_csr else x_host.shape[0]
-    graphable = (self.use_graph and allreduce is None and not host_extras and rows == self.batch and
+    graphable = (self.use_graph and not host_extras and rows == self.batch and
                  eng.cfg.model_kind in (0, 2) and eng.cfg.n_proteins == 0)
     if not graphable:
       out = self.host_loss[self.i % len(self.host_loss)]
@@ -138,7 +147,7 @@ class HostTrainPipeline:
                    torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
     if fmt == "u16" and sl["x16"] is None:
       sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
-    graph = self._graph(s, fmt, lr, clipnorm)
+    graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None)
     if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
       eng.reset_step_counter(step - 1)
     main = torch.cuda.current_stream(eng.device)
@@ -160,6 +169,9 @@ class HostTrainPipeline:
     main.wait_event(sl["filled"])
     graph.replay()
     sl["consumed"].record(main)
+    if graph_opt is not None:
+      allreduce(eng.grads)
+      graph_opt.replay()
     eng.step_count += 1
     return self.host_loss[s]
 

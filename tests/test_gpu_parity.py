@@ -386,7 +386,7 @@ def test_host_buffer_step_rejects_bad_input():
 
 
 @pytest.mark.parametrize("fmt", ["f32", "u16", "csr"])
-@pytest.mark.parametrize("use_graph", [True, False])
+@pytest.mark.parametrize("use_graph", [True, False, "split"])
 def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
   """HostTrainPipeline (per-slot CUDA graphs fed by a copy stream, or the library's host-buffer entry point) trains
   exactly like explicit device-side steps on the same minibatches."""
@@ -397,7 +397,10 @@ def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
   mov = PR.init_bn_moving(cfg)
   a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
   b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
-  pipe = HostTrainPipeline(a, 64, use_graph=use_graph)
+  pipe = HostTrainPipeline(a, 64, use_graph=bool(use_graph))
+  calls = []
+  # "split": the data-parallel arrangement (two graphs with a gradient callback between them), here with one rank
+  reduce_cb = (lambda g: calls.append(float(g.abs().sum()))) if use_graph == "split" else None
   la, lb, keep = [], [], []
   for t in range(1, 8):
     batch = Hh.make_batch(cfg, 64, seed=t, stress=(t == 3))
@@ -405,7 +408,7 @@ def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
     xh = {"f32": lambda: torch.from_numpy(x).pin_memory(), "u16": lambda: quantize_counts(x), "csr": lambda: CsrBatch(x)}[fmt]()
     eh = torch.from_numpy(batch["eps_z"]).pin_memory()
     keep.append((xh, eh))
-    out = pipe.step(xh, eh, step=t, lr=1e-3, clipnorm=100.0)
+    out = pipe.step(xh, eh, step=t, lr=1e-3, clipnorm=100.0, allreduce=reduce_cb)
     torch.cuda.synchronize()
     la.append(float(out))
     _, ls = b.train_step(**batch, seed=0, step=t)
@@ -414,4 +417,6 @@ def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
   np.testing.assert_allclose(la, lb, rtol=2e-4)
   assert float((a.params - b.params).abs().max()) <= 4e-3 and float((a.params - b.params).abs().mean()) <= 1e-5
   assert la[0] != la[1]
+  if use_graph == "split":
+    assert len(calls) == 7 and all(c > 0 for c in calls)      # the callback saw this step's gradients every time
   a.close(); b.close()
