@@ -68,3 +68,31 @@ def test_param_layout_properties():
     if model == "scvi":   # the two first-layer operands must be adjacent ([2H, G] streamed once)
       e0, e1 = entries[0], entries[1]
       assert (e0.name, e1.name) == ("enc.0.W", "encl.0.W") and e1.offset == e0.offset + e0.size
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+  """sizeof / offsetof of every struct that crosses the C ABI, as gcc sees include/sisua_b200.h, equal the ctypes
+  mirrors (sisua_step_config, sisua_param_desc, sisua_host_batch)."""
+  import shutil
+  import subprocess
+  import pytest
+  gcc = shutil.which("gcc")
+  if gcc is None:
+    pytest.skip("gcc not available")
+  pairs = [("sisua_step_config", C.StepConfig), ("sisua_param_desc", _lib.ParamDesc), ("sisua_host_batch", _lib.HostBatch)]
+  lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "sisua_b200.h")}"',
+           'int main(void) {']
+  for cname, st in pairs:
+    lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+    for fname, _ in st._fields_:
+      lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+  lines += ['  return 0;', '}']
+  src = tmp_path / "layout.c"
+  src.write_text("\n".join(lines))
+  exe = tmp_path / "layout"
+  subprocess.run([gcc, "-std=c99", "-o", str(exe), str(src)], check=True)
+  got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+  for cname, st in pairs:
+    assert int(got[cname]) == ctypes.sizeof(st), cname
+    for fname, _ in st._fields_:
+      assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
