@@ -176,3 +176,138 @@ def test_philox_known_answers():
   m = dropout_mask(512, 200, 0.3, seed=1234, step=7, stream=0)
   assert m.shape == (512, 200) and abs(m.mean() - 0.7) < 0.01
   assert not np.array_equal(m, dropout_mask(512, 200, 0.3, seed=1234, step=8, stream=0))
+
+
+def test_oracle_matches_torch_nn_composition():
+  """The oracle's ZINB-VAE train-mode forward against an independent composition out of stock building blocks
+  (nn.Linear, nn.BatchNorm1d(eps=1e-3), torch.distributions.Normal / NegativeBinomial / kl_divergence): per-cell ELBO,
+  its terms, the updated moving statistics and the gradient of the loss wrt the first weight matrix."""
+  import torch.nn as nn
+  import torch.distributions as TD
+  cfg = C.make_step_config("vae", n_genes=30, n_latent=5, input_dropout=0.0)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  batch = Hh.make_batch(cfg, 24)
+  P = Hh.oracle_params(cfg, flat)
+  for p in P.values():
+    p.requires_grad_(True)
+  o = O.forward(cfg, P, Hh.oracle_moving(cfg, mov), training=True, **batch)
+  (-o["elbo"].mean()).backward()
+
+  dt = torch.float64
+  W = {k: v.detach().clone() for k, v in P.items()}
+  def unit(prefix, n_in):
+    lin = nn.Linear(n_in, 64, bias=False).to(dt)
+    bn = nn.BatchNorm1d(64, eps=cfg.bn_eps, momentum=1.0 - cfg.bn_momentum).to(dt)
+    with torch.no_grad():
+      lin.weight.copy_(W[prefix + ".W"][:, :n_in]); bn.weight.copy_(W[prefix + ".gamma"]); bn.bias.copy_(W[prefix + ".beta"])
+    return lin, bn
+  x = torch.tensor(batch["x"], dtype=dt)
+  h = torch.log1p(x)
+  mods = []
+  first = None
+  for i, (name, n_in) in enumerate([("enc.0", 30), ("enc.1", 64)]):
+    lin, bn = unit(name, n_in)
+    mods.append((name, bn))
+    if first is None:
+      first = lin
+    h = torch.relu(bn.train()(lin(h)))
+  pl = h @ W["lat.W"].T + W["lat.b"]
+  loc, scale = pl[:, :5], torch.nn.functional.softplus(pl[:, 5:] + np.log(np.e - 1.0))
+  qz = TD.Normal(loc, scale)
+  z = loc + scale * torch.tensor(batch["eps_z"], dtype=dt)
+  kl = TD.kl_divergence(qz, TD.Normal(torch.zeros_like(loc), torch.ones_like(scale))).sum(-1)
+  d = z
+  for name, n_in in [("dec.0", 5), ("dec.1", 64)]:
+    lin, bn = unit(name, n_in)
+    mods.append((name, bn))
+    d = torch.relu(bn.train()(lin(d)))
+  G = 30
+  out = d @ W["out.W"].T + W["out.b"]
+  mu = torch.nn.functional.softplus(out[:, :G])
+  theta = torch.nn.functional.softplus(out[:, G:2 * G] + np.log(np.e - 1.0))
+  pi_logit = out[:, 2 * G:]
+  # NB(mean, inverse dispersion) == NegativeBinomial(total_count = theta, probs = mu / (mu + theta))
+  nb = TD.NegativeBinomial(total_count=theta, probs=mu / (mu + theta))
+  log_nb = nb.log_prob(x)
+  log_pi, log_1m_pi = torch.nn.functional.logsigmoid(pi_logit), torch.nn.functional.logsigmoid(-pi_logit)
+  llk = torch.where(x < 1e-8, torch.logsumexp(torch.stack([log_pi, log_1m_pi + log_nb]), 0), log_1m_pi + log_nb).sum(-1)
+  elbo = llk - kl
+  np.testing.assert_allclose(o["llk_x"].detach().numpy(), llk.detach().numpy(), rtol=1e-5)
+  np.testing.assert_allclose(o["kl_z"].detach().numpy(), kl.detach().numpy(), rtol=1e-9)
+  np.testing.assert_allclose(o["elbo"].detach().numpy(), elbo.detach().numpy(), rtol=1e-5)
+  (-elbo.mean()).backward()
+  g_ref = first.weight.grad.numpy()
+  g_or = P["enc.0.W"].grad.numpy()[:, :30]
+  np.testing.assert_allclose(g_or, g_ref, rtol=1e-4, atol=1e-9 + 1e-6 * np.abs(g_ref).max())
+  # moving statistics (Keras: moving <- m * moving + (1 - m) * batch, biased batch variance; torch keeps the unbiased one)
+  B = 24
+  for name, bn in mods:
+    np.testing.assert_allclose(o["new_moving"][name + ".mean"].numpy(), bn.running_mean.numpy(), rtol=1e-9, atol=1e-12)
+    keras_var = (bn.running_var.numpy() - cfg.bn_momentum * 1.0) * (B - 1) / B + cfg.bn_momentum * 1.0
+    np.testing.assert_allclose(o["new_moving"][name + ".var"].numpy(), keras_var, rtol=1e-8)
+
+
+def test_oracle_scvi_and_sisua_heads_match_torch_distributions():
+  """Inference-mode (moving-statistics BatchNorm) forward of scVI and SISUA against stock torch modules: library
+  latent with its dataset prior, gene softmax scaled by the clipped library, exp dispersion, and the protein head as
+  TFP's NegativeBinomial(total_count = exp(a), logits = b), masked and weighted by alpha."""
+  import torch.nn.functional as F
+  import torch.distributions as TD
+  dt = torch.float64
+
+  def hidden(P, M, prefix, n_layers, h):
+    for i in range(n_layers):
+      n = f"{prefix}.{i}"
+      a = h @ P[n + ".W"][:, :h.shape[1]].T
+      a = (a - M[n + ".mean"]) / torch.sqrt(M[n + ".var"] + 1e-3) * P[n + ".gamma"] + P[n + ".beta"]
+      h = torch.relu(a)
+    return h
+
+  def zinb(x, mu, theta, pi_logit):
+    log_nb = TD.NegativeBinomial(total_count=theta, probs=mu / (mu + theta)).log_prob(x)
+    lp, l1 = F.logsigmoid(pi_logit), F.logsigmoid(-pi_logit)
+    return torch.where(x < 1e-8, torch.logsumexp(torch.stack([lp, l1 + log_nb]), 0), l1 + log_nb).sum(-1)
+
+  for model, kw in (("scvi", dict(clip_library=7.0)), ("sisua", dict(n_proteins=4, alpha=10.0))):
+    cfg = C.make_step_config(model, n_genes=20, n_latent=3, **kw)
+    flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+    mov = PR.init_bn_moving(cfg)
+    rng = np.random.default_rng(3)
+    mov[:, 0, :] = rng.normal(0, 0.2, mov[:, 0, :].shape); mov[:, 1, :] = rng.uniform(0.5, 1.5, mov[:, 1, :].shape)
+    batch = Hh.make_batch(cfg, 16)
+    P, M = Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov)
+    o = O.forward(cfg, P, M, training=False, **batch)
+    x = torch.tensor(batch["x"], dtype=dt)
+    G, Z = 20, 3
+    h = hidden(P, M, "enc", cfg.n_enc_layers, torch.log1p(x))
+    pl = h @ P["lat.W"].T + P["lat.b"]
+    loc, scale = pl[:, :Z], F.softplus(pl[:, Z:] + np.log(np.e - 1.0))
+    z = loc + scale * torch.tensor(batch["eps_z"], dtype=dt)
+    kl = TD.kl_divergence(TD.Normal(loc, scale), TD.Normal(torch.zeros_like(loc), torch.ones_like(scale))).sum(-1)
+    d = hidden(P, M, "dec", cfg.n_dec_layers, z)
+    out = d @ P["out.W"].T + P["out.b"]
+    if model == "scvi":
+      hl = hidden(P, M, "encl", cfg.n_encl_layers, torch.log1p(x))
+      pll = hl @ P["lib.W"].T + P["lib.b"]
+      l_loc, l_scale = pll[:, 0], F.softplus(pll[:, 1] + np.log(np.e - 1.0))
+      lib = l_loc + l_scale * torch.tensor(batch["eps_l"], dtype=dt)
+      prior = torch.tensor(batch["library"], dtype=dt)
+      kl_l = TD.kl_divergence(TD.Normal(l_loc, l_scale), TD.Normal(prior[:, 0], torch.sqrt(prior[:, 1])))
+      mu = torch.exp(lib.clamp(0.0, 7.0))[:, None] * torch.softmax(out[:, :G], 1).clamp(1e-7, 1 - 1e-7)
+      llk = zinb(x, mu, torch.exp(out[:, G:2 * G]), out[:, 2 * G:])
+      elbo = llk - kl - kl_l
+      np.testing.assert_allclose(o["kl_l"].numpy(), kl_l.numpy(), rtol=1e-9)
+      assert float((lib > 7.0).sum()) > 0 or float(lib.max()) <= 7.0      # clip path exercised or trivially inactive
+    else:
+      mu = F.softplus(out[:, :G])
+      llk = zinb(x, mu, F.softplus(out[:, G:2 * G] + np.log(np.e - 1.0)), out[:, 2 * G:])
+      py = d @ P["y.W"].T + P["y.b"]
+      y = torch.tensor(batch["y"], dtype=dt)
+      llk_y = TD.NegativeBinomial(total_count=torch.exp(py[:, :4]), logits=py[:, 4:], validate_args=False).log_prob(y).sum(-1)   # y is real-valued
+      m = torch.tensor(batch["mask"], dtype=dt)
+      elbo = llk + 10.0 * m * llk_y - kl
+      np.testing.assert_allclose(o["llk_y"].numpy(), llk_y.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(o["mu"].numpy(), mu.numpy(), rtol=1e-9)
+    np.testing.assert_allclose(o["llk_x"].numpy(), llk.numpy(), rtol=1e-5)
+    np.testing.assert_allclose(o["elbo"].numpy(), elbo.numpy(), rtol=1e-5)
