@@ -693,6 +693,39 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ At, const flo
       for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
 }
+// Narrow variants for the latent block (latent width <= 16, so one side of the product has <= 16 / <= 32 useful
+// columns and the 4x4 blocking would spend 3/4 of its FMAs on padding): all 256 threads share the narrow side.
+//   tile_mma_n16: C[4 rg + i][c]       = sum_k At[k][4 rg + i] * Bt[k][c],       rg = t >> 4, c = t & 15
+//   tile_mma_n32: C[4 rg + i][2 cp + j] = sum_k At[k][4 rg + i] * Bt[k][2 cp + j], rg = t >> 4, cp = t & 15
+//   tile_mma_m32: C[4 mg + i][2 kp + j] = sum_k At[k][4 mg + i] * Bt[k][2 kp + j], mg = t >> 5 (rows < 32), kp = t & 31
+__device__ __forceinline__ void tile_mma_n16(const float* __restrict__ At, const float* __restrict__ Bt, int K, int t, float (&acc)[4]) {
+  const int rg = t >> 4, c = t & 15;
+  for (int k = 0; k < K; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(At + k * kTS + 4 * rg);
+    const float b = Bt[k * kTS + c];
+    acc[0] = fmaf(a4.x, b, acc[0]); acc[1] = fmaf(a4.y, b, acc[1]); acc[2] = fmaf(a4.z, b, acc[2]); acc[3] = fmaf(a4.w, b, acc[3]);
+  }
+}
+__device__ __forceinline__ void tile_mma_n32(const float* __restrict__ At, const float* __restrict__ Bt, int K, int t, float (&acc)[4][2]) {
+  const int rg = t >> 4, cp = t & 15;
+  for (int k = 0; k < K; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(At + k * kTS + 4 * rg);
+    const float2 b2 = *reinterpret_cast<const float2*>(Bt + k * kTS + 2 * cp);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = fmaf(av[i], b2.x, acc[i][0]); acc[i][1] = fmaf(av[i], b2.y, acc[i][1]); }
+  }
+}
+__device__ __forceinline__ void tile_mma_m32(const float* __restrict__ At, const float* __restrict__ Bt, int K, int t, float (&acc)[4][2]) {
+  const int mg = t >> 5, kp = t & 31;
+  for (int k = 0; k < K; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(At + k * kTS + 4 * mg);
+    const float2 b2 = *reinterpret_cast<const float2*>(Bt + k * kTS + 2 * kp);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = fmaf(av[i], b2.x, acc[i][0]); acc[i][1] = fmaf(av[i], b2.y, acc[i][1]); }
+  }
+}
 __device__ __forceinline__ void zero16(float (&acc)[4][4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -772,17 +805,33 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
     }
     __syncthreads();
     float acc[4][4];
-    zero16(acc);
-    tile_mma(HT, W1T, kH, ty, tx, acc);
+    if (ZP <= 32) {          // only the first 32 columns of PL are meaningful: 8 outputs per thread instead of 16
+      float pn[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) { pn[i][0] = 0.f; pn[i][1] = 0.f; }
+      tile_mma_n32(HT, W1T, kH, t, pn);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = 4 * ty + i, m = 4 * tx + j;
-        float v = m < ZP ? acc[i][j] + a.b_lat[m] : 0.f;
-        PLs[r * kTS + m] = v;
-        if (r0 + r < a.B && m < ZP) a.PL[(size_t)(r0 + r) * ZP + m] = v;
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int r = 4 * ty + i, m = 2 * tx + j;
+          float v = m < ZP ? pn[i][j] + a.b_lat[m] : 0.f;
+          PLs[r * kTS + m] = v;
+          if (r0 + r < a.B && m < ZP) a.PL[(size_t)(r0 + r) * ZP + m] = v;
+        }
+    } else {
+      zero16(acc);
+      tile_mma(HT, W1T, kH, ty, tx, acc);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 4 * ty + i, m = 4 * tx + j;
+          float v = m < ZP ? acc[i][j] + a.b_lat[m] : 0.f;
+          PLs[r * kTS + m] = v;
+          if (r0 + r < a.B && m < ZP) a.PL[(size_t)(r0 + r) * ZP + m] = v;
+        }
+    }
     __syncthreads();
     if (t < kTileR) {      // one thread per row: loc / scale / sample / KL
       const int r = t, b = r0 + r;
@@ -898,6 +947,9 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
   __syncthreads();
   float accW0[4][4], accW1[4][4];
   zero16(accW0); zero16(accW1);
+  // latent width <= 16: the three products with a narrow side use all 256 threads on the useful columns
+  const bool narrow = Z <= 16;
+  float nW0[4] = {0.f, 0.f, 0.f, 0.f}, nW1[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   float accb = 0.f;
   const float in_drop_scale = a.ns_enc.drop.rate > 0.f ? a.ns_enc.drop.scale : 1.f;
   for (int r0 = blockIdx.x * kTileR; r0 < a.B; r0 += gridDim.x * kTileR) {
@@ -931,15 +983,24 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
     }
     __syncthreads();
     // dW_dec0[n][j] += sum_r G[r][n] z[r][j] ;  dz[r][j] = sum_n G[r][n] W_dec0[n][j]
-    tile_mma(Gn, Zn, kTileR, ty, tx, accW0);
-    float dz[4][4];
-    zero16(dz);
-    tile_mma(GT, Wd0n, kH, ty, tx, dz);
-    __syncthreads();                       // everyone is done reading z and G
+    if (narrow) {
+      tile_mma_n16(Gn, Zn, kTileR, t, nW0);            // dW_dec0[4 ty + i][tx]
+      float dzn[4] = {0.f, 0.f, 0.f, 0.f};
+      tile_mma_n16(GT, Wd0n, kH, t, dzn);              // dz[4 ty + i][tx]
+      __syncthreads();                     // everyone is done reading z and G
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) Zn[(4 * ty + i) * kTS + tx] = dzn[i];
+    } else {
+      tile_mma(Gn, Zn, kTileR, ty, tx, accW0);
+      float dz[4][4];
+      zero16(dz);
+      tile_mma(GT, Wd0n, kH, ty, tx, dz);
+      __syncthreads();                     // everyone is done reading z and G
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Zn[(4 * ty + i) * kTS + 4 * tx + j] = dz[i][j];
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Zn[(4 * ty + i) * kTS + 4 * tx + j] = dz[i][j];
+    }
     __syncthreads();
     // latent backward, one thread per row: dz -> dPL = (d loc | d scale_raw); overwrites G with dPL
     for (int i = t; i < kTileR * kH; i += kMidThreads) { Gn[(i >> 6) * kTS + (i & 63)] = 0.f; GT[(i & 63) * kTS + (i >> 6)] = 0.f; }
@@ -966,7 +1027,8 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
     }
     __syncthreads();
     // dW_lat[m][k] += sum_r dPL[r][m] h[r][k] ; db_lat[m] += sum_r dPL[r][m] ; dH_enc[r][k] = sum_m dPL[r][m] W_lat[m][k]
-    tile_mma(Gn, Hn, kTileR, ty, tx, accW1);
+    if (narrow) tile_mma_m32(Gn, Hn, kTileR, t, nW1);  // dW_lat[4 (t >> 5) + i][2 (t & 31) + j]
+    else tile_mma(Gn, Hn, kTileR, ty, tx, accW1);
     if (t < ZP) {
       for (int r = 0; r < kTileR; ++r) accb += Gn[r * kTS + t];
     }
@@ -999,14 +1061,26 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
     }
     __syncthreads();
   }
+  if (narrow) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = 4 * ty + i, k = 4 * tx + j;
-      if (k < Z) atomicAdd(&a.dW_d0[(size_t)n * Z + k], accW0[i][j]);
-      if (n < ZP) atomicAdd(&a.dW_lat[(size_t)n * kH + k], accW1[i][j]);
+    for (int i = 0; i < 4; ++i) {
+      if (tx < Z) atomicAdd(&a.dW_d0[(size_t)(4 * ty + i) * Z + tx], nW0[i]);
+      const int m = 4 * (t >> 5) + i;
+      if (m < ZP) {
+        atomicAdd(&a.dW_lat[(size_t)m * kH + 2 * (t & 31)], nW1[i][0]);
+        atomicAdd(&a.dW_lat[(size_t)m * kH + 2 * (t & 31) + 1], nW1[i][1]);
+      }
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * ty + i, k = 4 * tx + j;
+        if (k < Z) atomicAdd(&a.dW_d0[(size_t)n * Z + k], accW0[i][j]);
+        if (n < ZP) atomicAdd(&a.dW_lat[(size_t)n * kH + k], accW1[i][j]);
+      }
+  }
   if (t < ZP) atomicAdd(&a.db_lat[t], accb);
   if (t < kH) {
     atomicAdd(&a.prev_sdy[t], dacc[t]);
