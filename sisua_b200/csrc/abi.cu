@@ -684,7 +684,7 @@ static void launch_dense_fwd(sisua_model* h, cudaStream_t st, const float* A_in,
 
 static void launch_col_stats(sisua_model* h, cudaStream_t st, const Layer& L, int R) {
   double* s = h->stats + (size_t)L.stat_index * 4 * kH;
-  int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+  int grid = std::max(1, std::min((R + 15) / 16, 2 * h->num_sms));
   ++h->launches;
   launch_pdl(col_stats_kernel, dim3(grid), dim3(256), 0, st, L.A, L.lda, R, kH, s, s + kH);
 }
@@ -916,7 +916,7 @@ static int stack_backward(sisua_model* h, cudaStream_t st, std::vector<Layer>& L
     if (i == (int)Ls.size() - 1 && !top_reduced) {   // top unit: no consumer kernel produced its reductions
       float* dgamma = L.g_off >= 0 ? h->Gd + L.g_off : nullptr;
       float* dbeta = h->Gd + L.b_off;
-      int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+      int grid = std::max(1, std::min((R + 15) / 16, 2 * h->num_sms));
       ++h->launches;
       launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, dH, kH, L.A, L.lda, ns, R, sdy, sdyx, dgamma, dbeta);
     }
@@ -1003,7 +1003,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     NormSpec ns0 = make_norm(h, L0, true, R);
     double* sdy0 = h->stats + (size_t)L0.stat_index * 4 * kH + 2 * kH;
     if (h->dec.size() == 1) {     // no decoder unit above produced unit 0's norm-backward reductions
-      int grid = std::max(1, std::min((R + 3) / 4, 2 * h->num_sms));
+      int grid = std::max(1, std::min((R + 15) / 16, 2 * h->num_sms));
       ++h->launches;
       launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, (const float*)dH_d0, kH, (const float*)L0.A, L0.lda, ns0, R, sdy0,
                  sdy0 + kH, L0.g_off >= 0 ? h->Gd + L0.g_off : (float*)nullptr, h->Gd + L0.b_off);

@@ -64,24 +64,38 @@ __device__ __forceinline__ void norm_coeffs(const NormSpec& ns, int c, float& sc
 // ------------------------------------------------------------------------------------------
 // column sums / sums of squares of A[R, ncols<=128] in double (BN batch statistics)
 // ------------------------------------------------------------------------------------------
+// 16 threads per row (one float4 each), 16 rows per block pass, four row passes in flight; per-thread partial sums in
+// fp32 (a handful of rows), combined in fp64.  ncols must be 64 (lda a multiple of 4, A 16-byte aligned).
 __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ A, int lda, int R, int ncols,
                                                         double* __restrict__ sum, double* __restrict__ sumsq) {
-  __shared__ double s1[256], s2[256];
+  __shared__ float s1[16][kH], s2[16][kH];
   // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
   pdl_wait();
-  int groups = 256 / ncols;                    // ncols in {64,128}
-  int c = threadIdx.x % ncols, grp = threadIdx.x / ncols;
-  double a1 = 0.0, a2 = 0.0;
-  for (int r = blockIdx.x * groups + grp; r < R; r += gridDim.x * groups) {
-    double v = (double)A[(size_t)r * lda + c];
-    a1 += v; a2 += v * v;
+  const int c4 = (threadIdx.x & 15) * 4, rg = threadIdx.x >> 4;
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int stride = gridDim.x * 16;
+  auto acc = [&](const float4& v) {
+    a1[0] += v.x; a1[1] += v.y; a1[2] += v.z; a1[3] += v.w;
+    a2[0] = fmaf(v.x, v.x, a2[0]); a2[1] = fmaf(v.y, v.y, a2[1]); a2[2] = fmaf(v.z, v.z, a2[2]); a2[3] = fmaf(v.w, v.w, a2[3]);
+  };
+  int r = blockIdx.x * 16 + rg;
+  for (; r + 3 * stride < R; r += 4 * stride) {
+    const float4 v0 = *reinterpret_cast<const float4*>(A + (size_t)r * lda + c4);
+    const float4 v1 = *reinterpret_cast<const float4*>(A + (size_t)(r + stride) * lda + c4);
+    const float4 v2 = *reinterpret_cast<const float4*>(A + (size_t)(r + 2 * stride) * lda + c4);
+    const float4 v3 = *reinterpret_cast<const float4*>(A + (size_t)(r + 3 * stride) * lda + c4);
+    acc(v0); acc(v1); acc(v2); acc(v3);
   }
-  s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
+  for (; r < R; r += stride) acc(*reinterpret_cast<const float4*>(A + (size_t)r * lda + c4));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s1[rg][c4 + j] = a1[j]; s2[rg][c4 + j] = a2[j]; }
   __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < groups; ++g) { a1 += s1[g * ncols + c]; a2 += s2[g * ncols + c]; }
-    atomicAdd(&sum[c], a1);
-    atomicAdd(&sumsq[c], a2);
+  if (threadIdx.x < kH) {
+    const int c = threadIdx.x;
+    double t1 = 0.0, t2 = 0.0;
+    for (int g = 0; g < 16; ++g) { t1 += (double)s1[g][c]; t2 += (double)s2[g][c]; }
+    atomicAdd(&sum[c], t1);
+    atomicAdd(&sumsq[c], t2);
   }
 }
 
@@ -397,30 +411,60 @@ __global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(
     const float* __restrict__ dH, int ldd, const float* __restrict__ A, int lda, NormSpec ns, int R,
     double* __restrict__ sdy, double* __restrict__ sdyx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ double s1[256], s2[256];
+  __shared__ float s1[16][kH], s2[16][kH];
+  __shared__ float sc[kH], sh[kH], mean[kH], rstd[kH];
   // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
   pdl_wait();
-  int c = threadIdx.x % kH, grp = threadIdx.x / kH;  // 4 row groups
-  float sc, sh, mean, rstd;
-  norm_coeffs(ns, c, sc, sh, mean, rstd);
-  double a1 = 0.0, a2 = 0.0;
-  for (int r = blockIdx.x * 4 + grp; r < R; r += gridDim.x * 4) {
-    float av = A[(size_t)r * lda + c];
-    float dy = (av * sc + sh > 0.f) ? dH[(size_t)r * ldd + c] * dropout_mult(ns.drop, (uint32_t)r, (uint32_t)c) : 0.f;
-    a1 += (double)dy;
-    a2 += (double)(dy * ((av - mean) * rstd));
+  if (threadIdx.x < kH) {
+    const float4 q = norm_coeffs4(ns, threadIdx.x);
+    sc[threadIdx.x] = q.x; sh[threadIdx.x] = q.y; mean[threadIdx.x] = q.z; rstd[threadIdx.x] = q.w;
   }
-  s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
   __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < 4; ++g) { a1 += s1[g * kH + c]; a2 += s2[g * kH + c]; }
-    atomicAdd(&sdy[c], a1);
-    atomicAdd(&sdyx[c], a2);
+  // 16 threads per row (one float4 each), 16 rows per block pass, two row passes in flight; fp32 partials per thread
+  const int c4 = (threadIdx.x & 15) * 4, rg = threadIdx.x >> 4;
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int stride = gridDim.x * 16;
+  const bool drop = ns.drop.rate > 0.f;
+  auto acc = [&](const float4& g4, const float4& v4, int r) {
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, av[4] = {v4.x, v4.y, v4.z, v4.w};
+    float dm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop) {
+      DropMult8 m = dropout_mult8(ns.drop, (uint32_t)r, (uint32_t)(c4 >> 3));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = m.m[(c4 & 4) + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c4 + j;
+      const float dy = (av[j] * sc[c] + sh[c] > 0.f) ? gv[j] * dm[j] : 0.f;
+      a1[j] += dy;
+      a2[j] = fmaf(dy, (av[j] - mean[c]) * rstd[c], a2[j]);
+    }
+  };
+  int r = blockIdx.x * 16 + rg;
+  for (; r + stride < R; r += 2 * stride) {
+    const float4 g0 = *reinterpret_cast<const float4*>(dH + (size_t)r * ldd + c4);
+    const float4 v0 = *reinterpret_cast<const float4*>(A + (size_t)r * lda + c4);
+    const float4 g1 = *reinterpret_cast<const float4*>(dH + (size_t)(r + stride) * ldd + c4);
+    const float4 v1 = *reinterpret_cast<const float4*>(A + (size_t)(r + stride) * lda + c4);
+    acc(g0, v0, r); acc(g1, v1, r + stride);
+  }
+  for (; r < R; r += stride)
+    acc(*reinterpret_cast<const float4*>(dH + (size_t)r * ldd + c4), *reinterpret_cast<const float4*>(A + (size_t)r * lda + c4), r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s1[rg][c4 + j] = a1[j]; s2[rg][c4 + j] = a2[j]; }
+  __syncthreads();
+  if (threadIdx.x < kH) {
+    const int c = threadIdx.x;
+    double t1 = 0.0, t2 = 0.0;
+    for (int g = 0; g < 16; ++g) { t1 += (double)s1[g][c]; t2 += (double)s2[g][c]; }
+    atomicAdd(&sdy[c], t1);
+    atomicAdd(&sdyx[c], t2);
     if (ns.mode == NORM_BIAS) {
-      atomicAdd(&dbeta[c], (float)a1);             // bias gradient
+      atomicAdd(&dbeta[c], (float)t1);             // bias gradient
     } else {
-      atomicAdd(&dgamma[c], (float)a2);
-      atomicAdd(&dbeta[c], (float)a1);
+      atomicAdd(&dgamma[c], (float)t2);
+      atomicAdd(&dbeta[c], (float)t1);
     }
   }
 }
