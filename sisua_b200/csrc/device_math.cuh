@@ -406,6 +406,14 @@ __device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, u
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// vector reductions into global memory (sm_90+): one L2 atomic operation for 2 / 4 consecutive floats
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2f(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
 // warp / block reductions -------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

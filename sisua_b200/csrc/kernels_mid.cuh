@@ -662,13 +662,21 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
     __syncthreads();
   }
   if (has_in && a.dW) {
+    // full 64-wide rows that start on 16-byte boundaries: one vector reduction per four weights
+    const bool vec = Kin == kH && (a.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      const int n = 4 * ty + i;
+      if (vec) {
+        if (n < Nout) red_add_v4f(&a.dW[(size_t)n * a.ldw + 4 * tx], accW[i][0], accW[i][1], accW[i][2], accW[i][3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = 4 * ty + i, k = 4 * tx + j;
-        if (n < Nout && k < Kin) atomicAdd(&a.dW[(size_t)n * a.ldw + k], accW[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          const int k = 4 * tx + j;
+          if (n < Nout && k < Kin) atomicAdd(&a.dW[(size_t)n * a.ldw + k], accW[i][j]);
+        }
       }
+    }
   }
   if (a.db && t < Nout) atomicAdd(&a.db[t], accb);
   if (fuse_prev && t < Kin) {
@@ -1111,8 +1119,7 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
       if (tx < Z) atomicAdd(&a.dW_d0[(size_t)(4 * ty + i) * Z + tx], nW0[i]);
       const int m = 4 * (t >> 5) + i;
       if (m < ZP) {
-        atomicAdd(&a.dW_lat[(size_t)m * kH + 2 * (t & 31)], nW1[i][0]);
-        atomicAdd(&a.dW_lat[(size_t)m * kH + 2 * (t & 31) + 1], nW1[i][1]);
+        red_add_v2f(&a.dW_lat[(size_t)m * kH + 2 * (t & 31)], nW1[i][0], nW1[i][1]);     // rows of 64 floats, 64-float aligned tensor
       }
     }
   } else {
