@@ -200,17 +200,21 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
     }
     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
+    const bool vec_out = Nout == kH && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(A_out) & 15) == 0;
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = r0 + 4 * ty + i;
+      float vv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = 4 * tx + j;
-        float v = acc[i][j] + ((bias && n < Nout) ? bias[n] : 0.f);
+        vv[j] = acc[i][j] + ((bias && n < Nout) ? bias[n] : 0.f);
         if (r < R && n < Nout) {
-          A_out[(size_t)r * ldo + n] = v;
-          cs[j] += v; cq[j] += v * v;
+          if (!vec_out) A_out[(size_t)r * ldo + n] = vv[j];
+          cs[j] += vv[j]; cq[j] += vv[j] * vv[j];
         }
       }
+      if (vec_out && r < R) *reinterpret_cast<float4*>(A_out + (size_t)r * ldo + 4 * tx) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
     if (out_sum) {
 #pragma unroll
@@ -630,15 +634,28 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
       }
       float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
+      const bool vec_in = Kin == kH && (a.ldi & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dIn) & 15) == 0;
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rl = 4 * ty + i, r = r0 + rl;
+        if (vec_in && r < a.R) {
+          float4* p4 = reinterpret_cast<float4*>(a.dIn + (size_t)r * a.ldi + 4 * tx);
+          if (a.accumulate_dIn) {
+            const float4 o = *p4;
+            acc[i][0] += o.x; acc[i][1] += o.y; acc[i][2] += o.z; acc[i][3] += o.w;
+          }
+          *p4 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = 4 * tx + j;
           if (r < a.R && k < Kin) {
-            float* p = a.dIn + (size_t)r * a.ldi + k;
-            float v = a.accumulate_dIn ? (*p + acc[i][j]) : acc[i][j];
-            *p = v;
+            float v = acc[i][j];
+            if (!vec_in) {
+              float* p = a.dIn + (size_t)r * a.ldi + k;
+              v = a.accumulate_dIn ? (*p + acc[i][j]) : acc[i][j];
+              *p = v;
+            }
             if (fuse_prev) {
               // gradient wrt the producing unit's norm output: relu mask (and dropout scale) of h = Hn
               float dy = Hn[rl * kTS + k] > 0.f ? v * in_drop_scale : 0.f;
@@ -915,10 +932,12 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
       for (int j = 0; j < 4; ++j) {
         if (r < a.B) {
           float v = acc[i][j];
-          a.A_d0[(size_t)r * a.ldd0 + 4 * tx + j] = v;
+          if (a.ldd0 & 3) a.A_d0[(size_t)r * a.ldd0 + 4 * tx + j] = v;
           cs[j] += v; cq[j] += v * v;
         }
       }
+      if (r < a.B && (a.ldd0 & 3) == 0)
+        *reinterpret_cast<float4*>(a.A_d0 + (size_t)r * a.ldd0 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     if (a.out_sum) {
 #pragma unroll
@@ -1096,12 +1115,12 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
         const int k = 4 * tx + j;
         if (r < a.B) {
           const float v = dh[i][j];
-          a.dH_enc[(size_t)r * kH + k] = v;
           float dy = Hn[rl * kTS + k] > 0.f ? v * in_drop_scale : 0.f;
           float xh = (An[rl * kTS + k] - mean_i[k]) * rstd_i[k];
           cs[j] += dy; cq[j] += dy * xh;
         }
       }
+      if (r < a.B) *reinterpret_cast<float4*>(a.dH_enc + (size_t)r * kH + 4 * tx) = make_float4(dh[i][0], dh[i][1], dh[i][2], dh[i][3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red1[ty * kH + 4 * tx + j] = cs[j]; red2[ty * kH + 4 * tx + j] = cq[j]; }
