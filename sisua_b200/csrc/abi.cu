@@ -1022,7 +1022,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.prev_dgamma = Le.g_off >= 0 ? h->Gd + Le.g_off : nullptr; a.prev_dbeta = h->Gd + Le.b_off;
     a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
     ++h->launches;
-    launch_pdl(latent_block_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kLatentBwdSmem, st, a);
+    launch_pdl(latent_block_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), Z <= 16 ? kLatentBwdSmemNarrow : kLatentBwdSmem, st, a);
     LAUNCH_OK(h, "latent_block_bwd_kernel");
     if (scvi) {     // library latent: d lib -> d(raw loc, raw scale)
       LibraryBwdArgs lb;

@@ -767,11 +767,12 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ At, const flo
 //   tile_mma_n16: C[4 rg + i][c]       = sum_k At[k][4 rg + i] * Bt[k][c],       rg = t >> 4, c = t & 15
 //   tile_mma_n32: C[4 rg + i][2 cp + j] = sum_k At[k][4 rg + i] * Bt[k][2 cp + j], rg = t >> 4, cp = t & 15
 //   tile_mma_m32: C[4 mg + i][2 kp + j] = sum_k At[k][4 mg + i] * Bt[k][2 kp + j], mg = t >> 5 (rows < 32), kp = t & 31
-__device__ __forceinline__ void tile_mma_n16(const float* __restrict__ At, const float* __restrict__ Bt, int K, int t, float (&acc)[4]) {
+__device__ __forceinline__ void tile_mma_n16(const float* __restrict__ At, const float* __restrict__ Bt, int bstride, int K, int t,
+                                             float (&acc)[4]) {
   const int rg = t >> 4, c = t & 15;
   for (int k = 0; k < K; ++k) {
     const float4 a4 = *reinterpret_cast<const float4*>(At + k * kTS + 4 * rg);
-    const float b = Bt[k * kTS + c];
+    const float b = Bt[k * bstride + c];
     acc[0] = fmaf(a4.x, b, acc[0]); acc[1] = fmaf(a4.y, b, acc[1]); acc[2] = fmaf(a4.z, b, acc[2]); acc[3] = fmaf(a4.w, b, acc[3]);
   }
 }
@@ -966,9 +967,13 @@ struct LatentBlockBwdArgs {
   int B, Z, deterministic, scale_act;
   float kl_weight;
 };
+constexpr int kNarrowTS = 20;     // row stride of the two tiles that only hold <= 16 latent columns (narrow path)
 constexpr size_t kLatentBwdSmem = (size_t)(7 * kH * kTS + 11 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
+// latent width <= 16: 104 KB instead of 129 KB, so that two CTAs fit on an SM
+constexpr size_t kLatentBwdSmemNarrow =
+    (size_t)(5 * kH * kTS + 2 * kH * kNarrowTS + 11 * kH + 2 * 16 * kH) * sizeof(float) + 2 * kH * sizeof(double);
 
-__global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlockBwdArgs a) {
+__global__ void __launch_bounds__(kMidThreads, 2) latent_block_bwd_kernel(LatentBlockBwdArgs a) {
   SISUA_GLOBAL(a.dH_d0); SISUA_GLOBAL(a.A_d0); SISUA_GLOBAL(a.sdy); SISUA_GLOBAL(a.sdyx); SISUA_GLOBAL(a.W_d0); SISUA_GLOBAL(a.dW_d0);
   SISUA_GLOBAL(a.z); SISUA_GLOBAL(a.PL); SISUA_GLOBAL(a.eps_z); SISUA_GLOBAL(a.loc); SISUA_GLOBAL(a.scale); SISUA_GLOBAL(a.W_lat);
   SISUA_GLOBAL(a.dW_lat); SISUA_GLOBAL(a.db_lat); SISUA_GLOBAL(a.A_enc); SISUA_GLOBAL(a.dH_enc); SISUA_GLOBAL(a.prev_sdy);
@@ -976,9 +981,10 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
   extern __shared__ __align__(16) float lsm[];
   float* Gn = lsm;                    // [r][n]  (stage 1: decoder-0 pre-activation gradient; stage 2: dPL)
   float* GT = Gn + kH * kTS;          // [n][r]
+  const int zs = a.Z <= 16 ? kNarrowTS : kTS;   // the launch sizes the dynamic shared memory accordingly
   float* Zn = GT + kH * kTS;          // [r][j]  z, later dz
-  float* Wd0n = Zn + kH * kTS;        // [n][j]
-  float* Hn = Wd0n + kH * kTS;        // [r][k]  activated encoder output
+  float* Wd0n = Zn + kH * zs;         // [n][j]
+  float* Hn = Wd0n + kH * zs;         // [r][k]  activated encoder output
   float* An = Hn + kH * kTS;          // [r][k]  its raw pre-activation
   float* Wln = An + kH * kTS;         // [m][k]  W_lat
   float* sc_i = Wln + kH * kTS;
@@ -1000,7 +1006,7 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       int i = t + kMidThreads * j, n = i >> 6, k = i & 63;
-      Wd0n[n * kTS + k] = w1[j];
+      if (k < zs) Wd0n[n * zs + k] = w1[j];
       Wln[n * kTS + k] = w2[j];
     }
   }
@@ -1049,18 +1055,18 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
         }
         Gn[r * kTS + n] = g; GT[n * kTS + r] = g;
         Hn[r * kTS + n] = v; An[r * kTS + n] = hi[j];
-        Zn[r * kTS + n] = zv[j];
+        if (n < zs) Zn[r * zs + n] = zv[j];
       }
     }
     __syncthreads();
     // dW_dec0[n][j] += sum_r G[r][n] z[r][j] ;  dz[r][j] = sum_n G[r][n] W_dec0[n][j]
     if (narrow) {
-      tile_mma_n16(Gn, Zn, kTileR, t, nW0);            // dW_dec0[4 ty + i][tx]
+      tile_mma_n16(Gn, Zn, zs, kTileR, t, nW0);        // dW_dec0[4 ty + i][tx]
       float dzn[4] = {0.f, 0.f, 0.f, 0.f};
-      tile_mma_n16(GT, Wd0n, kH, t, dzn);              // dz[4 ty + i][tx]
+      tile_mma_n16(GT, Wd0n, zs, kH, t, dzn);          // dz[4 ty + i][tx]
       __syncthreads();                     // everyone is done reading z and G
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Zn[(4 * ty + i) * kTS + tx] = dzn[i];
+      for (int i = 0; i < 4; ++i) Zn[(4 * ty + i) * zs + tx] = dzn[i];
     } else {
       tile_mma(Gn, Zn, kTileR, ty, tx, accW0);
       float dz[4][4];
@@ -1080,7 +1086,7 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_bwd_kernel(LatentBlo
       const int r = t, b = r0 + r;
       if (b < a.B) {
         for (int j = 0; j < Z; ++j) {
-          const float dzz = Zn[r * kTS + j];
+          const float dzz = Zn[r * zs + j];
           if (a.deterministic) {
             float g = a.PL[(size_t)b * Z + j] > 0.f ? dzz : 0.f;
             Gn[r * kTS + j] = g; GT[j * kTS + r] = g;
