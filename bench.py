@@ -35,7 +35,7 @@ def parse():
   ap.add_argument("--batch", type=int, default=18944,
                   help="cells per GPU per step (148 tiles of 128 cells: one fused output-head CTA per SM; the BatchNorm statistics "
                        "force a handful of latency-bound grid-wide kernels per step, which larger minibatches amortise: "
-                       "9472 -> 23.4 M, 18944 -> 28.8 M, 37888 -> 32.2 M cells/s on one B200)")
+                       "9472 -> 24.8 M, 18944 -> 32.0 M, 37888 -> 34.9 M cells/s on one B200)")
   ap.add_argument("--genes", type=int, default=GENES)
   ap.add_argument("--shard-cells", type=int, default=SHARD_CELLS)
   ap.add_argument("--gemm-mode", type=int, default=-1, help="-1: best available (tcgen05 3xTF32 if built)")
