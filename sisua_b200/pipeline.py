@@ -10,14 +10,20 @@ import torch
 from .engine import Engine
 
 
+def _pin(t: torch.Tensor) -> torch.Tensor:
+  """Page-locked when a CUDA device is present (asynchronous H2D); plain host memory otherwise, so the format helpers
+  also work on a machine without a GPU (tests, data preparation)."""
+  return t.pin_memory() if torch.cuda.is_available() else t
+
+
 def quantize_counts(X):
   """float32 count matrix -> pinned uint16 host tensor when every value is an integer below 65536 (done once per
   dataset, like the reference's cached tf.data pipeline); otherwise the pinned float32 tensor."""
   import numpy as np
   X = np.ascontiguousarray(X)
   if X.dtype != np.uint16 and (X.min() < 0 or X.max() >= 65536 or not np.array_equal(X, np.rint(X))):
-    return torch.from_numpy(X.astype(np.float32, copy=False)).pin_memory()
-  return torch.from_numpy(X.astype(np.uint16).view(np.int16)).pin_memory()
+    return _pin(torch.from_numpy(X.astype(np.float32, copy=False)))
+  return _pin(torch.from_numpy(X.astype(np.uint16).view(np.int16)))
 
 
 class CsrBatch:
@@ -30,9 +36,9 @@ class CsrBatch:
       raise ValueError("CsrBatch needs non-negative integer counts below 65536 and at most 65536 genes")
     r, c = np.nonzero(X)
     self.rows, self.genes = X.shape
-    self.indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(r, minlength=X.shape[0]))]).astype(np.int32)).pin_memory()
-    self.cols = torch.from_numpy(c.astype(np.uint16).view(np.int16)).pin_memory()
-    self.vals = torch.from_numpy(X[r, c].astype(np.uint16).view(np.int16)).pin_memory()
+    self.indptr = _pin(torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(r, minlength=X.shape[0]))]).astype(np.int32)))
+    self.cols = _pin(torch.from_numpy(c.astype(np.uint16).view(np.int16)))
+    self.vals = _pin(torch.from_numpy(X[r, c].astype(np.uint16).view(np.int16)))
 
   @property
   def nbytes(self) -> int:
