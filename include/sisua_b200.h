@@ -76,7 +76,9 @@ int sisua_bind_buffers(sisua_handle h, float* params, float* grads, float* adam_
 /* One minibatch forward + backward: replaces the body of odin-ai's `optimize` under GradientTape —
  * train_steps -> encode -> decode -> _elbo -> tape.gradient (call site
  * single_cell_model.py:236).  x [B,G] counts; y [B,P] or NULL; library [B,2] (mean,var) or NULL;
- * mask [B] bytes or NULL; eps_z [B,z]; eps_l [B] (scVI).  Outputs: terms [5,B] =
+ * mask [B] bytes or NULL; eps_z [B,z] and eps_l [B] (scVI): injected reparameterisation noise (tests), or NULL to draw
+ * it in-kernel: standard normals by Box-Muller on Philox4x32-10(seed; row, column / 4, step, stream 0x100 (z) / 0x101
+ * (library)), regenerated by the backward pass and reproduced by oracle/philox.py.  Outputs: terms [5,B] =
  * (elbo | llk_x | llk_y | kl_z | kl_l), loss [1].  Gradients land in the bound `grads` buffer and
  * BN moving statistics are updated.  Dropout masks (NetConf input_dropout / dropout) are the pure function
  * Philox4x32-10(seed; row, col/8, step, stream), 16 bits per column, regenerated in forward and backward; step < 0 makes the kernels
@@ -107,6 +109,24 @@ int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float ep
 const float* sisua_debug_buffer(sisua_handle h, const char* name);
 
 int sisua_debug_copy(sisua_handle h, const char* name, float* dst, int64_t n_floats, void* stream);
+
+/* Launch geometry the tcgen05 kernels would use for a train step of B cells (tests assert the pipeline depth they
+ * exercise): out[9] = first layer (cell tiles, k-chunks, k-blocks per chunk) | output heads (cell tiles, gene chunks,
+ * gene tiles per chunk) | first-layer weight gradient (gene tiles, cell chunks, cell tiles per chunk). */
+int sisua_debug_geometry(sisua_handle h, int B, int32_t* out);
+/* Tests only: force how many chunks the output-head / first-layer / weight-gradient kernels split their gene or cell
+ * walk into (0 = automatic heuristic), so a small batch can run the single-chunk deep pipeline of a full-size one. */
+int sisua_debug_force_chunks(sisua_handle h, int out_chunks, int enc_chunks, int bwd_chunks);
+
+/* Declares the largest count (or predicted mean) the step will see.  The fused kernels pass d llk / d (head outputs) to
+ * the tensor cores as fp16 tiles whose entries are bounded by that value; above 2^15 they are scaled by a power of two
+ * (and the products scaled back) so that nothing overflows fp16.  Default bound: 32768.  Without the declaration a
+ * larger count produces inf -> NaN gradients (loud), never a silently clamped one. */
+int sisua_set_count_bound(sisua_handle h, float max_count);
+
+/* Noise of sisua_infer calls that pass eps_z / eps_l == NULL: call k after this draws Philox(seed; row, column / 4,
+ * call_index + k, stream 0x100 + 2 s (z) / 0x101 + 2 s (library) for Monte-Carlo sample s). */
+int sisua_set_infer_seed(sisua_handle h, uint64_t seed, int64_t call_index);
 
 /* Sets the device-side optimiser step counter (t = Adam steps applied so far); synchronises the stream. */
 int sisua_set_step(sisua_handle h, int64_t t, void* stream);

@@ -40,3 +40,23 @@ def dropout_mask(rows: int, cols: int, rate: float, seed: int, step: int, stream
   u = np.stack([lo, hi], axis=-1).reshape(rows, c8 * 8)[:, :cols]   # word-major, low half first
   thr = np.uint64(int(np.float32(rate) * np.float32(65536.0)))
   return (u >= thr).astype(np.float64)
+
+
+NOISE_STREAM_Z, NOISE_STREAM_L = 0x100, 0x101
+
+
+def normal_noise(rows: int, cols: int, seed: int, step: int, stream: int) -> np.ndarray:
+  """[rows, cols] standard normals as the CUDA step draws them when no eps is injected
+  (sisua_b200/csrc/device_math.cuh: philox_normal4): one Philox4x32-10 call per (row, column group of 4),
+  counter = (row, col // 4, step, stream); Box-Muller on (w0, w1) and (w2, w3) with
+  u1 = ((w >> 8) + 0.5) 2^-24, u2 = (w >> 8) 2^-24: n = sqrt(-2 ln u1) (cos, sin)(2 pi u2)."""
+  c4 = (cols + 3) // 4
+  r = np.repeat(np.arange(rows, dtype=np.uint64)[:, None], c4, axis=1)
+  c = np.repeat(np.arange(c4, dtype=np.uint64)[None, :], rows, axis=0)
+  w = philox4x32_10(r, c, np.full_like(r, step & 0xFFFFFFFF), np.full_like(r, stream), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+  k24 = 2.0 ** -24
+  u = [(x >> np.uint64(8)).astype(np.float64) for x in w]
+  ra = np.sqrt(-2.0 * np.log((u[0] + 0.5) * k24)); rb = np.sqrt(-2.0 * np.log((u[2] + 0.5) * k24))
+  ta = 2.0 * np.pi * u[1] * k24; tb = 2.0 * np.pi * u[3] * k24
+  out = np.stack([ra * np.cos(ta), ra * np.sin(ta), rb * np.cos(tb), rb * np.sin(tb)], axis=-1).reshape(rows, c4 * 4)
+  return out[:, :cols]

@@ -104,7 +104,7 @@ def kl_normal_normal(loc, scale, prior_mean, prior_var):
 # ----------------------------------------------------------------------------
 def _hidden_stack(cfg, P: Dict[str, torch.Tensor], prefix: str, n_layers: int, h, training: bool,
                   bn_moving: Optional[Dict[str, torch.Tensor]], new_moving: Dict[str, torch.Tensor],
-                  drop: Optional[Dict[str, torch.Tensor]], rate: float):
+                  drop: Optional[Dict[str, torch.Tensor]], rate: float, trace: Optional[Dict[str, torch.Tensor]] = None):
   """Dense(no bias when BN) -> BatchNorm -> ReLU -> Dropout, n_layers times."""
   for i in range(n_layers):
     name = f"{prefix}.{i}"
@@ -122,6 +122,8 @@ def _hidden_stack(cfg, P: Dict[str, torch.Tensor], prefix: str, n_layers: int, h
       a = (a - mean) / torch.sqrt(var + cfg.bn_eps) * P[name + ".gamma"] + P[name + ".beta"]
     else:
       a = a + P[name + ".b"]
+    if trace is not None:       # ReLU inputs, for tests that need to know how close to zero they come
+      trace[name] = a.detach()
     h = torch.relu(a)
     if training and rate > 0.0:
       if drop is None or name not in drop:
@@ -132,7 +134,7 @@ def _hidden_stack(cfg, P: Dict[str, torch.Tensor], prefix: str, n_layers: int, h
 
 def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch.Tensor]], x, y=None,
             library=None, mask=None, eps_z=None, eps_l=None, training: bool = False,
-            drop: Optional[Dict[str, torch.Tensor]] = None):
+            drop: Optional[Dict[str, torch.Tensor]] = None, trace: Optional[Dict[str, torch.Tensor]] = None):
   """One ELBO evaluation.  x [B,G]; y [B,P]; library [B,2] = (mean, var) of log-library;
   mask [B] in {0,1}; eps_z [S,B,Z] or [B,Z]; eps_l [S,B] or [B].
   Returns a dict of per-cell terms (leading sample axis S kept when eps has one)."""
@@ -145,7 +147,7 @@ def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch
   if training and cfg.input_dropout > 0.0:
     xt = xt * drop["input"] / (1.0 - cfg.input_dropout)
   h = _hidden_stack(cfg, P, "enc", cfg.n_enc_layers, xt, training, bn_moving, new_moving, drop,
-                    cfg.enc_dropout)
+                    cfg.enc_dropout, trace)
   p = h @ P["lat.W"].T + P["lat.b"]
   out = {}
   deterministic = cfg.model_kind == MODEL_DCA
@@ -166,7 +168,7 @@ def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch
   lib = None
   if cfg.model_kind == MODEL_SCVI:
     hl = _hidden_stack(cfg, P, "encl", cfg.n_encl_layers, xt, training, bn_moving, new_moving, drop,
-                       cfg.encl_dropout)
+                       cfg.encl_dropout, trace)
     pl = hl @ P["lib.W"].T + P["lib.b"]
     l_loc = pl[:, 0]
     l_scale = activation(cfg.scale_act, pl[:, 1])
@@ -180,7 +182,9 @@ def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch
   # training-mode BN in the decoder sees all S*B rows (the reference flattens the MC
   # axis before the decoder: scvi.py:118-127)
   d = _hidden_stack(cfg, P, "dec", cfg.n_dec_layers, zf, training, bn_moving, new_moving, drop,
-                    cfg.dec_dropout)
+                    cfg.dec_dropout, trace)
+  if trace is not None and trace.get("__hidden_only__"):      # tests: ReLU inputs only, skip the gene-sized likelihood
+    return {"d": d}
   o = d @ P["out.W"].T + P["out.b"]
   xa = x.repeat(S, 1) if S > 1 else x
   a, b = o[:, :G], o[:, G:2 * G]

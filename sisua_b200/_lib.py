@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
-           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_launch_count", "sisua_set_step", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -63,6 +63,10 @@ def load():
   L.sisua_debug_buffer.restype = vp
   L.sisua_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]
   L.sisua_debug_copy.restype = ci
+  L.sisua_debug_geometry.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_int32)]
+  L.sisua_debug_geometry.restype = ci
+  L.sisua_debug_force_chunks.argtypes = [vp, ci, ci, ci]
+  L.sisua_debug_force_chunks.restype = ci
   L.sisua_launch_count.argtypes = [vp]
   L.sisua_launch_count.restype = ctypes.c_int64
   L.sisua_profile_enable.argtypes = [vp, ci]
@@ -79,6 +83,10 @@ def load():
   L.sisua_unpack_counts_csr.restype = ci
   L.sisua_train_step_host.argtypes = [vp, ctypes.POINTER(HostBatch), ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
   L.sisua_train_step_host.restype = ci
+  L.sisua_set_count_bound.argtypes = [vp, cf]
+  L.sisua_set_count_bound.restype = ci
+  L.sisua_set_infer_seed.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64]
+  L.sisua_set_infer_seed.restype = ci
   L.sisua_set_step.argtypes = [vp, ctypes.c_int64, vp]
   L.sisua_set_step.restype = ci
   L.sisua_last_error.argtypes = [vp]

@@ -2,6 +2,7 @@
 // the caller's stream; all arithmetic is in the .cuh kernels.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -100,6 +101,10 @@ struct sisua_model {
   bool drop_step_on_device = false;   // step < 0: kernels read the device-side optimiser counter (graph replays)
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
+  uint64_t infer_seed = 0;      // sisua_set_infer_seed
+  long long infer_calls = 0;
+  float gscale = 1.0f;          // scale of the fp16 gradient operand tiles (sisua_set_count_bound)
+  int force_out_chunks = 0, force_enc_chunks = 0, force_bwd_chunks = 0;   // tests: override the split heuristics (0 = automatic)
   // optional per-section device timing (CUDA events on the caller's stream)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sec_events[8];
@@ -153,10 +158,11 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  static const bool no_pdl = getenv("SISUA_NO_PDL") != nullptr;     // debugging aid: plain stream-ordered launches
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -252,6 +258,14 @@ static int ws_alloc(sisua_model* h, T** p, size_t count) {
   return SISUA_OK;
 }
 
+static NoiseSpec make_noise(const sisua_model* h) {     // in-kernel reparameterisation noise of the current step / call
+  NoiseSpec n;
+  n.seed_lo = (uint32_t)(h->drop_seed & 0xffffffffu); n.seed_hi = (uint32_t)(h->drop_seed >> 32);
+  n.step = h->drop_step;
+  n.step_ptr = h->drop_step_on_device ? h->d_step : nullptr;
+  return n;
+}
+
 static DropSpec make_drop(sisua_model* h, float rate, uint32_t stream, bool training) {
   DropSpec d;
   memset(&d, 0, sizeof(d));
@@ -304,6 +318,34 @@ static int tc_enc_attr(sisua_model* h) {
   return SISUA_OK;
 }
 
+// ---- launch geometry of the three tcgen05 kernels (also reported by sisua_debug_geometry so the tests can assert the
+// walk depth a batch size exercises) ----
+struct TcGeometry {
+  int enc_cell_tiles, enc_chunks, enc_kblocks_per_chunk;
+  int out_cell_tiles, out_chunks, out_tiles_per_chunk;
+  int bwd_gene_tiles, bwd_chunks, bwd_cell_tiles_per_chunk;
+};
+static TcGeometry tc_geometry(const sisua_model* h, int B, int R) {
+  TcGeometry g;
+  g.enc_cell_tiles = (B + 127) / 128;
+  int chunks = std::max(1, std::min(h->n_kblocks, h->num_sms / g.enc_cell_tiles));
+  if (h->force_enc_chunks > 0) chunks = std::min(h->n_kblocks, h->force_enc_chunks);
+  g.enc_kblocks_per_chunk = (h->n_kblocks + chunks - 1) / chunks;
+  g.enc_chunks = (h->n_kblocks + g.enc_kblocks_per_chunk - 1) / g.enc_kblocks_per_chunk;
+  g.out_cell_tiles = (R + tc::kCellTile - 1) / tc::kCellTile;
+  const int ngt = std::max(1, h->n_gene_tiles);
+  chunks = std::max(1, std::min(ngt, (h->num_sms + g.out_cell_tiles / 2) / g.out_cell_tiles));
+  if (h->force_out_chunks > 0) chunks = std::min(ngt, h->force_out_chunks);
+  g.out_tiles_per_chunk = (ngt + chunks - 1) / chunks;
+  g.out_chunks = (ngt + g.out_tiles_per_chunk - 1) / g.out_tiles_per_chunk;
+  g.bwd_gene_tiles = (h->cfg.n_genes + 127) / 128;
+  chunks = std::max(1, std::min(g.enc_cell_tiles, h->num_sms / g.bwd_gene_tiles));
+  if (h->force_bwd_chunks > 0) chunks = std::min(g.enc_cell_tiles, h->force_bwd_chunks);
+  g.bwd_cell_tiles_per_chunk = (g.enc_cell_tiles + chunks - 1) / chunks;
+  g.bwd_chunks = (g.enc_cell_tiles + g.bwd_cell_tiles_per_chunk - 1) / g.bwd_cell_tiles_per_chunk;
+  return g;
+}
+
 static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int B, int N0, bool training) {
   const sisua_step_config& c = h->cfg;
   {
@@ -321,10 +363,9 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   a.x = x; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
   a.log_norm = c.log_norm; a.drop = make_drop(h, c.input_dropout, 0u, training);
   a.xt = training ? h->xt_tiles : nullptr; a.xt_kblocks = h->xt_kblocks;
-  const int cell_tiles = (B + 127) / 128;
-  int chunks = std::max(1, std::min(h->n_kblocks, h->num_sms / cell_tiles));
-  a.kblocks_per_chunk = (h->n_kblocks + chunks - 1) / chunks;
-  chunks = (h->n_kblocks + a.kblocks_per_chunk - 1) / a.kblocks_per_chunk;
+  const TcGeometry geo = tc_geometry(h, B, B);
+  const int cell_tiles = geo.enc_cell_tiles, chunks = geo.enc_chunks;
+  a.kblocks_per_chunk = geo.enc_kblocks_per_chunk;
   a.atomic_out = chunks > 1 ? 1 : 0;
   if (a.atomic_out) CUDA_OK(h, cudaMemsetAsync(h->A0, 0, (size_t)B * h->ld0 * sizeof(float), st));
   const bool vec = (c.n_genes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -350,10 +391,9 @@ static int tc_encoder_first_bwd(sisua_model* h, cudaStream_t st, const float* x,
   a.n_cell_tiles = (B + 127) / 128; a.log_norm = c.log_norm;
   a.in_scale = (float)B; a.out_scale = 1.0f / (float)B;
   a.drop = make_drop(h, c.input_dropout, 0u, true);
-  const int gene_tiles = (c.n_genes + 127) / 128;
-  int chunks = std::max(1, std::min(a.n_cell_tiles, h->num_sms / gene_tiles));
-  a.tiles_per_chunk = (a.n_cell_tiles + chunks - 1) / chunks;
-  chunks = (a.n_cell_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  const TcGeometry geo = tc_geometry(h, B, B);
+  const int gene_tiles = geo.bwd_gene_tiles, chunks = geo.bwd_chunks;
+  a.tiles_per_chunk = geo.bwd_cell_tiles_per_chunk;
   const bool vec = (c.n_genes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   dim3 grid(gene_tiles, chunks);
   ++h->launches;
@@ -452,10 +492,10 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
   a.dD = h->dD; a.dW = h->Gd ? h->Gd + h->out_w : nullptr; a.db = h->Gd ? h->Gd + h->out_b : nullptr;
   a.R = R; a.B = B; a.G = G; a.n_tiles = h->n_gene_tiles;
   a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.upstream = -1.0f / (float)R;
-  const int cell_tiles = (R + tc::kCellTile - 1) / tc::kCellTile;
-  int chunks = std::max(1, std::min(h->n_gene_tiles, (h->num_sms + cell_tiles / 2) / cell_tiles));
-  a.tiles_per_chunk = (h->n_gene_tiles + chunks - 1) / chunks;
-  chunks = (h->n_gene_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  a.gscale = h->gscale; a.inv_gscale = 1.0f / h->gscale;
+  const TcGeometry geo = tc_geometry(h, B, R);
+  const int cell_tiles = geo.out_cell_tiles, chunks = geo.out_chunks;
+  a.tiles_per_chunk = geo.out_tiles_per_chunk;
   dim3 grid(cell_tiles, chunks);
   const bool vec = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (c.model_kind == SISUA_MODEL_SCVI) {
@@ -631,6 +671,32 @@ extern "C" int sisua_debug_copy(sisua_handle h, const char* name, float* dst, in
   return SISUA_OK;
 }
 
+// Launch geometry of the tcgen05 kernels for a train step of B cells (tests assert the walk depths they claim to cover).
+// out[9] = first layer (cell tiles, k-chunks, k-blocks per chunk) | output heads (cell tiles, gene chunks, gene tiles per
+// chunk) | first-layer weight gradient (gene tiles, cell chunks, cell tiles per chunk).  Zeros without the tcgen05 path.
+extern "C" int sisua_debug_geometry(sisua_handle h, int B, int32_t* out) {
+  if (!h || !out || B < 1) return SISUA_ERR_INVALID;
+  for (int i = 0; i < 9; ++i) out[i] = 0;
+#ifdef SISUA_WITH_TC
+  if (h->cfg.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
+    const TcGeometry g = tc_geometry(h, B, B);
+    const int v[9] = {g.enc_cell_tiles, g.enc_chunks, g.enc_kblocks_per_chunk, g.out_cell_tiles, g.out_chunks, g.out_tiles_per_chunk,
+                      g.bwd_gene_tiles, g.bwd_chunks, g.bwd_cell_tiles_per_chunk};
+    for (int i = 0; i < 9; ++i) out[i] = v[i];
+    if (!tc_heads_enabled(h)) out[3] = out[4] = out[5] = 0;
+  }
+#endif
+  return SISUA_OK;
+}
+
+// Tests only: force the number of chunks the three tcgen05 kernels split their walk into (0 = automatic), so that a
+// small batch can exercise the single-chunk, deep-pipeline geometry a full-size minibatch gets.
+extern "C" int sisua_debug_force_chunks(sisua_handle h, int out_chunks, int enc_chunks, int bwd_chunks) {
+  if (!h || out_chunks < 0 || enc_chunks < 0 || bwd_chunks < 0) return SISUA_ERR_INVALID;
+  h->force_out_chunks = out_chunks; h->force_enc_chunks = enc_chunks; h->force_bwd_chunks = bwd_chunks;
+  return SISUA_OK;
+}
+
 // ---- helpers ------------------------------------------------------------------------------------
 static NormSpec make_norm(sisua_model* h, const Layer& L, bool training, int rows) {
   NormSpec ns;
@@ -734,8 +800,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   if (!h->P) SET_ERR(h, SISUA_ERR_STATE, "bind_buffers has not been called");
   if (B < 1 || S < 1 || R > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "rows S*B=%d exceed max_batch=%d", R, c.max_batch);
   if (!x || !terms) SET_ERR(h, SISUA_ERR_INVALID, "x / terms must not be null");
-  if (!dca && !eps_z) SET_ERR(h, SISUA_ERR_INVALID, "eps_z is required (stochastic latent)");
-  if (scvi && (!library || !eps_l)) SET_ERR(h, SISUA_ERR_INVALID, "scVI needs library [B,2] and eps_l");
+  if (scvi && !library) SET_ERR(h, SISUA_ERR_INVALID, "scVI needs library [B,2]");      // eps_z / eps_l NULL: Philox noise in-kernel
   if (P > 0 && !y) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs y [B,P]");
   if (training) CUDA_OK(h, cudaMemsetAsync(h->stats, 0, (size_t)h->n_units * 4 * H * sizeof(double), st));
   if (loss) CUDA_OK(h, cudaMemsetAsync(loss, 0, sizeof(float), st));
@@ -769,7 +834,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     memset(&a, 0, sizeof(a));
     a.A_enc = L.A; a.lda = L.lda; a.ns_enc = make_norm(h, L, training, B);
     a.W_lat = h->P + h->lat_w; a.b_lat = h->P + h->lat_b; a.ZP = dca ? Z : 2 * Z;
-    a.eps_z = eps_z; a.W_d0 = h->P + h->dec[0].w_off;
+    a.eps_z = eps_z; a.noise = make_noise(h); a.W_d0 = h->P + h->dec[0].w_off;
     a.PL = h->PL; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs; a.kl_z = terms + (size_t)3 * R;
     a.A_d0 = h->dec[0].A; a.ldd0 = h->dec[0].lda;
     if (training && h->dec[0].bn_index >= 0) { a.out_sum = h->stats + (size_t)h->dec[0].stat_index * 4 * kH; a.out_sumsq = a.out_sum + kH; }
@@ -793,7 +858,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   if (!fused_latent || scvi) {
     LatentArgs a;
     memset(&a, 0, sizeof(a));
-    a.PL = fused_latent ? nullptr : h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
+    a.PL = fused_latent ? nullptr : h->PL; a.eps_z = eps_z; a.noise = make_noise(h); a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
     a.kl_z = terms + (size_t)3 * R; a.kl_l = terms + (size_t)4 * R;
     if (scvi) {
       a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc; a.lib_scale = h->lib_scale;
@@ -1014,7 +1079,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     memset(&a, 0, sizeof(a));
     a.dH_d0 = dH_d0; a.A_d0 = L0.A; a.ldd0 = L0.lda; a.ns_d0 = ns0; a.sdy = sdy0; a.sdyx = sdy0 + kH;
     a.W_d0 = h->P + L0.w_off; a.dW_d0 = h->Gd + L0.w_off;
-    a.z = h->Zs; a.PL = h->PL; a.eps_z = eps_z; a.loc = h->loc; a.scale = h->scale;
+    a.z = h->Zs; a.PL = h->PL; a.eps_z = eps_z; a.noise = make_noise(h); a.loc = h->loc; a.scale = h->scale;
     a.W_lat = h->P + h->lat_w; a.dW_lat = h->Gd + h->lat_w; a.db_lat = h->Gd + h->lat_b; a.ZP = dca ? Z : 2 * Z;
     a.A_enc = Le.A; a.lda = Le.lda; a.ns_enc = make_norm(h, Le, true, B);
     a.dH_enc = dH_enc;
@@ -1027,7 +1092,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     if (scvi) {     // library latent: d lib -> d(raw loc, raw scale)
       LibraryBwdArgs lb;
       memset(&lb, 0, sizeof(lb));
-      lb.dLib = h->dLib; lb.PLIB = h->PLIB; lb.eps_l = eps_l; lb.library = library; lb.lib_loc = h->lib_loc;
+      lb.dLib = h->dLib; lb.PLIB = h->PLIB; lb.eps_l = eps_l; lb.noise = make_noise(h); lb.library = library; lb.lib_loc = h->lib_loc;
       lb.lib_scale = h->lib_scale; lb.dPLIB = h->dPLIB;
       lb.B = B; lb.scale_act = c.scale_act; lb.kl_weight = c.beta / (float)B;
       ++h->launches;
@@ -1084,6 +1149,8 @@ extern "C" int sisua_infer(sisua_handle h, const float* x, const float* y, const
   cudaStream_t st = (cudaStream_t)stream;
   const sisua_step_config& c = h->cfg;
   float* t = terms ? terms : h->scratch_terms;
+  // noise of a call without injected eps: Philox(infer seed; row, column, call index, stream)
+  h->drop_seed = h->infer_seed; h->drop_step = (uint32_t)(h->infer_calls++); h->drop_step_on_device = false;
   int rc = forward_common(h, st, false, x, y, library, mask, eps_z, eps_l, B, S, t, nullptr, out_mean, out_disp, out_pi, y_mean);
   if (rc != SISUA_OK) return rc;
   const size_t zb = (size_t)B * c.n_latent * sizeof(float);
@@ -1278,6 +1345,25 @@ extern "C" int sisua_train_step_host(sisua_handle h, const sisua_host_batch* hb,
 extern "C" int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event) {
   if (!h) return SISUA_ERR_INVALID;
   h->ev_out_grads = (cudaEvent_t)cuda_event;
+  return SISUA_OK;
+}
+
+// The fused kernels hand d llk / d (head outputs) to the tensor cores as fp16 tiles; its entries are bounded by the
+// largest count (or predicted mean), and fp16 ends at 65504.  Declaring a bound above 2^15 makes the kernels scale the
+// tiles by a power of two (and the results back), instead of overflowing to inf -> NaN gradients.
+extern "C" int sisua_set_count_bound(sisua_handle h, float max_count) {
+  if (!h || !(max_count >= 0.f)) return SISUA_ERR_INVALID;
+  float s = 1.0f;
+  while (max_count * s > 32768.f && s > 1e-30f) s *= 0.5f;
+  h->gscale = s;
+  return SISUA_OK;
+}
+
+// Seed (and call index) of the reparameterisation noise sisua_infer draws in-kernel when eps_z / eps_l are NULL: call k
+// after this uses Philox(seed; row, column, call_index + k, stream), so a fixed seed makes predict reproducible.
+extern "C" int sisua_set_infer_seed(sisua_handle h, uint64_t seed, int64_t call_index) {
+  if (!h || call_index < 0) return SISUA_ERR_INVALID;
+  h->infer_seed = seed; h->infer_calls = call_index;
   return SISUA_OK;
 }
 

@@ -297,6 +297,18 @@ __device__ __forceinline__ void count_core_fast(const float (&mu)[U], const floa
   }
 }
 
+// scalar fall-back of the pair-wise epilogue mathematics (pair_math.cuh) for counts above 3 / non-integer counts; every
+// lane of the warp calls it together (count_core_fast votes warp-wide)
+namespace pm {
+template <bool ZI, bool GRAD>
+__device__ __noinline__ void core_scalar_fallback(float mu, float th, float pi, float x, float& llk, float& gmu, float& gth, float& gl) {
+  const float mu1[1] = {mu}, th1[1] = {th}, pi1[1] = {pi}, x1[1] = {x};
+  CoreResult c[1];
+  count_core_fast<ZI, GRAD, 1>(mu1, th1, pi1, x1, c);
+  llk = c[0].llk; gmu = c[0].gmu; gth = c[0].gth; gl = c[0].gl;
+}
+}  // namespace pm
+
 // default links of the VAE / DCA / SISUA heads: mean = softplus(ra), dispersion = softplus(rb + log(e-1))
 template <bool kZeroInflated, bool kGrad, int U>
 __device__ __forceinline__ void count_elem_fast(const float (&ra)[U], const float (&rb)[U], const float (&pi)[U],
@@ -399,6 +411,34 @@ __device__ __forceinline__ float dropout_mult(const DropSpec& d, uint32_t row, u
   if (d.rate <= 0.f) return 1.f;
   DropMult8 m = dropout_mult8(d, row, col >> 3);
   return m.m[col & 7u];
+}
+
+// Reparameterisation noise drawn in-kernel (eps == NULL -> Philox): standard normals as a pure
+// function of (seed; row, column group of 4, step, stream), Box-Muller on the four words of one Philox4x32-10 call:
+//   u1 = ((w0 >> 8) + 0.5) 2^-24 in (0, 1), u2 = (w1 >> 8) 2^-24 in [0, 1): n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = .. sin ..
+// and the same on (w2, w3).  Forward and backward regenerate it; oracle/philox.py:normal_noise reproduces it.
+// stream = kNoiseStreamZ + 2 s for the latent of Monte-Carlo sample s, kNoiseStreamL + 2 s for scVI's library latent.
+constexpr uint32_t kNoiseStreamZ = 0x100u, kNoiseStreamL = 0x101u;
+struct NoiseSpec {
+  uint32_t seed_lo, seed_hi, step;
+  const long long* step_ptr;   // non-null: step = *step_ptr + 1 (device-side optimiser step counter; CUDA-graph replays)
+};
+__device__ __noinline__ float4 philox_normal4(NoiseSpec n, uint32_t row, uint32_t group, uint32_t stream) {
+  const uint32_t step = n.step_ptr ? (uint32_t)(*n.step_ptr + 1) : n.step;
+  const uint4 r = philox4x32_10(make_uint4(row, group, step, stream), make_uint2(n.seed_lo, n.seed_hi));
+  const float k24 = 5.9604644775390625e-08f;     // 2^-24
+  const float ra = sqrtf(-2.0f * logf(((float)(r.x >> 8) + 0.5f) * k24));
+  const float rb = sqrtf(-2.0f * logf(((float)(r.z >> 8) + 0.5f) * k24));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * ((float)(r.y >> 8) * k24), &sa, &ca);
+  sincospif(2.0f * ((float)(r.w >> 8) * k24), &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+// element `col` of the noise row (one Philox call per element: for the scalar library latent and ragged accesses)
+__device__ __forceinline__ float philox_normal(NoiseSpec n, uint32_t row, uint32_t col, uint32_t stream) {
+  const float4 q = philox_normal4(n, row, col >> 2, stream);
+  const uint32_t k = col & 3u;
+  return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
 }
 
 // Programmatic dependent launch (sm_90+): let the next kernel on the stream be scheduled early / wait until every

@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
 // ------------------------------------------------------------------------------------------
 struct LatentArgs {
   const float* PL;     // [B, ZP] raw latent projection (ZP = 2Z, or Z for the deterministic DCA latent)
-  const float* eps_z;  // [S, B, Z]
+  const float* eps_z;  // [S, B, Z]; null -> Philox normals (noise)
+  NoiseSpec noise;
   float* loc;          // [B, Z]
   float* scale;        // [B, Z]
   float* z;            // [S*B, Z]
@@ -272,8 +273,10 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
       activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], sg, dsg);
       a.loc[(size_t)b * Z + j] = mu; a.scale[(size_t)b * Z + j] = sg;
       kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
-      for (int s = 0; s < a.S; ++s)
-        a.z[((size_t)s * a.B + b) * Z + j] = fmaf(sg, a.eps_z[((size_t)s * a.B + b) * Z + j], mu);
+      for (int s = 0; s < a.S; ++s) {
+        const float e = a.eps_z ? a.eps_z[((size_t)s * a.B + b) * Z + j] : philox_normal(a.noise, (uint32_t)b, (uint32_t)j, kNoiseStreamZ + 2u * s);
+        a.z[((size_t)s * a.B + b) * Z + j] = fmaf(sg, e, mu);
+      }
     }
     a.kl_z[b] = 0.5f * kl;
   }
@@ -284,7 +287,10 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
     float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
     a.lib_loc[b] = mu; a.lib_scale[b] = sg;
     a.kl_l[b] = logf(sqrtf(pv) / sg) + (sg * sg + (mu - pm) * (mu - pm)) / (2.f * pv) - 0.5f;
-    for (int s = 0; s < a.S; ++s) a.lib[(size_t)s * a.B + b] = fmaf(sg, a.eps_l[(size_t)s * a.B + b], mu);
+    for (int s = 0; s < a.S; ++s) {
+      const float e = a.eps_l ? a.eps_l[(size_t)s * a.B + b] : philox_normal(a.noise, (uint32_t)b, 0u, kNoiseStreamL + 2u * s);
+      a.lib[(size_t)s * a.B + b] = fmaf(sg, e, mu);
+    }
   } else if (a.kl_l) {
     a.kl_l[b] = 0.f;
   }
@@ -296,6 +302,7 @@ struct LibraryBwdArgs {
   const float* dLib;   // [B] d loss / d sampled log-library
   const float* PLIB; const float* eps_l; const float* library; const float* lib_loc; const float* lib_scale;
   float* dPLIB;        // [B, 2]
+  NoiseSpec noise;     // eps_l == null
   int B, scale_act;
   float kl_weight;     // beta / B : d loss / d KL_b
 };
@@ -309,7 +316,8 @@ __global__ void library_bwd_kernel(LibraryBwdArgs a) {
   float v, dv;
   activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], v, dv);
   a.dPLIB[(size_t)b * 2] = dl + a.kl_weight * (mu - pm) / pv;
-  a.dPLIB[(size_t)b * 2 + 1] = (dl * a.eps_l[b] + a.kl_weight * (sg / pv - 1.f / sg)) * dv;
+  const float e = a.eps_l ? a.eps_l[b] : philox_normal(a.noise, (uint32_t)b, 0u, kNoiseStreamL);
+  a.dPLIB[(size_t)b * 2 + 1] = (dl * e + a.kl_weight * (sg / pv - 1.f / sg)) * dv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -806,7 +814,8 @@ __device__ __forceinline__ void zero16(float (&acc)[4][4]) {
 struct LatentBlockFwdArgs {
   const float* A_enc; int lda; NormSpec ns_enc;     // last encoder unit (pre-activation + norm)
   const float* W_lat; const float* b_lat; int ZP;   // [ZP, 64]
-  const float* eps_z;                               // [B, Z]
+  const float* eps_z;                               // [B, Z]; null -> Philox normals (noise)
+  NoiseSpec noise;
   const float* W_d0;                                // [64, Z]
   float* PL; float* loc; float* scale; float* z; float* kl_z;
   float* A_d0; int ldd0;                            // [B, 64]
@@ -906,6 +915,7 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
     if (t < kTileR) {      // one thread per row: loc / scale / sample / KL
       const int r = t, b = r0 + r;
       float kl = 0.f;
+      float4 nz4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < Z; ++j) {
         float mu, sg, zz;
         if (a.deterministic) {
@@ -914,7 +924,17 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
           float dsg;
           mu = PLs[r * kTS + j];
           activation(a.scale_act, PLs[r * kTS + Z + j], sg, dsg);
-          zz = b < a.B ? fmaf(sg, a.eps_z[(size_t)b * Z + j], mu) : 0.f;
+          float e = 0.f;
+          if (b < a.B) {
+            if (a.eps_z) {
+              e = a.eps_z[(size_t)b * Z + j];
+            } else {                      // four normals per Philox call
+              if ((j & 3) == 0) nz4 = philox_normal4(a.noise, (uint32_t)b, (uint32_t)(j >> 2), kNoiseStreamZ);
+              const int k = j & 3;
+              e = k == 0 ? nz4.x : (k == 1 ? nz4.y : (k == 2 ? nz4.z : nz4.w));
+            }
+          }
+          zz = b < a.B ? fmaf(sg, e, mu) : 0.f;
           kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
         }
         ZT[j * kTS + r] = b < a.B ? zz : 0.f;
@@ -960,6 +980,7 @@ struct LatentBlockBwdArgs {
   const float* A_d0; int ldd0; NormSpec ns_d0; const double* sdy; const double* sdyx;
   const float* W_d0; float* dW_d0;          // [64, Z]
   const float* z; const float* PL; const float* eps_z; const float* loc; const float* scale;
+  NoiseSpec noise;                          // eps_z == null
   const float* W_lat; float* dW_lat; float* db_lat; int ZP;     // [ZP, 64]
   const float* A_enc; int lda; NormSpec ns_enc;
   float* dH_enc;                            // [B, 64] gradient wrt the activated output of the last encoder unit
@@ -1085,6 +1106,7 @@ __global__ void __launch_bounds__(kMidThreads, 2) latent_block_bwd_kernel(Latent
     if (t < kTileR) {
       const int r = t, b = r0 + r;
       if (b < a.B) {
+        float4 nz4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < Z; ++j) {
           const float dzz = Zn[r * zs + j];
           if (a.deterministic) {
@@ -1095,7 +1117,15 @@ __global__ void __launch_bounds__(kMidThreads, 2) latent_block_bwd_kernel(Latent
             float v, dv;
             activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], v, dv);
             float dmu = dzz + a.kl_weight * mu;
-            float dsr = (dzz * a.eps_z[(size_t)b * Z + j] + a.kl_weight * (sg - 1.f / sg)) * dv;
+            float e;
+            if (a.eps_z) {
+              e = a.eps_z[(size_t)b * Z + j];
+            } else {
+              if ((j & 3) == 0) nz4 = philox_normal4(a.noise, (uint32_t)b, (uint32_t)(j >> 2), kNoiseStreamZ);
+              const int k = j & 3;
+              e = k == 0 ? nz4.x : (k == 1 ? nz4.y : (k == 2 ? nz4.z : nz4.w));
+            }
+            float dsr = (dzz * e + a.kl_weight * (sg - 1.f / sg)) * dv;
             Gn[r * kTS + j] = dmu; GT[j * kTS + r] = dmu;
             Gn[r * kTS + Z + j] = dsr; GT[(Z + j) * kTS + r] = dsr;
           }

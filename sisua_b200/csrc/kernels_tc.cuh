@@ -11,6 +11,7 @@
 #pragma once
 #include "device_math.cuh"
 #include "kernels_mid.cuh"
+#include "pair_math.cuh"
 #include "tc_ptx.cuh"
 
 namespace sisua {
@@ -80,6 +81,8 @@ struct OutHeadsArgs {
   int R, B, G, n_tiles, tiles_per_chunk;
   int mean_act, disp_act;
   float upstream;          // d loss / d llk_x = -1 / R
+  float gscale, inv_gscale;   // power of two <= 1 applied to d llk / d out before the fp16 operand tile (|g| <= max count, and
+                           // fp16 ends at 65504): 1 unless the caller declared larger counts (sisua_set_count_bound)
   // scVI (gene softmax over head 0, library-scaled mean, exp dispersion): see the MODE table below
   float2* lse_part;        // [R, n_lse_parts] running (max, sum exp) of the head-0 logits per gene chunk and slice
   int n_lse_parts;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     if (lane == 0) {
       for (int i = 0; i < nt; ++i) {
         const int s = i & 1;
-        if (i >= 2) mbar_wait(&bars[W_FREE + s], ((i >> 1) - 1) & 1);
+        if (i >= 2) mbar_wait_backoff(&bars[W_FREE + s], ((i >> 1) - 1) & 1);
         mbar_arrive_expect_tx(&bars[W_FULL + s], packed_tile_bytes(NH));
         bulk_copy_g2s(smem + OutSmem::W0 + s * OutSmem::Wstage(NH),
                       a.packed + (size_t)(tile_begin + i) * packed_tile_stride(NH), packed_tile_bytes(NH), &bars[W_FULL + s]);
@@ -214,13 +217,14 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       const uint32_t idesc_fwd = make_idesc_f16(kCellTile, NF, 0, 0);
       const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
       const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
+      const uint32_t idesc_dwo_lo = make_idesc_f16(kCellTile, kK, 1, 1);
       const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
       const uint32_t sG0 = smem_u32(smem + OutSmem::G0(NH));
       auto fwd = [&](int i) {
         const int s = i & 1;
         const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
-        mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);
-        if (i >= 2) mbar_wait(&bars[ACC_FREE + s], ((i >> 1) - 1) & 1);
+        mbar_wait_backoff(&bars[W_FULL + s], (i >> 1) & 1);
+        if (i >= 2) mbar_wait_backoff(&bars[ACC_FREE + s], ((i >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t d_t = tmem + (uint32_t)(s * N);
         uint32_t acc = 0;
@@ -243,19 +247,30 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           const int s = i & 1;
           const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH));
           const uint32_t sG = sG0 + s * OutSmem::Gstage;
-          mbar_wait(&bars[G_FULL + s], (i >> 1) & 1);
-          if (i >= 2) mbar_wait(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
+          mbar_wait_backoff(&bars[G_FULL + s], (i >> 1) & 1);
+          if (i >= 2) mbar_wait_backoff(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
           tc_fence_after();
-          // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 MN-major)
+          // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 then w2, MN-major).  Both halves of the weight
+          // split are used: the fp16 rounding of a weight is the same for every cell, so with w1 alone the error of dD
+          // is correlated across the batch and survives the sums of the backward pass below (measured: 6e-3 of the
+          // largest dec.0.W gradient at 18 944 cells); the rounding of G is independent per entry and averages out.
 #pragma unroll
           for (int ks = 0; ks < N / 16; ++ks)
             umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128), make_smem_desc(sW1 + ks * 256, 128, W_CS),
                      idesc_dd, (i > 0 || ks > 0) ? 1u : 0u);
-          // dW[n, k | 1] = G^T[n, cells] . [d | 1][cells, k]   (A: G MN-major, B: d1 MN-major)
+#pragma unroll
+          for (int ks = 0; ks < N / 16; ++ks)
+            umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128),
+                     make_smem_desc(sW1 + w_tile_bytes(NH) + ks * 256, 128, W_CS), idesc_dd, 1u);
+          // dW[n, k | 1] = G^T[n, cells] . [d | 1][cells, k]   (A: G MN-major, B: d1 (+ ones column) then d2, MN-major)
 #pragma unroll
           for (int ks = 0; ks < kCellTile / 16; ++ks)
             umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
                      make_smem_desc(sA1 + ks * 256, 128, 2048), idesc_dwo, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kCellTile / 16; ++ks)
+            umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
+                     make_smem_desc(sA2 + ks * 256, 128, 2048), idesc_dwo_lo, 1u);
           umma_commit(&bars[G_FREE + s]);
           umma_commit(&bars[DWO_FULL + s]);
           umma_commit(&bars[W_FREE + s]);
@@ -270,9 +285,8 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     const int row = row0 + cell;
     const bool row_ok = row < a.R;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float llk_acc = 0.f;
     // scVI row state: logsumexp of the gene logits (merged from the MODE 1 partials), exp(clipped library)
-    float lse = 0.f, eL = 1.f, t_row = 0.f, t_acc = 0.f, dl_acc = 0.f;
+    float lse = 0.f, eL = 1.f, t_row = 0.f;
     float m_run = -1e30f, s_run = 0.f;
     bool lib_open = false;
     if (SCVI && row_ok) {
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       if (lane == 0) mbar_arrive(&bars[DWO_FREE + s]);
       if (ok) {
         float* dst = a.dW + ((size_t)h * a.G + g) * kK + sub * 16;
-        const float sc = a.upstream;
+        const float sc = a.upstream * a.inv_gscale;
 #pragma unroll
         for (int j = 0; j < 4; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
         if (sub == 0) atomicAdd(a.db + (size_t)h * a.G + g, sc * vb[0]);
@@ -329,13 +343,18 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 
     float xnext[8];
     if (MODE != MODE_SCVI_LSE) load_x(0, xnext);
-    float* xs = reinterpret_cast<float*>(smem + OutSmem::XS(NH, TRAIN)) + t;     // this thread's column of the [8][512] stash
+    // this thread's column of the [4 gene pairs][512 threads] count stash
+    float2* xs = reinterpret_cast<float2*>(smem + OutSmem::XS(NH, TRAIN)) + t;
+    const bool rows_full = row0 + kCellTile <= a.R;
+    pm::F2 llk2 = pm::bc(0.f), t2 = pm::bc(0.f), dl2 = pm::bc(0.f);
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
+      // no masking inside tiles that lie fully inside the matrix (all but the last cell tile / gene tile)
+      const bool full = rows_full && (tile_begin + i + 1) * kGeneTile <= a.G;
       if (MODE != MODE_SCVI_LSE) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xs[j * kEpiThreads] = xnext[j];
+        for (int j = 0; j < 4; ++j) xs[j * kEpiThreads] = make_float2(xnext[2 * j], xnext[2 * j + 1]);
         if (i + 1 < nt) load_x(i + 1, xnext);
       }
       mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
@@ -362,91 +381,101 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_run += mufu_ex2((u[j] - m_run) * kLog2e);
       }
-      // rolled on purpose: kU genes per trip keep the hot loop inside the instruction cache
-#ifndef SISUA_OUT_KU
-#define SISUA_OUT_KU 2
-#endif
-      constexpr int kU = SISUA_OUT_KU;
-      // the TMEM reads of trip j+1 are in flight while trip j is evaluated
-      float pa[kU], pb[kU], pl[kU];
+      // Two genes per trip, evaluated in lock-step with packed fp32x2 arithmetic (pair_math.cuh); rolled on purpose: one
+      // trip's code stays inside the instruction cache.  The TMEM reads of trip j+1 are in flight while trip j is evaluated.
+      float pa[2], pb[2], pl[2];
       if (MODE != MODE_SCVI_LSE) {
-        tmem_ldn<kU>(tb, pa);
-        tmem_ldn<kU>(tb + 32, pb);
-        if (ZI) tmem_ldn<kU>(tb + 64, pl);
+        tmem_ld2(tb, pa);
+        tmem_ld2(tb + 32, pb);
+        if (ZI) tmem_ld2(tb + 64, pl);
       }
 #pragma unroll 1
-      for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += kU) {
-        float va[kU], vb[kU], vl[kU];
-        tmem_ld_wait_tie<kU>(pa); tmem_ld_tie<kU>(pb);
-        if (ZI) tmem_ld_tie<kU>(pl);
-#pragma unroll
-        for (int u = 0; u < kU; ++u) { va[u] = pa[u]; vb[u] = pb[u]; vl[u] = ZI ? pl[u] : 0.f; }
-        if (j + kU < 8) {
-          tmem_ldn<kU>(tb + j + kU, pa);
-          tmem_ldn<kU>(tb + 32 + j + kU, pb);
-          if (ZI) tmem_ldn<kU>(tb + 64 + j + kU, pl);
+      for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += 2) {
+        tmem_ld_wait_tie<2>(pa); tmem_ld_tie<2>(pb);
+        if (ZI) tmem_ld_tie<2>(pl);
+        const float2 ba = *reinterpret_cast<const float2*>(bias_s + j), bb = *reinterpret_cast<const float2*>(bias_s + 32 + j);
+        pm::F2 ra = pm::add(pm::mk(pa[0], pa[1]), pm::mk(ba.x, ba.y));
+        pm::F2 rb = pm::add(pm::mk(pb[0], pb[1]), pm::mk(bb.x, bb.y));
+        pm::F2 pi = pm::bc(0.f);
+        if (ZI) {
+          const float2 bl = *reinterpret_cast<const float2*>(bias_s + 64 + j);
+          pi = pm::add(pm::mk(pl[0], pl[1]), pm::mk(bl.x, bl.y));
         }
-        float x2[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) x2[u] = xs[(j + u) * kEpiThreads];
-        float ga2[kU], gb2[kU], gl2[kU];
-        float ra[kU], rb[kU], pi[kU];
-        bool ok[kU];
-        ElemResult e[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          ok[u] = row_ok && (g0 + j + u) < a.G;
-          ra[u] = va[u] + bias_s[j + u];
-          rb[u] = vb[u] + bias_s[32 + j + u];
-          pi[u] = ZI ? vl[u] + bias_s[64 + j + u] : 0.f;
+        if (j + 2 < 8) {
+          tmem_ld2(tb + j + 2, pa);
+          tmem_ld2(tb + 32 + j + 2, pb);
+          if (ZI) tmem_ld2(tb + 64 + j + 2, pl);
         }
-        // one element at a time on purpose: evaluating the kU elements in lock-step (count_*<.., U = kU>) measured
-        // 12 % slower (longer live ranges, product loop runs to the larger count of the pair)
+        const float2 xv = xs[(j >> 1) * kEpiThreads];
+        const pm::F2 x2 = pm::mk(xv.x, xv.y);
+        pm::F2 llk, ga, gb, gl, mu, th;
+        if (SCVI) {
+          const pm::Scvi2 e = pm::elem_pair_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS)>(pm::sub(ra, pm::bc(lse)), rb, pi, x2, eL);
+          llk = e.llk; mu = e.mu; th = e.th; gb = e.gb; gl = e.gl;
+          ga = pm::mul(e.s_raw, pm::sub(e.t, pm::bc(t_row)));          // softmax Jacobian (row sum from the MODE 3 pass)
+          if (MODE == MODE_SCVI_SUMS) {
+            pm::F2 st = pm::mul(e.s_raw, e.t), dl = e.gmu_mu;
+            if (!full) {
+              const bool ok0 = row_ok && (g0 + j) < a.G, ok1 = row_ok && (g0 + j + 1) < a.G;
+              st = pm::mk(ok0 ? st.x : 0.f, ok1 ? st.y : 0.f); dl = pm::mk(ok0 ? dl.x : 0.f, ok1 ? dl.y : 0.f);
+            }
+            t2 = pm::add(t2, st); dl2 = pm::add(dl2, dl);
+          }
+        } else if (FAST) {
+          const pm::Elem2 e = pm::elem_pair_softplus<ZI, TRAIN>(ra, rb, pi, x2);
+          llk = e.llk; ga = e.ga; gb = e.gb; gl = e.gl; mu = e.mu; th = e.th;
+        } else {
+          // other link functions (SURVEY.md section 8a Q1 alternatives): generic scalar evaluation
+          float l_[2], ga_[2], gb_[2], gl_[2], mu_[2], th_[2];
+          const float ra_[2] = {ra.x, ra.y}, rb_[2] = {rb.x, rb.y}, pi_[2] = {pi.x, pi.y}, x_[2] = {x2.x, x2.y};
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const float ra1[1] = {ra[u] - lse}, rb1[1] = {rb[u]}, pi1[1] = {pi[u]}, x1[1] = {x2[u]};
-          if (SCVI) {
-            ScviElem se[1];
-            count_elem_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS), 1>(ra1, rb1, pi1, x1, eL, se);
-            e[u].llk = se[0].llk; e[u].mu = se[0].mu; e[u].th = se[0].th;
-            e[u].ga = se[0].s_raw * (se[0].t - t_row);          // softmax Jacobian (row sum from the MODE 3 pass)
-            e[u].gb = se[0].gb; e[u].gl = se[0].gl;
-            if (MODE == MODE_SCVI_SUMS && ok[u]) { t_acc = fmaf(se[0].s_raw, se[0].t, t_acc); dl_acc += se[0].gmu_mu; }
-          } else if (FAST) {
-            ElemResult e1[1];
-            count_elem_fast<ZI, TRAIN, 1>(ra1, rb1, pi1, x1, e1);
-            e[u] = e1[0];
-          } else {
+          for (int u = 0; u < 2; ++u) {
             float dmu, dth;
-            activation(a.mean_act, ra[u], e[u].mu, dmu);
-            activation(a.disp_act, rb[u], e[u].th, dth);
+            activation(a.mean_act, ra_[u], mu_[u], dmu);
+            activation(a.disp_act, rb_[u], th_[u], dth);
             CountGrad cg;
             cg.dmu = cg.dth = cg.dpi = 0.f;
-            e[u].llk = count_llk<ZI, TRAIN>(x2[u], e[u].mu, e[u].th, pi[u], cg);
-            e[u].ga = cg.dmu * dmu; e[u].gb = cg.dth * dth; e[u].gl = cg.dpi;
+            l_[u] = count_llk<ZI, TRAIN>(x_[u], mu_[u], th_[u], pi_[u], cg);
+            ga_[u] = cg.dmu * dmu; gb_[u] = cg.dth * dth; gl_[u] = cg.dpi;
           }
+          llk = pm::mk(l_[0], l_[1]); ga = pm::mk(ga_[0], ga_[1]); gb = pm::mk(gb_[0], gb_[1]); gl = pm::mk(gl_[0], gl_[1]);
+          mu = pm::mk(mu_[0], mu_[1]); th = pm::mk(th_[0], th_[1]);
         }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          llk_acc += ok[u] ? e[u].llk : 0.f;
+        if (!full) {
+          const bool ok0 = row_ok && (g0 + j) < a.G, ok1 = row_ok && (g0 + j + 1) < a.G;
+          llk = pm::mk(ok0 ? llk.x : 0.f, ok1 ? llk.y : 0.f);
           if (TRAIN) {
-            ga2[u] = ok[u] ? e[u].ga : 0.f; gb2[u] = ok[u] ? e[u].gb : 0.f; gl2[u] = (ok[u] && ZI) ? e[u].gl : 0.f;
-          } else if (ok[u]) {
-            if (a.out_mean) a.out_mean[o + j + u] = e[u].mu;
-            if (a.out_disp) a.out_disp[o + j + u] = e[u].th;
-            if (ZI && a.out_pi) a.out_pi[o + j + u] = pi[u];
+            ga = pm::mk(ok0 ? ga.x : 0.f, ok1 ? ga.y : 0.f); gb = pm::mk(ok0 ? gb.x : 0.f, ok1 ? gb.y : 0.f);
+            gl = pm::mk(ok0 ? gl.x : 0.f, ok1 ? gl.y : 0.f);
+          } else {
+            if (ok0) {
+              if (a.out_mean) a.out_mean[o + j] = mu.x;
+              if (a.out_disp) a.out_disp[o + j] = th.x;
+              if (ZI && a.out_pi) a.out_pi[o + j] = pi.x;
+            }
+            if (ok1) {
+              if (a.out_mean) a.out_mean[o + j + 1] = mu.y;
+              if (a.out_disp) a.out_disp[o + j + 1] = th.y;
+              if (ZI && a.out_pi) a.out_pi[o + j + 1] = pi.y;
+            }
+          }
+        } else if (!TRAIN) {
+          if (VEC) {       // even gene count and 16-byte aligned rows: (row * G + g0 + j) is even
+            if (a.out_mean) *reinterpret_cast<float2*>(a.out_mean + o + j) = make_float2(mu.x, mu.y);
+            if (a.out_disp) *reinterpret_cast<float2*>(a.out_disp + o + j) = make_float2(th.x, th.y);
+            if (ZI && a.out_pi) *reinterpret_cast<float2*>(a.out_pi + o + j) = make_float2(pi.x, pi.y);
+          } else {
+            if (a.out_mean) { a.out_mean[o + j] = mu.x; a.out_mean[o + j + 1] = mu.y; }
+            if (a.out_disp) { a.out_disp[o + j] = th.x; a.out_disp[o + j + 1] = th.y; }
+            if (ZI && a.out_pi) { a.out_pi[o + j] = pi.x; a.out_pi[o + j + 1] = pi.y; }
           }
         }
-        if (TRAIN) {   // two genes -> one packed fp16x2 word per head (|g| is clamped into fp16 range; sigmoids need no clamp)
-          const float lim16 = 60000.f;
-#pragma unroll
-          for (int u = 0; u < kU; u += 2) {
-            __half2 ha = __floats2half2_rn(fminf(fmaxf(ga2[u], -lim16), lim16), fminf(fmaxf(ga2[u + 1], -lim16), lim16));
-            __half2 hb = __floats2half2_rn(fminf(fmaxf(gb2[u], -lim16), lim16), fminf(fmaxf(gb2[u + 1], -lim16), lim16));
-            *reinterpret_cast<__half2*>(gt + 0 * 4 * 2048 + (j + u) * 2) = ha;
-            *reinterpret_cast<__half2*>(gt + 1 * 4 * 2048 + (j + u) * 2) = hb;
-            if (ZI) *reinterpret_cast<__half2*>(gt + 2 * 4 * 2048 + (j + u) * 2) = __floats2half2_rn(gl2[u], gl2[u + 1]);
-          }
+        llk2 = pm::add(llk2, llk);
+        if (TRAIN) {   // two genes -> one packed fp16x2 word per head
+          if (a.gscale != 1.f) { ga = pm::mul(ga, pm::bc(a.gscale)); gb = pm::mul(gb, pm::bc(a.gscale)); gl = pm::mul(gl, pm::bc(a.gscale)); }
+          *reinterpret_cast<__half2*>(gt + 0 * 4 * 2048 + j * 2) = __floats2half2_rn(ga.x, ga.y);
+          *reinterpret_cast<__half2*>(gt + 1 * 4 * 2048 + j * 2) = __floats2half2_rn(gb.x, gb.y);
+          if (ZI) *reinterpret_cast<__half2*>(gt + 2 * 4 * 2048 + j * 2) = __floats2half2_rn(gl.x, gl.y);
         }
       }
       tc_fence_before();
@@ -466,10 +495,10 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     if (MODE == MODE_SCVI_LSE) {
       if (row_ok) a.lse_part[(size_t)row * a.n_lse_parts + blockIdx.y * 4 + sub] = make_float2(m_run, s_run);
     } else if (MODE != MODE_SCVI_TRAIN) {      // the scVI training pass re-walks the tiles: llk came from MODE 3
-      atomicAdd(&llk_s[cell], llk_acc);
+      atomicAdd(&llk_s[cell], llk2.x + llk2.y);
       if (MODE == MODE_SCVI_SUMS) {
-        atomicAdd(&llk_s[kCellTile + cell], t_acc);
-        atomicAdd(&llk_s[2 * kCellTile + cell], dl_acc);
+        atomicAdd(&llk_s[kCellTile + cell], t2.x + t2.y);
+        atomicAdd(&llk_s[2 * kCellTile + cell], dl2.x + dl2.y);
       }
       named_bar_sync(1, kEpiThreads);
       if (sub == 0 && row_ok) {
@@ -491,7 +520,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       tmem_ld_wait();
       if (row_ok) {
         float* dst = a.dD + (size_t)row * kK + sub * 16;
-        const float sc = a.upstream;
+        const float sc = a.upstream * a.inv_gscale;
 #pragma unroll
         for (int j = 0; j < 4; ++j) red_add_v4(dst + 4 * j, sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]);
       }

@@ -1,0 +1,276 @@
+// Pair-wise (two genes per thread, lock-step) evaluation of the (ZI)NB count log-likelihood and its derivatives for the
+// fused output-head epilogue.  Same mathematics as device_math.cuh:count_llk (odin-ai's
+// NegativeBinomialDisp / ZeroInflated following scVI's log_zinb_positive, eps = 1e-8), arranged for Blackwell's issue
+// and special-function limits, which are what bound that epilogue (profiles/README.md):
+//   * both genes advance through one straight-line instruction stream, so every add / mul / fma is ONE packed
+//     FADD2 / FMUL2 / FFMA2 (sm_100 fp32x2 instructions) instead of two scalar ones: half the issue slots;
+//   * reciprocals are merged (one MUFU.RCP of a product, two multiplies to take it apart), logarithms of products are
+//     taken once, and the small-count rising factorial is branch-free, so a zero count costs 11 MUFU operations and a
+//     count in 1..3 costs 3 more (18 before);
+//   * selected exponentials run on the FMA pipe as a degree-5 polynomial (Cody-Waite split, packed Horner steps) to
+//     balance the MUFU and FMA pipes;
+//   * counts above 3 or non-integer counts (rare, warp-uniform vote) fall back to the scalar routines of device_math.cuh.
+// Compiles for the host as well (plain float arithmetic in place of the packed / MUFU instructions): tests/csrc/ builds
+// it with g++ and checks the formulas against a float64 restatement without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define PM_HD __device__ __forceinline__
+#define PM_DEVICE_CODE 1
+#else
+#define PM_HD inline
+#define PM_DEVICE_CODE 0
+#endif
+
+namespace sisua {
+namespace pm {
+
+struct F2 { float x, y; };
+
+constexpr float kEps = 1e-8f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kSoftplus1Shift = 0.5413248546129181f;
+constexpr float kLinkClamp = 40.f;      // exp(40) = 2^57.7: products of two such terms stay inside fp32
+constexpr float kTiny = 1.2e-38f;
+
+PM_HD F2 mk(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+PM_HD F2 bc(float a) { return mk(a, a); }
+
+#if PM_DEVICE_CODE
+__device__ __forceinline__ float2 as2(F2 a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ F2 fr2(float2 a) { return mk(a.x, a.y); }
+__device__ __forceinline__ F2 add(F2 a, F2 b) { return fr2(__fadd2_rn(as2(a), as2(b))); }
+__device__ __forceinline__ F2 mul(F2 a, F2 b) { return fr2(__fmul2_rn(as2(a), as2(b))); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return fr2(__ffma2_rn(as2(a), as2(b), as2(c))); }
+__device__ __forceinline__ float ex2s(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2s(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcps(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sat(float x) { return __saturatef(x); }
+__device__ __forceinline__ bool any_lane(bool p) { return __any_sync(0xffffffffu, p); }
+#else
+inline F2 add(F2 a, F2 b) { return mk(a.x + b.x, a.y + b.y); }
+inline F2 mul(F2 a, F2 b) { return mk(a.x * b.x, a.y * b.y); }
+inline F2 fma2(F2 a, F2 b, F2 c) { return mk(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float ex2s(float x) { return exp2f(x); }
+inline float lg2s(float x) { return log2f(x); }
+inline float rcps(float x) { return 1.0f / x; }
+inline float sat(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+inline bool any_lane(bool p) { return p; }
+#endif
+
+PM_HD F2 sub(F2 a, F2 b) { return add(a, mk(-b.x, -b.y)); }
+PM_HD F2 neg(F2 a) { return mk(-a.x, -a.y); }
+PM_HD F2 ex2(F2 a) { return mk(ex2s(a.x), ex2s(a.y)); }
+PM_HD F2 lg2(F2 a) { return mk(lg2s(a.x), lg2s(a.y)); }
+PM_HD F2 rcp(F2 a) { return mk(rcps(a.x), rcps(a.y)); }
+PM_HD F2 min2(F2 a, float m) { return mk(fminf(a.x, m), fminf(a.y, m)); }
+PM_HD F2 max2(F2 a, float m) { return mk(fmaxf(a.x, m), fmaxf(a.y, m)); }
+
+PM_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+PM_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+// 2^t on the FMA pipe: t = n + f, n = rint(t), f in [-1/2, 1/2]; 2^f by a degree-5 polynomial (max relative error 2.4e-7
+// in fp32), 2^n by adding n to the exponent field.  t is clamped below at -125 (result 2^-125 instead of a denormal).
+PM_HD F2 ex2_poly(F2 t) {
+  const float kMagic = 12582912.f;     // 1.5 * 2^23: adding it leaves rint(t) in the low mantissa bits
+  t = max2(t, -125.f);
+  const F2 j = add(t, bc(kMagic));
+  const F2 f = sub(t, sub(j, bc(kMagic)));
+  F2 p = fma2(f, bc(0.0013276468962430954f), bc(0.009675540961325169f));
+  p = fma2(p, f, bc(0.05550713464617729f));
+  p = fma2(p, f, bc(0.24022120237350464f));
+  p = fma2(p, f, bc(0.6931469440460205f));
+  p = fma2(p, f, bc(1.0000001192092896f));
+  // (bits(j) << 23) keeps exactly n << 23: the magic constant's own bits shift out of the word
+  return mk(u2f(f2u(p.x) + (f2u(j.x) << 23)), u2f(f2u(p.y) + (f2u(j.y) << 23)));
+}
+
+template <bool POLY>
+PM_HD F2 ex2_sel(F2 t) { return POLY ? ex2_poly(t) : ex2(t); }
+
+// ---- which exponentials leave the MUFU pipe (tuned on the B200: see profiles/) ----
+#ifndef SISUA_PM_POLY_LINKS
+#define SISUA_PM_POLY_LINKS 1     // the two softplus links
+#endif
+#ifndef SISUA_PM_POLY_PI
+#define SISUA_PM_POLY_PI 0        // exp(-pi) of the dropout logit
+#endif
+
+// softplus(r) and its derivative sigmoid(r) for both lanes: v = log(1 + e^r), dv = e^r / (1 + e^r).
+//   m = min(r, 40); e = 2^(m log2 e); s = 1 + e; v = ln2 lg2(s) + (e - (s - 1)) / s + (r - m)
+// The middle term restores the bits the rounding of 1 + e loses (full relative accuracy for very negative r without a
+// branch); (r - m) is exact 0 below the clamp and makes v = r above it.  `rs` = 1 / s is supplied by the caller, who
+// merges the reciprocals of both links into one MUFU operation.
+struct Link { F2 e, s, L; };
+PM_HD Link link_begin(F2 r) {
+  Link k;
+  const F2 m = min2(r, kLinkClamp);
+  k.e = ex2_sel<SISUA_PM_POLY_LINKS != 0>(mul(m, bc(kLog2e)));
+  k.s = add(k.e, bc(1.f));
+  k.L = lg2(k.s);
+  return k;
+}
+PM_HD F2 link_value(const Link& k, F2 r, F2 rs) {
+  const F2 resid = sub(k.e, sub(k.s, bc(1.f)));
+  const F2 over = sub(r, min2(r, kLinkClamp));
+  return fma2(k.L, bc(kLn2), fma2(resid, rs, over));
+}
+// value only (inference): the correction uses (2 - s) in place of 1 / s, exact enough where it matters (e << 1)
+PM_HD F2 link_value_nograd(const Link& k, F2 r) {
+  const F2 resid = sub(k.e, sub(k.s, bc(1.f)));
+  const F2 over = sub(r, min2(r, kLinkClamp));
+  const F2 w = max2(sub(bc(2.f), k.s), 0.f);
+  return fma2(k.L, bc(kLn2), fma2(resid, w, over));
+}
+
+struct Core { F2 llk, gmu, gth, gl; };     // natural-log units; d llk / d (mean, inverse dispersion, dropout logit)
+
+// Scalar fall-back for one element: sisua::pm::core_scalar_fallback<ZI, GRAD>(mu, th, pi, x, llk&, gmu&, gth&, gl&) must be
+// declared BEFORE this header is included -- device_math.cuh does (out of line, on top of count_core_fast<.., 1>); the
+// host harness restates it in double precision.
+
+// (ZI)NB log-likelihood of two counts given positive (mean, inverse dispersion) and the dropout logit.
+template <bool ZI, bool GRAD>
+PM_HD Core core_pair(F2 mu, F2 th, F2 pi, F2 x) {
+  Core o;
+  const F2 tm = add(add(th, mu), bc(kEps));
+  const F2 Rt = rcp(tm);
+  const F2 rho = mul(th, Rt);
+  // log2(theta / (theta + mu)).  rho carries the rounding of the approximate reciprocal (~1e-7 relative), which the
+  // logarithm turns into an ABSOLUTE error that n0 = theta * log(rho) then scales by theta; the exact residual
+  // theta - rho * tm (one fma) restores it to first order where it matters (rho ~ 1, i.e. theta >> mu).
+  const F2 res = fma2(neg(rho), tm, th);
+  const F2 lr = fma2(mul(res, Rt), bc(kLog2e), lg2(add(rho, bc(1e-30f))));
+  const F2 n0 = mul(th, lr);                          // log2 NB(0)
+  const F2 dn0_dth = fma2(lr, bc(kLn2), sub(bc(1.f), rho));
+  F2 Ep = bc(0.f), Rp = bc(1.f), p2 = bc(0.f);
+  if (ZI) {
+    const F2 pc = max2(min2(pi, kLinkClamp), -kLinkClamp);
+    p2 = mul(pc, bc(kLog2e));
+    Ep = ex2_sel<SISUA_PM_POLY_PI != 0>(neg(p2));     // exp(-pi)
+    const F2 Eu = ex2(sub(n0, p2));                   // exp(n0 - pi)
+    const F2 Sp = add(Ep, bc(1.f)), Su = add(Eu, bc(1.f));
+    if (GRAD) {
+      const F2 R2 = rcp(mul(Sp, Su));
+      Rp = mul(R2, Su);                               // sigmoid(pi)
+      const F2 w = mul(Eu, mul(R2, Sp));              // sigmoid(n0 - pi)
+      o.llk = mul(lg2(mul(Su, Rp)), bc(kLn2));        // softplus(n0 - pi) - softplus(-pi)
+      o.gl = fma2(Ep, Rp, neg(w));
+      o.gmu = neg(mul(w, rho));
+      o.gth = mul(w, dn0_dth);
+    } else {
+      Rp = rcp(Sp);
+      o.llk = mul(lg2(mul(Su, Rp)), bc(kLn2));
+      o.gl = o.gmu = o.gth = bc(0.f);
+    }
+  } else {
+    o.llk = mul(n0, bc(kLn2));
+    o.gmu = neg(rho); o.gth = dn0_dth; o.gl = bc(0.f);
+  }
+  const bool nz0 = x.x >= kEps, nz1 = x.y >= kEps;
+  if (!any_lane(nz0 || nz1)) return o;               // every cell of the warp has a zero at both genes
+  // counts 1..3 (the bulk of the non-zero entries) stay on the packed path; anything else votes the warp out of it
+  const float r0 = (x.x + 8388608.f) - 8388608.f, r1 = (x.y + 8388608.f) - 8388608.f;
+  const bool big = (nz0 && !(x.x == r0 && x.x <= 3.f)) || (nz1 && !(x.y == r1 && x.y <= 3.f));
+  if (any_lane(big)) {
+    float l, gm, gt, gg;
+    if (any_lane(nz0)) {
+      core_scalar_fallback<ZI, GRAD>(mu.x, th.x, pi.x, x.x, l, gm, gt, gg);
+      o.llk.x = l; o.gmu.x = gm; o.gth.x = gt; o.gl.x = gg;
+    }
+    if (any_lane(nz1)) {
+      core_scalar_fallback<ZI, GRAD>(mu.y, th.y, pi.y, x.y, l, gm, gt, gg);
+      o.llk.y = l; o.gmu.y = gm; o.gth.y = gt; o.gl.y = gg;
+    }
+    return o;
+  }
+  // lgamma(x + th) - lgamma(th) - lgamma(x + 1) = log(q / x!),  q = th (th+1)^[x>=2] (th+2)^[x>=3]
+  const F2 i2 = mk(sat(x.x - 1.f), sat(x.y - 1.f)), i3 = mk(sat(x.x - 2.f), sat(x.y - 2.f));
+  const F2 t1 = add(th, bc(1.f));
+  const F2 g1 = fma2(i2, th, bc(1.f)), g2 = fma2(i3, t1, bc(1.f));
+  const F2 g12 = mul(g1, g2);
+  const F2 q = mul(th, g12);
+  const F2 mue = add(mu, bc(kEps));
+  const F2 m = mul(mue, Rt);                          // mu / (theta + mu)
+  // m^x = m * (x >= 2 ? m : 1) * (x >= 3 ? m : 1); the factors are blended as i*m + (1 - i): no cancellation for tiny m
+  const F2 mx = mul(m, mul(fma2(i2, m, sub(bc(1.f), i2)), fma2(i3, m, sub(bc(1.f), i3))));
+  const F2 finv = fma2(fma2(x, bc(1.f / 12.f), bc(-0.75f)), x, bc(5.f / 3.f));    // 1 / x! for x = 1, 2, 3
+  const F2 prod = max2(mul(mul(mx, q), finv), kTiny);
+  F2 l2 = add(n0, lg2(prod));                         // log2 units
+  if (ZI) {
+    // log sigmoid(-pi) = log2(Ep Rp) (clamped logit) - the part of pi above the clamp
+    const F2 over = max2(sub(pi, bc(kLinkClamp)), 0.f);
+    l2 = add(l2, fma2(over, bc(-kLog2e), lg2(mul(Ep, Rp))));
+  }
+  const F2 llk1 = mul(l2, bc(kLn2));
+  F2 gmu1 = bc(0.f), gth1 = bc(0.f), gl1 = bc(0.f);
+  if (GRAD) {
+    const F2 dq = fma2(th, fma2(i2, g2, mul(g1, i3)), g12);     // dq / dth
+    const F2 R3 = rcp(mul(q, mue));
+    const F2 Rq = mul(R3, mue), Rm = mul(R3, q);
+    gmu1 = fma2(x, sub(Rm, Rt), neg(rho));
+    gth1 = fma2(dq, Rq, fma2(neg(x), Rt, dn0_dth));
+    gl1 = neg(Rp);
+  }
+  o.llk = mk(nz0 ? llk1.x : o.llk.x, nz1 ? llk1.y : o.llk.y);
+  if (GRAD) {
+    o.gmu = mk(nz0 ? gmu1.x : o.gmu.x, nz1 ? gmu1.y : o.gmu.y);
+    o.gth = mk(nz0 ? gth1.x : o.gth.x, nz1 ? gth1.y : o.gth.y);
+    if (ZI) o.gl = mk(nz0 ? gl1.x : o.gl.x, nz1 ? gl1.y : o.gl.y);
+  }
+  return o;
+}
+
+struct Elem2 { F2 llk, ga, gb, gl, mu, th; };    // ga, gb, gl = d llk / d raw head outputs (mean, dispersion, dropout)
+
+// default links of the VAE / DCA / SISUA heads: mean = softplus(ra), dispersion = softplus(rb + log(e - 1))
+template <bool ZI, bool GRAD>
+PM_HD Elem2 elem_pair_softplus(F2 ra, F2 rb, F2 pi, F2 x) {
+  Elem2 o;
+  const F2 rbs = add(rb, bc(kSoftplus1Shift));
+  const Link ka = link_begin(ra), kb = link_begin(rbs);
+  F2 dmu = bc(0.f), dth = bc(0.f);
+  if (GRAD) {
+    const F2 R = rcp(mul(ka.s, kb.s));
+    const F2 rsa = mul(R, kb.s), rsb = mul(R, ka.s);
+    o.mu = link_value(ka, ra, rsa);
+    o.th = link_value(kb, rbs, rsb);
+    dmu = mul(ka.e, rsa); dth = mul(kb.e, rsb);
+  } else {
+    o.mu = link_value_nograd(ka, ra);
+    o.th = link_value_nograd(kb, rbs);
+  }
+  const Core c = core_pair<ZI, GRAD>(o.mu, o.th, pi, x);
+  o.llk = c.llk;
+  o.ga = mul(c.gmu, dmu); o.gb = mul(c.gth, dth); o.gl = c.gl;
+  return o;
+}
+
+// scVI links (scvi.py:117-138): mean = exp(clip(library)) * clamp(softmax_g(u)), dispersion = exp(rb).
+//   u_lse = u_g - logsumexp_g(u), eL = exp(clipped library).  t = d llk / d s_raw_g (softmax output before the clamp);
+//   the caller finishes the softmax Jacobian once the row sum of s_raw t is known.  gmu_mu -> d llk / d library.
+struct Scvi2 { F2 llk, mu, th, s_raw, t, gmu_mu, gb, gl; };
+template <bool ZI, bool GRAD>
+PM_HD Scvi2 elem_pair_scvi(F2 u_lse, F2 rb, F2 pi, F2 x, float eL) {
+  Scvi2 o;
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  o.s_raw = ex2(mul(u_lse, bc(kLog2e)));
+  o.mu = mul(bc(eL), min2(max2(o.s_raw, lo), hi));
+  o.th = ex2(mul(rb, bc(kLog2e)));
+  const Core c = core_pair<ZI, GRAD>(o.mu, o.th, pi, x);
+  o.llk = c.llk;
+  const F2 ge = mul(c.gmu, bc(eL));
+  o.t = mk((o.s_raw.x >= lo && o.s_raw.x <= hi) ? ge.x : 0.f, (o.s_raw.y >= lo && o.s_raw.y <= hi) ? ge.y : 0.f);
+  o.gmu_mu = mul(c.gmu, o.mu);
+  o.gb = mul(c.gth, o.th);
+  o.gl = c.gl;
+  return o;
+}
+
+}  // namespace pm
+}  // namespace sisua

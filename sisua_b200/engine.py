@@ -199,6 +199,14 @@ class Engine:
       self._check(self.lib.sisua_train_step_host(self.handle, ctypes.byref(hb), int(seed), int(step), hp(host_loss),
                                                  hp(host_terms), self._stream()))
 
+  def set_count_bound(self, max_count: float):
+    """Largest count the step will see (sisua_set_count_bound): keeps the fp16 gradient operand tiles in range."""
+    self._check(self.lib.sisua_set_count_bound(self.handle, float(max_count)))
+
+  def set_infer_seed(self, seed: int, call_index: int = 0):
+    """Seed / call index of the in-kernel noise of `infer` calls without injected eps (sisua_set_infer_seed)."""
+    self._check(self.lib.sisua_set_infer_seed(self.handle, int(seed), int(call_index)))
+
   def reset_step_counter(self, t: int):
     """Sets the device-side optimiser step counter (what `adam_step(t=0)` and `train_step(step=-1)` follow)."""
     with torch.cuda.device(self.device):
@@ -219,6 +227,18 @@ class Engine:
     with torch.cuda.device(self.device):
       self._check(self.lib.sisua_profile_read(self.handle, ms, cnt))
     return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(self.SECTIONS)}
+
+  def geometry(self, B: int) -> Dict[str, int]:
+    """Launch geometry of the tcgen05 kernels for a train step of B cells (sisua_debug_geometry; tests only)."""
+    out = (ctypes.c_int32 * 9)()
+    self._check(self.lib.sisua_debug_geometry(self.handle, int(B), out))
+    keys = ("enc_cell_tiles", "enc_chunks", "enc_kblocks_per_chunk", "out_cell_tiles", "out_chunks", "out_tiles_per_chunk",
+            "bwd_gene_tiles", "bwd_chunks", "bwd_cell_tiles_per_chunk")
+    return {k: int(out[i]) for i, k in enumerate(keys)}
+
+  def force_chunks(self, out_chunks: int = 0, enc_chunks: int = 0, bwd_chunks: int = 0):
+    """Override the chunk heuristics of the tcgen05 kernels (tests only; 0 = automatic)."""
+    self._check(self.lib.sisua_debug_force_chunks(self.handle, int(out_chunks), int(enc_chunks), int(bwd_chunks)))
 
   def debug_buffer(self, name: str, rows: int, cols: int) -> torch.Tensor:
     """Copy of a private workspace buffer (tests only)."""

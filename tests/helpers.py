@@ -67,3 +67,38 @@ def oracle_dropout_masks(cfg, B, seed, step, dtype=torch.float64):
     if rate > 0:
       drop[name] = torch.tensor(dropout_mask(B, cfg.n_hidden, rate, seed, step, 1 + u), dtype=dtype)
   return drop
+
+
+def separate_relu_ties(cfg, flat, mov, batch, drop=None, training=True):
+  """Nudges the beta / bias of every hidden unit (by less than the spacing of its inputs, ~1e-4) so that no ReLU input of
+  THIS batch lies close to zero, layer by layer in forward order; returns the smallest |ReLU input| margin reached.
+
+  Why: with millions of ReLU inputs per step a few always sit within float32 rounding of zero.  Such a unit is "on" in one
+  arithmetic and "off" in another, and the gradients then differ by that cell's whole contribution (1e-3 .. 1e-2 of a
+  tensor's largest entry) -- the float32 and float64 ORACLES disagree with each other in exactly that way.  It is a
+  property of ReLU in finite precision, not of the kernels, and it would make a full-batch gradient comparison random."""
+  from oracle import step_oracle as O
+  names = [f"enc.{i}" for i in range(cfg.n_enc_layers)]
+  if cfg.model_kind == C.MODEL_SCVI:
+    names += [f"encl.{i}" for i in range(cfg.n_encl_layers)]
+  names += [f"dec.{i}" for i in range(cfg.n_dec_layers)]
+  d = PR.flat_to_dict(cfg, flat)         # views into `flat`
+  key = ".beta" if cfg.batchnorm else ".b"
+  margin = np.inf
+  for name in names:
+    trace = {"__hidden_only__": True}
+    with torch.no_grad():
+      O.forward(cfg, oracle_params(cfg, flat), oracle_moving(cfg, mov), training=training, drop=drop, trace=trace, **batch)
+    a = trace[name].numpy()              # [rows, H] ReLU inputs of this unit under the current parameters
+    for c in range(a.shape[1]):
+      v = np.sort(a[:, c])
+      # shifting beta by -m moves every input by -m: m = the centre of the widest gap among the inputs closest to zero
+      k = np.searchsorted(v, 0.0)
+      w = v[max(0, k - 8):min(v.size, k + 8)]
+      if w.size < 2:
+        continue
+      gaps = np.diff(w)
+      j = int(np.argmax(gaps))
+      d[name + key][c] -= np.float32(0.5 * (w[j] + w[j + 1]))
+      margin = min(margin, 0.5 * gaps[j])
+  return float(margin)

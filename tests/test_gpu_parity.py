@@ -132,25 +132,47 @@ def test_variants_nbd_nobn_stress(mode):
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("model,kw", [("vae", {}), ("scvi", {}), ("sisua", dict(n_proteins=10))])
 def test_multi_step_training_matches_oracle(model, kw, mode):
+  """T Adam steps on the GPU vs T oracle steps.  Adam's first updates are sign-like (|update| ~ lr whatever |g| is), so a
+  bound on the parameter DIFFERENCE cannot fail below T * lr; what carries signal is the loss trajectory and the
+  DIRECTION of the total update: cosine similarity per tensor and overall, plus a T = 1 check scaled to the update."""
   G, B, T = 300, 64, 5
   cfg, flat, mov, _ = _setup(model, kw, G, B, mode, trained_moving=False)
   eng = _engine(cfg, flat, mov)
   P = Hh.oracle_params(cfg, flat)
+  P0 = {k: v.clone() for k, v in P.items()}
   om = Hh.oracle_moving(cfg, mov)
   m = {k: torch.zeros_like(v) for k, v in P.items()}
   v = {k: torch.zeros_like(p) for k, p in P.items()}
+
+  def cosines():
+    got = eng.params_dict()
+    dg = {k: got[k].astype(np.float64) - P0[k].numpy() for k in P}
+    dr = {k: P[k].numpy() - P0[k].numpy() for k in P}
+    per = {k: float((dg[k].ravel() @ dr[k].ravel()) / (np.linalg.norm(dg[k]) * np.linalg.norm(dr[k]) + 1e-300)) for k in P}
+    a = np.concatenate([dg[k].ravel() for k in P]); b = np.concatenate([dr[k].ravel() for k in P])
+    return per, float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
   for t in range(1, T + 1):
     batch = Hh.make_batch(cfg, B, seed=t)
     terms, loss = eng.train_step(**batch)
     eng.adam_step(lr=1e-3, clipnorm=100.0, t=t)
     out, _ = O.train_step(cfg, P, om, m, v, t, batch, lr=1e-3, clipnorm=100.0)
     _close(loss.cpu().numpy()[0], float(out["loss"]), rtol=2e-4, what=f"loss step {t}")
-  got = eng.params_dict()
-  for name, p in P.items():
-    # Adam's normalised update amplifies tiny gradient differences: compare against the step size
-    err = np.abs(got[name] - p.numpy()).max()
-    lim = 2e-4 if mode == C.GEMM_FP32_UNFUSED else 5e-3   # fp16-grade gradients can flip Adam's sign-like first steps
-    assert err <= lim, f"{name}: drift {err:.3e} after {T} steps (lr 1e-3)"
+    if t == 1:
+      # one step: update = lr * sign-like(g); entries whose gradient is below the arithmetic's noise may flip, the rest
+      # must agree to a small fraction of the step
+      got = eng.params_dict()
+      flips, total = 0, 0
+      for name, p in P.items():
+        d = np.abs(got[name] - p.numpy())
+        flips += int((d > 2e-4).sum()); total += d.size
+      frac = flips / total
+      assert frac <= (1e-4 if mode == C.GEMM_FP32_UNFUSED else 2e-2), f"{flips}/{total} entries moved differently in step 1"
+  per, overall = cosines()
+  lim = 0.9999 if mode == C.GEMM_FP32_UNFUSED else 0.999
+  assert overall >= lim, f"total update direction: cosine {overall:.6f} after {T} steps"
+  for name, c in per.items():
+    assert c >= (0.999 if mode == C.GEMM_FP32_UNFUSED else 0.99), f"{name}: update cosine {c:.5f}"
   eng.close()
 
 
@@ -207,18 +229,20 @@ def test_tcgen05_descriptor_selftest(a_mn, b_mn, N, K):
 
 @pytest.mark.parametrize("mode", MODES)
 def test_deep_gene_pipeline(mode):
-  """Many 32-gene tiles per CTA (weight / TMEM stages are recycled dozens of times) in inference and training."""
+  """Many 32-gene tiles per CTA in inference and training: the chunk heuristic is overridden so that every output-head
+  CTA walks all 63 gene tiles (weight / accumulator / gradient stages recycled 31 times), and the depth is asserted."""
   cfg, flat, mov, batch = _setup("vae", {}, 2000, 300, mode, trained_moving=True)
   eng = _engine(cfg, flat, mov)
+  if mode == C.GEMM_TC_3XFP16:
+    eng.force_chunks(out_chunks=1, enc_chunks=1, bwd_chunks=1)
+    geo = eng.geometry(300)
+    assert geo["out_chunks"] == 1 and geo["out_tiles_per_chunk"] == 63 and geo["enc_kblocks_per_chunk"] == 32, geo
   out = eng.infer(want_mean=True, **batch)
   torch.cuda.synchronize()
   ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=False, **batch)
   _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo")
   _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="imputed mean")
-  terms, loss = eng.train_step(**batch)
-  torch.cuda.synchronize()
-  reft = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, **batch)
-  _close(terms[0].cpu().numpy(), reft["elbo"].numpy(), what="train elbo")
+  _grad_check(cfg, flat, mov, batch, eng)
   eng.close()
 
 
