@@ -46,6 +46,8 @@ def parse():
                   help="record the per-section CUDA events inside the headline loop (costs ~40 us per step: 12 event records "
                        "that also break the kernel-to-kernel overlap); default: a separate pass right after it")
   ap.add_argument("--cpu-steps", type=int, default=6)
+  ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of one step at the benchmarked shape")
+  ap.add_argument("--no-latency", action="store_true", help="skip the batch-64 / 128 latency-regime measurement")
   return ap.parse_args()
 
 
@@ -95,41 +97,53 @@ def run_cpu(cfg, B, steps, warmup):
 
 
 class ClockSampler:
-  Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+  """SM clock and throttle reasons DURING the timed region: an in-process NVML poller (a thread, ~1 ms period; the timed
+  region of a short run is a few ms, far below what an external `nvidia-smi -lms` loop resolves)."""
 
   def __init__(self, index):
-    self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    import threading
+    self.sm, self.mx, self.reasons, self.err = [], [], set(), None
+    self._stop = threading.Event()
     try:
-      self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                 "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
-    except Exception:
-      self.p = None
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+      vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+      phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.t = threading.Thread(target=self._run, daemon=True)
+      self.t.start()
+    except Exception as e:      # noqa: BLE001
+      self.err, self.t = f"NVML unavailable: {e}", None
+
+  def _run(self):
+    nv = self.nv
+    names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+             "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+    while not self._stop.is_set():
+      try:
+        self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.mx.append(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+          r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:      # noqa: BLE001
+          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for n, bit in names.items():
+          if r & bit:
+            self.reasons.add(n)
+      except Exception as e:      # noqa: BLE001
+        self.err = str(e)
+        return
+      time.sleep(0.001)
 
   def stop(self):
-    if self.p is None:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    self.p.terminate()
-    try:
-      self.p.wait(timeout=5)
-    except Exception:
-      self.p.kill()
-    self.f.flush(); self.f.seek(0)
-    sm, mx, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for line in self.f.read().strip().splitlines():
-      parts = [p.strip() for p in line.split(",")]
-      if len(parts) < 7:
-        continue
-      try:
-        sm.append(float(parts[0])); mx.append(float(parts[1]))
-      except ValueError:
-        continue
-      for n, v in zip(names, parts[3:7]):
-        if v.lower().startswith("active"):
-          reasons.add(n)
-    os.unlink(self.f.name)
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "reasons": sorted(reasons), "samples": len(sm)}
+    if self.t is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err], "samples": 0}
+    self._stop.set()
+    self.t.join(timeout=2)
+    return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+            "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def ncu_entry(kernel, B, G):
@@ -191,6 +205,16 @@ def main():
       return
     # bounded sample: every "step" is one train step on `bs` cells of the same workload, with `bs` sized from a short
     # calibration so that warmup + steps finish in about two minutes whatever K the driver asks for
+    probe = {}
+    for mod in ("tensorflow", "tensorflow_probability", "odin"):     # the real stack, should a driver ever provide it (baseline/_ref)
+      try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        __import__(mod)
+        probe[mod] = "importable"
+      except Exception as e:      # noqa: BLE001
+        probe[mod] = f"absent ({type(e).__name__})"
+      finally:
+        sys.path.pop(0)
     budget_s = 120.0
     cal_b = min(1024, a.batch)
     t_cal, _ = run_cpu(cfg, cal_b, 2, 1)
@@ -209,6 +233,7 @@ def main():
                 "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0})
     out["cpu_baseline"]["cells_per_sample_step"] = bs      # `config` stays identical to the GPU arm's
+    out["cpu_baseline"]["reference_stack_probe"] = probe   # TF / TFP / odin-ai: if ever importable, the port is what ran anyway (said here)
     print(json.dumps(out))
     return
 
@@ -226,19 +251,32 @@ def main():
   B, G = a.batch, a.genes
   a.shard_cells = max(a.shard_cells // B, 4) * B      # whole batches, at least four (each > L2 together)
   X = synth_on_device(a.shard_cells, G, dev, seed=87654321 + rank)
+  eng.set_count_bound(float(X.max()))
   n_batches = a.shard_cells // B
   gen = torch.Generator(device=dev); gen.manual_seed(8 + rank)
-  eps_pool = torch.randn((16, B, LATENT), device=dev, generator=gen)
   terms = torch.empty((5, B), device=dev)
   loss = torch.empty((1,), device=dev)
   step_no = [0]
 
+  # ---- parity at the benchmarked shape: one train step on minibatch 0 (fresh weights) vs the float64 oracle
+  parity = None
+  if rank == 0 and not a.no_parity:
+    parity = parity_at_bench_shape(eng, cfg, X[:B], seed=rank)
+
   from sisua_b200.distributed import OverlappedAllReduce
   reducer = OverlappedAllReduce(eng)
 
-  def one_step(xb):
+  # The headline loop issues exactly what SingleCellModel.fit(shuffle=True) issues per step: the minibatch is B row
+  # indices (a fresh device permutation of the shard every epoch) into the HBM-resident matrix, gathered inside the
+  # kernels; dropout masks and the reparameterisation noise are Philox streams of (seed, step) drawn in-kernel.
+  perm = [torch.randperm(a.shard_cells, device=dev, generator=gen).to(torch.int32)]
+
+  def one_step(i):
+    j = i % n_batches
+    if j == 0 and i > 0:
+      perm[0] = torch.randperm(a.shard_cells, device=dev, generator=gen).to(torch.int32)     # next epoch
     step_no[0] += 1
-    eng.train_step(xb, eps_z=eps_pool[step_no[0] % 16], terms=terms, loss=loss, seed=rank, step=step_no[0])
+    eng.train_step_gather(X, perm[0][j * B:(j + 1) * B], terms=terms, loss=loss, seed=rank, step=step_no[0])
     scale = reducer()        # output-head gradients are reduced under the rest of the backward pass
     eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=scale, t=step_no[0])
 
@@ -247,17 +285,18 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local_rank) if rank == 0 else None     # started before the warm-up: samples exist however short the run
   for i in range(a.warmup):
-    one_step(X[(i % n_batches) * B:(i % n_batches + 1) * B])
+    one_step(i)
   sync_all()
-  sampler = ClockSampler(local_rank) if rank == 0 else None
+  if sampler:
+    sampler.sm.clear(); sampler.mx.clear()                        # keep only what is sampled during the timed region
   launches0 = eng.launch_count()
   eng.profile(a.sections_in_loop)
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
   for i in range(a.steps):
-    j = (a.warmup + i) % n_batches
-    one_step(X[j * B:(j + 1) * B])
+    one_step(a.warmup + i)
   e1.record()
   sync_all()
   ms = e0.elapsed_time(e1)
@@ -270,8 +309,7 @@ def main():
     prof_steps = max(10, min(200, a.steps))
     eng.profile(True)
     for i in range(prof_steps):
-      j = (a.warmup + i) % n_batches
-      one_step(X[j * B:(j + 1) * B])
+      one_step(a.warmup + a.steps + i)
     sync_all()
     prof = eng.profile_read()
     eng.profile(False)
@@ -282,52 +320,12 @@ def main():
   value = world * B * a.steps / (ms * 1e-3)
   final_loss = float(loss.item())
 
-  # ---- end-to-end arm: host-resident minibatches through the host-buffer entry point
-  from sisua_b200.pipeline import CsrBatch, HostTrainPipeline, quantize_counts
-  pipe = HostTrainPipeline(eng, B)
-  n_host = 6
-  host_f32 = [torch.empty((B, G), dtype=torch.float32).pin_memory() for _ in range(n_host)]
-  for i, hb in enumerate(host_f32):
-    hb.copy_(X[(i % n_batches) * B:(i % n_batches + 1) * B])
-  # what the public host pipeline ships for integer count matrices (done once per dataset, outside the step)
-  host_u16 = [quantize_counts(hb.numpy()) for hb in host_f32]
-  host_eps = [torch.randn((B, LATENT)).pin_memory() for _ in range(n_host)]
-  e2e_steps = max(10, min(200, a.steps // 3))
-
-  def e2e_measure(host_batches):
-    def run(n):
-      losses = []
-      for i in range(n):
-        step_no[0] += 1
-        losses.append(pipe.step(host_batches[i % n_host], host_eps[i % n_host], step=step_no[0], world=world,
-                                allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None))
-      return pipe.flush(losses)
-    run(3)
-    sync_all()
-    t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    run(e2e_steps)
-    ev1.record()
-    sync_all()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
-    tt = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    return world * B * e2e_steps / (float(tt.item()) * 1e-3)
-
-  host_csr = [CsrBatch(hb.numpy()) for hb in host_f32]
-  e2e_val = e2e_measure(host_csr)
-  e2e_u16 = e2e_measure(host_u16)
-  e2e_f32 = e2e_measure(host_f32)
-  x_bytes = int(np.mean([c.nbytes for c in host_csr]))
-
   # ---- inference: predict-style step (ELBO terms, latent mean/scale, imputed means written to HBM)
   inf_steps = max(10, min(100, a.steps // 6))
   def infer_run(n):
     for i in range(n):
       j = i % n_batches
-      eng.infer(X[j * B:(j + 1) * B], eps_z=eps_pool[i % 16], want_mean=True)
+      eng.infer(X[j * B:(j + 1) * B], want_mean=True)
   infer_run(3)
   sync_all()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,41 +340,55 @@ def main():
 
   # ---- latency regime: the reference's own minibatch sizes (configs/base.yaml:23 -> 64, tests/test_scalability.py:27 -> 128)
   small = {}
-  if rank == 0:
+  if rank == 0 and not a.no_latency:
+    from sisua_b200.pipeline import GraphedGatherStep
     for sb in (64, 128):
       cfg_s = cfg.clone(max_batch=sb)
       eng_s = Engine(cfg_s, local_rank, seed=8)
-      tm, ls = torch.empty((5, sb), device=dev), torch.empty((1,), device=dev)
-      def small_step(i):
-        k = i % (a.shard_cells // sb)
-        eng_s.train_step(X[k * sb:(k + 1) * sb], eps_z=eps_pool[i % 16, :sb], terms=tm, loss=ls, seed=0, step=i + 1)
-        eng_s.adam_step(lr=1e-3, clipnorm=100.0, t=i + 1)
+      gts = GraphedGatherStep(eng_s, sb, X, lr=1e-3, clipnorm=100.0, seed=0)     # what fit() does for batch <= 2048
+      nsb = a.shard_cells // sb
       for i in range(10):
-        small_step(i)
+        gts.step(perm[0][(i % nsb) * sb:(i % nsb + 1) * sb])
       torch.cuda.synchronize()
       ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       n_small = 200
       ev0.record()
       for i in range(n_small):
-        small_step(10 + i)
+        k = (10 + i) % nsb
+        gts.step(perm[0][k * sb:(k + 1) * sb])
       ev1.record()
       torch.cuda.synchronize()
-      small[str(sb)] = {"ms_per_step": ev0.elapsed_time(ev1) / n_small, "cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)}
-      # the same step replayed as one CUDA graph (what fit() does for batch <= 2048)
-      from sisua_b200.pipeline import GraphedTrainStep
-      gts = GraphedTrainStep(eng_s, sb, lr=1e-3, clipnorm=100.0, seed=0)
-      for i in range(10):
-        gts.step(X[(i % (a.shard_cells // sb)) * sb:(i % (a.shard_cells // sb) + 1) * sb], eps_z=eps_pool[i % 16, :sb])
-      torch.cuda.synchronize()
-      ev0.record()
-      for i in range(n_small):
-        k = (10 + i) % (a.shard_cells // sb)
-        gts.step(X[k * sb:(k + 1) * sb], eps_z=eps_pool[i % 16, :sb])
-      ev1.record()
-      torch.cuda.synchronize()
-      small[str(sb)].update({"graph_ms_per_step": ev0.elapsed_time(ev1) / n_small,
-                             "graph_cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)})
+      small[str(sb)] = {"graph_ms_per_step": ev0.elapsed_time(ev1) / n_small,
+                        "graph_cells_per_s": sb * n_small / (ev0.elapsed_time(ev1) * 1e-3)}
       eng_s.close()
+  eng_total = eng.total
+  eng.close()
+  del eng
+
+  # ---- end-to-end arm: SingleCellModel.fit on a HOST-resident array (the call a user of the reference makes,
+  # sisua/models/single_cell_model.py:213-236).  Every step ships its minibatch from pinned host memory over PCIe and
+  # reads the loss back; the timed region is steps [warmup, warmup + K) of that fit (CUDA-synchronised wall clock, max over
+  # ranks); building the host cache (the reference's tf.data `cache()`) and the CUDA-graph capture are outside it.
+  from sisua_b200.models import VAE, NetConf, RVmeta, SingleCellData
+  host_cells = min(a.shard_cells, max(4, (a.steps + a.warmup + 1)) * B)      # no need for more rows than the run consumes
+  host_cells = min(a.shard_cells, max(host_cells, 4 * B))
+  Xh = X[:host_cells].cpu().numpy()
+  del X
+  torch.cuda.empty_cache()
+  sco = SingleCellData(Xh, name="bench_shard")
+  model = VAE(RVmeta(G, "zinbd", True, "transcriptomic"), latents=RVmeta(LATENT, "diag", True, "Latents"),
+              encoder=NetConf([64, 64], batchnorm=True, input_dropout=a.input_dropout), decoder=NetConf([64, 64], batchnorm=True),
+              max_batch=B, seed=8, device=local_rank, gemm_mode=mode)
+  timing = {"skip": a.warmup}
+  model.fit(sco, batch_size=B, max_iter=a.warmup + a.steps, epochs=10 ** 6, learning_rate=1e-3, clipnorm=100.0, data_on="host",
+            timing=timing, logging_interval=0, dp_shard=False)
+  tt = torch.tensor([timing["seconds"]], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  e2e_steps = int(timing["steps"])
+  e2e_val = world * B * e2e_steps / float(tt.item())
+  e2e_loss = model.train_history["loss"][-1] if model.train_history.get("loss") else None
+  x_bytes = int(timing.get("h2d_bytes_per_step", 0))
 
   if rank == 0:
     hbm_peak, peak_src = measured_peaks()
@@ -386,23 +398,24 @@ def main():
     # algorithmic bytes of one launch of the decoder-output + likelihood path: the
     # count tile (4 G B/cell) + decoder activations in/out (2 * 256 B/cell) + per-cell terms
     alg_bytes = {"out_heads": B * (4 * G + 2 * 256 + 8), "enc_first": B * (4 * G + 256), "enc_first_bwd": B * (2 * G + 256),
-                 "mid_fwd": B * 256 * 8, "mid_bwd": B * 256 * 12, "adam": eng.total * 28}
+                 "mid_fwd": B * 256 * 8, "mid_bwd": B * 256 * 12, "adam": eng_total * 28}
     dur_s = per_step[dom] * 1e-3
     achieved = alg_bytes[dom] / dur_s / 1e9
     out = dict(base)
+    out["config"] = dict(out["config"], shuffle=True, eps="philox (in-kernel)",
+                         step_entry="sisua_train_step_gather + sisua_adam_step (what SingleCellModel.fit issues per step)")
     out.update({
-        "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss,
+        "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss, "parity_at_bench_shape": parity,
         "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 fused (3xFP16 compensated forward, fp16 gradient GEMMs)"}[mode],
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": int(x_bytes + B * LATENT * 4),
-                "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "api": "HostTrainPipeline.step: pinned host minibatch in CSR form (int32 row pointers + uint16 gene ids and counts) "
-                       "-> H2D on a copy stream into a double-buffered slot -> that slot's CUDA graph (sisua_unpack_counts_csr -> "
-                       "sisua_train_step -> sisua_adam_step -> loss D2H); N > 1: the slot has two graphs with the NCCL all-reduce of the "
-                       "gradient buffer launched between them",
-                "dense_u16_host_value": e2e_u16, "dense_u16_h2d_bytes_per_step": int(B * G * 2 + B * LATENT * 4),
-                "dense_fp32_host_value": e2e_f32, "dense_fp32_h2d_bytes_per_step": int(B * G * 4 + B * LATENT * 4)},
-        "latency_regime": {"what": "same train step at the reference's default minibatch sizes (launch-bound)", **small},
+        "e2e": {"value": e2e_val, "unit": "cells/s", "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                "final_loss": e2e_loss,
+                "api": "SingleCellModel.fit(host array, batch_size=B, data_on='host'): the training set is cached in pinned host memory "
+                       "(CSR: int32 row pointers + uint16 gene ids and counts, built once like the reference's tf.data cache); every "
+                       "step copies its minibatch H2D on a copy stream into a double-buffered slot and replays that slot's CUDA graph "
+                       "(sisua_unpack_counts_csr -> sisua_train_step -> sisua_adam_step -> loss D2H); N > 1: two graphs per slot with "
+                       "the NCCL all-reduce of the gradient buffer between them"},
+        "latency_regime": {"what": "fit()'s CUDA-graph step (row gather + Philox noise) at the reference's default minibatch sizes", **small},
         "inference": {"value": infer_val, "unit": "cells/s", "steps": inf_steps,
                       "what": "sisua_infer per minibatch: ELBO terms, latent mean/scale, imputed means [B,G] written to HBM"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -412,8 +425,8 @@ def main():
                                            f"separate pass of {prof_steps} identical steps right after the headline loop, CUDA events "
                                            "around each kernel group on the launch stream (the 12 event records per step cost "
                                            "~40 us and break kernel overlap, so the headline loop runs without them)"),
-                     "relevant_bound": "special-function (MUFU) and issue rate of the fused likelihood epilogue, not HBM: "
-                                       "see ncu counters (profiles/r1_ncu_out_heads_details.txt)" if dom == "out_heads" else None,
+                     "relevant_bound": "issue rate / dependent-latency of the fused likelihood epilogue, not HBM: every pipe is "
+                                       "below 50 % (profiles/README.md, r2 ncu pages)" if dom == "out_heads" else None,
                      "ncu": ncu_entry(dom, B, G),
                      "sections_ms_per_step": per_step},
     })
@@ -424,6 +437,32 @@ def main():
     print(json.dumps(out))
   if world > 1:
     dist.destroy_process_group()
+
+
+def parity_at_bench_shape(eng, cfg, xb, seed):
+  """One train step at the benchmarked shape (fresh weights, minibatch 0, dropout masks and noise from Philox) against
+  the float64 oracle on the same inputs: max relative error of the per-cell ELBO and of the loss."""
+  import torch
+  from oracle import step_oracle as O
+  from oracle.philox import NOISE_STREAM_Z, normal_noise
+  from sisua_b200 import params as PR
+  from tests import helpers as Hh
+  B = xb.shape[0]
+  flat = eng.params.cpu().numpy()
+  mov = eng.bn_moving.cpu().numpy().copy()
+  terms, loss = eng.train_step(xb, seed=seed, step=0)
+  torch.cuda.synchronize()
+  eng.bn_moving.copy_(torch.from_numpy(mov))          # the probe step must not leave a trace in the timed run
+  x = xb.cpu().numpy()
+  drop = Hh.oracle_dropout_masks(cfg, B, seed=seed, step=0)
+  eps = normal_noise(B, cfg.n_latent, seed, 0, NOISE_STREAM_Z).astype(np.float32)
+  with torch.no_grad():
+    ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, mov), training=True, drop=drop, x=x, eps_z=eps)
+  e_ref = ref["elbo"].numpy()
+  rel = float(np.max(np.abs(terms[0].cpu().numpy() - e_ref) / np.abs(e_ref)))
+  return {"max_rel_err_per_cell_elbo": rel, "loss_gpu": float(loss.item()), "loss_oracle": float(ref["loss"]),
+          "rel_err_loss": abs(float(loss.item()) - float(ref["loss"])) / abs(float(ref["loss"])), "cells": int(B),
+          "tolerance": 1e-4, "ok": bool(rel <= 1e-4)}
 
 
 def _only_json_on_stdout():

@@ -46,6 +46,7 @@ typedef struct sisua_step_config {
   int32_t clip_mode;         /* Q5: 0 per-variable clipnorm (Keras), 1 global norm                   */
   int32_t gemm_mode;         /* SISUA_GEMM_*                                                         */
   int32_t max_batch;         /* rows the private workspace is sized for (S*B for inference)          */
+  int32_t latent_linear;     /* deterministic (DCA) latent without the ReLU: RVmeta(.., 'linear'), dca.py:22-27 */
   float bn_eps, bn_momentum; /* Keras BatchNormalization defaults 1e-3 / 0.99                        */
   float input_dropout, enc_dropout, dec_dropout, encl_dropout;
   float beta, alpha;         /* KL weight (single_cell_model.py:83), label weight (base.yaml:6)      */
@@ -88,6 +89,14 @@ int sisua_train_step(sisua_handle h, const float* x, const float* y, const float
                      const float* eps_z, const float* eps_l, int B, uint64_t seed, int64_t step, float* terms,
                      float* loss, void* stream);
 
+/* The same step on a minibatch given as ROW INDICES into matrices that stay resident in HBM -- what the reference's input
+ * pipeline produces every step (shuffle -> batch, sisua/data/_single_cell_base.py:593-601): x_all [N,G], y_all [N,P],
+ * library_all [N,2], mask_all [N], rows [B] int32 (device memory).  The fused kernels read the count rows through the index;
+ * no gathered copy of the minibatch is written.  rows == NULL behaves like sisua_train_step. */
+int sisua_train_step_gather(sisua_handle h, const float* x_all, const float* y_all, const float* library_all,
+                            const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                            uint64_t seed, int64_t step, float* terms, float* loss, void* stream);
+
 /* Replaces one `self(**data, training=False, sample_shape=S)` call of SingleCellModel.predict
  * (single_cell_model.py:176-181) plus the parameter tensors the returned distributions hold.
  * eps_z [S,B,z], eps_l [S,B]; terms [5,S*B]; z_loc/z_scale [B,z]; out_mean/out_disp/out_pi [S*B,G]
@@ -97,6 +106,36 @@ int sisua_infer(sisua_handle h, const float* x, const float* y, const float* lib
                 const float* eps_z, const float* eps_l, int B, int S, float* terms, float* z_loc, float* z_scale,
                 float* lib_loc, float* lib_scale, float* out_mean, float* out_disp, float* out_pi, float* y_mean,
                 void* stream);
+
+/* sisua_infer with the options the reference's Posterior needs (sisua/analysis/posterior.py:210-220, 919-976), all inside
+ * the fused kernels: x_eval [B,G] = counts the log-likelihood is evaluated on while the encoder reads x (NULL: x itself)
+ * -- llk of the ORIGINAL counts under the model of the CORRUPTED ones; strip_zi != 0 = likelihood of the count
+ * distribution without its zero inflation (the "imputed" distribution); out_mean_avg [B,G] = mean over the S samples of
+ * the NB mean (the imputed matrix, posterior.py:986-988); logw [S*B] = log p(z_s) - log q(z_s | x) (+ library latent). */
+int sisua_infer_ex(sisua_handle h, const float* x, const float* x_eval, const float* y, const float* library, const uint8_t* mask,
+                   const float* eps_z, const float* eps_l, int B, int S, int strip_zi, float* terms, float* z_loc, float* z_scale,
+                   float* lib_loc, float* lib_scale, float* out_mean, float* out_disp, float* out_pi, float* y_mean,
+                   float* out_mean_avg, float* logw, void* stream);
+
+/* Replaces SingleCellModel.marginal_log_prob(**batch, sample_shape=S) (call site posterior.py:964): importance-weighted
+ * bound per cell, mllk [B] = logsumexp_s(llk_x + alpha mask llk_y + log p(z_s) - log q(z_s | x)) - log S, and the
+ * per-output entries llk_x [B] (llk_y [B], nullable) = logsumexp_s(llk) - log S.  S*B <= max_batch. */
+int sisua_marginal_llk(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                       const float* eps_z, const float* eps_l, int B, int S, float* mllk, float* llk_x, float* llk_y, void* stream);
+
+/* `model(**batch, training=True)` outside fit (single_cell_model.py:178): training-mode forward pass -- BatchNorm batch
+ * statistics (folded into the moving ones), dropout masks and noise from (seed, step) -- without gradients or update.
+ * Outputs as sisua_infer with S = 1. */
+int sisua_forward_train_mode(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                             const float* eps_z, const float* eps_l, int B, uint64_t seed, int64_t step, float* terms,
+                             float* z_loc, float* z_scale, float* lib_loc, float* lib_scale, float* out_mean, float* out_disp,
+                             float* out_pi, float* y_mean, void* stream);
+
+/* Replaces SingleCellModel.decode(latents) (single_cell_model.py:141-151, scvi.py:108-171): latent samples z [R, z] (and
+ * scVI's sampled log-library sizes lib [R]) -> parameters of the output distributions under the moving BatchNorm
+ * statistics.  out_mean / out_disp / out_pi [R, G], y_mean [R, P]; any may be NULL. */
+int sisua_decode(sisua_handle h, const float* z, const float* lib, int R, float* out_mean, float* out_disp, float* out_pi,
+                 float* y_mean, void* stream);
 
 /* Replaces keras Adam.apply_gradients with clipnorm (configs/base.yaml:46-50). grad_scale multiplies
  * the gradients first (1/world_size after a sum all-reduce). t >= 1 sets the step index; t <= 0

@@ -152,7 +152,7 @@ def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch
   out = {}
   deterministic = cfg.model_kind == MODEL_DCA
   if deterministic:
-    z_loc = torch.relu(p)
+    z_loc = p if getattr(cfg, "latent_linear", 0) else torch.relu(p)      # RVmeta(.., 'relu') default, 'linear' when coerced (dca.py:16-27)
     z_scale = torch.zeros_like(z_loc)
     z = z_loc
     kl_z = torch.zeros(B, dtype=dt)

@@ -9,8 +9,8 @@ from .config import StepConfig
 
 _LIB = None
 
-EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step",
-           "sisua_infer", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step", "sisua_train_step_gather",
+           "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -55,8 +55,18 @@ def load():
   L.sisua_bind_buffers.restype = ci
   L.sisua_train_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
   L.sisua_train_step.restype = ci
+  L.sisua_train_step_gather.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
+  L.sisua_train_step_gather.restype = ci
   L.sisua_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci] + [vp] * 10
   L.sisua_infer.restype = ci
+  L.sisua_infer_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci] + [vp] * 12
+  L.sisua_infer_ex.restype = ci
+  L.sisua_marginal_llk.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
+  L.sisua_marginal_llk.restype = ci
+  L.sisua_forward_train_mode.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ctypes.c_uint64, ctypes.c_int64] + [vp] * 10
+  L.sisua_forward_train_mode.restype = ci
+  L.sisua_decode.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp]
+  L.sisua_decode.restype = ci
   L.sisua_adam_step.argtypes = [vp, cf, cf, cf, cf, cf, cf, ctypes.c_int64, vp]
   L.sisua_adam_step.restype = ci
   L.sisua_debug_buffer.argtypes = [vp, ctypes.c_char_p]

@@ -130,6 +130,7 @@ class StepConfig(ctypes.Structure):
       ("clip_mode", ctypes.c_int32),
       ("gemm_mode", ctypes.c_int32),
       ("max_batch", ctypes.c_int32),
+      ("latent_linear", ctypes.c_int32),
       ("bn_eps", ctypes.c_float),
       ("bn_momentum", ctypes.c_float),
       ("input_dropout", ctypes.c_float),
@@ -172,7 +173,7 @@ def make_step_config(model: str = "vae", n_genes: int = 2000, n_proteins: int = 
                      disp_act: str = "softplus1", scale_act: str = "softplus1",
                      scvi_reapply_act: bool = False, mask_norm: int = MASKNORM_ALL,
                      clip_mode: int = CLIP_PER_VARIABLE, gemm_mode: int = GEMM_TC_3XFP16,
-                     max_batch: int = 8192, bn_eps: float = 1e-3, bn_momentum: float = 0.99,
+                     max_batch: int = 8192, latent_linear: bool = False, bn_eps: float = 1e-3, bn_momentum: float = 0.99,
                      input_dropout: float = 0.0, enc_dropout: float = 0.0, dec_dropout: float = 0.0,
                      encl_dropout: float = 0.0, beta: float = 1.0, alpha: float = 10.0,
                      clip_library: float = 1e3) -> StepConfig:
@@ -198,7 +199,7 @@ def make_step_config(model: str = "vae", n_genes: int = 2000, n_proteins: int = 
       x_dist=xd[x_dist], y_dist=yd[y_dist], mean_act=ACT_NAMES[mean_act], disp_act=ACT_NAMES[disp_act],
       scale_act=ACT_NAMES[scale_act], scvi_reapply_act=int(bool(scvi_reapply_act)),
       mask_norm=int(mask_norm), clip_mode=int(clip_mode), gemm_mode=int(gemm_mode),
-      max_batch=int(max_batch), bn_eps=float(bn_eps), bn_momentum=float(bn_momentum),
+      max_batch=int(max_batch), latent_linear=int(bool(latent_linear) and kind == MODEL_DCA), bn_eps=float(bn_eps), bn_momentum=float(bn_momentum),
       input_dropout=float(input_dropout), enc_dropout=float(enc_dropout), dec_dropout=float(dec_dropout),
       encl_dropout=float(encl_dropout), beta=float(beta), alpha=float(alpha),
       clip_library=float(clip_library))

@@ -101,6 +101,18 @@ struct sisua_model {
   bool drop_step_on_device = false;   // step < 0: kernels read the device-side optimiser counter (graph replays)
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
+  const int* ridx = nullptr;    // row gather of the current sisua_train_step_gather call (consumed by the tcgen05 kernels)
+  float* mw_logw = nullptr;     // importance weights of sisua_marginal_llk
+  float* gx = nullptr;          // staging for gathered rows: counts (only the un-fused cross-check path needs them dense),
+  float *gy = nullptr, *glib = nullptr;   // proteins, library statistics,
+  uint8_t* gmask = nullptr;     // label mask
+  bool fwd_no_grads = false;       // training-mode forward only (sisua_forward_train_mode): batch statistics and dropout, no gradients
+  bool decode_only = false;        // sisua_decode: the latent samples are already in the workspace, start at the decoder
+  // one-call options of the posterior fast paths (set by sisua_infer_ex around forward_common)
+  const float* x_eval = nullptr;   // counts the likelihood is evaluated on (the encoder still reads x)
+  int nozi = 0;                    // likelihood without zero inflation
+  float* out_mean_avg = nullptr;   // [B, G] mean over Monte-Carlo samples of the NB mean
+  float* logw = nullptr;           // [S*B] importance weights log p(z) - log q(z | x)
   uint64_t infer_seed = 0;      // sisua_set_infer_seed
   long long infer_calls = 0;
   float gscale = 1.0f;          // scale of the fp16 gradient operand tiles (sisua_set_count_bound)
@@ -346,7 +358,7 @@ static TcGeometry tc_geometry(const sisua_model* h, int B, int R) {
   return g;
 }
 
-static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int B, int N0, bool training) {
+static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int B, int N0, bool training, bool grads) {
   const sisua_step_config& c = h->cfg;
   {
     // both packed operands in one launch (the output-head tiles are consumed later in the same step)
@@ -360,9 +372,9 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   }
   tc::EncFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
+  a.x = x; a.ridx = h->ridx; a.packed = h->packed_w1; a.A0 = h->A0; a.B = B; a.G = c.n_genes; a.ld0 = h->ld0; a.n_kblocks = h->n_kblocks;
   a.log_norm = c.log_norm; a.drop = make_drop(h, c.input_dropout, 0u, training);
-  a.xt = training ? h->xt_tiles : nullptr; a.xt_kblocks = h->xt_kblocks;
+  a.xt = grads ? h->xt_tiles : nullptr; a.xt_kblocks = h->xt_kblocks;
   const TcGeometry geo = tc_geometry(h, B, B);
   const int cell_tiles = geo.enc_cell_tiles, chunks = geo.enc_chunks;
   a.kblocks_per_chunk = geo.enc_kblocks_per_chunk;
@@ -486,9 +498,10 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
   CUDA_OK(h, cudaMemsetAsync(llk_x, 0, (size_t)R * sizeof(float), st));
   tc::OutHeadsArgs a;
   memset(&a, 0, sizeof(a));
-  a.D = h->D; a.ldD = kH; a.x = x; a.packed = h->packed_wout; a.llk_x = llk_x;
+  a.D = h->D; a.ldD = kH; a.x = x; a.ridx = h->ridx; a.packed = h->packed_wout; a.llk_x = llk_x;
   if (fused_norm) { a.D = h->dec.back().A; a.ldD = h->dec.back().lda; a.fuse_norm = 1; a.ns = *fused_norm; }
   a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
+  if (!training) { a.nozi = h->nozi; a.out_mean_avg = h->out_mean_avg; a.inv_S = 1.0f / (float)S; }
   a.dD = h->dD; a.dW = h->Gd ? h->Gd + h->out_w : nullptr; a.db = h->Gd ? h->Gd + h->out_b : nullptr;
   a.R = R; a.B = B; a.G = G; a.n_tiles = h->n_gene_tiles;
   a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.upstream = -1.0f / (float)R;
@@ -799,19 +812,28 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   const int R = S * B;
   if (!h->P) SET_ERR(h, SISUA_ERR_STATE, "bind_buffers has not been called");
   if (B < 1 || S < 1 || R > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "rows S*B=%d exceed max_batch=%d", R, c.max_batch);
-  if (!x || !terms) SET_ERR(h, SISUA_ERR_INVALID, "x / terms must not be null");
-  if (scvi && !library) SET_ERR(h, SISUA_ERR_INVALID, "scVI needs library [B,2]");      // eps_z / eps_l NULL: Philox noise in-kernel
-  if (P > 0 && !y) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs y [B,P]");
+  const bool decode_only = h->decode_only;
+  const bool grads = training && !h->fwd_no_grads;      // gradient side of the fused kernels
+  if ((!x && !decode_only) || !terms) SET_ERR(h, SISUA_ERR_INVALID, "x / terms must not be null");
+  if (scvi && !library && !decode_only) SET_ERR(h, SISUA_ERR_INVALID, "scVI needs library [B,2]");      // eps_z / eps_l NULL: Philox noise in-kernel
+  if (P > 0 && !y && !decode_only) SET_ERR(h, SISUA_ERR_INVALID, "SISUA needs y [B,P]");
   if (training) CUDA_OK(h, cudaMemsetAsync(h->stats, 0, (size_t)h->n_units * 4 * H * sizeof(double), st));
   if (loss) CUDA_OK(h, cudaMemsetAsync(loss, 0, sizeof(float), st));
 
+  const bool fused_latent = (S == 1) && !decode_only;    // one kernel: latent projection -> reparameterisation / KL -> first decoder layer
+  if (decode_only) {
+    CUDA_OK(h, cudaMemsetAsync(terms + (size_t)3 * R, 0, (size_t)2 * R * sizeof(float), st));   // kl_z = kl_l = 0
+#ifdef SISUA_WITH_TC
+    if (tc_heads_enabled(h)) h->wout_packed = false;      // (the first-layer launch that also packs the head tiles is skipped)
+#endif
+  } else {
   // ---- first layer: log1p(x) . W1^T  (z encoder and, for scVI, the library encoder in one pass)
   const int N0 = scvi ? 2 * H : H;
   bool first_done = false;
   sec_begin(h, st, SEC_ENC_FIRST);
 #ifdef SISUA_WITH_TC
   if (c.gemm_mode != SISUA_GEMM_FP32_UNFUSED) {
-    int rc = tc_encoder_first(h, st, x, B, N0, training);
+    int rc = tc_encoder_first(h, st, x, B, N0, training, grads);
     if (rc != SISUA_OK) return rc;
     first_done = true;
   }
@@ -827,7 +849,6 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   sec_end(h, st, SEC_ENC_FIRST);
   sec_begin(h, st, SEC_MID_FWD);
   stack_forward(h, st, h->enc, training, B);
-  const bool fused_latent = (S == 1);    // one kernel: latent projection -> reparameterisation / KL -> first decoder layer
   if (fused_latent) {
     Layer& L = h->enc.back();
     LatentBlockFwdArgs a;
@@ -836,9 +857,10 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     a.W_lat = h->P + h->lat_w; a.b_lat = h->P + h->lat_b; a.ZP = dca ? Z : 2 * Z;
     a.eps_z = eps_z; a.noise = make_noise(h); a.W_d0 = h->P + h->dec[0].w_off;
     a.PL = h->PL; a.loc = h->loc; a.scale = h->scale; a.z = h->Zs; a.kl_z = terms + (size_t)3 * R;
+    a.logw = h->logw;
     a.A_d0 = h->dec[0].A; a.ldd0 = h->dec[0].lda;
     if (training && h->dec[0].bn_index >= 0) { a.out_sum = h->stats + (size_t)h->dec[0].stat_index * 4 * kH; a.out_sumsq = a.out_sum + kH; }
-    a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
+    a.B = B; a.Z = Z; a.deterministic = dca ? (c.latent_linear ? 2 : 1) : 0; a.scale_act = c.scale_act;
     ++h->launches;
     launch_pdl(latent_block_fwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), kLatentFwdSmem, st, a);
     LAUNCH_OK(h, "latent_block_fwd_kernel");
@@ -860,17 +882,19 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     memset(&a, 0, sizeof(a));
     a.PL = fused_latent ? nullptr : h->PL; a.eps_z = eps_z; a.noise = make_noise(h); a.loc = h->loc; a.scale = h->scale; a.z = h->Zs;
     a.kl_z = terms + (size_t)3 * R; a.kl_l = terms + (size_t)4 * R;
+    a.logw = h->logw;
     if (scvi) {
       a.PLIB = h->PLIB; a.eps_l = eps_l; a.library = library; a.lib_loc = h->lib_loc; a.lib_scale = h->lib_scale;
       a.lib = h->lib;
     }
-    a.B = B; a.S = S; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act;
+    a.B = B; a.S = S; a.Z = Z; a.deterministic = dca ? (c.latent_linear ? 2 : 1) : 0; a.scale_act = c.scale_act;
     ++h->launches;
     launch_pdl(latent_fwd_kernel, dim3((B + 127) / 128), dim3(128), 0, st, a);
     LAUNCH_OK(h, "latent_fwd_kernel");
   } else {
     CUDA_OK(h, cudaMemsetAsync(terms + (size_t)4 * R, 0, (size_t)R * sizeof(float), st));   // kl_l = 0
   }
+  }   // !decode_only
   // ---- decoder
   if (!fused_latent) {
     double* st0 = (training && h->dec[0].bn_index >= 0) ? h->stats + (size_t)h->dec[0].stat_index * 4 * kH : nullptr;
@@ -897,7 +921,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     if (c.mask_norm == 1) { ++h->launches; mask_scale_kernel<<<1, 256, 0, st>>>(mask, B, h->mask_scale); }
     YHeadArgs a;
     memset(&a, 0, sizeof(a));
-    a.PY = h->PY; a.y = y; a.mask = mask; a.llk_y = terms + (size_t)2 * R; a.dPY = training ? h->dPY : nullptr;
+    a.PY = h->PY; a.y = y; a.mask = mask; a.llk_y = terms + (size_t)2 * R; a.dPY = grads ? h->dPY : nullptr;
     a.y_mean = y_mean; a.R = R; a.B = B; a.P = P; a.y_dist = c.y_dist; a.mean_act = c.mean_act; a.disp_act = c.disp_act;
     a.upstream = -c.alpha / (float)R;
     a.mask_scale = c.mask_norm == 1 ? h->mask_scale : nullptr;
@@ -913,13 +937,14 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
   bool out_done = false;
 #ifdef SISUA_WITH_TC
   if (tc_heads_enabled(h)) {
-    if (training) {   // the fused kernel adds its d loss / d D on top of the protein head's contribution
+    if (grads) {   // the fused kernel adds its d loss / d D on top of the protein head's contribution
       int rc0 = init_dD(h, st, R);
       if (rc0 != SISUA_OK) return rc0;
     }
-    int rc = tc_output_heads(h, st, training, x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi, fuse_dec_norm ? &ns_d : nullptr);
+    int rc = tc_output_heads(h, st, grads, (!training && h->x_eval) ? h->x_eval : x, B, S, terms + (size_t)R, out_mean, out_disp, out_pi,
+                             fuse_dec_norm ? &ns_d : nullptr);
     if (rc != SISUA_OK) return rc;
-    if (training && h->ev_out_grads) CUDA_OK(h, cudaEventRecord(h->ev_out_grads, st));
+    if (grads && h->ev_out_grads) CUDA_OK(h, cudaEventRecord(h->ev_out_grads, st));
     out_done = true;
   }
 #endif
@@ -927,11 +952,12 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     launch_sgemm<LOAD_NONE, LOAD_NONE>(h, st, h->D, H, 1, h->P + h->out_w, 1, H, h->OUT, h->NO, h->P + h->out_b, R, h->NO, H, false);
     CountRowArgs a;
     memset(&a, 0, sizeof(a));
-    a.OUT = h->OUT; a.ldo = h->NO; a.x = x; a.lib = scvi ? h->lib : nullptr; a.llk_x = terms + (size_t)R;
-    a.dlib = (scvi && training) ? h->dLib : nullptr;
+    if (!training && (h->nozi || h->out_mean_avg)) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "infer_ex options need the fused tcgen05 heads (gemm_mode 1)");
+    a.OUT = h->OUT; a.ldo = h->NO; a.x = (!training && h->x_eval) ? h->x_eval : x; a.lib = scvi ? h->lib : nullptr; a.llk_x = terms + (size_t)R;
+    a.dlib = (scvi && grads) ? h->dLib : nullptr;
     a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
     a.R = R; a.B = B; a.G = G; a.scvi = scvi ? 1 : 0; a.zero_inflated = c.x_dist == SISUA_XDIST_ZINBD;
-    a.train = training ? 1 : 0; a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.reapply = c.scvi_reapply_act;
+    a.train = grads ? 1 : 0; a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.reapply = c.scvi_reapply_act;
     a.upstream = -1.0f / (float)R; a.clip_library = c.clip_library;
     size_t smem = scvi ? (size_t)G * sizeof(float) : 0;
     ++h->launches;
@@ -1085,7 +1111,7 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
     a.dH_enc = dH_enc;
     a.prev_sdy = h->stats + (size_t)Le.stat_index * 4 * kH + 2 * kH; a.prev_sdyx = a.prev_sdy + kH;
     a.prev_dgamma = Le.g_off >= 0 ? h->Gd + Le.g_off : nullptr; a.prev_dbeta = h->Gd + Le.b_off;
-    a.B = B; a.Z = Z; a.deterministic = dca ? 1 : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
+    a.B = B; a.Z = Z; a.deterministic = dca ? (c.latent_linear ? 2 : 1) : 0; a.scale_act = c.scale_act; a.kl_weight = c.beta / (float)B;
     ++h->launches;
     launch_pdl(latent_block_bwd_kernel, dim3(mid_grid(h, B)), dim3(kMidThreads), Z <= 16 ? kLatentBwdSmemNarrow : kLatentBwdSmem, st, a);
     LAUNCH_OK(h, "latent_block_bwd_kernel");
@@ -1141,6 +1167,71 @@ extern "C" int sisua_train_step(sisua_handle h, const float* x, const float* y, 
   return SISUA_OK;
 }
 
+// rows of a resident matrix -> dense minibatch (small per-cell side inputs; counts only for the un-fused path)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ ridx, float* __restrict__ dst,
+                                                          int B, int width) {
+  const long long n = (long long)B * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / width), c = (int)(i % width);
+    dst[i] = src[(size_t)ridx[b] * width + c];
+  }
+}
+__global__ void __launch_bounds__(256) gather_bytes_kernel(const uint8_t* __restrict__ src, const int* __restrict__ ridx,
+                                                           uint8_t* __restrict__ dst, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) dst[b] = src[ridx[b]];
+}
+
+// Same step on a minibatch given as ROW INDICES into matrices that stay resident in HBM (what `fit(shuffle=True)` draws
+// every step: sisua/data/_single_cell_base.py:593-601 shuffle -> batch): x_all [N,G], y_all [N,P], library_all [N,2],
+// mask_all [N], rows [B] int32 (device).  The tcgen05 kernels read the count rows through the index (no gathered copy
+// of the minibatch is ever written); the small per-cell side inputs are gathered by one tiny kernel each.
+extern "C" int sisua_train_step_gather(sisua_handle h, const float* x_all, const float* y_all, const float* library_all,
+                                       const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                                       uint64_t seed, int64_t step, float* terms, float* loss, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  if (!rows) return sisua_train_step(h, x_all, y_all, library_all, mask_all, eps_z, eps_l, B, seed, step, terms, loss, stream);
+  const sisua_step_config& c = h->cfg;
+  if (B < 1 || B > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "train_step_gather: B=%d outside [1, max_batch=%d]", B, c.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t R = c.max_batch;
+  int rc;
+  const float* x = x_all; const float* y = y_all; const float* lib = library_all; const uint8_t* mask = mask_all;
+  bool tc_path = false;
+#ifdef SISUA_WITH_TC
+  tc_path = tc_heads_enabled(h);
+#endif
+  if (!tc_path) {       // cross-check path: dense copy of the counts
+    if (!h->gx && (rc = ws_alloc(h, &h->gx, R * c.n_genes)) != SISUA_OK) return rc;
+    ++h->launches;
+    gather_rows_kernel<<<std::max(1, std::min(4 * h->num_sms, (int)(((long long)B * c.n_genes + 255) / 256))), 256, 0, st>>>(x_all, rows, h->gx, B, c.n_genes);
+    x = h->gx;
+  }
+  if (y_all && c.n_proteins > 0) {
+    if (!h->gy && (rc = ws_alloc(h, &h->gy, R * c.n_proteins)) != SISUA_OK) return rc;
+    ++h->launches;
+    gather_rows_kernel<<<(B * c.n_proteins + 255) / 256, 256, 0, st>>>(y_all, rows, h->gy, B, c.n_proteins);
+    y = h->gy;
+  }
+  if (library_all) {
+    if (!h->glib && (rc = ws_alloc(h, &h->glib, R * 2)) != SISUA_OK) return rc;
+    ++h->launches;
+    gather_rows_kernel<<<(B * 2 + 255) / 256, 256, 0, st>>>(library_all, rows, h->glib, B, 2);
+    lib = h->glib;
+  }
+  if (mask_all) {
+    if (!h->gmask && (rc = ws_alloc(h, &h->gmask, R)) != SISUA_OK) return rc;
+    ++h->launches;
+    gather_bytes_kernel<<<(B + 255) / 256, 256, 0, st>>>(mask_all, rows, h->gmask, B);
+    mask = h->gmask;
+  }
+  LAUNCH_OK(h, "row gather");
+  h->ridx = tc_path ? rows : nullptr;
+  rc = sisua_train_step(h, x, y, lib, mask, eps_z, eps_l, B, seed, step, terms, loss, stream);
+  h->ridx = nullptr;
+  return rc;
+}
+
 extern "C" int sisua_infer(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
                            const float* eps_z, const float* eps_l, int B, int S, float* terms, float* z_loc,
                            float* z_scale, float* lib_loc, float* lib_scale, float* out_mean, float* out_disp,
@@ -1160,6 +1251,105 @@ extern "C" int sisua_infer(sisua_handle h, const float* x, const float* y, const
     if (lib_loc) CUDA_OK(h, cudaMemcpyAsync(lib_loc, h->lib_loc, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (lib_scale) CUDA_OK(h, cudaMemcpyAsync(lib_scale, h->lib_scale, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return SISUA_OK;
+}
+
+// sisua_infer with the options the Posterior fast paths need (sisua/analysis/posterior.py:210-220,919-976):
+//   x_eval       counts the log-likelihood is evaluated on while the encoder reads x (llk of ORIGINAL counts under the
+//                model of the CORRUPTED ones); NULL = x
+//   strip_zi     likelihood / parameters of the count distribution without its zero inflation ("imputed")
+//   out_mean_avg [B,G] mean over the S Monte-Carlo samples of the NB mean, accumulated in the fused epilogue
+//   logw         [S*B] log p(z_s) - log q(z_s | x) (+ the library latent's): importance weights
+extern "C" int sisua_infer_ex(sisua_handle h, const float* x, const float* x_eval, const float* y, const float* library,
+                              const uint8_t* mask, const float* eps_z, const float* eps_l, int B, int S, int strip_zi,
+                              float* terms, float* z_loc, float* z_scale, float* lib_loc, float* lib_scale, float* out_mean,
+                              float* out_disp, float* out_pi, float* y_mean, float* out_mean_avg, float* logw, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  if (out_mean_avg) {
+    cudaError_t e = cudaMemsetAsync(out_mean_avg, 0, (size_t)B * h->cfg.n_genes * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) SET_ERR(h, SISUA_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+  }
+  h->x_eval = x_eval; h->nozi = strip_zi ? 1 : 0; h->out_mean_avg = out_mean_avg; h->logw = logw;
+  const int rc = sisua_infer(h, x, y, library, mask, eps_z, eps_l, B, S, terms, z_loc, z_scale, lib_loc, lib_scale, out_mean, out_disp,
+                             out_pi, y_mean, stream);
+  h->x_eval = nullptr; h->nozi = 0; h->out_mean_avg = nullptr; h->logw = nullptr;
+  return rc;
+}
+
+// Training-mode forward pass WITHOUT gradients or weight update (`model(..., training=True)` outside fit,
+// single_cell_model.py:178): BatchNorm uses the batch statistics and folds them into the moving ones, dropout masks are
+// drawn from (seed, step); outputs as sisua_infer with S = 1.
+extern "C" int sisua_forward_train_mode(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                                        const float* eps_z, const float* eps_l, int B, uint64_t seed, int64_t step, float* terms,
+                                        float* z_loc, float* z_scale, float* lib_loc, float* lib_scale, float* out_mean,
+                                        float* out_disp, float* out_pi, float* y_mean, void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const sisua_step_config& c = h->cfg;
+  if (c.batchnorm && B < 2) SET_ERR(h, SISUA_ERR_INVALID, "training-mode batch norm needs B >= 2");
+  h->drop_seed = seed; h->drop_step = (uint32_t)(step >= 0 ? step : 0); h->drop_step_on_device = step < 0;
+  h->fwd_no_grads = true;
+  const int rc = forward_common(h, st, true, x, y, library, mask, eps_z, eps_l, B, 1, terms ? terms : h->scratch_terms, nullptr, out_mean,
+                                out_disp, out_pi, y_mean);
+  h->fwd_no_grads = false;
+  if (rc != SISUA_OK) return rc;
+  const size_t zb = (size_t)B * c.n_latent * sizeof(float);
+  if (z_loc) CUDA_OK(h, cudaMemcpyAsync(z_loc, h->loc, zb, cudaMemcpyDeviceToDevice, st));
+  if (z_scale) CUDA_OK(h, cudaMemcpyAsync(z_scale, h->scale, zb, cudaMemcpyDeviceToDevice, st));
+  if (c.model_kind == SISUA_MODEL_SCVI) {
+    if (lib_loc) CUDA_OK(h, cudaMemcpyAsync(lib_loc, h->lib_loc, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (lib_scale) CUDA_OK(h, cudaMemcpyAsync(lib_scale, h->lib_scale, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return SISUA_OK;
+}
+
+// Decoder only (SingleCellModel.decode(latents), single_cell_model.py:141-151; scvi.py:108-171): latent samples z [R, Z]
+// (and, for scVI, sampled log-library sizes lib [R]) -> parameters of the output distribution(s) with the moving
+// BatchNorm statistics: out_mean / out_disp / out_pi [R, G], y_mean [R, P]; any output may be NULL.
+extern "C" int sisua_decode(sisua_handle h, const float* z, const float* lib, int R, float* out_mean, float* out_disp, float* out_pi,
+                            float* y_mean, void* stream) {
+  if (!h || !z) return SISUA_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const sisua_step_config& c = h->cfg;
+  if (R < 1 || R > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "decode: R=%d outside [1, max_batch=%d]", R, c.max_batch);
+  if (c.model_kind == SISUA_MODEL_SCVI && !lib) SET_ERR(h, SISUA_ERR_INVALID, "decode: scVI needs the sampled log-library sizes");
+  CUDA_OK(h, cudaMemcpyAsync(h->Zs, z, (size_t)R * c.n_latent * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (c.model_kind == SISUA_MODEL_SCVI) CUDA_OK(h, cudaMemcpyAsync(h->lib, lib, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+#ifdef SISUA_WITH_TC
+  if (!tc_heads_enabled(h)) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "decode needs the fused tcgen05 output heads (gemm_mode 1)");
+#else
+  SET_ERR(h, SISUA_ERR_UNSUPPORTED, "decode needs the fused tcgen05 output heads");
+#endif
+  h->decode_only = true;
+  // S = 1, B = R: the count likelihood of the fused heads is evaluated against zeros (x == NULL) and discarded
+  const int rc = forward_common(h, st, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R, 1, h->scratch_terms, nullptr, out_mean,
+                                out_disp, out_pi, y_mean);
+  h->decode_only = false;
+  return rc;
+}
+
+// Importance-weighted marginal log-likelihood of one minibatch (SingleCellModel.marginal_log_prob,
+// posterior.py:964-968): S Monte-Carlo samples through sisua_infer_ex, then per cell
+//   mllk = logsumexp_s(llk_x + alpha * mask * llk_y + log p(z_s) - log q(z_s | x)) - log S
+// and llk_x / llk_y = logsumexp_s(.) - log S.  Outputs [B] each; llk_y may be NULL.
+extern "C" int sisua_marginal_llk(sisua_handle h, const float* x, const float* y, const float* library, const uint8_t* mask,
+                                  const float* eps_z, const float* eps_l, int B, int S, float* mllk, float* llk_x, float* llk_y,
+                                  void* stream) {
+  if (!h || !mllk || !llk_x) return SISUA_ERR_INVALID;
+  const sisua_step_config& c = h->cfg;
+  if (B < 1 || S < 1 || (long long)B * S > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "marginal_llk: S*B=%lld exceeds max_batch=%d", (long long)B * S, c.max_batch);
+  int rc;
+  if (!h->mw_logw && (rc = ws_alloc(h, &h->mw_logw, (size_t)c.max_batch)) != SISUA_OK) return rc;
+  rc = sisua_infer_ex(h, x, nullptr, y, library, mask, eps_z, eps_l, B, S, 0, h->scratch_terms, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, h->mw_logw, stream);
+  if (rc != SISUA_OK) return rc;
+  MarginalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.terms = h->scratch_terms; a.logw = h->mw_logw; a.mask = mask; a.alpha = c.alpha; a.B = B; a.S = S; a.has_y = c.n_proteins > 0 ? 1 : 0;
+  a.mllk = mllk; a.llk_x = llk_x; a.llk_y = llk_y;
+  ++h->launches;
+  marginal_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_OK(h, "marginal_kernel");
   return SISUA_OK;
 }
 
@@ -1226,7 +1416,10 @@ __global__ void __launch_bounds__(256) unpack_csr_kernel(const int* __restrict__
   }
   __syncwarp();
   const int b = indptr[warp], e = indptr[warp + 1];
-  for (int i = b + lane; i < e; i += 32) row[cols[i]] = (float)vals[i];
+  for (int i = b + lane; i < e; i += 32) {
+    const int c = cols[i];
+    if (c < G) row[c] = (float)vals[i];        // a batch built for a wider matrix must not write outside its row
+  }
 }
 
 extern "C" int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals,
@@ -1282,6 +1475,10 @@ extern "C" int sisua_train_step_host(sisua_handle h, const sisua_host_batch* hb,
   if (hb->format == SISUA_HOST_CSR) {
     if (!hb->indptr || hb->nnz < 0 || (hb->nnz > 0 && (!hb->cols || !hb->vals))) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: incomplete CSR batch");
     if (G > 65536) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "train_step_host: uint16 column ids need n_genes <= 65536");
+    // the row pointers are host memory: check them before anything is enqueued (they drive a device-side scatter)
+    if (hb->indptr[0] != 0 || (int64_t)hb->indptr[B] != hb->nnz) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: indptr[0] = %d, indptr[B] = %d but nnz = %lld", hb->indptr[0], hb->indptr[B], (long long)hb->nnz);
+    for (int i = 0; i < B; ++i)
+      if (hb->indptr[i + 1] < hb->indptr[i]) SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: indptr is not monotone at row %d", i);
   } else if (!hb->x) {
     SET_ERR(h, SISUA_ERR_INVALID, "train_step_host: x is NULL");
   }

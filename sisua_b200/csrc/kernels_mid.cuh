@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(kMidThreads) dense_fwd_kernel(
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
     const bool vec_out = Nout == kH && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(A_out) & 15) == 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -249,6 +248,7 @@ struct LatentArgs {
   float* lib_loc; float* lib_scale;  // [B]
   float* lib;          // [S*B] sampled log-library
   float* kl_l;         // [B]
+  float* logw;         // [S*B] log p(z_s) - log q(z_s | x) (+ the library latent's), nullable: importance weights of marginal_log_prob
   int B, S, Z, deterministic, scale_act;
 };
 __global__ void latent_fwd_kernel(LatentArgs a) {
@@ -257,28 +257,37 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   int Z = a.Z;
+  if (a.logw && a.PL && a.deterministic)       // (PL == null: the fused latent block already wrote the z part)
+    for (int s = 0; s < a.S; ++s) a.logw[(size_t)s * a.B + b] = 0.f;
   if (!a.PL) {
     // library-only call (the z path ran in latent_block_fwd_kernel)
   } else if (a.deterministic) {
     for (int j = 0; j < Z; ++j) {
-      float v = fmaxf(a.PL[(size_t)b * Z + j], 0.f);
-      a.loc[(size_t)b * Z + j] = v; a.scale[(size_t)b * Z + j] = 0.f; a.z[(size_t)b * Z + j] = v;
+      float v = a.PL[(size_t)b * Z + j];
+      if (a.deterministic == 1) v = fmaxf(v, 0.f);       // 1: 'relu' latent, 2: 'linear' latent (dca.py:16-27)
+      a.loc[(size_t)b * Z + j] = v; a.scale[(size_t)b * Z + j] = 0.f;
+      for (int s = 0; s < a.S; ++s) a.z[((size_t)s * a.B + b) * Z + j] = v;      // every "sample" of a deterministic latent is the same
     }
-    a.kl_z[b] = 0.f;
+    for (int s = 0; s < a.S; ++s) a.kl_z[(size_t)s * a.B + b] = 0.f;
   } else {
     float kl = 0.f;
+    if (a.logw) for (int s = 0; s < a.S; ++s) a.logw[(size_t)s * a.B + b] = 0.f;
     for (int j = 0; j < Z; ++j) {
       float mu = a.PL[(size_t)b * 2 * Z + j];
       float sg, dsg;
       activation(a.scale_act, a.PL[(size_t)b * 2 * Z + Z + j], sg, dsg);
       a.loc[(size_t)b * Z + j] = mu; a.scale[(size_t)b * Z + j] = sg;
-      kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
+      const float lsg = logf(sg);
+      kl += sg * sg + mu * mu - 1.f - 2.f * lsg;
       for (int s = 0; s < a.S; ++s) {
         const float e = a.eps_z ? a.eps_z[((size_t)s * a.B + b) * Z + j] : philox_normal(a.noise, (uint32_t)b, (uint32_t)j, kNoiseStreamZ + 2u * s);
-        a.z[((size_t)s * a.B + b) * Z + j] = fmaf(sg, e, mu);
+        const float zz = fmaf(sg, e, mu);
+        a.z[((size_t)s * a.B + b) * Z + j] = zz;
+        // log N(z; 0, 1) - log N(z; mu, sg) = -z^2/2 + eps^2/2 + log sg
+        if (a.logw) a.logw[(size_t)s * a.B + b] += 0.5f * (e * e - zz * zz) + lsg;
       }
     }
-    a.kl_z[b] = 0.5f * kl;
+    for (int s = 0; s < a.S; ++s) a.kl_z[(size_t)s * a.B + b] = 0.5f * kl;      // same value for every Monte-Carlo sample row
   }
   if (a.PLIB) {
     float mu = a.PLIB[(size_t)b * 2];
@@ -286,13 +295,17 @@ __global__ void latent_fwd_kernel(LatentArgs a) {
     activation(a.scale_act, a.PLIB[(size_t)b * 2 + 1], sg, dsg);
     float pm = a.library[(size_t)b * 2], pv = a.library[(size_t)b * 2 + 1];
     a.lib_loc[b] = mu; a.lib_scale[b] = sg;
-    a.kl_l[b] = logf(sqrtf(pv) / sg) + (sg * sg + (mu - pm) * (mu - pm)) / (2.f * pv) - 0.5f;
+    const float kll = logf(sqrtf(pv) / sg) + (sg * sg + (mu - pm) * (mu - pm)) / (2.f * pv) - 0.5f;
+    for (int s = 0; s < a.S; ++s) a.kl_l[(size_t)s * a.B + b] = kll;
     for (int s = 0; s < a.S; ++s) {
       const float e = a.eps_l ? a.eps_l[(size_t)s * a.B + b] : philox_normal(a.noise, (uint32_t)b, 0u, kNoiseStreamL + 2u * s);
-      a.lib[(size_t)s * a.B + b] = fmaf(sg, e, mu);
+      const float l = fmaf(sg, e, mu);
+      a.lib[(size_t)s * a.B + b] = l;
+      // log N(l; pm, pv) - log N(l; mu, sg)
+      if (a.logw) a.logw[(size_t)s * a.B + b] += -0.5f * (l - pm) * (l - pm) / pv - 0.5f * logf(pv) + 0.5f * e * e + logf(sg);
     }
   } else if (a.kl_l) {
-    a.kl_l[b] = 0.f;
+    for (int s = 0; s < a.S; ++s) a.kl_l[(size_t)s * a.B + b] = 0.f;
   }
 }
 
@@ -345,7 +358,7 @@ __global__ void yhead_kernel(YHeadArgs a) {
   float acc = 0.f;
   for (int j = 0; j < P; ++j) {
     float ra = a.PY[(size_t)r * 2 * P + j], rb = a.PY[(size_t)r * 2 * P + P + j];
-    float yv = a.y[(size_t)b * P + j];
+    float yv = a.y ? a.y[(size_t)b * P + j] : 0.f;      // (no targets: decode only, the likelihood is discarded)
     float da = 0.f, db = 0.f, llk, mean;
     if (a.y_dist == 0) {
       llk = a.dPY ? nb_tfp_llk<true>(yv, ra, rb, da, db) : nb_tfp_llk<false>(yv, ra, rb, da, db);
@@ -366,6 +379,40 @@ __global__ void yhead_kernel(YHeadArgs a) {
     if (a.y_mean) a.y_mean[(size_t)r * P + j] = mean;
   }
   a.llk_y[r] = acc;
+}
+
+// marginal_log_prob (sisua/analysis/posterior.py:941-976 -> odin-ai): per cell
+//   mllk_b = logsumexp_s( llk_x[s,b] + alpha * mask_b * llk_y[s,b] + logw[s,b] ) - log S      (importance-weighted bound)
+//   llk_x_b = logsumexp_s llk_x[s,b] - log S, same for llk_y                                   (the per-output entries)
+struct MarginalArgs {
+  const float* terms;    // [5, S*B]
+  const float* logw;     // [S*B]
+  const uint8_t* mask;   // [B] or null
+  float alpha;
+  int B, S, has_y;
+  float* mllk; float* llk_x; float* llk_y;   // [B] each (llk_y nullable)
+};
+__global__ void marginal_kernel(MarginalArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const size_t R = (size_t)a.S * a.B;
+  const float w = (a.has_y && a.mask && a.mask[b]) ? a.alpha : 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
+  for (int s = 0; s < a.S; ++s) {
+    const size_t r = (size_t)s * a.B + b;
+    const float lx = a.terms[R + r], ly = a.terms[2 * R + r];
+    m0 = fmaxf(m0, lx + w * ly + a.logw[r]); m1 = fmaxf(m1, lx); m2 = fmaxf(m2, ly);
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int s = 0; s < a.S; ++s) {
+    const size_t r = (size_t)s * a.B + b;
+    const float lx = a.terms[R + r], ly = a.terms[2 * R + r];
+    s0 += expf(lx + w * ly + a.logw[r] - m0); s1 += expf(lx - m1); s2 += expf(ly - m2);
+  }
+  const float lS = logf((float)a.S);
+  a.mllk[b] = m0 + logf(s0) - lS;
+  a.llk_x[b] = m1 + logf(s1) - lS;
+  if (a.llk_y) a.llk_y[b] = m2 + logf(s2) - lS;
 }
 
 // n_labelled -> mask_scale = B / max(n_labelled, 1)   (Q3 alternative)
@@ -641,7 +688,6 @@ __global__ void __launch_bounds__(kMidThreads) dense_bwd_kernel(DenseBwdArgs a) 
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
       float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
       const bool vec_in = Kin == kH && (a.ldi & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dIn) & 15) == 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -818,6 +864,7 @@ struct LatentBlockFwdArgs {
   NoiseSpec noise;
   const float* W_d0;                                // [64, Z]
   float* PL; float* loc; float* scale; float* z; float* kl_z;
+  float* logw;                                      // [B] log p(z) - log q(z | x), nullable
   float* A_d0; int ldd0;                            // [B, 64]
   double* out_sum; double* out_sumsq;               // BN statistics of A_d0 (nullable)
   int B, Z, deterministic, scale_act;
@@ -914,12 +961,14 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
     __syncthreads();
     if (t < kTileR) {      // one thread per row: loc / scale / sample / KL
       const int r = t, b = r0 + r;
-      float kl = 0.f;
+      float kl = 0.f, lw = 0.f;
       float4 nz4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < Z; ++j) {
         float mu, sg, zz;
         if (a.deterministic) {
-          mu = fmaxf(PLs[r * kTS + j], 0.f); sg = 0.f; zz = mu;
+          mu = PLs[r * kTS + j];
+          if (a.deterministic == 1) mu = fmaxf(mu, 0.f);
+          sg = 0.f; zz = mu;
         } else {
           float dsg;
           mu = PLs[r * kTS + j];
@@ -935,12 +984,15 @@ __global__ void __launch_bounds__(kMidThreads) latent_block_fwd_kernel(LatentBlo
             }
           }
           zz = b < a.B ? fmaf(sg, e, mu) : 0.f;
-          kl += sg * sg + mu * mu - 1.f - 2.f * logf(sg);
+          const float lsg = logf(sg);
+          kl += sg * sg + mu * mu - 1.f - 2.f * lsg;
+          lw += 0.5f * (e * e - zz * zz) + lsg;
         }
         ZT[j * kTS + r] = b < a.B ? zz : 0.f;
         if (b < a.B) { a.loc[(size_t)b * Z + j] = mu; a.scale[(size_t)b * Z + j] = sg; a.z[(size_t)b * Z + j] = zz; }
       }
       if (b < a.B) a.kl_z[b] = a.deterministic ? 0.f : 0.5f * kl;
+      if (b < a.B && a.logw) a.logw[b] = a.deterministic ? 0.f : lw;
     }
     __syncthreads();
     zero16(acc);
@@ -1110,7 +1162,7 @@ __global__ void __launch_bounds__(kMidThreads, 2) latent_block_bwd_kernel(Latent
         for (int j = 0; j < Z; ++j) {
           const float dzz = Zn[r * zs + j];
           if (a.deterministic) {
-            float g = a.PL[(size_t)b * Z + j] > 0.f ? dzz : 0.f;
+            float g = (a.deterministic == 2 || a.PL[(size_t)b * Z + j] > 0.f) ? dzz : 0.f;
             Gn[r * kTS + j] = g; GT[j * kTS + r] = g;
           } else {
             float mu = a.loc[(size_t)b * Z + j], sg = a.scale[(size_t)b * Z + j];

@@ -22,8 +22,13 @@ constexpr int kGeneTile = 32;
 constexpr int kK = 64;                 // hidden width = contraction length
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kOutThreads = kEpiThreads + 64;   // 16 epilogue warps + MMA warp + loader warp
-constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1;
+// 16 epilogue warps + one service warpgroup (MMA warp, loader warp, two idle warps).  The service warps sit in a warpgroup of
+// their own so that `setmaxnreg` can move registers from them to the epilogue warpgroups: the block is launched with 96
+// registers per thread (the most 20 warps can get), the service warpgroup drops to 32 and the four epilogue warpgroups
+// grow to 112 -- enough to keep two gene pairs in flight per thread.
+constexpr int kOutThreads = kEpiThreads + 128;
+constexpr int kOutRegsService = 32, kOutRegsEpilogue = 112;
+constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kGradWarp = kEpiWarps + 2;
 constexpr int kTmemCols = 512;
 constexpr int kTmemDD = 192, kTmemDWO = 256, kDwoCols = 80;
 
@@ -69,11 +74,15 @@ struct OutHeadsArgs {
   const float* D;          // [R, ldD] decoder output: activated (fuse_norm = 0) or the last unit's pre-activation
   int ldD, fuse_norm;      //          whose norm / bias + ReLU + dropout is then applied on load (ns)
   NormSpec ns;
-  const float* x;          // [B, G] counts
+  const float* x;          // [B, G] counts, or the resident [N, G] matrix when ridx is given
+  const int* ridx;         // [B] rows of x that make up this minibatch (nullable: rows 0 .. B-1)
   const uint8_t* packed;   // pre-packed weight tiles
   float* llk_x;            // [R], zeroed by the caller (gene chunks add atomically)
   // inference outputs (nullable)
   float* out_mean; float* out_disp; float* out_pi;
+  float* out_mean_avg;     // [B, G] += mean / S  (mean over the Monte-Carlo samples of the NB mean; zeroed by the caller)
+  float inv_S;
+  int nozi;                // inference: likelihood of the count distribution WITHOUT zero inflation ("imputed", posterior.py:210-220)
   // training outputs
   float* dD;               // [R, 64] += d loss / d D
   float* dW;               // [nh*G, 64] += d loss / d W_out
@@ -98,20 +107,24 @@ struct OutHeadsArgs {
 //   3 = llk + the two row sums the softmax / library gradients need, 4 = training pass (G tiles + gradient GEMMs)
 enum OutMode { MODE_PLAIN = 0, MODE_SCVI_LSE = 1, MODE_SCVI_EVAL = 2, MODE_SCVI_SUMS = 3, MODE_SCVI_TRAIN = 4 };
 
+// Weight tiles have THREE stages: a stage is released by the gradient GEMMs of its tile, i.e. only after the slowest
+// epilogue warp has finished that tile; with two stages the next-but-one tile's forward product (and with it every
+// faster warp) waited for that, which made each tile a barrier across the 16 warps.
+constexpr int kWStages = 3;
 struct OutSmem {     // offsets into dynamic shared memory (bytes)
   static constexpr int dA1 = 0;                          // [128][80] fp16 (cols 64.. = ones / zero pad, train)
   static constexpr int dA2 = dA1 + 10 * 2048;            // [128][64] fp16
   static constexpr int W0 = dA2 + 8 * 2048;              // 2 stages of packed tiles
   __host__ __device__ static constexpr int Wstage(int nh) { return packed_tile_stride(nh); }
-  __host__ __device__ static constexpr int G0(int nh) { return W0 + 2 * Wstage(nh); }       // [128][128] fp16 x 2 stages (train)
+  __host__ __device__ static constexpr int G0(int nh) { return W0 + kWStages * Wstage(nh); }       // [128][128] fp16 x 2 stages (train)
   static constexpr int Gstage = 16 * 2048;                                                 // two G stages when training
   __host__ __device__ static constexpr int XS(int nh, bool train) { return G0(nh) + (train ? 2 * Gstage : 0); }   // [8][512] count stash
-  __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 8 * kEpiThreads * 4; }
+  __host__ __device__ static constexpr int LLK(int nh, bool train) { return XS(nh, train) + 2 * 8 * kEpiThreads * 4; }   // two stash stages
   __host__ __device__ static constexpr int BAR(int nh, bool train) { return LLK(nh, train) + (3 * kCellTile + 2 * kK) * 4; }   // llk | T | dlib | norm scale, shift
   __host__ __device__ static constexpr int total(int nh, bool train) { return BAR(nh, train) + 32 * 8 + 16; }
 };
 
-enum OutBar { W_FULL = 0, W_FREE = 2, ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12, DWO_FREE = 14, DD_FULL = 16, NUM_BARS = 17 };
+enum OutBar { ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12, DWO_FREE = 14, DD_FULL = 16, W_FULL = 17, W_FREE = 20, NUM_BARS = 23 };
 
 template <int NH, bool TRAIN, bool VEC, bool FAST, int MODE = MODE_PLAIN>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
@@ -134,10 +147,9 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 
   // ---------------- prologue: barriers, TMEM, decoder-activation tile (hi/lo fp16), pads ----------------
   if (t == 0) {
-    mbar_init(&bars[W_FULL], 1); mbar_init(&bars[W_FULL + 1], 1);
-    // a weight stage is released by the MMA commit and, when there is no backward (whose commit already follows the
-    // epilogue), by every epilogue warp once it has read the stage's bias values
-    mbar_init(&bars[W_FREE], TRAIN ? 1 : 1 + kEpiWarps); mbar_init(&bars[W_FREE + 1], TRAIN ? 1 : 1 + kEpiWarps);
+    // a weight stage is released by the forward issuer's commit plus, when training, the gradient issuer's commit; without
+    // a backward pass, by every epilogue warp once it has read the stage's bias values
+    for (int ws = 0; ws < kWStages; ++ws) { mbar_init(&bars[W_FULL + ws], 1); mbar_init(&bars[W_FREE + ws], TRAIN ? 2 : 1 + kEpiWarps); }
     mbar_init(&bars[ACC_FULL], 1); mbar_init(&bars[ACC_FULL + 1], 1);
     mbar_init(&bars[ACC_FREE], kEpiWarps); mbar_init(&bars[ACC_FREE + 1], kEpiWarps);
     mbar_init(&bars[G_FULL], kEpiWarps); mbar_init(&bars[G_FULL + 1], kEpiWarps);
@@ -200,30 +212,35 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kLoadWarp) {
+  // (each role branch starts with its own setmaxnreg and the branches only meet again at the end of the kernel: that is
+  // what lets ptxas give the epilogue code the larger budget)
+  if (warp > kGradWarp) {
+    setmaxnreg_dec<kOutRegsService>();      // idle warp of the service warpgroup
+  } else if (warp == kLoadWarp) {
+    setmaxnreg_dec<kOutRegsService>();
     // =========================== loader: pre-packed weight tiles via 1-D TMA bulk copies ===========================
     if (lane == 0) {
       for (int i = 0; i < nt; ++i) {
-        const int s = i & 1;
-        if (i >= 2) mbar_wait_backoff(&bars[W_FREE + s], ((i >> 1) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[W_FULL + s], packed_tile_bytes(NH));
-        bulk_copy_g2s(smem + OutSmem::W0 + s * OutSmem::Wstage(NH),
-                      a.packed + (size_t)(tile_begin + i) * packed_tile_stride(NH), packed_tile_bytes(NH), &bars[W_FULL + s]);
+        const int ws = i % kWStages;
+        if (i >= kWStages) mbar_wait_backoff(&bars[W_FREE + ws], ((i / kWStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[W_FULL + ws], packed_tile_bytes(NH));
+        bulk_copy_g2s(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH),
+                      a.packed + (size_t)(tile_begin + i) * packed_tile_stride(NH), packed_tile_bytes(NH), &bars[W_FULL + ws]);
       }
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA issuer (one thread) ===========================
+    setmaxnreg_dec<kOutRegsService>();
+    // =========================== forward MMA issuer (one thread) ===========================
+    // Its own thread, so that the product of tile i+2 is issued as soon as ITS inputs are there (weight tile landed,
+    // accumulator stage handed back in the middle of tile i) and never queues behind the gradient GEMMs of tile i, which
+    // wait for the slowest epilogue warp.
     if (lane == 0) {
       const uint32_t idesc_fwd = make_idesc_f16(kCellTile, NF, 0, 0);
-      const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
-      const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
-      const uint32_t idesc_dwo_lo = make_idesc_f16(kCellTile, kK, 1, 1);
       const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
-      const uint32_t sG0 = smem_u32(smem + OutSmem::G0(NH));
-      auto fwd = [&](int i) {
-        const int s = i & 1;
-        const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
-        mbar_wait_backoff(&bars[W_FULL + s], (i >> 1) & 1);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1, ws = i % kWStages;
+        const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
+        mbar_wait_backoff(&bars[W_FULL + ws], (i / kWStages) & 1);
         if (i >= 2) mbar_wait_backoff(&bars[ACC_FREE + s], ((i >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t d_t = tmem + (uint32_t)(s * N);
@@ -238,48 +255,55 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           }
         }
         umma_commit(&bars[ACC_FULL + s]);
-        if (!TRAIN) umma_commit(&bars[W_FREE + s]);
-      };
-      fwd(0);
+        umma_commit(&bars[W_FREE + ws]);      // (training: the gradient issuer's commit is the stage's second arrival)
+      }
+    }
+  } else if (warp == kGradWarp) {
+    setmaxnreg_dec<kOutRegsService>();
+    // =========================== gradient MMA issuer (one thread) ===========================
+    if (TRAIN && lane == 0) {
+      const uint32_t idesc_dd = make_idesc_f16(kCellTile, kK, 0, 1);
+      const uint32_t idesc_dwo = make_idesc_f16(kCellTile, kDwoCols, 1, 1);
+      const uint32_t idesc_dwo_lo = make_idesc_f16(kCellTile, kK, 1, 1);
+      const uint32_t sA1 = smem_u32(smem + OutSmem::dA1), sA2 = smem_u32(smem + OutSmem::dA2);
+      const uint32_t sG0 = smem_u32(smem + OutSmem::G0(NH));
       for (int i = 0; i < nt; ++i) {
-        if (i + 1 < nt) fwd(i + 1);
-        if (TRAIN) {
-          const int s = i & 1;
-          const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + s * OutSmem::Wstage(NH));
-          const uint32_t sG = sG0 + s * OutSmem::Gstage;
-          mbar_wait_backoff(&bars[G_FULL + s], (i >> 1) & 1);
-          if (i >= 2) mbar_wait_backoff(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
-          tc_fence_after();
-          // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 then w2, MN-major).  Both halves of the weight
-          // split are used: the fp16 rounding of a weight is the same for every cell, so with w1 alone the error of dD
-          // is correlated across the batch and survives the sums of the backward pass below (measured: 6e-3 of the
-          // largest dec.0.W gradient at 18 944 cells); the rounding of G is independent per entry and averages out.
+        const int s = i & 1, ws = i % kWStages;
+        const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH));
+        const uint32_t sG = sG0 + s * OutSmem::Gstage;
+        mbar_wait_backoff(&bars[G_FULL + s], (i >> 1) & 1);
+        if (i >= 2) mbar_wait_backoff(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
+        tc_fence_after();
+        // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 then w2, MN-major).  Both halves of the weight
+        // split are used: the fp16 rounding of a weight is the same for every cell, so with w1 alone the error of dD
+        // is correlated across the batch and survives the sums of the backward pass below; the rounding of G is
+        // independent per entry and averages out.
 #pragma unroll
-          for (int ks = 0; ks < N / 16; ++ks)
-            umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128), make_smem_desc(sW1 + ks * 256, 128, W_CS),
-                     idesc_dd, (i > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < N / 16; ++ks)
+          umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128), make_smem_desc(sW1 + ks * 256, 128, W_CS),
+                   idesc_dd, (i > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < N / 16; ++ks)
-            umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128),
-                     make_smem_desc(sW1 + w_tile_bytes(NH) + ks * 256, 128, W_CS), idesc_dd, 1u);
-          // dW[n, k | 1] = G^T[n, cells] . [d | 1][cells, k]   (A: G MN-major, B: d1 (+ ones column) then d2, MN-major)
+        for (int ks = 0; ks < N / 16; ++ks)
+          umma_f16(tmem + kTmemDD, make_smem_desc(sG + ks * 4096, 2048, 128),
+                   make_smem_desc(sW1 + w_tile_bytes(NH) + ks * 256, 128, W_CS), idesc_dd, 1u);
+        // dW[n, k | 1] = G^T[n, cells] . [d | 1][cells, k]   (A: G MN-major, B: d1 (+ ones column) then d2, MN-major)
 #pragma unroll
-          for (int ks = 0; ks < kCellTile / 16; ++ks)
-            umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
-                     make_smem_desc(sA1 + ks * 256, 128, 2048), idesc_dwo, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < kCellTile / 16; ++ks)
+          umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
+                   make_smem_desc(sA1 + ks * 256, 128, 2048), idesc_dwo, ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < kCellTile / 16; ++ks)
-            umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
-                     make_smem_desc(sA2 + ks * 256, 128, 2048), idesc_dwo_lo, 1u);
-          umma_commit(&bars[G_FREE + s]);
-          umma_commit(&bars[DWO_FULL + s]);
-          umma_commit(&bars[W_FREE + s]);
-          if (i == nt - 1) umma_commit(&bars[DD_FULL]);
-        }
+        for (int ks = 0; ks < kCellTile / 16; ++ks)
+          umma_f16(tmem + kTmemDWO + s * kDwoCols, make_smem_desc(sG + ks * 256, 128, 2048),
+                   make_smem_desc(sA2 + ks * 256, 128, 2048), idesc_dwo_lo, 1u);
+        umma_commit(&bars[G_FREE + s]);
+        umma_commit(&bars[DWO_FULL + s]);
+        umma_commit(&bars[W_FREE + ws]);
+        if (i == nt - 1) umma_commit(&bars[DD_FULL]);
       }
     }
   } else {
     // =========================== epilogue warps ===========================
+    setmaxnreg_inc<kOutRegsEpilogue>();
     const int q = warp & 3, sub = warp >> 2;      // TMEM lane quarter, 8-gene slice of the 32-gene tile
     const int cell = q * 32 + lane;
     const int row = row0 + cell;
@@ -304,23 +328,24 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 
     // this thread's 8 counts of tile i straight from global memory (one 32-byte sector per lane; prefetched a
     // tile ahead into registers, so no shared-memory staging and no CTA-wide barriers in the tile loop)
-    const float* xrow = a.x + (size_t)((row_ok ? row : 0) % a.B) * a.G;
+    const int xb = (row_ok ? row : 0) % a.B;
+    const float* xrow = a.x + (size_t)(a.ridx ? a.ridx[xb] : xb) * a.G;
     auto load_x = [&](int i, float* xv) {
       const int g = (tile_begin + i) * kGeneTile + sub * 8;
       if (VEC) {
         float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-        if (row_ok && g < a.G) p0 = __ldg(reinterpret_cast<const float4*>(xrow + g));
-        if (row_ok && g + 4 < a.G) p1 = __ldg(reinterpret_cast<const float4*>(xrow + g + 4));
+        if (row_ok && g < a.G && a.x) p0 = __ldg(reinterpret_cast<const float4*>(xrow + g));
+        if (row_ok && g + 4 < a.G && a.x) p1 = __ldg(reinterpret_cast<const float4*>(xrow + g + 4));
         xv[0] = p0.x; xv[1] = p0.y; xv[2] = p0.z; xv[3] = p0.w; xv[4] = p1.x; xv[5] = p1.y; xv[6] = p1.z; xv[7] = p1.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = (row_ok && g + j < a.G) ? __ldg(xrow + g + j) : 0.f;
+        for (int j = 0; j < 8; ++j) xv[j] = (row_ok && g + j < a.G && a.x) ? __ldg(xrow + g + j) : 0.f;
       }
     };
 
     auto flush_dwo = [&](int i) {            // tile i's weight / bias gradient: TMEM -> vector reds
       const int s = i & 1;
-      mbar_wait(&bars[DWO_FULL + s], (i >> 1) & 1);
+      mbar_wait_backoff(&bars[DWO_FULL + s], (i >> 1) & 1);
       tc_fence_after();
       const int n = cell;                    // TMEM lane = output-unit row of the tile
       const int h = n >> 5, g = (tile_begin + i) * kGeneTile + (n & 31);
@@ -341,10 +366,24 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       }
     };
 
-    float xnext[8];
-    if (MODE != MODE_SCVI_LSE) load_x(0, xnext);
-    // this thread's column of the [4 gene pairs][512 threads] count stash
-    float2* xs = reinterpret_cast<float2*>(smem + OutSmem::XS(NH, TRAIN)) + t;
+    // Count stash: this thread's 8 counts of a tile as two 16-byte slots ([2 stages][2 halves][512 threads] x 16 B).  With
+    // 16-byte aligned rows (VEC) the slots of tile i+1 are filled by cp.async while tile i is evaluated: no registers
+    // hold prefetched counts and nobody but the owning thread touches a slot, so no barrier is needed; otherwise the
+    // counts travel through registers.
+    uint8_t* xs_base = smem + OutSmem::XS(NH, TRAIN) + t * 16;
+    constexpr int kXsHalf = kEpiThreads * 16, kXsStage = 2 * kXsHalf;
+    auto prefetch_x = [&](int i) {          // VEC only
+      const int g = (tile_begin + i) * kGeneTile + sub * 8;
+      uint8_t* dst = xs_base + (i & 1) * kXsStage;
+      const bool ok0 = row_ok && g < a.G && a.x, ok1 = row_ok && g + 4 < a.G && a.x;      // (x == NULL: decode only, zeros)
+      cp_async_16_zfill(dst, ok0 ? (const void*)(xrow + g) : (const void*)a.x, ok0 ? 16u : 0u);
+      cp_async_16_zfill(dst + kXsHalf, ok1 ? (const void*)(xrow + g + 4) : (const void*)a.x, ok1 ? 16u : 0u);
+      cp_async_commit();
+    };
+    float xnext[VEC ? 1 : 8];
+    if (MODE != MODE_SCVI_LSE) {
+      if (VEC) prefetch_x(0); else load_x(0, xnext);
+    }
     const bool rows_full = row0 + kCellTile <= a.R;
     pm::F2 llk2 = pm::bc(0.f), t2 = pm::bc(0.f), dl2 = pm::bc(0.f);
     for (int i = 0; i < nt; ++i) {
@@ -352,17 +391,24 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       const int g0 = (tile_begin + i) * kGeneTile + sub * 8;
       // no masking inside tiles that lie fully inside the matrix (all but the last cell tile / gene tile)
       const bool full = rows_full && (tile_begin + i + 1) * kGeneTile <= a.G;
+      const uint8_t* xs = xs_base + (i & 1) * kXsStage;
       if (MODE != MODE_SCVI_LSE) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xs[j * kEpiThreads] = make_float2(xnext[2 * j], xnext[2 * j + 1]);
-        if (i + 1 < nt) load_x(i + 1, xnext);
+        if (VEC) {
+          cp_async_wait<0>();               // this tile's counts have landed (issued one tile ago)
+          if (i + 1 < nt) prefetch_x(i + 1);
+        } else {
+          *reinterpret_cast<float4*>(xs_base + (i & 1) * kXsStage) = make_float4(xnext[0], xnext[1], xnext[2], xnext[3]);
+          *reinterpret_cast<float4*>(xs_base + (i & 1) * kXsStage + kXsHalf) = make_float4(xnext[VEC ? 0 : 4], xnext[VEC ? 0 : 5], xnext[VEC ? 0 : 6], xnext[VEC ? 0 : 7]);
+          if (i + 1 < nt) load_x(i + 1, xnext);
+        }
       }
-      mbar_wait(&bars[W_FULL + s], (i >> 1) & 1);   // bias values of this stage (bulk copy) visible to this thread
-      mbar_wait(&bars[ACC_FULL + s], (i >> 1) & 1);
-      if (TRAIN && i >= 2) mbar_wait(&bars[G_FREE + s], ((i >> 1) - 1) & 1);   // gradient GEMMs of tile i-2 consumed this G stage
+      const int ws = i % kWStages;
+      mbar_wait_backoff(&bars[W_FULL + ws], (i / kWStages) & 1);   // bias values of this stage (bulk copy) visible to this thread
+      mbar_wait_backoff(&bars[ACC_FULL + s], (i >> 1) & 1);
+      if (TRAIN && i >= 2) mbar_wait_backoff(&bars[G_FREE + s], ((i >> 1) - 1) & 1);   // gradient GEMMs of tile i-2 consumed this G stage
       tc_fence_after();
       const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + sub * 8);
-      const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + s * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
+      const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
       // this thread's 16-byte slot in column group `sub` of each head of the G stage
       uint8_t* gt = smem + OutSmem::G0(NH) + s * OutSmem::Gstage + sub * 2048 + (cell >> 3) * 128 + (cell & 7) * 16;
       const size_t o = (size_t)row * a.G + g0;
@@ -381,114 +427,156 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_run += mufu_ex2((u[j] - m_run) * kLog2e);
       }
-      // Two genes per trip, evaluated in lock-step with packed fp32x2 arithmetic (pair_math.cuh); rolled on purpose: one
-      // trip's code stays inside the instruction cache.  The TMEM reads of trip j+1 are in flight while trip j is evaluated.
-      float pa[2], pb[2], pl[2];
+      // kNP gene pairs per trip: each pair advances in lock-step through packed fp32x2 arithmetic (pair_math.cuh) and the
+      // pairs are independent dependency chains the compiler interleaves; the trip loop is rolled on purpose (its code
+      // stays inside the instruction cache).  The TMEM reads of trip j+1 are in flight while trip j is evaluated.
+#ifndef SISUA_OUT_NP
+#define SISUA_OUT_NP 1       // measured on the B200 (18 944 x 2 000, ZINB train): 1 pair 0.347 ms, 2 pairs 0.351 ms
+#endif
+      constexpr int kNP = SISUA_OUT_NP, kGT = 2 * kNP;     // genes per trip
+      float pa[kGT], pb[kGT], pl[kGT];
       if (MODE != MODE_SCVI_LSE) {
-        tmem_ld2(tb, pa);
-        tmem_ld2(tb + 32, pb);
-        if (ZI) tmem_ld2(tb + 64, pl);
+        tmem_ldn<kGT>(tb, pa);
+        tmem_ldn<kGT>(tb + 32, pb);
+        if (ZI) tmem_ldn<kGT>(tb + 64, pl);
       }
 #pragma unroll 1
-      for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += 2) {
-        tmem_ld_wait_tie<2>(pa); tmem_ld_tie<2>(pb);
-        if (ZI) tmem_ld_tie<2>(pl);
-        const float2 ba = *reinterpret_cast<const float2*>(bias_s + j), bb = *reinterpret_cast<const float2*>(bias_s + 32 + j);
-        pm::F2 ra = pm::add(pm::mk(pa[0], pa[1]), pm::mk(ba.x, ba.y));
-        pm::F2 rb = pm::add(pm::mk(pb[0], pb[1]), pm::mk(bb.x, bb.y));
-        pm::F2 pi = pm::bc(0.f);
-        if (ZI) {
-          const float2 bl = *reinterpret_cast<const float2*>(bias_s + 64 + j);
-          pi = pm::add(pm::mk(pl[0], pl[1]), pm::mk(bl.x, bl.y));
+      for (int j = 0; j < (MODE == MODE_SCVI_LSE ? 0 : 8); j += kGT) {
+        tmem_ld_wait_tie<kGT>(pa); tmem_ld_tie<kGT>(pb);
+        if (ZI) tmem_ld_tie<kGT>(pl);
+        if (j + kGT >= 8) {       // the last accumulator columns of this tile are in registers: hand the TMEM stage back now, so
+          tc_fence_before();      // the forward product of tile i+2 can start while this trip is still being evaluated
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[ACC_FREE + s]);
         }
-        if (j + 2 < 8) {
-          tmem_ld2(tb + j + 2, pa);
-          tmem_ld2(tb + 32 + j + 2, pb);
-          if (ZI) tmem_ld2(tb + 64 + j + 2, pl);
+        pm::F2 ra[kNP], rb[kNP], pi[kNP], x2[kNP];
+#pragma unroll
+        for (int p = 0; p < kNP; ++p) {
+          const float2 ba = *reinterpret_cast<const float2*>(bias_s + j + 2 * p), bb = *reinterpret_cast<const float2*>(bias_s + 32 + j + 2 * p);
+          ra[p] = pm::add(pm::mk(pa[2 * p], pa[2 * p + 1]), pm::mk(ba.x, ba.y));
+          rb[p] = pm::add(pm::mk(pb[2 * p], pb[2 * p + 1]), pm::mk(bb.x, bb.y));
+          pi[p] = pm::bc(0.f);
+          if (ZI) {
+            const float2 bl = *reinterpret_cast<const float2*>(bias_s + 64 + j + 2 * p);
+            pi[p] = pm::add(pm::mk(pl[2 * p], pl[2 * p + 1]), pm::mk(bl.x, bl.y));
+          }
+          const int pj = (j >> 1) + p;      // gene pair 0..3 of this thread's slice
+          const float2 xv = *reinterpret_cast<const float2*>(xs + (pj >> 1) * kXsHalf + (pj & 1) * 8);
+          x2[p] = pm::mk(xv.x, xv.y);
         }
-        const float2 xv = xs[(j >> 1) * kEpiThreads];
-        const pm::F2 x2 = pm::mk(xv.x, xv.y);
-        pm::F2 llk, ga, gb, gl, mu, th;
+        if (j + kGT < 8) {
+          tmem_ldn<kGT>(tb + j + kGT, pa);
+          tmem_ldn<kGT>(tb + 32 + j + kGT, pb);
+          if (ZI) tmem_ldn<kGT>(tb + 64 + j + kGT, pl);
+        }
+        pm::F2 llk[kNP], ga[kNP], gb[kNP], gl[kNP], mu[kNP], th[kNP];
         if (SCVI) {
-          const pm::Scvi2 e = pm::elem_pair_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS)>(pm::sub(ra, pm::bc(lse)), rb, pi, x2, eL);
-          llk = e.llk; mu = e.mu; th = e.th; gb = e.gb; gl = e.gl;
-          ga = pm::mul(e.s_raw, pm::sub(e.t, pm::bc(t_row)));          // softmax Jacobian (row sum from the MODE 3 pass)
-          if (MODE == MODE_SCVI_SUMS) {
-            pm::F2 st = pm::mul(e.s_raw, e.t), dl = e.gmu_mu;
-            if (!full) {
-              const bool ok0 = row_ok && (g0 + j) < a.G, ok1 = row_ok && (g0 + j + 1) < a.G;
-              st = pm::mk(ok0 ? st.x : 0.f, ok1 ? st.y : 0.f); dl = pm::mk(ok0 ? dl.x : 0.f, ok1 ? dl.y : 0.f);
+          pm::Scvi2 e[kNP];
+          pm::F2 ul[kNP];
+#pragma unroll
+          for (int p = 0; p < kNP; ++p) ul[p] = pm::sub(ra[p], pm::bc(lse));
+          pm::elem_multi_scvi<ZI, (TRAIN || MODE == MODE_SCVI_SUMS), kNP>(ul, rb, pi, x2, eL, e, (TRAIN || MODE == MODE_SCVI_SUMS) ? false : a.nozi != 0);
+#pragma unroll
+          for (int p = 0; p < kNP; ++p) {
+            llk[p] = e[p].llk; mu[p] = e[p].mu; th[p] = e[p].th; gb[p] = e[p].gb; gl[p] = e[p].gl;
+            ga[p] = pm::mul(e[p].s_raw, pm::sub(e[p].t, pm::bc(t_row)));          // softmax Jacobian (row sum from the MODE 3 pass)
+            if (MODE == MODE_SCVI_SUMS) {
+              pm::F2 st = pm::mul(e[p].s_raw, e[p].t), dl = e[p].gmu_mu;
+              if (!full) {
+                const bool ok0 = row_ok && (g0 + j + 2 * p) < a.G, ok1 = row_ok && (g0 + j + 2 * p + 1) < a.G;
+                st = pm::mk(ok0 ? st.x : 0.f, ok1 ? st.y : 0.f); dl = pm::mk(ok0 ? dl.x : 0.f, ok1 ? dl.y : 0.f);
+              }
+              t2 = pm::add(t2, st); dl2 = pm::add(dl2, dl);
             }
-            t2 = pm::add(t2, st); dl2 = pm::add(dl2, dl);
           }
         } else if (FAST) {
-          const pm::Elem2 e = pm::elem_pair_softplus<ZI, TRAIN>(ra, rb, pi, x2);
-          llk = e.llk; ga = e.ga; gb = e.gb; gl = e.gl; mu = e.mu; th = e.th;
+          pm::Elem2 e[kNP];
+          pm::elem_multi_softplus<ZI, TRAIN, kNP>(ra, rb, pi, x2, e, TRAIN ? false : a.nozi != 0);
+#pragma unroll
+          for (int p = 0; p < kNP; ++p) { llk[p] = e[p].llk; ga[p] = e[p].ga; gb[p] = e[p].gb; gl[p] = e[p].gl; mu[p] = e[p].mu; th[p] = e[p].th; }
         } else {
           // other link functions (SURVEY.md section 8a Q1 alternatives): generic scalar evaluation
-          float l_[2], ga_[2], gb_[2], gl_[2], mu_[2], th_[2];
-          const float ra_[2] = {ra.x, ra.y}, rb_[2] = {rb.x, rb.y}, pi_[2] = {pi.x, pi.y}, x_[2] = {x2.x, x2.y};
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            float dmu, dth;
-            activation(a.mean_act, ra_[u], mu_[u], dmu);
-            activation(a.disp_act, rb_[u], th_[u], dth);
-            CountGrad cg;
-            cg.dmu = cg.dth = cg.dpi = 0.f;
-            l_[u] = count_llk<ZI, TRAIN>(x_[u], mu_[u], th_[u], pi_[u], cg);
-            ga_[u] = cg.dmu * dmu; gb_[u] = cg.dth * dth; gl_[u] = cg.dpi;
-          }
-          llk = pm::mk(l_[0], l_[1]); ga = pm::mk(ga_[0], ga_[1]); gb = pm::mk(gb_[0], gb_[1]); gl = pm::mk(gl_[0], gl_[1]);
-          mu = pm::mk(mu_[0], mu_[1]); th = pm::mk(th_[0], th_[1]);
-        }
-        if (!full) {
-          const bool ok0 = row_ok && (g0 + j) < a.G, ok1 = row_ok && (g0 + j + 1) < a.G;
-          llk = pm::mk(ok0 ? llk.x : 0.f, ok1 ? llk.y : 0.f);
-          if (TRAIN) {
-            ga = pm::mk(ok0 ? ga.x : 0.f, ok1 ? ga.y : 0.f); gb = pm::mk(ok0 ? gb.x : 0.f, ok1 ? gb.y : 0.f);
-            gl = pm::mk(ok0 ? gl.x : 0.f, ok1 ? gl.y : 0.f);
-          } else {
-            if (ok0) {
-              if (a.out_mean) a.out_mean[o + j] = mu.x;
-              if (a.out_disp) a.out_disp[o + j] = th.x;
-              if (ZI && a.out_pi) a.out_pi[o + j] = pi.x;
+          for (int p = 0; p < kNP; ++p) {
+            float l_[2], ga_[2], gb_[2], gl_[2], mu_[2], th_[2];
+            const float ra_[2] = {ra[p].x, ra[p].y}, rb_[2] = {rb[p].x, rb[p].y}, pi_[2] = {pi[p].x, pi[p].y}, x_[2] = {x2[p].x, x2[p].y};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float dmu, dth;
+              activation(a.mean_act, ra_[u], mu_[u], dmu);
+              activation(a.disp_act, rb_[u], th_[u], dth);
+              CountGrad cg;
+              cg.dmu = cg.dth = cg.dpi = 0.f;
+              l_[u] = count_llk<ZI, TRAIN>(x_[u], mu_[u], th_[u], pi_[u], cg);
+              ga_[u] = cg.dmu * dmu; gb_[u] = cg.dth * dth; gl_[u] = cg.dpi;
             }
-            if (ok1) {
-              if (a.out_mean) a.out_mean[o + j + 1] = mu.y;
-              if (a.out_disp) a.out_disp[o + j + 1] = th.y;
-              if (ZI && a.out_pi) a.out_pi[o + j + 1] = pi.y;
-            }
-          }
-        } else if (!TRAIN) {
-          if (VEC) {       // even gene count and 16-byte aligned rows: (row * G + g0 + j) is even
-            if (a.out_mean) *reinterpret_cast<float2*>(a.out_mean + o + j) = make_float2(mu.x, mu.y);
-            if (a.out_disp) *reinterpret_cast<float2*>(a.out_disp + o + j) = make_float2(th.x, th.y);
-            if (ZI && a.out_pi) *reinterpret_cast<float2*>(a.out_pi + o + j) = make_float2(pi.x, pi.y);
-          } else {
-            if (a.out_mean) { a.out_mean[o + j] = mu.x; a.out_mean[o + j + 1] = mu.y; }
-            if (a.out_disp) { a.out_disp[o + j] = th.x; a.out_disp[o + j + 1] = th.y; }
-            if (ZI && a.out_pi) { a.out_pi[o + j] = pi.x; a.out_pi[o + j + 1] = pi.y; }
+            llk[p] = pm::mk(l_[0], l_[1]); ga[p] = pm::mk(ga_[0], ga_[1]); gb[p] = pm::mk(gb_[0], gb_[1]); gl[p] = pm::mk(gl_[0], gl_[1]);
+            mu[p] = pm::mk(mu_[0], mu_[1]); th[p] = pm::mk(th_[0], th_[1]);
           }
         }
-        llk2 = pm::add(llk2, llk);
-        if (TRAIN) {   // two genes -> one packed fp16x2 word per head
-          if (a.gscale != 1.f) { ga = pm::mul(ga, pm::bc(a.gscale)); gb = pm::mul(gb, pm::bc(a.gscale)); gl = pm::mul(gl, pm::bc(a.gscale)); }
-          *reinterpret_cast<__half2*>(gt + 0 * 4 * 2048 + j * 2) = __floats2half2_rn(ga.x, ga.y);
-          *reinterpret_cast<__half2*>(gt + 1 * 4 * 2048 + j * 2) = __floats2half2_rn(gb.x, gb.y);
-          if (ZI) *reinterpret_cast<__half2*>(gt + 2 * 4 * 2048 + j * 2) = __floats2half2_rn(gl.x, gl.y);
+#pragma unroll
+        for (int p = 0; p < kNP; ++p) {
+          const int jj = j + 2 * p;
+          if (!full) {
+            const bool ok0 = row_ok && (g0 + jj) < a.G, ok1 = row_ok && (g0 + jj + 1) < a.G;
+            llk[p] = pm::mk(ok0 ? llk[p].x : 0.f, ok1 ? llk[p].y : 0.f);
+            if (TRAIN) {
+              ga[p] = pm::mk(ok0 ? ga[p].x : 0.f, ok1 ? ga[p].y : 0.f); gb[p] = pm::mk(ok0 ? gb[p].x : 0.f, ok1 ? gb[p].y : 0.f);
+              gl[p] = pm::mk(ok0 ? gl[p].x : 0.f, ok1 ? gl[p].y : 0.f);
+            } else {
+              const size_t oa = (size_t)(row % a.B) * a.G + g0;
+              if (ok0 && a.out_mean_avg) atomicAdd(a.out_mean_avg + oa + jj, mu[p].x * a.inv_S);
+              if (ok1 && a.out_mean_avg) atomicAdd(a.out_mean_avg + oa + jj + 1, mu[p].y * a.inv_S);
+              if (ok0) {
+                if (a.out_mean) a.out_mean[o + jj] = mu[p].x;
+                if (a.out_disp) a.out_disp[o + jj] = th[p].x;
+                if (ZI && a.out_pi) a.out_pi[o + jj] = pi[p].x;
+              }
+              if (ok1) {
+                if (a.out_mean) a.out_mean[o + jj + 1] = mu[p].y;
+                if (a.out_disp) a.out_disp[o + jj + 1] = th[p].y;
+                if (ZI && a.out_pi) a.out_pi[o + jj + 1] = pi[p].y;
+              }
+            }
+          } else if (!TRAIN) {
+            if (a.out_mean_avg) {
+              const size_t oa = (size_t)(row % a.B) * a.G + g0;
+              atomicAdd(a.out_mean_avg + oa + jj, mu[p].x * a.inv_S);
+              atomicAdd(a.out_mean_avg + oa + jj + 1, mu[p].y * a.inv_S);
+            }
+            if (VEC) {       // even gene count and 16-byte aligned rows: (row * G + g0 + jj) is even
+              if (a.out_mean) *reinterpret_cast<float2*>(a.out_mean + o + jj) = make_float2(mu[p].x, mu[p].y);
+              if (a.out_disp) *reinterpret_cast<float2*>(a.out_disp + o + jj) = make_float2(th[p].x, th[p].y);
+              if (ZI && a.out_pi) *reinterpret_cast<float2*>(a.out_pi + o + jj) = make_float2(pi[p].x, pi[p].y);
+            } else {
+              if (a.out_mean) { a.out_mean[o + jj] = mu[p].x; a.out_mean[o + jj + 1] = mu[p].y; }
+              if (a.out_disp) { a.out_disp[o + jj] = th[p].x; a.out_disp[o + jj + 1] = th[p].y; }
+              if (ZI && a.out_pi) { a.out_pi[o + jj] = pi[p].x; a.out_pi[o + jj + 1] = pi[p].y; }
+            }
+          }
+          llk2 = pm::add(llk2, llk[p]);
+          if (TRAIN) {   // two genes -> one packed fp16x2 word per head
+            if (a.gscale != 1.f) { ga[p] = pm::mul(ga[p], pm::bc(a.gscale)); gb[p] = pm::mul(gb[p], pm::bc(a.gscale)); gl[p] = pm::mul(gl[p], pm::bc(a.gscale)); }
+            *reinterpret_cast<__half2*>(gt + 0 * 4 * 2048 + jj * 2) = __floats2half2_rn(ga[p].x, ga[p].y);
+            *reinterpret_cast<__half2*>(gt + 1 * 4 * 2048 + jj * 2) = __floats2half2_rn(gb[p].x, gb[p].y);
+            if (ZI) *reinterpret_cast<__half2*>(gt + 2 * 4 * 2048 + jj * 2) = __floats2half2_rn(gl[p].x, gl[p].y);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&bars[ACC_FREE + s]);
-        if (!TRAIN) mbar_arrive(&bars[W_FREE + s]);   // bias of this stage consumed
+        if (MODE == MODE_SCVI_LSE) mbar_arrive(&bars[ACC_FREE + s]);     // (the other modes released it inside the trip loop)
+        if (!TRAIN) mbar_arrive(&bars[W_FREE + ws]);   // bias of this stage consumed
       }
       if (TRAIN) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[G_FULL + s]);
-        if (i >= 1) flush_dwo(i - 1);
+        // the weight-gradient tile of tile i-2 (not i-1): its MMAs were committed together with the release of the G stage
+        // this warp waited for at the top of tile i, so the flush never waits for the slowest warp of the CTA (flushing
+        // tile i-1 here made every tile a barrier across the 16 epilogue warps: 9 % of the kernel's samples were polls)
+        if (i >= 2) flush_dwo(i - 2);
       }
     }
     // per-cell log-likelihood: four gene slices per cell -> shared -> one atomic per cell and chunk
@@ -512,8 +600,9 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       a.dLib[row] = lib_open ? a.upstream * a.dlibsum[row] : 0.f;
     }
     if (TRAIN) {
+      if (nt >= 2) flush_dwo(nt - 2);
       flush_dwo(nt - 1);
-      mbar_wait(&bars[DD_FULL], 0);
+      mbar_wait_backoff(&bars[DD_FULL], 0);
       tc_fence_after();
       float v[16];
       tmem_ld16(tmem + lane_addr + kTmemDD + sub * 16, v);

@@ -110,7 +110,8 @@ __device__ __forceinline__ void store8_hi(uint8_t* tile, uint32_t off, const flo
 }
 
 struct EncFwdArgs {
-  const float* x;           // [B, G]
+  const float* x;           // [B, G], or the resident [N, G] matrix when ridx is given
+  const int* ridx;          // [B] rows of x that make up this minibatch (nullable: rows 0 .. B-1)
   const uint8_t* packed;    // packed W1 k-blocks
   float* A0;                // [B, ld0] pre-activations (zeroed by the caller when k_chunks > 1)
   int B, G, ld0, n_kblocks, kblocks_per_chunk, atomic_out, log_norm;
@@ -221,13 +222,22 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
     auto fetch = [&](int i, float (*dst)[8]) {
       const int c0 = (kb_begin + i) * 64 + cg * 8;
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) load8<false>(a.x, a.G, a.B, a.G, row0 + rbase + RSTEP * j, c0, dst[j]);
+      for (int j = 0; j < RPT; ++j) {
+        const int r = row0 + rbase + RSTEP * j;
+        const int src = (a.ridx && r < a.B) ? a.ridx[r] : r;
+        // rows are addressed through their source index; the bound check stays on the minibatch row
+        load8<false>(a.x + ((size_t)src - (size_t)r) * a.G, a.G, a.B, a.G, r, c0, dst[j]);
+      }
     };
     // VEC: every converter thread issues four 16-byte async copies per k-block (rows (t >> 4) + 32 j, chunk t & 15 of the
     // 256-byte row segment), NR - 1 k-blocks ahead of the one it converts; cells / genes outside the matrix are zero-filled.
     // (A single loader warp issuing all 2048 copies of a tile was issue-bound: 1.5 TB/s.)
-    const float* cp_src = a.x + (size_t)min(row0 + (t >> 4), a.B - 1) * a.G + kb_begin * 64 + (t & 15) * 4;
-    const size_t cp_row_step = (size_t)32 * a.G;
+    const float* cp_rows[4];              // this thread's four source rows (gathered through ridx when given)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = min(row0 + (t >> 4) + 32 * j, a.B - 1);
+      cp_rows[j] = a.x + (size_t)(a.ridx ? a.ridx[r] : r) * a.G + kb_begin * 64 + (t & 15) * 4;
+    }
     uint8_t* cp_dst = smem + S::raw + (t >> 4) * 256 + (t & 15) * 16;
     auto issue = [&](int i) {
       const int rs = i % NR;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool ok = c_ok && row0 + (t >> 4) + 32 * j < a.B;
-        cp_async_16_zfill(cp_dst + rs * kRawTile + j * 32 * 256, ok ? (const void*)(cp_src + j * cp_row_step + (size_t)i * 64) : (const void*)a.x,
+        cp_async_16_zfill(cp_dst + rs * kRawTile + j * 32 * 256, ok ? (const void*)(cp_rows[j] + (size_t)i * 64) : (const void*)a.x,
                           ok ? 16u : 0u);
       }
       cp_async_mbar_arrive_noinc(&bars[EB_RAW_FULL + rs]);

@@ -95,7 +95,7 @@ PM_HD F2 ex2_sel(F2 t) { return POLY ? ex2_poly(t) : ex2(t); }
 
 // ---- which exponentials leave the MUFU pipe (tuned on the B200: see profiles/) ----
 #ifndef SISUA_PM_POLY_LINKS
-#define SISUA_PM_POLY_LINKS 1     // the two softplus links
+#define SISUA_PM_POLY_LINKS 0     // the two softplus links (measured: 0.404 ms with, 0.396 ms without -- the FMA pipe is the busier one)
 #endif
 #ifndef SISUA_PM_POLY_PI
 #define SISUA_PM_POLY_PI 0        // exp(-pi) of the dropout logit
@@ -134,96 +134,141 @@ struct Core { F2 llk, gmu, gth, gl; };     // natural-log units; d llk / d (mean
 // declared BEFORE this header is included -- device_math.cuh does (out of line, on top of count_core_fast<.., 1>); the
 // host harness restates it in double precision.
 
-// (ZI)NB log-likelihood of two counts given positive (mean, inverse dispersion) and the dropout logit.
+// (ZI)NB log-likelihood of two counts given positive (mean, inverse dispersion) and the dropout logit, in three pieces so
+// that a caller can run SEVERAL pairs through each straight-line piece back to back: the compiler then interleaves their
+// instruction streams (independent dependency chains), which is what hides the MUFU / FMA latencies -- a single pair is
+// one long chain.
+struct CoreState { F2 mu, th, pi, x, Rt, rho, n0, dn0_dth, Ep, Rp; };
+
+// piece 1: everything a zero count needs (and the shared terms of the non-zero case)
+// `nozi` (uniform): evaluate the count distribution WITHOUT its zero inflation although the head has a dropout logit --
+// the "imputed" distribution of sisua/analysis/posterior.py:210-220.
 template <bool ZI, bool GRAD>
-PM_HD Core core_pair(F2 mu, F2 th, F2 pi, F2 x) {
+PM_HD Core core_zero(CoreState& c, bool nozi = false) {
   Core o;
-  const F2 tm = add(add(th, mu), bc(kEps));
-  const F2 Rt = rcp(tm);
-  const F2 rho = mul(th, Rt);
+  const F2 tm = add(add(c.th, c.mu), bc(kEps));
+  c.Rt = rcp(tm);
+  c.rho = mul(c.th, c.Rt);
   // log2(theta / (theta + mu)).  rho carries the rounding of the approximate reciprocal (~1e-7 relative), which the
   // logarithm turns into an ABSOLUTE error that n0 = theta * log(rho) then scales by theta; the exact residual
   // theta - rho * tm (one fma) restores it to first order where it matters (rho ~ 1, i.e. theta >> mu).
-  const F2 res = fma2(neg(rho), tm, th);
-  const F2 lr = fma2(mul(res, Rt), bc(kLog2e), lg2(add(rho, bc(1e-30f))));
-  const F2 n0 = mul(th, lr);                          // log2 NB(0)
-  const F2 dn0_dth = fma2(lr, bc(kLn2), sub(bc(1.f), rho));
-  F2 Ep = bc(0.f), Rp = bc(1.f), p2 = bc(0.f);
-  if (ZI) {
-    const F2 pc = max2(min2(pi, kLinkClamp), -kLinkClamp);
-    p2 = mul(pc, bc(kLog2e));
-    Ep = ex2_sel<SISUA_PM_POLY_PI != 0>(neg(p2));     // exp(-pi)
-    const F2 Eu = ex2(sub(n0, p2));                   // exp(n0 - pi)
-    const F2 Sp = add(Ep, bc(1.f)), Su = add(Eu, bc(1.f));
+  const F2 res = fma2(neg(c.rho), tm, c.th);
+  const F2 lr = fma2(mul(res, c.Rt), bc(kLog2e), lg2(add(c.rho, bc(1e-30f))));
+  c.n0 = mul(c.th, lr);                               // log2 NB(0)
+  c.dn0_dth = fma2(lr, bc(kLn2), sub(bc(1.f), c.rho));
+  c.Ep = bc(0.f); c.Rp = bc(1.f);
+  if (ZI && !nozi) {
+    const F2 pc = max2(min2(c.pi, kLinkClamp), -kLinkClamp);
+    const F2 p2 = mul(pc, bc(kLog2e));
+    c.Ep = ex2_sel<SISUA_PM_POLY_PI != 0>(neg(p2));   // exp(-pi)
+    const F2 Eu = ex2(sub(c.n0, p2));                 // exp(n0 - pi)
+    const F2 Sp = add(c.Ep, bc(1.f)), Su = add(Eu, bc(1.f));
     if (GRAD) {
       const F2 R2 = rcp(mul(Sp, Su));
-      Rp = mul(R2, Su);                               // sigmoid(pi)
+      c.Rp = mul(R2, Su);                             // sigmoid(pi)
       const F2 w = mul(Eu, mul(R2, Sp));              // sigmoid(n0 - pi)
-      o.llk = mul(lg2(mul(Su, Rp)), bc(kLn2));        // softplus(n0 - pi) - softplus(-pi)
-      o.gl = fma2(Ep, Rp, neg(w));
-      o.gmu = neg(mul(w, rho));
-      o.gth = mul(w, dn0_dth);
+      o.llk = mul(lg2(mul(Su, c.Rp)), bc(kLn2));      // softplus(n0 - pi) - softplus(-pi)
+      o.gl = fma2(c.Ep, c.Rp, neg(w));
+      o.gmu = neg(mul(w, c.rho));
+      o.gth = mul(w, c.dn0_dth);
     } else {
-      Rp = rcp(Sp);
-      o.llk = mul(lg2(mul(Su, Rp)), bc(kLn2));
+      c.Rp = rcp(Sp);
+      o.llk = mul(lg2(mul(Su, c.Rp)), bc(kLn2));
       o.gl = o.gmu = o.gth = bc(0.f);
     }
   } else {
-    o.llk = mul(n0, bc(kLn2));
-    o.gmu = neg(rho); o.gth = dn0_dth; o.gl = bc(0.f);
+    o.llk = mul(c.n0, bc(kLn2));
+    o.gmu = neg(c.rho); o.gth = c.dn0_dth; o.gl = bc(0.f);
   }
-  const bool nz0 = x.x >= kEps, nz1 = x.y >= kEps;
-  if (!any_lane(nz0 || nz1)) return o;               // every cell of the warp has a zero at both genes
-  // counts 1..3 (the bulk of the non-zero entries) stay on the packed path; anything else votes the warp out of it
-  const float r0 = (x.x + 8388608.f) - 8388608.f, r1 = (x.y + 8388608.f) - 8388608.f;
-  const bool big = (nz0 && !(x.x == r0 && x.x <= 3.f)) || (nz1 && !(x.y == r1 && x.y <= 3.f));
-  if (any_lane(big)) {
-    float l, gm, gt, gg;
-    if (any_lane(nz0)) {
-      core_scalar_fallback<ZI, GRAD>(mu.x, th.x, pi.x, x.x, l, gm, gt, gg);
-      o.llk.x = l; o.gmu.x = gm; o.gth.x = gt; o.gl.x = gg;
-    }
-    if (any_lane(nz1)) {
-      core_scalar_fallback<ZI, GRAD>(mu.y, th.y, pi.y, x.y, l, gm, gt, gg);
-      o.llk.y = l; o.gmu.y = gm; o.gth.y = gt; o.gl.y = gg;
-    }
-    return o;
-  }
+  return o;
+}
+
+PM_HD bool pair_nonzero(F2 x) { return x.x >= kEps || x.y >= kEps; }
+// counts 1..3 (the bulk of the non-zero entries) stay on the packed path; anything else takes the scalar routines
+PM_HD bool count_big(float x) {
+  const float r = (x + 8388608.f) - 8388608.f;      // rint(x) for 0 <= x < 2^22
+  return x >= kEps && !(x == r && x <= 3.f);
+}
+
+// piece 2a: counts in {0, 1, 2, 3}, branch-free
+template <bool ZI, bool GRAD>
+PM_HD void core_small(const CoreState& c, Core& o, bool nozi = false) {
+  const F2 x = c.x, th = c.th;
   // lgamma(x + th) - lgamma(th) - lgamma(x + 1) = log(q / x!),  q = th (th+1)^[x>=2] (th+2)^[x>=3]
   const F2 i2 = mk(sat(x.x - 1.f), sat(x.y - 1.f)), i3 = mk(sat(x.x - 2.f), sat(x.y - 2.f));
   const F2 t1 = add(th, bc(1.f));
   const F2 g1 = fma2(i2, th, bc(1.f)), g2 = fma2(i3, t1, bc(1.f));
   const F2 g12 = mul(g1, g2);
   const F2 q = mul(th, g12);
-  const F2 mue = add(mu, bc(kEps));
-  const F2 m = mul(mue, Rt);                          // mu / (theta + mu)
+  const F2 mue = add(c.mu, bc(kEps));
+  const F2 m = mul(mue, c.Rt);                        // mu / (theta + mu)
   // m^x = m * (x >= 2 ? m : 1) * (x >= 3 ? m : 1); the factors are blended as i*m + (1 - i): no cancellation for tiny m
   const F2 mx = mul(m, mul(fma2(i2, m, sub(bc(1.f), i2)), fma2(i3, m, sub(bc(1.f), i3))));
   const F2 finv = fma2(fma2(x, bc(1.f / 12.f), bc(-0.75f)), x, bc(5.f / 3.f));    // 1 / x! for x = 1, 2, 3
   const F2 prod = max2(mul(mul(mx, q), finv), kTiny);
-  F2 l2 = add(n0, lg2(prod));                         // log2 units
-  if (ZI) {
+  F2 l2 = add(c.n0, lg2(prod));                       // log2 units
+  if (ZI && !nozi) {
     // log sigmoid(-pi) = log2(Ep Rp) (clamped logit) - the part of pi above the clamp
-    const F2 over = max2(sub(pi, bc(kLinkClamp)), 0.f);
-    l2 = add(l2, fma2(over, bc(-kLog2e), lg2(mul(Ep, Rp))));
+    const F2 over = max2(sub(c.pi, bc(kLinkClamp)), 0.f);
+    l2 = add(l2, fma2(over, bc(-kLog2e), lg2(mul(c.Ep, c.Rp))));
   }
   const F2 llk1 = mul(l2, bc(kLn2));
-  F2 gmu1 = bc(0.f), gth1 = bc(0.f), gl1 = bc(0.f);
+  const bool nz0 = x.x >= kEps, nz1 = x.y >= kEps;
+  o.llk = mk(nz0 ? llk1.x : o.llk.x, nz1 ? llk1.y : o.llk.y);
   if (GRAD) {
     const F2 dq = fma2(th, fma2(i2, g2, mul(g1, i3)), g12);     // dq / dth
     const F2 R3 = rcp(mul(q, mue));
     const F2 Rq = mul(R3, mue), Rm = mul(R3, q);
-    gmu1 = fma2(x, sub(Rm, Rt), neg(rho));
-    gth1 = fma2(dq, Rq, fma2(neg(x), Rt, dn0_dth));
-    gl1 = neg(Rp);
-  }
-  o.llk = mk(nz0 ? llk1.x : o.llk.x, nz1 ? llk1.y : o.llk.y);
-  if (GRAD) {
+    const F2 gmu1 = fma2(x, sub(Rm, c.Rt), neg(c.rho));
+    const F2 gth1 = fma2(dq, Rq, fma2(neg(x), c.Rt, c.dn0_dth));
     o.gmu = mk(nz0 ? gmu1.x : o.gmu.x, nz1 ? gmu1.y : o.gmu.y);
     o.gth = mk(nz0 ? gth1.x : o.gth.x, nz1 ? gth1.y : o.gth.y);
-    if (ZI) o.gl = mk(nz0 ? gl1.x : o.gl.x, nz1 ? gl1.y : o.gl.y);
+    if (ZI) o.gl = mk(nz0 ? -c.Rp.x : o.gl.x, nz1 ? -c.Rp.y : o.gl.y);
   }
-  return o;
+}
+
+// piece 2b: a gene at which some cell of the warp holds a count above 3 or a non-integer count is redone by the scalar
+// routines of device_math.cuh (every lane of the warp calls them together); voted per GENE, so that one large count does
+// not drag its neighbours out of the packed path
+template <bool ZI, bool GRAD>
+PM_HD void core_general(const CoreState& c, Core& o, bool nozi = false) {
+  float l, gm, gt, gg;
+  if (any_lane(count_big(c.x.x))) {
+    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, l, gm, gt, gg);
+    else core_scalar_fallback<false, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, l, gm, gt, gg);
+    o.llk.x = l; o.gmu.x = gm; o.gth.x = gt; o.gl.x = gg;
+  }
+  if (any_lane(count_big(c.x.y))) {
+    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, l, gm, gt, gg);
+    else core_scalar_fallback<false, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, l, gm, gt, gg);
+    o.llk.y = l; o.gmu.y = gm; o.gth.y = gt; o.gl.y = gg;
+  }
+}
+
+// NP pairs in lock-step: zero-count terms for all, one warp vote, then the small-count or the general path for all
+template <bool ZI, bool GRAD, int NP>
+PM_HD void core_multi(CoreState (&c)[NP], Core (&o)[NP], bool nozi = false) {
+  bool nz = false, big = false;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    o[p] = core_zero<ZI, GRAD>(c[p], nozi);
+    nz = nz || pair_nonzero(c[p].x); big = big || count_big(c[p].x.x) || count_big(c[p].x.y);
+  }
+  if (!any_lane(nz)) return;                         // every cell of the warp has zeros at all these genes
+#pragma unroll
+  for (int p = 0; p < NP; ++p) core_small<ZI, GRAD>(c[p], o[p], nozi);
+  if (any_lane(big)) {                               // (lanes with a large count got garbage from core_small: overwritten here)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) core_general<ZI, GRAD>(c[p], o[p], nozi);
+  }
+}
+
+template <bool ZI, bool GRAD>
+PM_HD Core core_pair(F2 mu, F2 th, F2 pi, F2 x) {
+  CoreState c[1]; Core o[1];
+  c[0].mu = mu; c[0].th = th; c[0].pi = pi; c[0].x = x;
+  core_multi<ZI, GRAD, 1>(c, o);
+  return o[0];
 }
 
 struct Elem2 { F2 llk, ga, gb, gl, mu, th; };    // ga, gb, gl = d llk / d raw head outputs (mean, dispersion, dropout)
@@ -270,6 +315,61 @@ PM_HD Scvi2 elem_pair_scvi(F2 u_lse, F2 rb, F2 pi, F2 x, float eL) {
   o.gb = mul(c.gth, o.th);
   o.gl = c.gl;
   return o;
+}
+
+// NP pairs at once (independent dependency chains the compiler interleaves)
+template <bool ZI, bool GRAD, int NP>
+PM_HD void elem_multi_softplus(const F2 (&ra)[NP], const F2 (&rb)[NP], const F2 (&pi)[NP], const F2 (&x)[NP], Elem2 (&o)[NP],
+                               bool nozi = false) {
+  CoreState c[NP]; Core k[NP];
+  F2 dmu[NP], dth[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const F2 rbs = add(rb[p], bc(kSoftplus1Shift));
+    const Link ka = link_begin(ra[p]), kb = link_begin(rbs);
+    dmu[p] = bc(0.f); dth[p] = bc(0.f);
+    if (GRAD) {
+      const F2 R = rcp(mul(ka.s, kb.s));
+      const F2 rsa = mul(R, kb.s), rsb = mul(R, ka.s);
+      c[p].mu = link_value(ka, ra[p], rsa);
+      c[p].th = link_value(kb, rbs, rsb);
+      dmu[p] = mul(ka.e, rsa); dth[p] = mul(kb.e, rsb);
+    } else {
+      c[p].mu = link_value_nograd(ka, ra[p]);
+      c[p].th = link_value_nograd(kb, rbs);
+    }
+    c[p].pi = pi[p]; c[p].x = x[p];
+  }
+  core_multi<ZI, GRAD, NP>(c, k, nozi);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    o[p].mu = c[p].mu; o[p].th = c[p].th; o[p].llk = k[p].llk;
+    o[p].ga = mul(k[p].gmu, dmu[p]); o[p].gb = mul(k[p].gth, dth[p]); o[p].gl = k[p].gl;
+  }
+}
+
+template <bool ZI, bool GRAD, int NP>
+PM_HD void elem_multi_scvi(const F2 (&u_lse)[NP], const F2 (&rb)[NP], const F2 (&pi)[NP], const F2 (&x)[NP], float eL, Scvi2 (&o)[NP],
+                           bool nozi = false) {
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  CoreState c[NP]; Core k[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    o[p].s_raw = ex2(mul(u_lse[p], bc(kLog2e)));
+    c[p].mu = mul(bc(eL), min2(max2(o[p].s_raw, lo), hi));
+    c[p].th = ex2(mul(rb[p], bc(kLog2e)));
+    c[p].pi = pi[p]; c[p].x = x[p];
+  }
+  core_multi<ZI, GRAD, NP>(c, k, nozi);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    o[p].mu = c[p].mu; o[p].th = c[p].th; o[p].llk = k[p].llk;
+    const F2 ge = mul(k[p].gmu, bc(eL));
+    o[p].t = mk((o[p].s_raw.x >= lo && o[p].s_raw.x <= hi) ? ge.x : 0.f, (o[p].s_raw.y >= lo && o[p].s_raw.y <= hi) ? ge.y : 0.f);
+    o[p].gmu_mu = mul(k[p].gmu, c[p].mu);
+    o[p].gb = mul(k[p].gth, c[p].th);
+    o[p].gl = k[p].gl;
+  }
 }
 
 }  // namespace pm

@@ -108,6 +108,26 @@ class Engine:
                                             _ptr(eps_l), B, int(seed), int(step), _ptr(terms), _ptr(loss), self._stream()))
     return terms, loss
 
+  def train_step_gather(self, x_all, rows, y_all=None, library_all=None, mask_all=None, eps_z=None, eps_l=None, terms=None,
+                        loss=None, seed: int = 0, step: int = -1):
+    """forward + backward on the minibatch `rows` (int32 device tensor [B]) of matrices resident in HBM
+    (sisua_train_step_gather): no gathered copy of the count rows is made."""
+    if rows.dtype != torch.int32 or not rows.is_cuda or not rows.is_contiguous():
+      raise ValueError("train_step_gather: rows must be a contiguous int32 device tensor")
+    for t in (x_all, y_all, library_all, mask_all, eps_z, eps_l):
+      if t is not None and (not t.is_cuda or not t.is_contiguous()):
+        raise ValueError("train_step_gather: inputs must be contiguous device tensors")
+    B = rows.numel()
+    if terms is None:
+      terms = torch.empty((5, B), dtype=torch.float32, device=self.device)
+    if loss is None:
+      loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_train_step_gather(self.handle, _ptr(x_all), _ptr(y_all), _ptr(library_all), _ptr(mask_all),
+                                                   _ptr(rows), _ptr(eps_z), _ptr(eps_l), B, int(seed), int(step), _ptr(terms),
+                                                   _ptr(loss), self._stream()))
+    return terms, loss
+
   def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps_hat=1e-7, clipnorm=100.0, grad_scale=1.0, t=0):
     with torch.cuda.device(self.device):
       self._check(self.lib.sisua_adam_step(self.handle, lr, beta1, beta2, eps_hat, clipnorm or 0.0, grad_scale,
@@ -135,6 +155,88 @@ class Engine:
                                        _ptr(out["lib_loc"]), _ptr(out["lib_scale"]), _ptr(out["mean"]),
                                        _ptr(out["disp"]), _ptr(out["pi_logit"]), _ptr(out["y_mean"]), self._stream()))
     return out
+
+  def infer_ex(self, x, x_eval=None, y=None, library=None, mask=None, eps_z=None, eps_l=None, S=1, strip_zi=False, want_mean=False,
+               want_disp=False, want_pi=False, want_mean_avg=False, want_logw=False, want_latent=True) -> Dict[str, torch.Tensor]:
+    """sisua_infer_ex: inference step with the Posterior options -- likelihood evaluated on `x_eval` while the encoder
+    reads `x`, zero inflation stripped, Monte-Carlo mean of the NB mean [B,G], importance weights [S*B]."""
+    cfg = self.cfg
+    x = self._dev(x); x_eval = self._dev(x_eval); y = self._dev(y); library = self._dev(library)
+    eps_z = self._dev(eps_z); eps_l = self._dev(eps_l); mask = self._dev(mask, torch.uint8)
+    B, G, Z, P = x.shape[0], cfg.n_genes, cfg.n_latent, cfg.n_proteins
+    R = S * B
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+    out = dict(terms=f(5, R))
+    out["z_loc"] = f(B, Z) if want_latent else None
+    out["z_scale"] = f(B, Z) if want_latent else None
+    out["mean"] = f(R, G) if want_mean else None
+    out["disp"] = f(R, G) if want_disp else None
+    out["pi_logit"] = f(R, G) if (want_pi and cfg.x_dist == 0) else None
+    out["lib_loc"] = f(B) if (cfg.model_kind == 1 and want_latent) else None
+    out["lib_scale"] = f(B) if (cfg.model_kind == 1 and want_latent) else None
+    out["y_mean"] = f(R, P) if P > 0 else None
+    out["mean_avg"] = f(B, G) if want_mean_avg else None
+    out["logw"] = f(R) if want_logw else None
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_infer_ex(self.handle, _ptr(x), _ptr(x_eval), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
+                                          _ptr(eps_l), B, S, 1 if strip_zi else 0, _ptr(out["terms"]), _ptr(out["z_loc"]),
+                                          _ptr(out["z_scale"]), _ptr(out["lib_loc"]), _ptr(out["lib_scale"]), _ptr(out["mean"]),
+                                          _ptr(out["disp"]), _ptr(out["pi_logit"]), _ptr(out["y_mean"]), _ptr(out["mean_avg"]),
+                                          _ptr(out["logw"]), self._stream()))
+    return out
+
+  def train_forward(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, seed: int = 0, step: int = 0):
+    """sisua_forward_train_mode: training-mode forward (batch statistics, dropout), no gradients; the outputs are kept
+    for `last_forward_outputs`."""
+    cfg = self.cfg
+    x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
+    mask = self._dev(mask, torch.uint8)
+    B, G, Z, P = x.shape[0], cfg.n_genes, cfg.n_latent, cfg.n_proteins
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+    out = dict(terms=f(5, B), z_loc=f(B, Z), z_scale=f(B, Z), mean=f(B, G), disp=f(B, G))
+    out["pi_logit"] = f(B, G) if cfg.x_dist == 0 else None
+    out["lib_loc"] = f(B) if cfg.model_kind == 1 else None
+    out["lib_scale"] = f(B) if cfg.model_kind == 1 else None
+    out["y_mean"] = f(B, P) if P > 0 else None
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_forward_train_mode(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
+                                                    _ptr(eps_l), B, int(seed), int(step), _ptr(out["terms"]), _ptr(out["z_loc"]),
+                                                    _ptr(out["z_scale"]), _ptr(out["lib_loc"]), _ptr(out["lib_scale"]),
+                                                    _ptr(out["mean"]), _ptr(out["disp"]), _ptr(out["pi_logit"]), _ptr(out["y_mean"]),
+                                                    self._stream()))
+    self._last_forward = out
+    return out
+
+  def last_forward_outputs(self, B: int):
+    return self._last_forward
+
+  def decode(self, z: torch.Tensor, lib: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """sisua_decode: latent samples [R, z] (+ scVI log-library [R]) -> output parameters, chunked by max_batch."""
+    cfg = self.cfg
+    R, G, P = z.shape[0], cfg.n_genes, cfg.n_proteins
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+    out = dict(mean=f(R, G), disp=f(R, G), pi_logit=f(R, G) if cfg.x_dist == 0 else None, y_mean=f(R, P) if P > 0 else None)
+    with torch.cuda.device(self.device):
+      for s in range(0, R, cfg.max_batch):
+        e = min(R, s + cfg.max_batch)
+        sub = lambda t: None if t is None else t[s:e]
+        self._check(self.lib.sisua_decode(self.handle, _ptr(z[s:e].contiguous()), _ptr(None if lib is None else lib[s:e].contiguous()),
+                                          e - s, _ptr(sub(out["mean"])), _ptr(sub(out["disp"])), _ptr(sub(out["pi_logit"])),
+                                          _ptr(sub(out["y_mean"])), self._stream()))
+    return out
+
+  def marginal_llk(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, S=100):
+    """sisua_marginal_llk: (mllk [B], llk_x [B], llk_y [B] or None) for one minibatch, S importance samples."""
+    x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
+    mask = self._dev(mask, torch.uint8)
+    B = x.shape[0]
+    f = lambda: torch.empty((B,), dtype=torch.float32, device=self.device)
+    mllk, llk_x = f(), f()
+    llk_y = f() if self.cfg.n_proteins > 0 else None
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_marginal_llk(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z), _ptr(eps_l),
+                                              B, int(S), _ptr(mllk), _ptr(llk_x), _ptr(llk_y), self._stream()))
+    return mllk, llk_x, llk_y
 
   # -------------------------------------------------------------------------------------------
   def unpack_counts_u16(self, src_u16: torch.Tensor, dst_f32: torch.Tensor):

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import os
 import pickle
+import time
 import warnings
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
@@ -61,11 +62,15 @@ class SingleCellData:
     mk = lambda ids, tag: self._take(ids, f"{self.name}_{tag}")
     return mk(np.sort(idx[:n]), "train"), mk(np.sort(idx[n:]), "test")
 
-  def _take(self, ids, name):
+  def _take(self, ids, name, recompute_library=True):
+    """Row subset.  The library statistics are those of the SUBSET, as in the reference (create_dataset recomputes them on
+    whatever dataset it is called on: _single_cell_base.py:566-570); data-parallel shards of one training set pass
+    recompute_library=False so that every rank keeps the statistics of the whole training set."""
     out = SingleCellData.__new__(SingleCellData)
     out.X = self.X[ids]; out.Y = None if self.Y is None else self.Y[ids]
     out.name = name; out.var_names = self.var_names
-    out.library = self.library[ids]; out.mask = self.mask[ids]
+    out.library = synthetic.library_stats(out.X) if recompute_library else self.library[ids]
+    out.mask = self.mask[ids]
     return out
 
 
@@ -148,6 +153,13 @@ class SingleCellModel:
     enc, dec = self._encoder, self._decoder
     if len(set(enc.units + dec.units)) != 1:
       raise ValueError("all hidden layers must share one width")
+    if bool(enc.batchnorm) != bool(dec.batchnorm):
+      raise ValueError("encoder and decoder must agree on batchnorm (one StepConfig flag drives both stacks)")
+    lat = self._latents.posterior
+    if not (lat in ("diag", "mvndiag", "normal") or self._latents.is_deterministic):
+      raise ValueError(f"latent posterior '{lat}' is outside the B200 hot path ('diag', or deterministic 'relu' / 'linear')")
+    if self.labels and self._kind != C.MODEL_SISUA:
+      raise ValueError("label heads are implemented for SISUA only (the hot path of vae / scvi / dca has no protein head)")
     kw = dict(self._cfg_overrides)
     for k in ("mean_act", "disp_act", "scale_act"):
       if k in rv.kwargs:
@@ -163,7 +175,8 @@ class SingleCellModel:
         n_hidden=enc.units[0], n_enc_layers=len(enc.units), n_dec_layers=len(dec.units), batchnorm=enc.batchnorm,
         log_norm=self._log_norm, x_dist=rv.posterior, y_dist=y_dist, gemm_mode=self._gemm_mode,
         max_batch=self._max_batch, input_dropout=enc.input_dropout, enc_dropout=enc.dropout,
-        dec_dropout=dec.dropout, beta=self.beta, alpha=self.alpha, **extra, **kw)
+        dec_dropout=dec.dropout, beta=self.beta, alpha=self.alpha,
+        latent_linear=self._latents.posterior in ("linear", "identity", "deterministic"), **extra, **kw)
 
   def _extra_config(self) -> Dict[str, Any]:
     return {}
@@ -221,6 +234,7 @@ class SingleCellModel:
   def _upload(self, data: SingleCellData) -> Dict[str, torch.Tensor]:
     dev = self.engine.device
     cache = dict(x=torch.from_numpy(data.X).to(dev))
+    self.engine.set_count_bound(float(data.X.max()) if data.X.size else 0.0)     # keeps the fp16 gradient tiles in range
     if self.labels:
       if data.Y is None:
         raise ValueError("semi-supervised model needs the protein matrix Y")
@@ -230,34 +244,30 @@ class SingleCellModel:
       cache["library"] = torch.from_numpy(data.library).to(dev)
     return cache
 
-  def _eps(self, B: int, S: Optional[int], gen: torch.Generator):
-    eng = self.engine
-    shape = (B,) if S is None else (S, B)
-    out = {}
-    if self._kind != C.MODEL_DCA:
-      out["eps_z"] = torch.randn(shape + (eng.cfg.n_latent,), device=eng.device, generator=gen)
-    if self._kind == C.MODEL_SCVI:
-      out["eps_l"] = torch.randn(shape, device=eng.device, generator=gen)
-    return out
-
   def __call__(self, inputs, library=None, mask=None, training=False, sample_shape=(), eps=None, **kwargs):
-    """One batch -> (pX_Z, qZ_X) like ``self(**data, training=False, sample_shape=S)``
-    (single_cell_model.py:178)."""
-    if training:
-      raise NotImplementedError("use fit() for training-mode steps")
+    """One batch -> (pX_Z, qZ_X) like ``self(**data, training=..., sample_shape=S)`` (single_cell_model.py:178).
+    ``training=True`` evaluates the training-mode graph (batch statistics in BatchNorm, dropout, moving statistics
+    updated) without touching the weights: the parameters it returns are those of a forward pass of ``fit``."""
     eng = self.engine
     xs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
     x = eng._dev(xs[0])
     y = eng._dev(xs[1]) if len(xs) > 1 and self.labels else None
     B = x.shape[0]
     S = int(np.prod(sample_shape)) if sample_shape not in ((), None, 0) else None
-    if eps is None:
-      gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + self.step)
-      eps = self._eps(B, S, gen)
     if self._kind == C.MODEL_SCVI and library is None:
       raise ValueError("scVI needs the `library` [B,2] statistics of the batch")
     if self.labels and y is None:
       y = torch.zeros((B, eng.cfg.n_proteins), device=eng.device)
+    eps = eps or {}
+    if training:
+      if S not in (None, 1):
+        raise ValueError("training-mode calls use sample_shape=() (configs/base.yaml:53)")
+      self._train_calls = getattr(self, "_train_calls", 0) + 1
+      eng.train_forward(x, y=y, library=library, mask=mask, seed=self._seed, step=self._train_calls, **eps)
+      out = eng.last_forward_outputs(B)
+      return self._wrap(out, B, None)
+    if not eps:
+      eng.set_infer_seed(self._seed, self.step)
     out = eng.infer(x, y=y, library=library, mask=mask, S=S or 1, want_mean=True, want_disp=True, want_pi=True, **eps)
     return self._wrap(out, B, S)
 
@@ -269,6 +279,13 @@ class SingleCellModel:
     base = D.ZeroInflated(nb, shp(out["pi_logit"], G)) if cfg.x_dist == C.XDIST_ZINBD else nb
     pX = D.Independent(base, 1, name=self.posteriors[0].name)
     pX.elbo_terms = out["terms"]
+    qZ = self._wrap_latents(out)
+    if self.labels:
+      pY = D.Independent(D.MeanOnly(shp(out["y_mean"], cfg.n_proteins)), 1, name=self.posteriors[1].name)
+      return (pX, pY), qZ
+    return pX, qZ
+
+  def _wrap_latents(self, out):
     if self._kind == C.MODEL_DCA:
       qZ = D.VectorDeterministic(out["z_loc"], name=self._latents.name)
     else:
@@ -276,64 +293,85 @@ class SingleCellModel:
     if self._kind == C.MODEL_SCVI:
       qL = D.Independent(D.Normal(out["lib_loc"][:, None], out["lib_scale"][:, None]), 1, name="Library")
       qZ = (qZ, qL)
-    if self.labels:
-      pY = D.Independent(D.MeanOnly(shp(out["y_mean"], cfg.n_proteins)), 1, name=self.posteriors[1].name)
-      return (pX, pY), qZ
-    return pX, qZ
+    return qZ
 
   def encode(self, inputs, library=None, training=None, mask=None, sample_shape=(), **kwargs):
-    return self(inputs, library=library, mask=mask, training=False, sample_shape=sample_shape, **kwargs)[1]
+    return self(inputs, library=library, mask=mask, training=bool(training), sample_shape=sample_shape, **kwargs)[1]
 
-  def decode(self, latents=None, training=None, mask=None, sample_shape=(), inputs=None, **kwargs):
-    if inputs is None:
-      raise NotImplementedError("the fused step decodes inside encode->decode; pass `inputs=`")
-    return self(inputs, mask=mask, training=False, sample_shape=sample_shape, **kwargs)[0]
+  def decode(self, latents=None, training=None, mask=None, sample_shape=(), inputs=None, library=None, **kwargs):
+    r""" ``decode(latents)`` (single_cell_model.py:141-151): latent samples ``[..., z]`` (a tensor, or the distribution
+    returned by ``encode``, which is sampled once) -> output distribution(s) through the decoder-only entry point
+    ``sisua_decode``.  scVI takes ``latents=(z, log_library)``.  ``inputs=`` keeps the round-1 behaviour (encode then
+    decode in one fused call). """
+    if latents is None:
+      if inputs is None:
+        raise ValueError("decode() needs `latents` (or `inputs=` for the fused encode -> decode call)")
+      return self(inputs, library=library, mask=mask, training=bool(training), sample_shape=sample_shape, **kwargs)[0]
+    eng = self.engine
+    lib_s = None
+    if self._kind == C.MODEL_SCVI:
+      if not isinstance(latents, (tuple, list)) or len(latents) != 2:
+        raise ValueError("scVI decodes (z, log_library)")
+      latents, lib_s = latents
+      lib_s = lib_s.sample() if isinstance(lib_s, D.Distribution) else lib_s
+    z = latents.sample() if isinstance(latents, D.Distribution) else latents
+    z = eng._dev(z)
+    lead = tuple(z.shape[:-1])
+    z2 = z.reshape(-1, z.shape[-1]).contiguous()
+    out = eng.decode(z2, None if lib_s is None else eng._dev(lib_s).reshape(-1).contiguous())
+    cfg = eng.cfg
+    G = cfg.n_genes
+    rs = lambda t, n: t.reshape(lead + (n,))
+    nb = D.NegativeBinomialDisp(rs(out["mean"], G), rs(out["disp"], G))
+    base = D.ZeroInflated(nb, rs(out["pi_logit"], G)) if cfg.x_dist == C.XDIST_ZINBD else nb
+    pX = D.Independent(base, 1, name=self.posteriors[0].name)
+    if self.labels:
+      return pX, D.Independent(D.MeanOnly(rs(out["y_mean"], cfg.n_proteins)), 1, name=self.posteriors[1].name)
+    return pX
 
   # ---------------------------------------------------------------- predict
-  def predict(self, inputs, sample_shape=(), batch_size=32, verbose=True, device="GPU"):
-    r""" Predict on minibatches then return a single distribution by concatenation
-    (single_cell_model.py:153-211).  Row order is preserved and every cell is kept. """
+  def predict(self, inputs, sample_shape=(), batch_size=32, verbose=True, device="GPU", seed=None):
+    r""" Predict on minibatches then return a single distribution (single_cell_model.py:153-211).  Row order is preserved
+    and every cell is kept.  ONE streamed pass computes the latent statistics and the per-cell ELBO terms; the output
+    distribution is *streamed* (``sisua_b200.streamed``): its ``[S, N, G]`` parameters are never stored -- ``log_prob``
+    and ``mean_over_samples`` run inside the fused kernels chunk by chunk, ``mean() / variance() / sample()`` build
+    dense tensors only when called.  ``device='CPU'`` returns the (small) latent statistics on the host. """
     assert device in ("CPU", "GPU"), f"Only support device CPU or GPU, but given: {device}"
+    from . import streamed as ST
     data = _to_data(inputs)
     eng = self.engine
     cache = self._upload(data)
     N = len(data)
     S = int(np.prod(sample_shape)) if sample_shape not in ((), None, 0) else None
+    # minibatch size does not change inference results (moving-average BN): the largest chunk that fits is used
     rows_per_call = max(1, eng.cfg.max_batch // (S or 1))
-    bs = min(max(int(batch_size), 1), rows_per_call)
-    # minibatch size does not change inference results (moving-average BN); use the largest that fits
-    bs = rows_per_call if N > bs else bs
-    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 12345)
-    parts = []
-    for s in range(0, N, bs):
-      idx = torch.arange(s, min(N, s + bs), device=eng.device)
-      b = self._batch_tensors(data, idx, cache)
-      eps = self._eps(idx.numel(), S, gen)
-      out = eng.infer(S=S or 1, want_mean=True, want_disp=True, want_pi=True, **b, **eps)
-      parts.append((out, idx.numel()))
-    cfg = eng.cfg
-
-    def cat(key, width):
-      ts = []
-      for out, n in parts:
-        t = out[key]
-        ts.append(t.reshape(S, n, width) if S else t.reshape(n, width))
-      return torch.cat(ts, dim=1 if S else 0)
-
-    merged = dict(mean=cat("mean", cfg.n_genes), disp=cat("disp", cfg.n_genes),
-                  z_loc=torch.cat([o["z_loc"] for o, _ in parts]), z_scale=torch.cat([o["z_scale"] for o, _ in parts]),
-                  terms=torch.cat([o["terms"].reshape(5, S or 1, n) for o, n in parts], dim=2))
-    merged["pi_logit"] = cat("pi_logit", cfg.n_genes) if cfg.x_dist == C.XDIST_ZINBD else None
+    src = ST.StreamSource(eng, cache, N, S, rows_per_call, seed=(self._seed + 12345) if seed is None else int(seed))
+    Z, cfg = eng.cfg.n_latent, eng.cfg
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=eng.device)
+    merged = dict(z_loc=f(N, Z), z_scale=f(N, Z), terms=f(5, S or 1, N))
     if self._kind == C.MODEL_SCVI:
-      merged["lib_loc"] = torch.cat([o["lib_loc"] for o, _ in parts])
-      merged["lib_scale"] = torch.cat([o["lib_scale"] for o, _ in parts])
-    if self.labels:
-      merged["y_mean"] = cat("y_mean", cfg.n_proteins)
+      merged["lib_loc"], merged["lib_scale"] = f(N), f(N)
+    y_mean = f(S or 1, N, cfg.n_proteins) if self.labels else None
+    for k, sl in src.chunks():
+      out = src.run(k, sl)
+      n = sl.stop - sl.start
+      merged["z_loc"][sl] = out["z_loc"]; merged["z_scale"][sl] = out["z_scale"]
+      merged["terms"][:, :, sl] = out["terms"].reshape(5, S or 1, n)
+      if self._kind == C.MODEL_SCVI:
+        merged["lib_loc"][sl] = out["lib_loc"]; merged["lib_scale"][sl] = out["lib_scale"]
+      if y_mean is not None:
+        y_mean[:, sl] = out["y_mean"].reshape(S or 1, n, cfg.n_proteins)
     if device == "CPU":
-      merged = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in merged.items()}
-    flat = {k: (v.reshape(-1, v.shape[-1]) if (isinstance(v, torch.Tensor) and k in ("mean", "disp", "pi_logit", "y_mean")) else v)
-            for k, v in merged.items()}
-    return self._wrap(flat, N, S)
+      merged = {k: v.cpu() for k, v in merged.items()}
+    base = ST.StreamedZeroInflated(src) if cfg.x_dist == C.XDIST_ZINBD else ST.StreamedNB(src)
+    pX = ST.StreamedIndependent(base, name=self.posteriors[0].name)
+    pX.elbo_terms = merged["terms"]
+    qZ = self._wrap_latents(merged)
+    if self.labels:
+      ym = y_mean if S else y_mean[0]
+      pY = D.Independent(D.MeanOnly(ym.cpu() if device == "CPU" else ym), 1, name=self.posteriors[1].name)
+      return (pX, pY), qZ
+    return pX, qZ
 
   # ---------------------------------------------------------------- fit
   def fit(self,
@@ -358,6 +396,8 @@ class SingleCellModel:
           seed=None,
           verbose=False,
           cuda_graph='auto',
+          data_on='auto',
+          timing=None,
           **kwargs):
     r""" `Model.compile` + `Model.fit` of the reference in one call
     (single_cell_model.py:213-236; keys of configs/base.yaml:45-62). """
@@ -371,6 +411,18 @@ class SingleCellModel:
       raise RuntimeError("First time call `fit`, set the 'metadata' argument to a "
                          "SingleCellData dataset to keep the dataset name and OMICs' "
                          "variables description.")
+    # the remaining keys of configs/base.yaml:45-62 are honoured or rejected, never silently swallowed
+    dp_shard = bool(kwargs.pop("dp_shard", True))     # data parallel: False = `train` already is this rank's shard
+    valid_interval = float(kwargs.pop("valid_interval", 0) or 0)          # seconds between validation passes (0: valid_freq only)
+    allow_rollback = bool(kwargs.pop("allow_rollback", False))            # restore the best validated weights when stopping
+    if int(kwargs.pop("earlystop_progress_length", 0) or 0) != 0:
+      raise NotImplementedError("earlystop_progress_length > 0 (progress-based early stopping) is not implemented")
+    for k in ("log_tag", "log_path", "skip_fitted", "compile_graph", "track_gradient_norm"):     # host-side logging knobs
+      if k in kwargs:
+        warnings.warn(f"fit(): '{k}' only affects the reference's TensorBoard / tf.function plumbing and is ignored here")
+        kwargs.pop(k)
+    if kwargs:
+      raise TypeError(f"fit() got unexpected arguments: {sorted(kwargs)}")
     if str(optimizer).lower() != 'adam':
       raise ValueError("the fused optimiser on the hot path is Adam (configs/base.yaml:46)")
     if sample_shape not in ((), None, [], 0, 1, (1,)):
@@ -384,10 +436,12 @@ class SingleCellModel:
     import torch.distributed as dist
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank() if world > 1 else 0
-    if world > 1:
+    if world > 1 and not dp_shard:
+      DP.broadcast_parameters(eng.params, eng.bn_moving)
+    if world > 1 and dp_shard:
       b0, e0 = DP.shard_range(len(train), rank, world)
       n_common = len(train) // world                      # every rank takes the same number of steps
-      train = train._take(np.arange(b0, b0 + n_common), train.name)
+      train = train._take(np.arange(b0, b0 + n_common), train.name, recompute_library=False)
       DP.broadcast_parameters(eng.params, eng.bn_moving)
     reducer = DP.OverlappedAllReduce(eng)
     B = int(batch_size)
@@ -400,9 +454,12 @@ class SingleCellModel:
     if epochs is None or epochs <= 0:
       epochs = 1 if (max_iter is None or max_iter <= 0) else int(np.ceil(max_iter / steps_per_epoch))
     total = epochs * steps_per_epoch if (max_iter is None or max_iter <= 0) else min(int(max_iter), epochs * steps_per_epoch)
-    cache = self._upload(train)
+    if data_on not in ("auto", "device", "host"):
+      raise ValueError("data_on must be 'auto', 'device' or 'host'")
+    host_stream = data_on == "host"
     vcache = self._upload(valid) if valid is not None else None
-    gen = torch.Generator(device=eng.device); gen.manual_seed((self._seed if seed is None else int(seed)) + 7919 * rank)
+    rng_seed = (self._seed if seed is None else int(seed)) + 7919 * rank
+    gen = torch.Generator(device=eng.device); gen.manual_seed(rng_seed)
     terms = torch.empty((5, B), device=eng.device)
     loss = torch.empty((1,), device=eng.device)
     names = ["loss", "llk_" + self.posteriors[0].name] + (["llk_" + self.posteriors[1].name] if self.labels else []) + \
@@ -410,44 +467,81 @@ class SingleCellModel:
     for n in names:
       self.train_history.setdefault(n, [])
       self.valid_history.setdefault(n, [])
-    # launch-bound regime (the reference's minibatch sizes): replay the whole step as one CUDA graph
-    use_graph = (cuda_graph is True) or (cuda_graph == 'auto' and B <= 2048 and world == 1)
-    graphed = None
-    if use_graph:
-      from .pipeline import GraphedTrainStep
+    lr, cn = float(learning_rate), float(clipnorm or 0.0)
+    step_seed = self._seed + 7919 * rank          # dropout masks and reparameterisation noise: Philox(step_seed; ..., step, stream)
+    graphed = pipe = None
+    if host_stream:
+      # the dataset stays in (pinned) host memory and every step ships its minibatch over PCIe: CSR for integer counts
+      # (single-cell matrices are 70-96 % zeros), the library's host-buffer entry point otherwise
+      from .pipeline import HostDataset, HostTrainPipeline
+      hds = HostDataset(train, B, shuffle=shuffle, seed=rng_seed, with_y=bool(self.labels), with_library=self._kind == C.MODEL_SCVI)
+      eng.set_count_bound(hds.max_count)
       eng.reset_step_counter(self.step)
-      graphed = GraphedTrainStep(eng, B, lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), seed=self._seed)
-      terms, loss = graphed.terms, graphed.loss
+      pipe = HostTrainPipeline(eng, B)
+      host_losses = []
+    else:
+      cache = self._upload(train)
+      # launch-bound regime (the reference's minibatch sizes): replay the whole step as one CUDA graph
+      use_graph = (cuda_graph is True) or (cuda_graph == 'auto' and B <= 2048 and world == 1)
+      if use_graph:
+        from .pipeline import GraphedGatherStep
+        eng.reset_step_counter(self.step)
+        graphed = GraphedGatherStep(eng, B, cache["x"], y_all=cache.get("y"), library_all=cache.get("library"),
+                                    mask_all=cache.get("mask"), lr=lr, clipnorm=cn, seed=step_seed)
+        terms, loss = graphed.terms, graphed.loss
     best, patience, done = float("inf"), 0, 0
+    best_state, last_valid = None, time.perf_counter()
     log_buf: List[torch.Tensor] = []
     stop = False
+    t_start = None
     for ep in range(epochs):
-      perm = torch.randperm(N, device=eng.device, generator=gen) if shuffle else torch.arange(N, device=eng.device)
+      if not host_stream:
+        perm = (torch.randperm(N, device=eng.device, generator=gen) if shuffle else torch.arange(N, device=eng.device)).to(torch.int32)
       for s in range(steps_per_epoch):
         if done >= total:
           stop = True
           break
-        idx = perm[s * B:(s + 1) * B]
-        b = self._batch_tensors(train, idx, cache)
-        eps = self._eps(B, None, gen)
+        if timing is not None and done == int(timing.get("skip", 0)):
+          torch.cuda.current_stream(eng.device).synchronize()
+          if world > 1:
+            dist.barrier()
+          t_start = (time.perf_counter(), done)
         self.step += 1
-        if graphed is not None:
-          graphed.step(b["x"], eps_z=eps.get("eps_z"), eps_l=eps.get("eps_l"), library=b.get("library"), y=b.get("y"),
-                       mask=b.get("mask"))
+        if host_stream:
+          xb, extras = hds.batch(ep, s)
+          host_losses.append(pipe.step(xb, None, step=self.step, lr=lr, clipnorm=cn, world=world,
+                                       allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None, seed=step_seed, **extras))
+        elif graphed is not None:
+          graphed.step(perm[s * B:(s + 1) * B])
         else:
-          eng.train_step(terms=terms, loss=loss, seed=self._seed + 7919 * rank, step=self.step, **b, **eps)
+          # one minibatch = B row indices into the matrices resident in HBM; the kernels gather the count rows themselves
+          # and draw the reparameterisation noise in-kernel (no per-step torch kernels on the hot path)
+          eng.train_step_gather(cache["x"], perm[s * B:(s + 1) * B], y_all=cache.get("y"), library_all=cache.get("library"),
+                                mask_all=cache.get("mask"), terms=terms, loss=loss, seed=step_seed, step=self.step)
           gscale = reducer()
-          eng.adam_step(lr=float(learning_rate), clipnorm=float(clipnorm or 0.0), grad_scale=gscale, t=self.step)
+          eng.adam_step(lr=lr, clipnorm=cn, grad_scale=gscale, t=self.step)
         done += 1
-        if logging_interval and done % int(logging_interval) == 0:
+        if logging_interval and done % int(logging_interval) == 0 and not host_stream:
           log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
-        if valid is not None and valid_freq and done % int(valid_freq) == 0:
+        due = valid_freq and done % int(valid_freq) == 0
+        if valid is not None and valid_interval > 0 and time.perf_counter() - last_valid >= valid_interval:
+          due = True
+        if world > 1 and valid is not None and valid_interval > 0:       # wall clocks differ between ranks
+          f = torch.tensor([1.0 if due else 0.0], device=eng.device); dist.all_reduce(f, op=dist.ReduceOp.MAX); due = bool(f.item() > 0)
+        if valid is not None and due:
+          last_valid = time.perf_counter()
           v = self._evaluate(valid, vcache, B)
+          if world > 1:       # every rank must take the same early-stop / NaN decision (BatchNorm moving statistics differ)
+            vt = torch.tensor(v, device=eng.device, dtype=torch.float64)
+            dist.all_reduce(vt)
+            v = (vt / world).tolist()
           self._log(self.valid_history, names, v)
           if terminate_on_nan and not np.isfinite(v[0]):
             raise FloatingPointError("validation loss is not finite")
           if v[0] < best - abs(earlystop_threshold) * abs(best if np.isfinite(best) else 1.0):
             best, patience = v[0], 0
+            if allow_rollback:
+              best_state = [t.clone() for t in (eng.params, eng.bn_moving, eng.adam_m, eng.adam_v)]
             if checkpoint is not None:
               checkpoint()
           else:
@@ -455,17 +549,42 @@ class SingleCellModel:
             if earlystop_patience and patience >= earlystop_patience and ep >= earlystop_min_epoch:
               stop = True
               break
-      if log_buf:
+      if host_stream and host_losses:
+        vals = np.array(pipe.flush_all(host_losses), dtype=np.float64)[:, None]
+        host_losses = []
+        for row in vals:
+          self.train_history["loss"].append(float(row[0]))
+        bad = not np.isfinite(vals).all()
+      elif log_buf:
         vals = torch.stack(log_buf).cpu().numpy()
         log_buf = []
         for row in vals:
           self._log(self.train_history, names, self._select(row))
-        if terminate_on_nan and not np.isfinite(vals[:, 0]).all():
-          raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
-        if verbose:
-          print(f"epoch {ep + 1}/{epochs} loss {vals[-1, 0]:.3f}")
+        bad = not np.isfinite(vals[:, 0]).all()
+      else:
+        vals, bad = None, False
+      if world > 1 and terminate_on_nan:       # collective decision: a rank leaving alone would dead-lock the others
+        flag = torch.tensor([1.0 if bad else 0.0], device=eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        bad = bool(flag.item() > 0)
+      if terminate_on_nan and bad:
+        raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
+      if verbose and vals is not None:
+        print(f"epoch {ep + 1}/{epochs} loss {vals[-1, 0]:.3f}")
       if stop:
         break
+    if timing is not None and t_start is not None:
+      torch.cuda.current_stream(eng.device).synchronize()
+      if world > 1:
+        dist.barrier()
+      timing["seconds"] = time.perf_counter() - t_start[0]
+      timing["steps"] = done - t_start[1]
+      timing["cells_per_step"] = B * world
+      if host_stream:
+        timing["h2d_bytes_per_step"] = hds.h2d_bytes / max(1, hds.batches_served)
+    if stop and allow_rollback and best_state is not None:
+      for t, b_ in zip((eng.params, eng.bn_moving, eng.adam_m, eng.adam_v), best_state):
+        t.copy_(b_)
     if world > 1:
       DP.average_moving_statistics(eng.bn_moving)
     torch.cuda.current_stream(eng.device).synchronize()
@@ -488,36 +607,54 @@ class SingleCellModel:
       hist[n].append(float(v))
 
   def _evaluate(self, data: SingleCellData, cache, B):
+    """Validation pass: mean ELBO terms over `data` (inference mode, one Philox sample per cell, fixed seed)."""
     eng = self.engine
-    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 777)
     acc, cnt = torch.zeros(5, device=eng.device), 0
-    for s in range(0, len(data), B):
+    for k, s in enumerate(range(0, len(data), B)):
       idx = torch.arange(s, min(len(data), s + B), device=eng.device)
       b = self._batch_tensors(data, idx, cache)
-      out = eng.infer(want_mean=False, **b, **self._eps(idx.numel(), None, gen))
+      eng.set_infer_seed(self._seed + 777, k)
+      out = eng.infer(want_mean=False, **b)
       acc += out["terms"].sum(dim=1)
       cnt += idx.numel()
     m = (acc / cnt).cpu().numpy()
     return self._select(np.concatenate([[-m[0]], m[1:]]))
 
-  def marginal_log_prob(self, inputs, library=None, mask=None, sample_shape=100, **kwargs):
-    """Importance-weighted estimate log p(x) ~= logsumexp_s[log p(x|z_s) + log p(z_s) - log q(z_s|x)] - log S
-    (used by sisua/analysis/posterior.py:941-976)."""
-    S = int(sample_shape)
+  def marginal_log_prob(self, inputs, library=None, mask=None, sample_shape=100, eps=None, **kwargs):
+    """``(marginal, {output name: llk})`` as ``Posterior.cal_marginal_llk`` consumes it (sisua/analysis/posterior.py:964-968):
+    the importance-weighted bound  log p(x) ~= logsumexp_s[log p(x|z_s) (+ alpha m log p(y|z_s)) + log p(z_s) - log q(z_s|x)]
+    - log S  per cell, and per output  logsumexp_s log p(.|z_s) - log S.  All of it runs in ``sisua_marginal_llk``; a batch
+    larger than max_batch / S cells is split."""
+    S = int(np.prod(sample_shape)) if sample_shape not in ((), None, 0) else 1
     eng = self.engine
-    x = eng._dev(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
+    xs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+    x = eng._dev(xs[0])
+    y = eng._dev(xs[1]) if len(xs) > 1 and self.labels else None
+    library = eng._dev(library); mask = eng._dev(mask, torch.uint8)
     B = x.shape[0]
-    gen = torch.Generator(device=eng.device); gen.manual_seed(self._seed + 4242)
-    eps = self._eps(B, S, gen)
-    out = eng.infer(x, library=library, mask=mask, S=S, want_mean=False, **eps)
-    llk = out["terms"][1].reshape(S, B)
-    if self._kind == C.MODEL_DCA:
-      return llk.mean(0)
-    e = eps["eps_z"]
-    z = out["z_loc"] + out["z_scale"] * e
-    log_q = (-0.5 * e * e - torch.log(out["z_scale"]) - 0.9189385332).sum(-1)
-    log_p = (-0.5 * z * z - 0.9189385332).sum(-1)
-    return torch.logsumexp(llk + log_p - log_q, dim=0) - float(np.log(S))
+    if S > eng.cfg.max_batch:
+      raise ValueError(f"sample_shape {S} exceeds max_batch {eng.cfg.max_batch}")
+    if self._kind == C.MODEL_SCVI and library is None:
+      raise ValueError("scVI needs the `library` [B,2] statistics of the batch")
+    if self.labels and y is None:
+      y = torch.zeros((B, eng.cfg.n_proteins), device=eng.device)
+    rows = max(1, eng.cfg.max_batch // S)
+    m_parts, x_parts, y_parts = [], [], []
+    eps = eps or {}
+    for k, s0 in enumerate(range(0, B, rows)):
+      sl = slice(s0, min(B, s0 + rows))
+      if not eps:
+        eng.set_infer_seed(self._seed + 4242, k)
+      e = {n: v[:, sl] for n, v in eps.items()}
+      m, lx, ly = eng.marginal_llk(x[sl], y=None if y is None else y[sl], library=None if library is None else library[sl],
+                                   mask=None if mask is None else mask[sl], S=S, **e)
+      m_parts.append(m); x_parts.append(lx)
+      if ly is not None:
+        y_parts.append(ly)
+    llk = {self.posteriors[0].name: torch.cat(x_parts)}
+    if y_parts:
+      llk[self.posteriors[1].name] = torch.cat(y_parts)
+    return torch.cat(m_parts), llk
 
   # ---------------------------------------------------------------- posterior / persistence
   def create_posterior(self, test_sco=None, dropout_rate=0.2, retain_rate=0.2, corrupt_distribution='binomial',
@@ -560,9 +697,12 @@ class SingleCellModel:
     if os.path.exists(filepath) and not overwrite:
       raise FileExistsError(filepath)
     snap = self._snapshot()
-    snap["layout"] = [list(x) for x in snap["layout"]]
+    # plain arrays + a JSON layout (no pickle: loading a weights file must not be able to execute code; only the
+    # .metamodel sidecar is a pickle, as in the reference)
+    import json
     with open(filepath, "wb") as f:
-      pickle.dump(snap, f)
+      np.savez(f, params=snap["params"], bn_moving=snap["bn_moving"], adam_m=snap["adam_m"], adam_v=snap["adam_v"],
+               step=np.int64(snap["step"]), layout=np.frombuffer(json.dumps([list(x) for x in snap["layout"]]).encode(), dtype=np.uint8))
     with open(f"{filepath}.metamodel", "wb") as f:
       pickle.dump([self.__class__.__name__, self.dataset, self.metadata, dict(self.init_args)], f)
     return self
@@ -573,8 +713,10 @@ class SingleCellModel:
       if raise_notfound:
         raise FileNotFoundError(filepath)
       return self
-    with open(filepath, "rb") as f:
-      snap = pickle.load(f)
+    import json
+    with np.load(filepath, allow_pickle=False) as z:
+      snap = dict(params=z["params"], bn_moving=z["bn_moving"], adam_m=z["adam_m"], adam_v=z["adam_v"], step=int(z["step"]),
+                  layout=[(n, o, tuple(sh), ld) for n, o, sh, ld in json.loads(bytes(z["layout"]).decode())])
     if self._engine is None and not torch.cuda.is_available():
       self._pending_weights = snap
     else:
@@ -589,8 +731,34 @@ class SingleCellModel:
     self.is_fitted = True
     return self
 
-  def plot_learning_curves(self, path=None):
-    raise NotImplementedError("plotting is host-side tooling outside the hot path (SURVEY.md section 2, rows 9, 15)")
+  def plot_learning_curves(self, path=None, **kwargs):
+    r""" Learning curves of ``fit`` (sisua/analysis/posterior.py:677-683 reads this off the model).  Draws with matplotlib
+    when it is installed; otherwise writes the curves as CSV (``path`` required) -- the data, not the picture, is what
+    the hot path produces. """
+    hist = {"train_" + k: v for k, v in self.train_history.items()}
+    hist.update({"valid_" + k: v for k, v in self.valid_history.items()})
+    try:
+      import matplotlib
+      matplotlib.use("Agg")
+      from matplotlib import pyplot as plt
+    except ImportError:
+      if path is None:
+        raise RuntimeError("matplotlib is not installed: pass `path=` to get the learning curves as CSV")
+      n = max((len(v) for v in hist.values()), default=0)
+      with open(path, "w") as f:
+        f.write(",".join(hist) + "\n")
+        for i in range(n):
+          f.write(",".join(str(v[i]) if i < len(v) else "" for v in hist.values()) + "\n")
+      return path
+    fig, axes = plt.subplots(1, max(1, len(self.train_history)), figsize=(4 * max(1, len(self.train_history)), 3))
+    for ax, k in zip(np.atleast_1d(axes), self.train_history):
+      ax.plot(self.train_history[k], label="train")
+      if self.valid_history.get(k):
+        ax.plot(np.linspace(0, len(self.train_history[k]), len(self.valid_history[k])), self.valid_history[k], label="valid")
+      ax.set_title(k); ax.legend()
+    if path is not None:
+      fig.savefig(path)
+    return fig
 
 
 class VAE(SingleCellModel):
@@ -622,6 +790,9 @@ class SCVI(SingleCellModel):
     assert out0.posterior in ('zinbd', 'nbd'), \
         "scVI only support transcriptomic distribution: 'zinbd' or 'nbd', but given: %s" % str(outputs)
     self.clip_library = float(clip_library)
+    if set(self._encoder_l.units) != set(encoder.units[:1]) or bool(self._encoder_l.batchnorm) != bool(encoder.batchnorm):
+      raise ValueError("encoder_l must use the encoder's layer width and batchnorm setting (both first layers are one "
+                       "fused [2H, G] tensor-core operand)")
     super().__init__(outputs, latents=latents, encoder=encoder, **kwargs)
     self.init_args.update(library=self._library, encoder_l=self._encoder_l, clip_library=clip_library)
 
@@ -639,7 +810,7 @@ class DeepCountAutoencoder(SingleCellModel):
     if not latents.is_deterministic:
       warnings.warn("DeepCountAutoencoder only support deterministic latents, "
                     f"but given {latents}, use default linear Dense layer for latents.")
-      latents = latents.copy(posterior='relu')
+      latents = latents.copy(posterior='linear')      # sisua/models/dca.py:22-27
     super().__init__(outputs=outputs, latents=latents, **kwargs)
 
 

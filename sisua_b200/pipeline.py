@@ -40,9 +40,90 @@ class CsrBatch:
     self.cols = _pin(torch.from_numpy(c.astype(np.uint16).view(np.int16)))
     self.vals = _pin(torch.from_numpy(X[r, c].astype(np.uint16).view(np.int16)))
 
+  @classmethod
+  def view(cls, rows: int, genes: int, indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor) -> "CsrBatch":
+    """A minibatch that is a row range of a larger pinned CSR matrix: `indptr` [rows + 1] int32 rebased to 0, `cols` /
+    `vals` the matching 16-bit slices (no copies)."""
+    b = cls.__new__(cls)
+    b.rows, b.genes, b.indptr, b.cols, b.vals = rows, genes, indptr, cols, vals
+    return b
+
   @property
   def nbytes(self) -> int:
     return self.indptr.numel() * 4 + self.cols.numel() * 2 + self.vals.numel() * 2
+
+
+class HostDataset:
+  """A training set kept in pinned HOST memory and served as minibatches for `HostTrainPipeline` (what `fit(data_on='host')`
+  uses).  Mirrors the reference's input pipeline (sisua/data/_single_cell_base.py:593-601: map -> cache -> shuffle ->
+  batch(drop_remainder)): the rows are permuted ONCE when the cache is built (the reference shuffles through a
+  1000-element buffer) and every step takes the next B rows.  Integer count matrices are cached in CSR form (int64 row
+  pointers, uint16 gene ids and counts; single-cell matrices are 70-96 % zeros), so a minibatch is three pinned slices
+  plus B + 1 rebased row pointers; anything else stays dense float32."""
+
+  def __init__(self, data, batch: int, shuffle: bool = True, seed: int = 0, with_y: bool = False, with_library: bool = False):
+    import numpy as np
+    X = np.asarray(data.X)
+    N, G = X.shape
+    self.B, self.genes, self.n = int(batch), G, N
+    order = np.random.default_rng(seed).permutation(N) if shuffle else np.arange(N)
+    self.order = order
+    self.max_count = float(X.max()) if X.size else 0.0
+    self.h2d_bytes, self.batches_served = 0, 0
+    integer = G <= 65536 and X.min() >= 0 and self.max_count < 65536
+    if integer:
+      for s in range(0, N, 65536):           # integrality check in chunks (no full-size temporary)
+        blk = X[s:s + 65536]
+        if not np.array_equal(blk, np.rint(blk)):
+          integer = False
+          break
+    self.csr = integer
+    if integer:
+      counts = np.zeros(N + 1, dtype=np.int64)
+      cols_l, vals_l = [], []
+      for s in range(0, N, 32768):
+        blk = X[order[s:s + 32768]]
+        r, c = np.nonzero(blk)
+        counts[1 + s:1 + s + blk.shape[0]] = np.bincount(r, minlength=blk.shape[0])
+        cols_l.append(c.astype(np.uint16)); vals_l.append(blk[r, c].astype(np.uint16))
+      self.indptr = np.cumsum(counts)
+      self.cols = _pin(torch.from_numpy(np.concatenate(cols_l).view(np.int16)))
+      self.vals = _pin(torch.from_numpy(np.concatenate(vals_l).view(np.int16)))
+      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
+    else:
+      self.dense = _pin(torch.from_numpy(np.ascontiguousarray(X[order], dtype=np.float32)))
+    self.y = _pin(torch.from_numpy(np.ascontiguousarray(data.Y[order], dtype=np.float32))) if (with_y and data.Y is not None) else None
+    self.mask = _pin(torch.from_numpy(np.ascontiguousarray(data.mask[order], dtype=np.uint8))) if with_y else None
+    self.library = _pin(torch.from_numpy(np.ascontiguousarray(data.library[order], dtype=np.float32))) if with_library else None
+
+  def __len__(self):
+    return self.n // self.B
+
+  def batch_at(self, s: int):
+    """(x, extras): minibatch s of the cached order; x is a `CsrBatch` view or a pinned float32 [B, G] slice."""
+    B = self.B
+    lo, hi = s * B, (s + 1) * B
+    if self.csr:
+      a, b = int(self.indptr[lo]), int(self.indptr[hi])
+      ip = self._ip[self.batches_served % len(self._ip)]
+      ip.copy_(torch.from_numpy((self.indptr[lo:hi + 1] - a).astype("int32")))
+      x = CsrBatch.view(B, self.genes, ip, self.cols[a:b], self.vals[a:b])
+      self.h2d_bytes += x.nbytes
+    else:
+      x = self.dense[lo:hi]
+      self.h2d_bytes += x.numel() * 4
+    extras = {}
+    if self.y is not None:
+      extras["y"] = self.y[lo:hi]; extras["mask"] = self.mask[lo:hi]
+      self.h2d_bytes += extras["y"].numel() * 4 + B
+    if self.library is not None:
+      extras["library"] = self.library[lo:hi]
+      self.h2d_bytes += B * 8
+    self.batches_served += 1
+    return x, extras
+
+  def batch(self, epoch: int, s: int):
+    return self.batch_at(s % max(1, len(self)))
 
 
 def _capture_step(eng: Engine, run: Callable[[], None]) -> "torch.cuda.CUDAGraph":
@@ -103,9 +184,10 @@ class HostTrainPipeline:
       self.slots[s]["consumed"].record()
     return self.slots[s]
 
-  def _graph(self, s: int, fmt: str, lr: float, clipnorm: float, world: int = 1, split: bool = False):
+  def _graph(self, s: int, fmt: str, lr: float, clipnorm: float, world: int = 1, split: bool = False, seed: int = 0,
+             with_eps: bool = True):
     """(graph, None), or (backward graph, optimiser graph) when an all-reduce sits between them."""
-    key = (s, fmt, float(lr), float(clipnorm), int(world), bool(split))
+    key = (s, fmt, float(lr), float(clipnorm), int(world), bool(split), int(seed), bool(with_eps))
     if key not in self.graphs:
       eng, sl = self.eng, self._slot(s)
       def fwd_bwd():
@@ -113,8 +195,9 @@ class HostTrainPipeline:
           eng.unpack_counts_csr(*sl["csr"], sl["x"])
         elif fmt == "u16":
           eng.unpack_counts_u16(sl["x16"], sl["x"])
-        eng.train_step(sl["x"], eps_z=sl["eps"] if eng.cfg.model_kind != 2 else None, terms=sl["terms"], loss=sl["loss"],
-                       seed=0, step=-1)
+        # eps from the host when one is shipped (tests), otherwise Philox noise drawn in-kernel
+        eng.train_step(sl["x"], eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
+                       loss=sl["loss"], seed=seed, step=-1)
       def optimise():
         eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=0)
         self.host_loss[s].copy_(sl["loss"], non_blocking=True)
@@ -127,7 +210,7 @@ class HostTrainPipeline:
     return self.graphs[key]
 
   def step(self, x_host, eps_host: Optional[torch.Tensor], step: int, lr: float = 1e-3, clipnorm: float = 100.0,
-           world: int = 1, allreduce: Optional[Callable] = None, **host_extras):
+           world: int = 1, allreduce: Optional[Callable] = None, seed: int = 0, **host_extras):
     """Enqueue one train step; returns the pinned host tensor that will hold the loss once the stream has drained
     (read it after `flush`; it is reused `depth` steps later)."""
     eng = self.eng
@@ -138,7 +221,7 @@ class HostTrainPipeline:
     if not graphable:
       out = self.host_loss[self.i % len(self.host_loss)]
       self.i += 1
-      eng.train_step_host(x_host, eps_z=eps_host, host_loss=out, seed=0, step=step, **host_extras)
+      eng.train_step_host(x_host, eps_z=eps_host, host_loss=out, seed=seed, step=step, **host_extras)
       if allreduce is not None:
         allreduce(eng.grads)
       eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=step)
@@ -153,7 +236,7 @@ class HostTrainPipeline:
                    torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
     if fmt == "u16" and sl["x16"] is None:
       sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
-    graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None)
+    graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None, seed, eps_host is not None)
     if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
       eng.reset_step_counter(step - 1)
     main = torch.cuda.current_stream(eng.device)
@@ -184,6 +267,11 @@ class HostTrainPipeline:
   def flush(self, losses: List[torch.Tensor]):
     torch.cuda.current_stream(self.eng.device).synchronize()
     return [float(l.item()) for l in losses[-self.depth:]]
+
+  def flush_all(self, losses: List[torch.Tensor]):
+    """Synchronise and return the losses that are still readable: the pinned result slots are reused every `depth`
+    steps, so only the last `depth` entries of `losses` are distinct values."""
+    return self.flush(losses)
 
 
 class GraphedTrainStep:
@@ -218,6 +306,34 @@ class GraphedTrainStep:
     for dst, src in ((self.eps_z, eps_z), (self.eps_l, eps_l), (self.library, library), (self.y, y), (self.mask, mask)):
       if dst is not None and src is not None:
         dst.copy_(src, non_blocking=True)
+    self.graph.replay()
+    self.eng.step_count += 1
+    return self.terms, self.loss
+
+
+class GraphedGatherStep:
+  """`sisua_train_step_gather` + `sisua_adam_step` captured once and replayed per minibatch: the step reads its rows out
+  of the HBM-resident matrices through a static index buffer, draws dropout masks and reparameterisation noise from the
+  device-side step counter, so a replay only needs the B row indices copied in (what `fit()` does for minibatches
+  <= 2048, where the ~20 kernels of a step are launch-bound)."""
+
+  def __init__(self, eng: Engine, batch: int, x_all: torch.Tensor, y_all=None, library_all=None, mask_all=None,
+               lr: float = 1e-3, clipnorm: float = 100.0, seed: int = 0):
+    dev = eng.device
+    self.eng, self.batch = eng, batch
+    self.rows = torch.arange(batch, device=dev, dtype=torch.int32)
+    self.terms = torch.empty((5, batch), device=dev)
+    self.loss = torch.empty((1,), device=dev)
+    self._keep = (x_all, y_all, library_all, mask_all)
+
+    def run():
+      eng.train_step_gather(x_all, self.rows, y_all=y_all, library_all=library_all, mask_all=mask_all, terms=self.terms,
+                            loss=self.loss, seed=seed, step=-1)
+      eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0, t=0)
+    self.graph = _capture_step(eng, run)
+
+  def step(self, rows: torch.Tensor):
+    self.rows.copy_(rows, non_blocking=True)
     self.graph.replay()
     self.eng.step_count += 1
     return self.terms, self.loss

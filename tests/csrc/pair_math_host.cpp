@@ -63,6 +63,17 @@ extern "C" void pm_elem_scvi(const float* u_lse, const float* rb, const float* p
   }
 }
 
+// zero-inflated head evaluated without its zero inflation ("imputed" distribution): out[n][3] = llk, mu, th
+extern "C" void pm_elem_softplus_nozi(const float* ra, const float* rb, const float* pi, const float* x, int n, float* out) {
+  for (int i = 0; i + 1 < n; i += 2) {
+    F2 a[1] = {mk(ra[i], ra[i + 1])}, b[1] = {mk(rb[i], rb[i + 1])}, p[1] = {mk(pi[i], pi[i + 1])}, c[1] = {mk(x[i], x[i + 1])};
+    Elem2 e[1];
+    elem_multi_softplus<true, false, 1>(a, b, p, c, e, true);
+    out[i * 3] = e[0].llk.x; out[i * 3 + 1] = e[0].mu.x; out[i * 3 + 2] = e[0].th.x;
+    out[i * 3 + 3] = e[0].llk.y; out[i * 3 + 4] = e[0].mu.y; out[i * 3 + 5] = e[0].th.y;
+  }
+}
+
 extern "C" void pm_ex2_poly(const float* t, int n, float* out) {
   for (int i = 0; i + 1 < n; i += 2) { const F2 r = ex2_poly(mk(t[i], t[i + 1])); out[i] = r.x; out[i + 1] = r.y; }
 }

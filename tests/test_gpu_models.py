@@ -89,8 +89,42 @@ def test_fit_predict_roundtrip(name, gemm_mode, tmp_path):
   post = model.create_posterior(test, sample_shape=2, batch_size=16)
   assert post.imputed.shape == (len(test), 60) and post.latents.shape[0] == len(test)
   llk = post.cal_llk()
-  assert np.isfinite(llk["original"]) and np.isfinite(llk["corrupted"])
-  mll = model.marginal_log_prob(test.X[:8], library=torch.from_numpy(test.library[:8]).cuda() if name == "scvi" else None,
-                                sample_shape=20) if name != "sisua" else None
-  if mll is not None:
-    assert mll.shape == (8,) and torch.isfinite(mll).all()
+  assert len(llk) == 4 and all(np.isfinite(v) for v in llk.values())
+  lib = torch.from_numpy(test.library[:8]).cuda() if name == "scvi" else None
+  inputs = (test.X[:8], test.Y[:8]) if name == "sisua" else test.X[:8]
+  mll, parts = model.marginal_log_prob(inputs, library=lib, mask=test.mask[:8] if name == "sisua" else None, sample_shape=20)
+  assert mll.shape == (8,) and torch.isfinite(mll).all() and "transcriptomic" in parts and parts["transcriptomic"].shape == (8,)
+  # decode(latents): decoder-only entry point
+  if gemm_mode == 1:
+    z = torch.randn(5, 10, device="cuda")
+    lat = (z, torch.full((5,), 6.0, device="cuda")) if name == "scvi" else z
+    pz = model.decode(lat)
+    pz = pz[0] if isinstance(pz, tuple) else pz
+    assert pz.mean().shape == (5, 60) and torch.isfinite(pz.mean()).all()
+
+
+@pytest.mark.gpu
+def test_fit_argument_handling_and_host_streaming(tmp_path):
+  """The remaining keys of configs/base.yaml:45-62 are honoured or rejected; fit(data_on='host') streams minibatches from
+  pinned host memory (CSR) through HostTrainPipeline and trains like the device-resident path."""
+  sco = _data(n=1024)
+  train, valid = sco.split(0.75)
+  m = _make("vae", seed=2)
+  with pytest.raises(TypeError):
+    m.fit(train, batch_size=64, epochs=1, no_such_option=1)
+  with pytest.raises(NotImplementedError):
+    m.fit(train, batch_size=64, epochs=1, earlystop_progress_length=5)
+  timing = {"skip": 2}
+  m.fit(train, valid=valid, batch_size=64, epochs=4, valid_freq=6, learning_rate=2e-3, logging_interval=1, allow_rollback=True,
+        valid_interval=0, data_on="host", timing=timing)
+  loss = np.array(m.train_history["loss"])
+  assert np.isfinite(loss).all() and len(loss) >= 4
+  assert timing["steps"] == 4 * (len(train) // 64) - 2 and timing["seconds"] > 0 and timing["h2d_bytes_per_step"] > 0
+  m2 = _make("vae", seed=2)
+  m2.fit(train, batch_size=64, epochs=4, learning_rate=2e-3, logging_interval=1)
+  l2 = np.array(m2.train_history["loss"])
+  assert l2[-6:].mean() < l2[:6].mean()
+  # both paths reach a comparable loss (different minibatch orders, same data / model / optimiser)
+  assert abs(loss[-1] - l2[-6:].mean()) < 0.25 * abs(l2[-6:].mean())
+  p = m2.plot_learning_curves(path=os.path.join(tmp_path, "curves.csv"))
+  assert p is not None

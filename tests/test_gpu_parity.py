@@ -444,3 +444,80 @@ def test_host_train_pipeline_matches_device_steps(fmt, use_graph):
   if use_graph == "split":
     assert len(calls) == 7 and all(c > 0 for c in calls)      # the callback saw this step's gradients every time
   a.close(); b.close()
+
+
+@pytest.mark.parametrize("model,kw", [("vae", {}), ("scvi", {}), ("sisua", dict(n_proteins=10))])
+def test_philox_reparameterisation_noise_matches_oracle(model, kw):
+  """eps_z / eps_l == NULL: the kernels draw the reparameterisation noise themselves (Box-Muller on Philox4x32-10,
+  regenerated by the backward pass); oracle/philox.py reproduces the same normals, so ELBO and gradients must agree."""
+  from oracle.philox import NOISE_STREAM_L, NOISE_STREAM_Z, normal_noise
+  G, B, seed, step = 300, 200, 0x1234567890ABCDEF, 7
+  cfg, flat, mov, batch = _setup(model, kw, G, B, C.GEMM_TC_3XFP16, trained_moving=False)
+  eng = _engine(cfg, flat, mov)
+  inj = dict(batch)
+  inj["eps_z"] = normal_noise(B, cfg.n_latent, seed, step, NOISE_STREAM_Z).astype(np.float32)
+  if model == "scvi":
+    inj["eps_l"] = normal_noise(B, 1, seed, step, NOISE_STREAM_L)[:, 0].astype(np.float32)
+  drawn = {k: v for k, v in batch.items() if k not in ("eps_z", "eps_l")}
+  terms, loss = eng.train_step(seed=seed, step=step, **drawn)
+  torch.cuda.synchronize()
+  z_gpu = eng.debug_buffer("z", B, cfg.n_latent).cpu().numpy()
+  P = Hh.oracle_params(cfg, flat)
+  for p in P.values():
+    p.requires_grad_(True)
+  ref = O.forward(cfg, P, Hh.oracle_moving(cfg, mov), training=True, **inj)
+  ref["loss"].backward()
+  _close(z_gpu, ref["z"].detach().numpy(), rtol=1e-4, atol=2e-5, what="sampled z")
+  _close(terms[0].cpu().numpy(), ref["elbo"].detach().numpy(), what="elbo (Philox noise)")
+  got = eng.grads_dict()
+  for name, p in P.items():
+    g_ref = p.grad.numpy() if p.grad is not None else np.zeros(p.shape)
+    assert np.abs(got[name] - g_ref).max() <= 6e-3 * (np.abs(g_ref).max() + 1e-12) + 1e-9, name
+  # a different step draws different noise; the same (seed, step) reproduces it
+  t2, _ = eng.train_step(seed=seed, step=step + 1, **drawn)
+  t3, _ = eng.train_step(seed=seed, step=step, **drawn)
+  assert not torch.allclose(t2[0], terms[0]) and torch.allclose(t3[0], terms[0], rtol=1e-6)
+  # inference: S Monte-Carlo samples, call index as the step
+  S = 3
+  eng.set_infer_seed(seed, 5)
+  out = eng.infer(S=S, **drawn)
+  inj["eps_z"] = np.stack([normal_noise(B, cfg.n_latent, seed, 5, NOISE_STREAM_Z + 2 * s) for s in range(S)]).astype(np.float32)
+  if model == "scvi":
+    inj["eps_l"] = np.stack([normal_noise(B, 1, seed, 5, NOISE_STREAM_L + 2 * s)[:, 0] for s in range(S)]).astype(np.float32)
+  refi = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, eng.bn_moving.cpu().numpy()), training=False, **inj)
+  _close(out["terms"][0].cpu().numpy().reshape(S, B), refi["elbo"].numpy(), what="elbo [S,B] (Philox noise)")
+  eng.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw,G", [("vae", {}, 300), ("scvi", {}, 203), ("sisua", dict(n_proteins=10), 64)])
+def test_row_gather_step_equals_step_on_gathered_copy(model, kw, G, mode):
+  """sisua_train_step_gather (row indices into HBM-resident matrices, what fit(shuffle=True) issues) == sisua_train_step
+  on an explicitly gathered copy of the same rows: ELBO terms, loss and every gradient."""
+  from sisua_b200.engine import Engine
+  N, B = 1000, 200
+  cfg = C.make_step_config(model, n_genes=G, gemm_mode=mode, max_batch=256, input_dropout=0.3, **kw)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  full = Hh.make_batch(cfg, N, seed=4)
+  rng = np.random.default_rng(0)
+  rows = rng.permutation(N)[:B].astype(np.int32)
+  a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  dev = lambda v, dt=torch.float32: None if v is None else torch.from_numpy(np.ascontiguousarray(v)).to("cuda", dt)
+  eps = {k: dev(full[k][:B]) for k in ("eps_z", "eps_l") if k in full}
+  ta, la = a.train_step_gather(dev(full["x"]), dev(rows, torch.int32), y_all=dev(full.get("y")), library_all=dev(full.get("library")),
+                               mask_all=dev(full.get("mask"), torch.uint8), seed=9, step=2, **eps)
+  sub = {k: (v[rows] if k in ("x", "y", "library", "mask") else v[:B]) for k, v in full.items()}
+  tb, lb = b.train_step(seed=9, step=2, **sub)
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(ta.cpu().numpy(), tb.cpu().numpy(), rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(float(la), float(lb), rtol=1e-6)
+  ga, gb = a.grads_dict(), b.grads_dict()
+  # fp32 path: only the order of float atomics differs.  Fused path: the gradient GEMMs round their operands to fp16, and a
+  # 1e-7 difference in an operand (atomics order upstream) can flip that rounding: fp16-grade agreement.
+  tol = 1e-6 if mode == C.GEMM_FP32_UNFUSED else 3e-3
+  for k in ga:
+    np.testing.assert_allclose(ga[k], gb[k], rtol=1e-4 if mode == C.GEMM_FP32_UNFUSED else 0.0,
+                               atol=tol * (np.abs(gb[k]).max() + 1e-12) + 1e-9, err_msg=k)
+  a.close(); b.close()

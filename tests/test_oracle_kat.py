@@ -311,3 +311,21 @@ def test_oracle_scvi_and_sisua_heads_match_torch_distributions():
     np.testing.assert_allclose(o["mu"].numpy(), mu.numpy(), rtol=1e-9)
     np.testing.assert_allclose(o["llk_x"].numpy(), llk.numpy(), rtol=1e-5)
     np.testing.assert_allclose(o["elbo"].numpy(), elbo.numpy(), rtol=1e-5)
+
+
+def test_philox_normal_noise_is_standard_normal_and_counter_based():
+  """The reparameterisation noise generator (Box-Muller on Philox words): distribution, independence across columns /
+  steps / streams, and pure-function behaviour (what lets the backward pass regenerate it)."""
+  from scipy import stats
+  from oracle.philox import NOISE_STREAM_L, NOISE_STREAM_Z, normal_noise
+  n = normal_noise(40000, 10, 0xDEADBEEFCAFE, 3, NOISE_STREAM_Z)
+  assert n.shape == (40000, 10)
+  assert stats.kstest(n.ravel(), "norm").pvalue > 1e-3
+  assert abs(n.mean()) < 5e-3 and abs(n.std() - 1) < 5e-3
+  c = np.corrcoef(n.T)
+  assert np.abs(c - np.eye(10)).max() < 0.02
+  assert np.array_equal(n, normal_noise(40000, 10, 0xDEADBEEFCAFE, 3, NOISE_STREAM_Z))
+  assert np.array_equal(n[:100, :6], normal_noise(100, 6, 0xDEADBEEFCAFE, 3, NOISE_STREAM_Z))     # ragged widths share the stream
+  for other in (normal_noise(40000, 10, 0xDEADBEEFCAFE, 4, NOISE_STREAM_Z), normal_noise(40000, 10, 0xDEADBEEFCAFE, 3, NOISE_STREAM_L),
+                normal_noise(40000, 10, 0xDEADBEEFCAFF, 3, NOISE_STREAM_Z)):
+    assert abs(np.corrcoef(n.ravel(), other.ravel())[0, 1]) < 0.01

@@ -28,6 +28,7 @@ def lib(tmp_path_factory):
   L.pm_elem_softplus.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
   L.pm_elem_scvi.argtypes = [fp, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
   L.pm_ex2_poly.argtypes = [fp, ctypes.c_int, fp]
+  L.pm_elem_softplus_nozi.argtypes = [fp, fp, fp, fp, ctypes.c_int, fp]
   return L
 
 
@@ -79,6 +80,17 @@ def test_softplus_pair_matches_float64(lib, zi, grad):
     for got, ref, name in ((out[:, 1], ga, "ga"), (out[:, 2], gb, "gb"), (out[:, 3], gl, "gl")):
       e = np.abs(got - ref)
       assert (e <= 2e-5 * np.abs(ref) + 2e-6 * (1.0 + np.abs(x))).all(), f"{name} worst {e.max():.3e} at {np.argmax(e)}"
+
+
+def test_zero_inflated_head_without_zero_inflation(lib):
+  """`nozi`: the NB part of a zero-inflated head (what the reference calls the "imputed" distribution,
+  sisua/analysis/posterior.py:210-220) = the plain NB log-likelihood of the same mean / dispersion."""
+  ra, rb, pi, x = _grid(seed=5, n=20000)
+  out = np.zeros((ra.size, 3), dtype=np.float32)
+  lib.pm_elem_softplus_nozi(_p(ra), _p(rb), _p(pi), _p(x), ra.size, _p(out))
+  llk = _reference(ra, rb, pi, x, 0)[0]
+  err = np.abs(out[:, 0] - llk)
+  assert (err <= 2e-5 * np.abs(llk) + 5e-6).all(), err.max()
 
 
 def test_exp2_polynomial(lib):
