@@ -21,7 +21,10 @@ extern "C" {
 enum { SISUA_OK = 0, SISUA_ERR_INVALID = 1, SISUA_ERR_CUDA = 2, SISUA_ERR_UNSUPPORTED = 3, SISUA_ERR_STATE = 4 };
 
 enum { SISUA_MODEL_VAE = 0, SISUA_MODEL_SCVI = 1, SISUA_MODEL_DCA = 2, SISUA_MODEL_SISUA = 3 };
-enum { SISUA_XDIST_ZINBD = 0, SISUA_XDIST_NBD = 1 };
+/* gene-count likelihood: 'zinbd' / 'nbd' = (zero-inflated) NB by mean and inverse dispersion (odin-ai NegativeBinomialDisp,
+ * configs/base.yaml:32-34); 'zinb' / 'nb' = TFP NegativeBinomial(total_count = exp(.), logits = .)
+ * (tests/test_singlecell_models.py:60-80): the same likelihood with other links */
+enum { SISUA_XDIST_ZINBD = 0, SISUA_XDIST_NBD = 1, SISUA_XDIST_ZINB = 2, SISUA_XDIST_NB = 3 };
 enum { SISUA_YDIST_NB = 0, SISUA_YDIST_NBD = 1 };
 enum { SISUA_ACT_SOFTPLUS = 0, SISUA_ACT_SOFTPLUS1 = 1, SISUA_ACT_SOFTPLUS_P1 = 2, SISUA_ACT_EXP = 3,
        SISUA_ACT_IDENTITY = 4 };

@@ -40,7 +40,7 @@ import torch.nn.functional as F
 
 # enums duplicated on purpose (the oracle must not import the product package)
 MODEL_VAE, MODEL_SCVI, MODEL_DCA, MODEL_SISUA = 0, 1, 2, 3
-XDIST_ZINBD, XDIST_NBD = 0, 1
+XDIST_ZINBD, XDIST_NBD, XDIST_ZINB, XDIST_NB = 0, 1, 2, 3
 YDIST_NB, YDIST_NBD = 0, 1
 ACT_SOFTPLUS, ACT_SOFTPLUS1, ACT_SOFTPLUS_P1, ACT_EXP, ACT_IDENTITY = 0, 1, 2, 3, 4
 SOFTPLUS1_SHIFT = 0.5413248546129181
@@ -196,10 +196,23 @@ def forward(cfg, P: Dict[str, torch.Tensor], bn_moving: Optional[Dict[str, torch
     if cfg.scvi_reapply_act:           # Q2, literal reading of projection=False
       mu = activation(cfg.mean_act, mu)
       theta = activation(cfg.disp_act, theta)
+  elif cfg.x_dist in (XDIST_ZINB, XDIST_NB):
+    # TFP NegativeBinomial(total_count = exp(a), logits = b) (tests/test_singlecell_models.py:60-80): reported through its
+    # (mean, inverse dispersion) = (exp(a + b), exp(a))
+    theta = torch.exp(a)
+    mu = torch.exp(a + b)
   else:
     mu = activation(cfg.mean_act, a)
     theta = activation(cfg.disp_act, b)
-  if cfg.x_dist == XDIST_ZINBD:
+  if cfg.x_dist in (XDIST_ZINB, XDIST_NB):
+    base = log_nb_tfp(xa, a, b)
+    if cfg.x_dist == XDIST_ZINB:
+      pi = o[:, 2 * G:3 * G]
+      llk_x = torch.where(xa < EPS, F.softplus(base - pi) - F.softplus(-pi), base - F.softplus(pi)).sum(dim=1)
+    else:
+      pi = None
+      llk_x = base.sum(dim=1)
+  elif cfg.x_dist == XDIST_ZINBD:
     pi = o[:, 2 * G:3 * G]
     llk_x = log_zinb_disp(xa, mu, theta, pi).sum(dim=1)
   else:

@@ -22,7 +22,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 MODEL_VAE, MODEL_SCVI, MODEL_DCA, MODEL_SISUA = 0, 1, 2, 3
 MODEL_NAMES = {MODEL_VAE: "vae", MODEL_SCVI: "scvi", MODEL_DCA: "dca", MODEL_SISUA: "sisua"}
 
-XDIST_ZINBD, XDIST_NBD = 0, 1
+XDIST_ZINBD, XDIST_NBD, XDIST_ZINB, XDIST_NB = 0, 1, 2, 3
 YDIST_NB, YDIST_NBD = 0, 1
 
 ACT_SOFTPLUS, ACT_SOFTPLUS1, ACT_SOFTPLUS_P1, ACT_EXP, ACT_IDENTITY = 0, 1, 2, 3, 4
@@ -155,7 +155,7 @@ class StepConfig(ctypes.Structure):
 
   @property
   def n_out_heads(self) -> int:
-    return 3 if self.x_dist == XDIST_ZINBD else 2
+    return 3 if self.x_dist in (XDIST_ZINBD, XDIST_ZINB) else 2
 
   @property
   def genes_padded(self) -> int:
@@ -180,13 +180,15 @@ def make_step_config(model: str = "vae", n_genes: int = 2000, n_proteins: int = 
   kinds = {"vae": MODEL_VAE, "scvi": MODEL_SCVI, "dca": MODEL_DCA, "sisua": MODEL_SISUA}
   if model not in kinds:
     raise ValueError(f"unknown model kind '{model}'")
-  xd = {"zinbd": XDIST_ZINBD, "nbd": XDIST_NBD}
+  xd = {"zinbd": XDIST_ZINBD, "nbd": XDIST_NBD, "zinb": XDIST_ZINB, "nb": XDIST_NB}
   yd = {"nb": YDIST_NB, "nbd": YDIST_NBD}
   if x_dist not in xd:
-    raise ValueError(f"gene-count distribution '{x_dist}' is not on the B200 hot path (zinbd, nbd)")
+    raise ValueError(f"gene-count distribution '{x_dist}' is not on the B200 hot path (zinbd, nbd, zinb, nb)")
   if y_dist not in yd:
     raise ValueError(f"protein distribution '{y_dist}' is not on the B200 hot path (nb, nbd)")
   kind = kinds[model]
+  if kind == MODEL_SCVI and x_dist not in ("zinbd", "nbd"):
+    raise ValueError("scVI only supports 'zinbd' / 'nbd' (sisua/models/scvi.py:50-52)")
   if kind != MODEL_SISUA:
     n_proteins = 0
   if kind == MODEL_SISUA and n_proteins <= 0:

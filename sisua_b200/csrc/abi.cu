@@ -178,6 +178,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+static int n_heads(const sisua_step_config& c) { return (c.x_dist == SISUA_XDIST_ZINBD || c.x_dist == SISUA_XDIST_ZINB) ? 3 : 2; }
+static bool tfp_links(const sisua_step_config& c) { return c.x_dist == SISUA_XDIST_ZINB || c.x_dist == SISUA_XDIST_NB; }
 static long long align64(long long n) { return (n + 63) / 64 * 64; }
 
 // ---- parameter table: must agree with sisua_b200/config.py:param_layout -------------------------
@@ -238,7 +240,7 @@ static void build_layout(sisua_model* h) {
   }
   h->y_w = h->y_b = -1;
   if (P > 0) { h->y_w = add("y.W", 2 * P, H, H, 0); h->y_b = add("y.b", 2 * P, 0, 2 * P, 1); }
-  const int nheads = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  const int nheads = n_heads(c);
   h->NO = nheads * G;
   h->out_w = add("out.W", h->NO, H, H, 0);     // last: one contiguous early-ready all-reduce bucket
   h->out_b = add("out.b", h->NO, 0, h->NO, 1);
@@ -301,22 +303,24 @@ constexpr int kLseChunks = 16;   // gene chunks of the scVI logsumexp pass (x 4 
 
 template <int NH, bool VEC>
 static int tc_set_attr_scvi(sisua_model* h) {
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, true, true, tc::MODE_SCVI_LSE>,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, true, tc::LINK_SOFTPLUS, tc::MODE_SCVI_LSE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_EVAL>,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_EVAL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_SUMS>,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, false, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_SUMS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, false)));
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, VEC, true, tc::MODE_SCVI_TRAIN>,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_TRAIN>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, true)));
   return SISUA_OK;
 }
 
 template <int NH, bool TRAIN, bool VEC>
 static int tc_set_attr(sisua_model* h) {
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::OutSmem::total(NH, TRAIN)));
-  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::OutSmem::total(NH, TRAIN)));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_TFP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::OutSmem::total(NH, TRAIN)));
   return SISUA_OK;
 }
@@ -363,7 +367,7 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   {
     // both packed operands in one launch (the output-head tiles are consumed later in the same step)
     const bool heads = tc_heads_enabled(h);
-    const int nh = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+    const int nh = n_heads(c);
     ++h->launches;
     tc::pack_weights_kernel<<<h->n_kblocks + (heads ? h->n_gene_tiles : 0), 256, 0, st>>>(
         h->P + h->enc[0].w_off, h->Gp, h->packed_w1, c.n_genes, N0, h->n_kblocks, heads ? h->P + h->out_w : nullptr,
@@ -435,7 +439,7 @@ static int tc_create(sisua_model* h) {
     if (rc0 != SISUA_OK) return rc0;
   }
   if (!tc_heads_enabled(h)) return SISUA_OK;
-  const int nh = h->cfg.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  const int nh = n_heads(h->cfg);
   h->n_gene_tiles = (h->cfg.n_genes + tc::kGeneTile - 1) / tc::kGeneTile;
   int rc = ws_alloc(h, &h->packed_wout, (size_t)h->n_gene_tiles * tc::packed_tile_stride(nh));
   if (rc != SISUA_OK) return rc;
@@ -466,20 +470,20 @@ static int tc_scvi_passes(sisua_model* h, cudaStream_t st, bool training, tc::Ou
   grid_lse.y = (a.n_tiles + l.tiles_per_chunk - 1) / l.tiles_per_chunk;
   l.n_lse_parts = a.n_lse_parts = (int)grid_lse.y * 4;
   ++h->launches;
-  tc::out_heads_kernel<NH, false, true, true, tc::MODE_SCVI_LSE><<<grid_lse, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(l);
+  tc::out_heads_kernel<NH, false, true, tc::LINK_SOFTPLUS, tc::MODE_SCVI_LSE><<<grid_lse, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(l);
   LAUNCH_OK(h, "out_heads_kernel (scVI logsumexp)");
   ++h->launches;
   if (!training) {
-    tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_EVAL><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
+    tc::out_heads_kernel<NH, false, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_EVAL><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
     LAUNCH_OK(h, "out_heads_kernel (scVI evaluation)");
     return SISUA_OK;
   }
   CUDA_OK(h, cudaMemsetAsync(a.Trow, 0, (size_t)a.R * sizeof(float), st));
   CUDA_OK(h, cudaMemsetAsync(a.dlibsum, 0, (size_t)a.R * sizeof(float), st));
-  tc::out_heads_kernel<NH, false, VEC, true, tc::MODE_SCVI_SUMS><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
+  tc::out_heads_kernel<NH, false, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_SUMS><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, false), st>>>(a);
   LAUNCH_OK(h, "out_heads_kernel (scVI row sums)");
   ++h->launches;
-  tc::out_heads_kernel<NH, true, VEC, true, tc::MODE_SCVI_TRAIN><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);
+  tc::out_heads_kernel<NH, true, VEC, tc::LINK_SOFTPLUS, tc::MODE_SCVI_TRAIN><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);
   LAUNCH_OK(h, "out_heads_kernel (scVI gradients)");
   return SISUA_OK;
 }
@@ -488,7 +492,7 @@ static int tc_scvi_passes(sisua_model* h, cudaStream_t st, bool training, tc::Ou
 static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const float* x, int B, int S, float* llk_x,
                            float* out_mean, float* out_disp, float* out_pi, const NormSpec* fused_norm) {
   const sisua_step_config& c = h->cfg;
-  const int nh = c.x_dist == SISUA_XDIST_ZINBD ? 3 : 2;
+  const int nh = n_heads(c);
   const int R = S * B, G = c.n_genes;
   if (!h->wout_packed) {      // normally packed together with the first-layer operand at the start of the step
     ++h->launches;
@@ -518,11 +522,12 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
     return vec ? tc_scvi_passes<2, true>(h, st, training, a, grid) : tc_scvi_passes<2, false>(h, st, training, a, grid);
   }
   ++h->launches;
-  const bool fast = c.mean_act == SISUA_ACT_SOFTPLUS && c.disp_act == SISUA_ACT_SOFTPLUS1;
+  const int link = tfp_links(c) ? tc::LINK_TFP : ((c.mean_act == SISUA_ACT_SOFTPLUS && c.disp_act == SISUA_ACT_SOFTPLUS1) ? tc::LINK_SOFTPLUS : tc::LINK_GENERIC);
 #define TC_LAUNCH(NH, TRAIN, VEC)                                                                                   \
   do {                                                                                                              \
-    if (fast) tc::out_heads_kernel<NH, TRAIN, VEC, true><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);  \
-    else tc::out_heads_kernel<NH, TRAIN, VEC, false><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);      \
+    if (link == tc::LINK_SOFTPLUS) tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_SOFTPLUS><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);  \
+    else if (link == tc::LINK_TFP) tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_TFP><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);  \
+    else tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_GENERIC><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);      \
   } while (0)
   if (nh == 3) {
     if (training) { if (vec) TC_LAUNCH(3, true, true); else TC_LAUNCH(3, true, false); }
@@ -956,7 +961,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     a.OUT = h->OUT; a.ldo = h->NO; a.x = (!training && h->x_eval) ? h->x_eval : x; a.lib = scvi ? h->lib : nullptr; a.llk_x = terms + (size_t)R;
     a.dlib = (scvi && grads) ? h->dLib : nullptr;
     a.out_mean = out_mean; a.out_disp = out_disp; a.out_pi = out_pi;
-    a.R = R; a.B = B; a.G = G; a.scvi = scvi ? 1 : 0; a.zero_inflated = c.x_dist == SISUA_XDIST_ZINBD;
+    a.R = R; a.B = B; a.G = G; a.scvi = scvi ? 1 : 0; a.zero_inflated = n_heads(c) == 3; a.tfp = tfp_links(c) ? 1 : 0;
     a.train = grads ? 1 : 0; a.mean_act = c.mean_act; a.disp_act = c.disp_act; a.reapply = c.scvi_reapply_act;
     a.upstream = -1.0f / (float)R; a.clip_library = c.clip_library;
     size_t smem = scvi ? (size_t)G * sizeof(float) : 0;

@@ -83,8 +83,10 @@ struct CountGrad {  // d llk / d(mu, theta, pi_logit)
 };
 
 // Zero-inflated NB (mean / inverse dispersion / dropout logit). Returns log-likelihood of one entry.
-template <bool kZeroInflated, bool kGrad>
+// kNoEps: TFP's NegativeBinomial form (no 1e-8 inside the logarithms)
+template <bool kZeroInflated, bool kGrad, bool kNoEps = false>
 __device__ __forceinline__ float count_llk(float x, float mu, float th, float pi, CountGrad& g) {
+  const float kEps = kNoEps ? 1e-30f : sisua::kEps;
   float tm = th + mu + kEps;
   float lt = __logf(th + kEps);
   float ltm = __logf(tm);
@@ -97,7 +99,7 @@ __device__ __forceinline__ float count_llk(float x, float mu, float th, float pi
     dn0_dth = dlog + th * (__frcp_rn(th + kEps) - r_tm);
   }
   float llk;
-  if (x < kEps) {
+  if (x < sisua::kEps) {
     if (kZeroInflated) {
       float sp_a, sg_a, sp_b, sg_b;
       softplus_sigmoid(n0 - pi, sp_a, sg_a);   // sg_a = w = sigmoid(n0 - pi)
@@ -203,12 +205,12 @@ __constant__ float c_inv_int[9] = {1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.f / 5
 // their dependent MUFU / FMA chains inside each basic block (one element at a time leaves the issue slots idle).
 template <bool kZeroInflated, bool kGrad, int U>
 __device__ __forceinline__ void count_core_fast(const float (&mu)[U], const float (&th)[U], const float (&pi)[U],
-                                                const float (&x)[U], CoreResult (&o)[U]) {
+                                                const float (&x)[U], CoreResult (&o)[U], const float eps = kEps) {
   float Rt[U], n0[U], dn0_dmu[U], dn0_dth[U], Ep[U], Rp[U];
   bool nz[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    Rt[u] = mufu_rcp(th[u] + mu[u] + kEps);
+    Rt[u] = mufu_rcp(th[u] + mu[u] + eps);
     const float rho = th[u] * Rt[u];
     const float dlog = kLn2 * mufu_lg2(rho + 1e-30f);
     n0[u] = th[u] * dlog;
@@ -282,9 +284,9 @@ __device__ __forceinline__ void count_core_fast(const float (&mu)[U], const floa
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      float lnm = kLn2 * mufu_lg2((mu[u] + kEps) * Rt[u]);
+      float lnm = kLn2 * mufu_lg2((mu[u] + eps) * Rt[u]);
       float llk1 = n0[u] + x[u] * lnm + lg[u];
-      float gmu1 = dn0_dmu[u] + x[u] * (mufu_rcp(mu[u] + kEps) - Rt[u]);
+      float gmu1 = dn0_dmu[u] + x[u] * (mufu_rcp(mu[u] + eps) - Rt[u]);
       float gth1 = dn0_dth[u] - x[u] * Rt[u] + dg[u];
       float gl1 = 0.f;
       if (kZeroInflated) {
@@ -301,10 +303,11 @@ __device__ __forceinline__ void count_core_fast(const float (&mu)[U], const floa
 // lane of the warp calls it together (count_core_fast votes warp-wide)
 namespace pm {
 template <bool ZI, bool GRAD>
-__device__ __noinline__ void core_scalar_fallback(float mu, float th, float pi, float x, float& llk, float& gmu, float& gth, float& gl) {
+__device__ __noinline__ void core_scalar_fallback(float mu, float th, float pi, float x, float eps, float& llk, float& gmu, float& gth,
+                                                  float& gl) {
   const float mu1[1] = {mu}, th1[1] = {th}, pi1[1] = {pi}, x1[1] = {x};
   CoreResult c[1];
-  count_core_fast<ZI, GRAD, 1>(mu1, th1, pi1, x1, c);
+  count_core_fast<ZI, GRAD, 1>(mu1, th1, pi1, x1, c, eps);
   llk = c[0].llk; gmu = c[0].gmu; gth = c[0].gth; gl = c[0].gl;
 }
 }  // namespace pm

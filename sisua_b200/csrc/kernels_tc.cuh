@@ -126,7 +126,10 @@ struct OutSmem {     // offsets into dynamic shared memory (bytes)
 
 enum OutBar { ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12, DWO_FREE = 14, DD_FULL = 16, W_FULL = 17, W_FREE = 20, NUM_BARS = 23 };
 
-template <int NH, bool TRAIN, bool VEC, bool FAST, int MODE = MODE_PLAIN>
+// LINK: how the raw head outputs become (mean, inverse dispersion): the default softplus pair (packed fast path), TFP's
+// total_count / logits form of the 'zinb' / 'nb' enums (packed), or any other activation pair (scalar evaluation)
+enum OutLink { LINK_GENERIC = 0, LINK_SOFTPLUS = 1, LINK_TFP = 2 };
+template <int NH, bool TRAIN, bool VEC, int LINK, int MODE = MODE_PLAIN>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
   static_assert(TRAIN == (MODE == MODE_SCVI_TRAIN) || MODE == MODE_PLAIN, "only the plain and scVI-train modes run the gradient GEMMs");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -489,9 +492,10 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
               t2 = pm::add(t2, st); dl2 = pm::add(dl2, dl);
             }
           }
-        } else if (FAST) {
+        } else if (LINK != LINK_GENERIC) {
           pm::Elem2 e[kNP];
-          pm::elem_multi_softplus<ZI, TRAIN, kNP>(ra, rb, pi, x2, e, TRAIN ? false : a.nozi != 0);
+          if (LINK == LINK_TFP) pm::elem_multi_tfp<ZI, TRAIN, kNP>(ra, rb, pi, x2, e, TRAIN ? false : a.nozi != 0);
+          else pm::elem_multi_softplus<ZI, TRAIN, kNP>(ra, rb, pi, x2, e, TRAIN ? false : a.nozi != 0);
 #pragma unroll
           for (int p = 0; p < kNP; ++p) { llk[p] = e[p].llk; ga[p] = e[p].ga; gb[p] = e[p].gb; gl[p] = e[p].gl; mu[p] = e[p].mu; th[p] = e[p].th; }
         } else {

@@ -106,6 +106,7 @@ struct CountRowArgs {
   float* out_mean; float* out_disp; float* out_pi;   // [R, G] each, nullable (inference)
   int R, B, G;
   int scvi, zero_inflated, train, mean_act, disp_act, reapply;
+  int tfp;                        // 'zinb' / 'nb': head 0 = log total_count, head 1 = logits (TFP NegativeBinomial)
   float upstream;                 // d loss / d llk_x = -1 / R
   float clip_library;
 };
@@ -148,14 +149,22 @@ __global__ void __launch_bounds__(256) count_row_kernel(CountRowArgs a) {
         activation(a.disp_act, th, v, dv); th = v; dth_db *= dv;
       }
       s_cache[g] = s_raw;
+    } else if (a.tfp) {
+      th = expf(ra); mu = expf(ra + rb); dmu_da = 1.f; dth_db = 1.f;     // chain rule below
     } else {
       activation(a.mean_act, ra, mu, dmu_da);
       activation(a.disp_act, rb, th, dth_db);
     }
     CountGrad cg;
-    float l = a.train ? count_llk<ZI, true>(xr[g], mu, th, pi, cg) : count_llk<ZI, false>(xr[g], mu, th, pi, cg);
+    float l = a.tfp ? (a.train ? count_llk<ZI, true, true>(xr[g], mu, th, pi, cg) : count_llk<ZI, false, true>(xr[g], mu, th, pi, cg))
+                    : (a.train ? count_llk<ZI, true>(xr[g], mu, th, pi, cg) : count_llk<ZI, false>(xr[g], mu, th, pi, cg));
     llk += l;
-    if (a.train) {
+    if (a.train && a.tfp) {      // d / d log total_count = gmu mu + gth theta, d / d logits = gmu mu
+      const float up = a.upstream, gm = cg.dmu * mu;
+      row[g] = up * (gm + cg.dth * th);
+      row[G + g] = up * gm;
+      if (ZI) row[2 * G + g] = up * cg.dpi;
+    } else if (a.train) {
       float up = a.upstream;
       row[G + g] = up * cg.dth * dth_db;
       if (ZI) row[2 * G + g] = up * cg.dpi;

@@ -130,7 +130,7 @@ PM_HD F2 link_value_nograd(const Link& k, F2 r) {
 
 struct Core { F2 llk, gmu, gth, gl; };     // natural-log units; d llk / d (mean, inverse dispersion, dropout logit)
 
-// Scalar fall-back for one element: sisua::pm::core_scalar_fallback<ZI, GRAD>(mu, th, pi, x, llk&, gmu&, gth&, gl&) must be
+// Scalar fall-back for one element: sisua::pm::core_scalar_fallback<ZI, GRAD>(mu, th, pi, x, eps, llk&, gmu&, gth&, gl&) must be
 // declared BEFORE this header is included -- device_math.cuh does (out of line, on top of count_core_fast<.., 1>); the
 // host harness restates it in double precision.
 
@@ -138,7 +138,10 @@ struct Core { F2 llk, gmu, gth, gl; };     // natural-log units; d llk / d (mean
 // that a caller can run SEVERAL pairs through each straight-line piece back to back: the compiler then interleaves their
 // instruction streams (independent dependency chains), which is what hides the MUFU / FMA latencies -- a single pair is
 // one long chain.
-struct CoreState { F2 mu, th, pi, x, Rt, rho, n0, dn0_dth, Ep, Rp; };
+struct CoreState {
+  F2 mu, th, pi, x, Rt, rho, n0, dn0_dth, Ep, Rp;
+  float eps = kEps;      // the 1e-8 inside the logarithms of the mean / dispersion form (scVI's log_nb_positive); ~0 for TFP's form
+};
 
 // piece 1: everything a zero count needs (and the shared terms of the non-zero case)
 // `nozi` (uniform): evaluate the count distribution WITHOUT its zero inflation although the head has a dropout logit --
@@ -146,7 +149,7 @@ struct CoreState { F2 mu, th, pi, x, Rt, rho, n0, dn0_dth, Ep, Rp; };
 template <bool ZI, bool GRAD>
 PM_HD Core core_zero(CoreState& c, bool nozi = false) {
   Core o;
-  const F2 tm = add(add(c.th, c.mu), bc(kEps));
+  const F2 tm = add(add(c.th, c.mu), bc(c.eps));
   c.Rt = rcp(tm);
   c.rho = mul(c.th, c.Rt);
   // log2(theta / (theta + mu)).  rho carries the rounding of the approximate reciprocal (~1e-7 relative), which the
@@ -200,7 +203,7 @@ PM_HD void core_small(const CoreState& c, Core& o, bool nozi = false) {
   const F2 g1 = fma2(i2, th, bc(1.f)), g2 = fma2(i3, t1, bc(1.f));
   const F2 g12 = mul(g1, g2);
   const F2 q = mul(th, g12);
-  const F2 mue = add(c.mu, bc(kEps));
+  const F2 mue = add(c.mu, bc(c.eps));
   const F2 m = mul(mue, c.Rt);                        // mu / (theta + mu)
   // m^x = m * (x >= 2 ? m : 1) * (x >= 3 ? m : 1); the factors are blended as i*m + (1 - i): no cancellation for tiny m
   const F2 mx = mul(m, mul(fma2(i2, m, sub(bc(1.f), i2)), fma2(i3, m, sub(bc(1.f), i3))));
@@ -234,13 +237,13 @@ template <bool ZI, bool GRAD>
 PM_HD void core_general(const CoreState& c, Core& o, bool nozi = false) {
   float l, gm, gt, gg;
   if (any_lane(count_big(c.x.x))) {
-    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, l, gm, gt, gg);
-    else core_scalar_fallback<false, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, l, gm, gt, gg);
+    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, c.eps, l, gm, gt, gg);
+    else core_scalar_fallback<false, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, c.eps, l, gm, gt, gg);
     o.llk.x = l; o.gmu.x = gm; o.gth.x = gt; o.gl.x = gg;
   }
   if (any_lane(count_big(c.x.y))) {
-    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, l, gm, gt, gg);
-    else core_scalar_fallback<false, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, l, gm, gt, gg);
+    if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, c.eps, l, gm, gt, gg);
+    else core_scalar_fallback<false, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, c.eps, l, gm, gt, gg);
     o.llk.y = l; o.gmu.y = gm; o.gth.y = gt; o.gl.y = gg;
   }
 }
@@ -368,6 +371,31 @@ PM_HD void elem_multi_scvi(const F2 (&u_lse)[NP], const F2 (&rb)[NP], const F2 (
     o[p].t = mk((o[p].s_raw.x >= lo && o[p].s_raw.x <= hi) ? ge.x : 0.f, (o[p].s_raw.y >= lo && o[p].s_raw.y <= hi) ? ge.y : 0.f);
     o[p].gmu_mu = mul(k[p].gmu, c[p].mu);
     o[p].gb = mul(k[p].gth, c[p].th);
+    o[p].gl = k[p].gl;
+  }
+}
+
+// TFP parameterisation of the 'zinb' / 'nb' output enums (tests/test_singlecell_models.py:60-80): head 0 = log total_count
+// a, head 1 = logits b:  NegativeBinomial(total_count = e^a, logits = b)  ==  NB(mean = e^(a+b), inverse dispersion = e^a)
+// (theta log(theta/(theta+mu)) = r log sigmoid(-b), x log(mu/(theta+mu)) = x log sigmoid(b)), so only the links differ:
+//   d/da = gmu mu + gth theta,   d/db = gmu mu.
+template <bool ZI, bool GRAD, int NP>
+PM_HD void elem_multi_tfp(const F2 (&ra)[NP], const F2 (&rb)[NP], const F2 (&pi)[NP], const F2 (&x)[NP], Elem2 (&o)[NP],
+                          bool nozi = false) {
+  CoreState c[NP]; Core k[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    c[p].th = ex2(mul(min2(ra[p], 80.f), bc(kLog2e)));
+    c[p].mu = ex2(mul(min2(add(ra[p], rb[p]), 80.f), bc(kLog2e)));
+    c[p].pi = pi[p]; c[p].x = x[p]; c[p].eps = 1e-30f;
+  }
+  core_multi<ZI, GRAD, NP>(c, k, nozi);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    o[p].mu = c[p].mu; o[p].th = c[p].th; o[p].llk = k[p].llk;
+    const F2 gm = mul(k[p].gmu, c[p].mu);
+    o[p].gb = gm;                                   // d llk / d logits
+    o[p].ga = fma2(k[p].gth, c[p].th, gm);          // d llk / d log total_count
     o[p].gl = k[p].gl;
   }
 }

@@ -145,7 +145,7 @@ class Engine:
     out = dict(terms=f(5, R), z_loc=f(B, Z), z_scale=f(B, Z))
     out["mean"] = f(R, G) if want_mean else None
     out["disp"] = f(R, G) if want_disp else None
-    out["pi_logit"] = f(R, G) if (want_pi and cfg.x_dist == 0) else None
+    out["pi_logit"] = f(R, G) if (want_pi and cfg.n_out_heads == 3) else None
     out["lib_loc"] = f(B) if cfg.model_kind == 1 else None
     out["lib_scale"] = f(B) if cfg.model_kind == 1 else None
     out["y_mean"] = f(R, P) if P > 0 else None
@@ -171,7 +171,7 @@ class Engine:
     out["z_scale"] = f(B, Z) if want_latent else None
     out["mean"] = f(R, G) if want_mean else None
     out["disp"] = f(R, G) if want_disp else None
-    out["pi_logit"] = f(R, G) if (want_pi and cfg.x_dist == 0) else None
+    out["pi_logit"] = f(R, G) if (want_pi and cfg.n_out_heads == 3) else None
     out["lib_loc"] = f(B) if (cfg.model_kind == 1 and want_latent) else None
     out["lib_scale"] = f(B) if (cfg.model_kind == 1 and want_latent) else None
     out["y_mean"] = f(R, P) if P > 0 else None
@@ -194,7 +194,7 @@ class Engine:
     B, G, Z, P = x.shape[0], cfg.n_genes, cfg.n_latent, cfg.n_proteins
     f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
     out = dict(terms=f(5, B), z_loc=f(B, Z), z_scale=f(B, Z), mean=f(B, G), disp=f(B, G))
-    out["pi_logit"] = f(B, G) if cfg.x_dist == 0 else None
+    out["pi_logit"] = f(B, G) if cfg.n_out_heads == 3 else None
     out["lib_loc"] = f(B) if cfg.model_kind == 1 else None
     out["lib_scale"] = f(B) if cfg.model_kind == 1 else None
     out["y_mean"] = f(B, P) if P > 0 else None
@@ -215,7 +215,7 @@ class Engine:
     cfg = self.cfg
     R, G, P = z.shape[0], cfg.n_genes, cfg.n_proteins
     f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
-    out = dict(mean=f(R, G), disp=f(R, G), pi_logit=f(R, G) if cfg.x_dist == 0 else None, y_mean=f(R, P) if P > 0 else None)
+    out = dict(mean=f(R, G), disp=f(R, G), pi_logit=f(R, G) if cfg.n_out_heads == 3 else None, y_mean=f(R, P) if P > 0 else None)
     with torch.cuda.device(self.device):
       for s in range(0, R, cfg.max_batch):
         e = min(R, s + cfg.max_batch)

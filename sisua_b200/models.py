@@ -148,8 +148,8 @@ class SingleCellModel:
   # ---------------------------------------------------------------- configuration -> StepConfig
   def _step_config(self) -> C.StepConfig:
     rv = self._outputs[0]
-    if rv.posterior not in ("zinbd", "nbd"):
-      raise ValueError(f"posterior '{rv.posterior}' is outside the B200 hot path (zinbd, nbd)")
+    if rv.posterior not in ("zinbd", "nbd", "zinb", "nb"):
+      raise ValueError(f"posterior '{rv.posterior}' is outside the B200 hot path (zinbd, nbd, zinb, nb)")
     enc, dec = self._encoder, self._decoder
     if len(set(enc.units + dec.units)) != 1:
       raise ValueError("all hidden layers must share one width")
@@ -276,7 +276,7 @@ class SingleCellModel:
     G = cfg.n_genes
     shp = (lambda t, n: t.reshape(S, B, n)) if S else (lambda t, n: t.reshape(B, n))
     nb = D.NegativeBinomialDisp(shp(out["mean"], G), shp(out["disp"], G))
-    base = D.ZeroInflated(nb, shp(out["pi_logit"], G)) if cfg.x_dist == C.XDIST_ZINBD else nb
+    base = D.ZeroInflated(nb, shp(out["pi_logit"], G)) if cfg.n_out_heads == 3 else nb
     pX = D.Independent(base, 1, name=self.posteriors[0].name)
     pX.elbo_terms = out["terms"]
     qZ = self._wrap_latents(out)
@@ -323,7 +323,7 @@ class SingleCellModel:
     G = cfg.n_genes
     rs = lambda t, n: t.reshape(lead + (n,))
     nb = D.NegativeBinomialDisp(rs(out["mean"], G), rs(out["disp"], G))
-    base = D.ZeroInflated(nb, rs(out["pi_logit"], G)) if cfg.x_dist == C.XDIST_ZINBD else nb
+    base = D.ZeroInflated(nb, rs(out["pi_logit"], G)) if cfg.n_out_heads == 3 else nb
     pX = D.Independent(base, 1, name=self.posteriors[0].name)
     if self.labels:
       return pX, D.Independent(D.MeanOnly(rs(out["y_mean"], cfg.n_proteins)), 1, name=self.posteriors[1].name)
@@ -363,7 +363,7 @@ class SingleCellModel:
         y_mean[:, sl] = out["y_mean"].reshape(S or 1, n, cfg.n_proteins)
     if device == "CPU":
       merged = {k: v.cpu() for k, v in merged.items()}
-    base = ST.StreamedZeroInflated(src) if cfg.x_dist == C.XDIST_ZINBD else ST.StreamedNB(src)
+    base = ST.StreamedZeroInflated(src) if cfg.n_out_heads == 3 else ST.StreamedNB(src)
     pX = ST.StreamedIndependent(base, name=self.posteriors[0].name)
     pX.elbo_terms = merged["terms"]
     qZ = self._wrap_latents(merged)

@@ -144,7 +144,7 @@ class StreamedZeroInflated(D.ZeroInflated):
 def _cell_log_prob(src: StreamSource, x, strip_zi: bool) -> torch.Tensor:
   eng = src.eng
   x = eng._dev(x)
-  if strip_zi and not src.fused and eng.cfg.x_dist == 0:      # un-fused cross-check path: dense parameters, eager log-prob
+  if strip_zi and not src.fused and eng.cfg.n_out_heads == 3:      # un-fused cross-check path: dense parameters, eager log-prob
     nb = D.NegativeBinomialDisp(src.gather("mean", eng.cfg.n_genes, want_mean=True), src.gather("disp", eng.cfg.n_genes, want_disp=True))
     return nb.log_prob(x).sum(-1)
   if tuple(x.shape) != (src.N, eng.cfg.n_genes):

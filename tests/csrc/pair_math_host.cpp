@@ -13,14 +13,14 @@ static double digamma(double t) {
 }
 // scalar fall-back of the device build = device_math.cuh:count_core_fast<.., 1>; here: the same closed forms in double
 template <bool ZI, bool GRAD>
-inline void core_scalar_fallback(float muf, float thf, float pif, float xf, float& llk, float& gmu, float& gth, float& gl) {
-  const double mu = muf, th = thf, pi = pif, x = xf, eps = 1e-8;
+inline void core_scalar_fallback(float muf, float thf, float pif, float xf, float epsf, float& llk, float& gmu, float& gth, float& gl) {
+  const double mu = muf, th = thf, pi = pif, x = xf, eps = epsf;
   const double ltm = std::log(th + mu + eps), dlog = std::log(th + eps) - ltm, n0 = th * dlog;
   const double rt = 1.0 / (th + mu + eps);
   const double dn0_dmu = -th * rt, dn0_dth = dlog + th * (1.0 / (th + eps) - rt);
   auto sp = [](double v) { return v > 0 ? v + std::log1p(std::exp(-v)) : std::log1p(std::exp(v)); };
   auto sg = [](double v) { return 1.0 / (1.0 + std::exp(-v)); };
-  if (x < eps) {
+  if (x < 1e-8) {
     if (ZI) { llk = (float)(sp(n0 - pi) - sp(-pi)); const double w = sg(n0 - pi); gl = (float)(sg(-pi) - w); gmu = (float)(w * dn0_dmu); gth = (float)(w * dn0_dth); }
     else { llk = (float)n0; gmu = (float)dn0_dmu; gth = (float)dn0_dth; gl = 0.f; }
   } else {
@@ -71,6 +71,18 @@ extern "C" void pm_elem_softplus_nozi(const float* ra, const float* rb, const fl
     elem_multi_softplus<true, false, 1>(a, b, p, c, e, true);
     out[i * 3] = e[0].llk.x; out[i * 3 + 1] = e[0].mu.x; out[i * 3 + 2] = e[0].th.x;
     out[i * 3 + 3] = e[0].llk.y; out[i * 3 + 4] = e[0].mu.y; out[i * 3 + 5] = e[0].th.y;
+  }
+}
+
+// TFP links ('zinb' / 'nb'): out[n][6] = llk, ga (d / d log total_count), gb (d / d logits), gl, mean, total_count
+extern "C" void pm_elem_tfp(const float* ra, const float* rb, const float* pi, const float* x, int n, int zi, float* out) {
+  for (int i = 0; i + 1 < n; i += 2) {
+    F2 a[1] = {mk(ra[i], ra[i + 1])}, b[1] = {mk(rb[i], rb[i + 1])}, p[1] = {mk(pi[i], pi[i + 1])}, c[1] = {mk(x[i], x[i + 1])};
+    Elem2 e[1];
+    if (zi) elem_multi_tfp<true, true, 1>(a, b, p, c, e); else elem_multi_tfp<false, true, 1>(a, b, p, c, e);
+    float* o = out + (size_t)i * 6;
+    o[0] = e[0].llk.x; o[1] = e[0].ga.x; o[2] = e[0].gb.x; o[3] = e[0].gl.x; o[4] = e[0].mu.x; o[5] = e[0].th.x;
+    o[6] = e[0].llk.y; o[7] = e[0].ga.y; o[8] = e[0].gb.y; o[9] = e[0].gl.y; o[10] = e[0].mu.y; o[11] = e[0].th.y;
   }
 }
 

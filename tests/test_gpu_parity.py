@@ -521,3 +521,24 @@ def test_row_gather_step_equals_step_on_gathered_copy(model, kw, G, mode):
     np.testing.assert_allclose(ga[k], gb[k], rtol=1e-4 if mode == C.GEMM_FP32_UNFUSED else 0.0,
                                atol=tol * (np.abs(gb[k]).max() + 1e-12) + 1e-9, err_msg=k)
   a.close(); b.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("model,kw", [("vae", {}), ("sisua", dict(n_proteins=10)), ("dca", {})])
+@pytest.mark.parametrize("x_dist", ["zinb", "nb"])
+def test_tfp_parameterised_output_enums(x_dist, model, kw, mode):
+  """'zinb' / 'nb' outputs (TFP NegativeBinomial(total_count = exp(.), logits = .), tests/test_singlecell_models.py:60-80)
+  through the same fused kernel as 'zinbd' / 'nbd': ELBO, parameters and every gradient vs the oracle."""
+  cfg, flat, mov, batch = _setup(model, dict(kw, x_dist=x_dist), 300, 128, mode, trained_moving=False)
+  # keep exp(a + b) in a sane range: shrink the random output-head weights
+  d = PR.flat_to_dict(cfg, flat)
+  d["out.W"] *= 0.3
+  eng = _engine(cfg, flat, mov)
+  _grad_check(cfg, flat, mov, batch, eng)
+  out = eng.infer(**batch, want_disp=True, want_pi=True)
+  ref = O.forward(cfg, Hh.oracle_params(cfg, flat), Hh.oracle_moving(cfg, eng.bn_moving.cpu().numpy()), training=False, **batch)
+  _close(out["terms"][0].cpu().numpy(), ref["elbo"].numpy(), what="elbo")
+  _close(out["mean"].cpu().numpy(), ref["mu"].numpy(), atol=1e-7, what="mean = total_count * exp(logits)")
+  _close(out["disp"].cpu().numpy(), ref["theta"].numpy(), atol=1e-7, what="total_count")
+  assert (out["pi_logit"] is not None) == (x_dist == "zinb")
+  eng.close()

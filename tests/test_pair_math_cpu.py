@@ -28,6 +28,7 @@ def lib(tmp_path_factory):
   L.pm_elem_softplus.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
   L.pm_elem_scvi.argtypes = [fp, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
   L.pm_ex2_poly.argtypes = [fp, ctypes.c_int, fp]
+  L.pm_elem_tfp.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, fp]
   L.pm_elem_softplus_nozi.argtypes = [fp, fp, fp, fp, ctypes.c_int, fp]
   return L
 
@@ -91,6 +92,33 @@ def test_zero_inflated_head_without_zero_inflation(lib):
   llk = _reference(ra, rb, pi, x, 0)[0]
   err = np.abs(out[:, 0] - llk)
   assert (err <= 2e-5 * np.abs(llk) + 5e-6).all(), err.max()
+
+
+@pytest.mark.parametrize("zi", [1, 0])
+def test_tfp_links_match_float64(lib, zi):
+  """'zinb' / 'nb' output enums: TFP NegativeBinomial(total_count = e^a, logits = b) (+ zero inflation) against the
+  oracle's log_nb_tfp and its autograd derivatives."""
+  rng = np.random.default_rng(7)
+  n = 20000
+  ra = rng.uniform(-4, 5, n).astype(np.float32); rb = rng.uniform(-8, 4, n).astype(np.float32)
+  pi = rng.uniform(-10, 10, n).astype(np.float32)
+  x = rng.choice([0, 0, 0, 1, 2, 3, 5, 9, 40], size=n).astype(np.float32)
+  out = np.zeros((n, 6), dtype=np.float32)
+  lib.pm_elem_tfp(_p(ra), _p(rb), _p(pi), _p(x), n, zi, _p(out))
+  a = torch.tensor(ra, dtype=torch.float64, requires_grad=True); b = torch.tensor(rb, dtype=torch.float64, requires_grad=True)
+  p = torch.tensor(pi, dtype=torch.float64, requires_grad=True); xx = torch.tensor(x, dtype=torch.float64)
+  base = O.log_nb_tfp(xx, a, b)
+  if zi:
+    llk = torch.where(xx < 1e-8, F.softplus(base - p) - F.softplus(-p), base - F.softplus(p))
+  else:
+    llk = base
+  llk.sum().backward()
+  th = np.exp(ra.astype(np.float64))
+  for got, ref, name in ((out[:, 0], llk.detach().numpy(), "llk"), (out[:, 1], a.grad.numpy(), "ga"), (out[:, 2], b.grad.numpy(), "gb")) + \
+      (((out[:, 3], p.grad.numpy(), "gl"),) if zi else ()):
+    e = np.abs(got - ref)
+    assert (e <= 3e-5 * np.abs(ref) + 5e-6 * (1 + np.abs(x)) + 3e-7 * th).all(), f"{name} worst {e.max():.3e} at {np.argmax(e)}"
+  np.testing.assert_allclose(out[:, 4], np.exp(ra.astype(np.float64) + rb), rtol=3e-6)
 
 
 def test_exp2_polynomial(lib):
