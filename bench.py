@@ -46,6 +46,9 @@ def parse():
                   help="record the per-section CUDA events inside the headline loop (costs ~40 us per step: 12 event records "
                        "that also break the kernel-to-kernel overlap); default: a separate pass right after it")
   ap.add_argument("--cpu-steps", type=int, default=6)
+  ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                  help="multi-GPU gradient exchange: 'peer' = one kernel over NVLink peer memory (reduce-scatter + sharded Adam + "
+                       "all-gather), 'nccl' = two overlapped NCCL all-reduces + Adam")
   ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of one step at the benchmarked shape")
   ap.add_argument("--no-latency", action="store_true", help="skip the batch-64 / 128 latency-regime measurement")
   return ap.parse_args()
@@ -196,7 +199,9 @@ def main():
           "config": {"workload": workload_name(a), "network": "vae/zinbd", "genes": a.genes, "latent": LATENT,
                      "hidden": [64, 64], "batchnorm": True, "input_dropout": a.input_dropout, "batch_per_gpu": a.batch,
                      "cells_per_step": a.batch * a.gpus,
-                     "sharding": f"{a.gpus} rank(s), cells sharded, flat gradient buffer all-reduced",
+                     "sharding": f"{a.gpus} rank(s), cells sharded; gradient exchange + optimiser: " +
+                                 ("one kernel over NVLink peer memory (reduce-scatter, sharded Adam, all-gather)" if a.exchange == "peer"
+                                  else "NCCL all-reduce of the flat gradient buffer, then Adam"),
                      "l2": "inputs larger than L2: each step streams a fresh minibatch of a >= 1 GB resident shard"}}
 
   # ------------------------------------------------------------------ reference arm (CPU)
@@ -263,8 +268,14 @@ def main():
   if rank == 0 and not a.no_parity:
     parity = parity_at_bench_shape(eng, cfg, X[:B], seed=rank)
 
-  from sisua_b200.distributed import OverlappedAllReduce
-  reducer = OverlappedAllReduce(eng)
+  from sisua_b200.distributed import OverlappedAllReduce, PeerExchange, broadcast_parameters
+  px = reducer = None
+  if world > 1:
+    if a.exchange == "peer":
+      px = PeerExchange(eng)          # moves the flat parameter / gradient buffers into symmetric (peer-mapped) memory
+    else:
+      reducer = OverlappedAllReduce(eng)
+    broadcast_parameters(eng.params, eng.bn_moving)
 
   # The headline loop issues exactly what SingleCellModel.fit(shuffle=True) issues per step: the minibatch is B row
   # indices (a fresh device permutation of the shard every epoch) into the HBM-resident matrix, gathered inside the
@@ -277,8 +288,11 @@ def main():
       perm[0] = torch.randperm(a.shard_cells, device=dev, generator=gen).to(torch.int32)     # next epoch
     step_no[0] += 1
     eng.train_step_gather(X, perm[0][j * B:(j + 1) * B], terms=terms, loss=loss, seed=rank, step=step_no[0])
-    scale = reducer()        # output-head gradients are reduced under the rest of the backward pass
-    eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=scale, t=step_no[0])
+    if px is not None:       # reduce-scatter + clipnorm + sharded Adam + all-gather: ONE kernel over NVLink peer memory
+      px.step(lr=1e-3, clipnorm=100.0, t=step_no[0])
+    else:
+      scale = reducer() if reducer is not None else 1.0     # NCCL: output-head gradients reduced under the rest of the backward
+      eng.adam_step(lr=1e-3, clipnorm=100.0, grad_scale=scale, t=step_no[0])
 
   def sync_all():
     if world > 1:
@@ -381,7 +395,7 @@ def main():
               max_batch=B, seed=8, device=local_rank, gemm_mode=mode)
   timing = {"skip": a.warmup}
   model.fit(sco, batch_size=B, max_iter=a.warmup + a.steps, epochs=10 ** 6, learning_rate=1e-3, clipnorm=100.0, data_on="host",
-            timing=timing, logging_interval=0, dp_shard=False)
+            timing=timing, logging_interval=0, dp_shard=False, dp_exchange=a.exchange)
   tt = torch.tensor([timing["seconds"]], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -146,6 +146,19 @@ int sisua_decode(sisua_handle h, const float* z, const float* lib, int R, float*
 int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta2, float eps_hat, float clipnorm,
                     float grad_scale, int64_t t, void* stream);
 
+/* Data-parallel optimiser step as ONE kernel over NVLink / NVSwitch peer memory: reduce-scatter of
+ * the flat gradient buffer by peer loads, per-variable clipnorm, Adam on this rank's shard (optimiser state is sharded),
+ * all-gather of the updated parameters by peer stores; the ranks meet at device-side barriers in symmetric memory.
+ * sisua_dp_bind: peer_*[r] = rank r's SYMMETRIC buffer as mapped into this process -- gradients and parameters
+ * [total_floats] (this rank's own must be the ones given to sisua_bind_buffers), a table of 8 x 48 doubles and 3 x 8 flag
+ * words (zero-initialised).  grid = CTAs of the kernel (0: one per SM; all must be resident; equal on every rank).
+ * sisua_adam_step_dp: every rank calls it once per step after sisua_train_step; no other collective is needed.
+ * sisua_dp_shard: the [begin, end) range of the flat buffers whose Adam moments this rank maintains. */
+int sisua_dp_bind(sisua_handle h, int rank, int world, void* const* peer_grads, void* const* peer_params, void* const* peer_sq,
+                  void* const* peer_flags, int grid);
+int sisua_adam_step_dp(sisua_handle h, float lr, float beta1, float beta2, float eps_hat, float clipnorm, int64_t t, void* stream);
+int sisua_dp_shard(sisua_handle h, int64_t* begin, int64_t* end);
+
 /* Workspace peeks for tests (device pointers valid until destroy): "d" decoder output [rows,H],
  * "delta1" first-layer pre-activation gradient. Returns NULL for unknown names. */
 const float* sisua_debug_buffer(sisua_handle h, const char* name);

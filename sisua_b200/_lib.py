@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step", "sisua_train_step_gather",
-           "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_dp_bind", "sisua_adam_step_dp", "sisua_dp_shard", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -69,6 +69,12 @@ def load():
   L.sisua_decode.restype = ci
   L.sisua_adam_step.argtypes = [vp, cf, cf, cf, cf, cf, cf, ctypes.c_int64, vp]
   L.sisua_adam_step.restype = ci
+  L.sisua_dp_bind.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ci]
+  L.sisua_dp_bind.restype = ci
+  L.sisua_adam_step_dp.argtypes = [vp, cf, cf, cf, cf, cf, ctypes.c_int64, vp]
+  L.sisua_adam_step_dp.restype = ci
+  L.sisua_dp_shard.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+  L.sisua_dp_shard.restype = ci
   L.sisua_debug_buffer.argtypes = [vp, ctypes.c_char_p]
   L.sisua_debug_buffer.restype = vp
   L.sisua_debug_copy.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64, vp]

@@ -11,6 +11,7 @@
 
 #include "../../include/sisua_b200.h"
 #include "adam.cuh"
+#include "dp_adam.cuh"
 #include "device_math.cuh"
 #include "kernels_mid.cuh"
 #include "kernels_unfused.cuh"
@@ -102,6 +103,10 @@ struct sisua_model {
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
   const int* ridx = nullptr;    // row gather of the current sisua_train_step_gather call (consumed by the tcgen05 kernels)
+  // data-parallel optimiser step over peer memory (sisua_dp_bind / sisua_adam_step_dp)
+  DpArgs dp;
+  bool dp_bound = false;
+  int dp_grid = 0;
   float* mw_logw = nullptr;     // importance weights of sisua_marginal_llk
   float* gx = nullptr;          // staging for gathered rows: counts (only the un-fused cross-check path needs them dense),
   float *gy = nullptr, *glib = nullptr;   // proteins, library statistics,
@@ -1373,6 +1378,68 @@ extern "C" int sisua_adam_step(sisua_handle h, float lr, float beta1, float beta
                                      clipnorm, h->cfg.clip_mode, grad_scale);
   LAUNCH_OK(h, "adam");
   sec_end(h, st, SEC_ADAM);
+  return SISUA_OK;
+}
+
+// ---- data-parallel optimiser step as one kernel over NVLink peer memory (dp_adam.cuh) -------------------------------
+// The host allocates four SYMMETRIC buffers per rank (same size on every rank, peer-mapped; torch's symmetric memory or
+// cudaIpc / VMM -- the library only sees pointers): the flat gradient buffer, the flat parameter buffer (both also bound
+// through sisua_bind_buffers), a table of kMaxRanks x 48 doubles and 3 x 8 flag words (zero-initialised).  peer_*[r] is
+// rank r's copy as mapped into THIS process.  grid: CTAs of the exchange kernel (0 = one per SM); all of them must be
+// resident at once, and every rank must use the same value.
+extern "C" int sisua_dp_bind(sisua_handle h, int rank, int world, void* const* peer_grads, void* const* peer_params,
+                             void* const* peer_sq, void* const* peer_flags, int grid) {
+  if (!h || !peer_grads || !peer_params || !peer_sq || !peer_flags) return SISUA_ERR_INVALID;
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) SET_ERR(h, SISUA_ERR_INVALID, "dp_bind: rank %d / world %d (at most %d ranks)", rank, world, kMaxRanks);
+  if (!h->M || !h->V) SET_ERR(h, SISUA_ERR_STATE, "dp_bind needs bound optimiser state");
+  if (peer_grads[rank] != (void*)h->Gd || peer_params[rank] != (void*)h->P)
+    SET_ERR(h, SISUA_ERR_INVALID, "dp_bind: this rank's symmetric gradient / parameter buffers must be the ones bound with sisua_bind_buffers");
+  memset(&h->dp, 0, sizeof(h->dp));
+  h->dp.rank = rank; h->dp.world = world;
+  for (int r = 0; r < world; ++r) {
+    h->dp.grads[r] = (float*)peer_grads[r]; h->dp.params[r] = (float*)peer_params[r];
+    h->dp.sqp[r] = (double*)peer_sq[r]; h->dp.flags[r] = (unsigned int*)peer_flags[r];
+  }
+  unsigned int* loc = nullptr; double* sql = nullptr;
+  int rc;
+  if ((rc = ws_alloc(h, &loc, 8)) != SISUA_OK || (rc = ws_alloc(h, &sql, kMaxSegments)) != SISUA_OK) return rc;
+  CUDA_OK(h, cudaMemset(loc, 0, 8 * sizeof(unsigned int)));
+  CUDA_OK(h, cudaMemset(sql, 0, kMaxSegments * sizeof(double)));
+  h->dp.local = loc; h->dp.sq_local = sql;
+  h->dp_grid = grid > 0 ? grid : h->num_sms;
+  int per_sm = 0;
+  CUDA_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_adam_kernel, 256, 0));
+  if (h->dp_grid > per_sm * h->num_sms) SET_ERR(h, SISUA_ERR_INVALID, "dp_bind: grid %d cannot be resident at once (%d CTAs fit)", h->dp_grid, per_sm * h->num_sms);
+  h->dp_bound = true;
+  return SISUA_OK;
+}
+
+// Replaces all-reduce + Adam.apply_gradients for data-parallel training: reduce-scatter over peer memory, clipnorm, Adam on
+// this rank's shard, all-gather of the updated parameters -- one kernel, graph-capturable.  Every rank must call it once
+// per step with the same arguments.  Optimiser state (m, v) is maintained for this rank's shard only.
+extern "C" int sisua_adam_step_dp(sisua_handle h, float lr, float beta1, float beta2, float eps_hat, float clipnorm, int64_t t,
+                                  void* stream) {
+  if (!h) return SISUA_ERR_INVALID;
+  if (!h->dp_bound) SET_ERR(h, SISUA_ERR_STATE, "adam_step_dp needs sisua_dp_bind");
+  cudaStream_t st = (cudaStream_t)stream;
+  sec_begin(h, st, SEC_ADAM);
+  DpArgs a = h->dp;
+  a.m = h->M; a.v = h->V; a.st = h->seg; a.total = h->total_floats; a.step = h->d_step; a.step_override = (long long)t;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps_hat = eps_hat; a.clipnorm = clipnorm; a.clip_mode = h->cfg.clip_mode;
+  ++h->launches;
+  dp_adam_kernel<<<h->dp_grid, 256, 0, st>>>(a);
+  LAUNCH_OK(h, "dp_adam_kernel");
+  sec_end(h, st, SEC_ADAM);
+  return SISUA_OK;
+}
+
+// [shard_begin, shard_end) of the flat buffers whose optimiser state this rank maintains under sisua_adam_step_dp
+extern "C" int sisua_dp_shard(sisua_handle h, int64_t* begin, int64_t* end) {
+  if (!h || !begin || !end) return SISUA_ERR_INVALID;
+  if (!h->dp_bound) SET_ERR(h, SISUA_ERR_STATE, "dp_shard needs sisua_dp_bind");
+  const long long n4 = (h->total_floats + 3) / 4, per4 = (n4 + h->dp.world - 1) / h->dp.world;
+  *begin = (int64_t)h->dp.rank * per4 * 4;
+  *end = h->dp.rank == h->dp.world - 1 ? h->total_floats : std::min<long long>(h->total_floats, *begin + per4 * 4);
   return SISUA_OK;
 }
 

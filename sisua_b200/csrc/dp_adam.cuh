@@ -1,0 +1,177 @@
+// Data-parallel optimiser step as ONE kernel over NVLink / NVSwitch peer memory:
+//   reduce-scatter of the flat gradient buffer (P2P loads from every rank's symmetric gradient buffer)
+//   -> per-variable clipnorm (partial sums of squares exchanged through a small symmetric table)
+//   -> Keras-formulation Adam on this rank's shard of the flat parameter buffer (optimiser state is sharded)
+//   -> all-gather (P2P stores of the updated shard into every rank's symmetric parameter buffer).
+// Every rank launches the same kernel on its own GPU; the ranks meet at three device-side barriers built from flag words
+// in symmetric memory (release / acquire at system scope).  No NCCL call, no host round trip: the step can live inside
+// one CUDA graph.  Gradients are 2 MB (2 000 genes), so the exchange is latency-bound: ~10 us of barriers plus ~2 x 2 MB
+// over NVLink per rank, against two eager NCCL all-reduces (~90 us at 8 GPUs, measured in round 1).
+#pragma once
+#include "adam.cuh"
+
+namespace sisua {
+
+constexpr int kMaxRanks = 8;
+
+struct DpArgs {
+  int rank, world;
+  float* grads[kMaxRanks];           // symmetric gradient buffers, [r] = rank r's (own buffer at [rank])
+  float* params[kMaxRanks];          // symmetric parameter buffers
+  double* sqp[kMaxRanks];            // symmetric [kMaxRanks][kMaxSegments]: row s = partial sums of squares computed by rank s
+  unsigned int* flags[kMaxRanks];    // symmetric [3][kMaxRanks] epoch words: flags[dst][phase][src]
+  float* m; float* v;                // local optimiser state (only this rank's shard is maintained)
+  SegTable st;
+  long long total;
+  long long* step; long long step_override;
+  float lr, b1, b2, eps_hat, clipnorm;
+  int clip_mode;
+  unsigned int* local;               // local scratch words: [0] grid-barrier counter, [1] release word, [2] epoch
+  double* sq_local;                  // [kMaxSegments] local partial sums (zero on entry, re-zeroed on exit)
+};
+
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of this rank and (through CTA 0) all ranks: nobody passes before everybody has arrived and everybody's prior
+// writes (local and to peers) are visible.  `phase` in 0..2, `epoch` >= 1 monotone across calls.  Bounded spins.
+__device__ __forceinline__ void dp_barrier(const DpArgs& a, unsigned int epoch, int phase) {
+  __syncthreads();
+  const unsigned int ticket = (epoch - 1u) * 3u + (unsigned int)phase + 1u;          // 1, 2, 3, ... over the whole run
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(&a.local[0], 1u);
+    if (blockIdx.x == 0) {
+      unsigned int spins = 0;
+      while (ld_acquire_gpu(&a.local[0]) < ticket * gridDim.x) { if (++spins > (1u << 28)) __trap(); }
+      for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + phase * kMaxRanks + a.rank, epoch);
+      for (int r = 0; r < a.world; ++r) {
+        spins = 0;
+        while (ld_acquire_sys(a.flags[a.rank] + phase * kMaxRanks + r) < epoch) { if (++spins > (1u << 28)) __trap(); }
+      }
+      __threadfence_system();
+      atomicExch(&a.local[1], ticket);
+    }
+    unsigned int spins = 0;
+    while (ld_acquire_gpu(&a.local[1]) < ticket) { if (++spins > (1u << 28)) __trap(); }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
+  __shared__ double part[kMaxSegments];
+  __shared__ float seg_scale[kMaxSegments];
+  __shared__ float lr_t_s;
+  const unsigned int epoch = a.local[2] + 1u;       // (written only at the very end of the previous call)
+  const int W = a.world;
+  // shard [lo, hi): whole float4s, the last rank takes the remainder
+  const long long n4 = (a.total + 3) / 4, per4 = (n4 + W - 1) / W;
+  const long long lo = (long long)a.rank * per4 * 4, hi = a.rank == W - 1 ? a.total : min(a.total, lo + per4 * 4);
+  const float inv_w = 1.0f / (float)W;
+  for (int i = threadIdx.x; i < a.st.n; i += blockDim.x) part[i] = 0.0;
+
+  // ---- every rank's gradients are final (its backward kernels precede this one on its stream)
+  dp_barrier(a, epoch, 0);
+
+  // ---- reduce-scatter: this rank's shard summed over all ranks, mean written back in place; partial squared norms
+  for (long long o = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; o < hi; o += (long long)gridDim.x * blockDim.x * 4) {
+    float4 s = ld_volatile_f4(a.grads[a.rank] + o);
+    for (int k = 1; k < W; ++k) {                     // start at a different peer on every rank: spreads the NVLink traffic
+      const float4 q = ld_volatile_f4(a.grads[(a.rank + k) % W] + o);
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
+    *reinterpret_cast<float4*>(a.grads[a.rank] + o) = s;
+    const double sq = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+    if (sq != 0.0) atomicAdd(&part[find_segment(a.st, o)], sq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.st.n; i += blockDim.x)
+    if (part[i] != 0.0) atomicAdd(&a.sq_local[i], part[i]);
+  // local grid barrier (phase-1 barrier below also is one, but the partials must be complete BEFORE they are published)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&a.local[3], 1u) + 1u;
+    if (done == epoch * gridDim.x) {                  // last CTA of this rank: publish this rank's row to every peer
+      for (int r = 0; r < W; ++r)
+        for (int i = 0; i < a.st.n; ++i) a.sqp[r][a.rank * kMaxSegments + i] = ld_volatile_f64(&a.sq_local[i]);
+      for (int i = 0; i < a.st.n; ++i) a.sq_local[i] = 0.0;      // ready for the next call
+      __threadfence_system();
+      atomicExch(&a.local[4], epoch);
+    }
+    unsigned int spins = 0;
+    while (ld_acquire_gpu(&a.local[4]) < epoch) { if (++spins > (1u << 28)) __trap(); }
+  }
+  dp_barrier(a, epoch, 1);
+
+  // ---- clip scales (per variable over ALL ranks' partial sums), Keras / TF learning rate, sharded Adam, all-gather
+  if (threadIdx.x < a.st.n) {
+    float scale = 1.f;
+    if (a.clipnorm > 0.f) {
+      double n2 = 0.0;
+      if (a.clip_mode == 0) {
+        for (int r = 0; r < W; ++r) n2 += ld_volatile_f64(&a.sqp[a.rank][r * kMaxSegments + threadIdx.x]);
+      } else {
+        for (int r = 0; r < W; ++r)
+          for (int i = 0; i < a.st.n; ++i) n2 += ld_volatile_f64(&a.sqp[a.rank][r * kMaxSegments + i]);
+      }
+      const double nrm = sqrt(n2);
+      if (nrm > (double)a.clipnorm) scale = (float)((double)a.clipnorm / nrm);
+    }
+    seg_scale[threadIdx.x] = scale;
+  }
+  if (threadIdx.x == 0) {
+    const long long t = a.step_override > 0 ? a.step_override : (*a.step + 1);
+    lr_t_s = (float)((double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t)));
+  }
+  __syncthreads();
+  const float lr_t = lr_t_s, b1 = a.b1, b2 = a.b2;
+  for (long long o = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; o < hi; o += (long long)gridDim.x * blockDim.x * 4) {
+    const float scale = seg_scale[find_segment(a.st, o)];
+    const float4 gv = *reinterpret_cast<const float4*>(a.grads[a.rank] + o);
+    const float4 mv = *reinterpret_cast<const float4*>(a.m + o), vv = *reinterpret_cast<const float4*>(a.v + o);
+    const float4 pv = *reinterpret_cast<const float4*>(a.params[a.rank] + o);
+    float ga[4] = {gv.x * scale, gv.y * scale, gv.z * scale, gv.w * scale};
+    float ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, pa[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
+      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
+      pa[k] -= lr_t * ma[k] / (sqrtf(va[k]) + a.eps_hat);
+    }
+    *reinterpret_cast<float4*>(a.m + o) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(a.v + o) = make_float4(va[0], va[1], va[2], va[3]);
+    const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    for (int k = 0; k < W; ++k) *reinterpret_cast<float4*>(a.params[(a.rank + k) % W] + o) = pn;
+  }
+  // ---- every rank's parameter buffer is complete before anybody's next forward pass reads it
+  dp_barrier(a, epoch, 2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *a.step = a.step_override > 0 ? a.step_override : (*a.step + 1);
+    a.local[2] = epoch;
+  }
+}
+
+}  // namespace sisua

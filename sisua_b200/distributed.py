@@ -74,3 +74,53 @@ class OverlappedAllReduce:
       w2.wait()
     main.wait_stream(self.side)
     return 1.0 / dist.get_world_size()
+
+
+class PeerExchange:
+  """Gradient exchange + optimiser as ONE kernel over NVLink peer memory (csrc/dp_adam.cuh, `sisua_adam_step_dp`):
+  reduce-scatter by peer loads -> per-variable clipnorm -> Adam on this rank's shard -> all-gather by peer stores.
+
+  torch is only the plumbing: `torch.distributed._symmetric_memory` allocates the four symmetric buffers (flat gradients,
+  flat parameters, the partial-norm table, the flag words) and exchanges the peer mappings; the engine's parameter and
+  gradient buffers are moved into them.  After this, a data-parallel step is `train_step` + `adam_step_dp` -- no NCCL call
+  on the data path, and the whole step can be captured in one CUDA graph."""
+
+  def __init__(self, engine, group=None, grid: int = 0):
+    import torch.distributed._symmetric_memory as symm
+    if not (dist.is_available() and dist.is_initialized()):
+      raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+    group = group or dist.group.WORLD
+    self.eng, self.world, self.rank = engine, dist.get_world_size(group), dist.get_rank(group)
+    if self.world > 8:
+      raise ValueError("the peer-memory optimiser step supports up to 8 ranks (one NVSwitch box)")
+    dev, total = engine.device, engine.total
+    with torch.cuda.device(dev):
+      self.params = symm.empty(total, dtype=torch.float32, device=dev)
+      self.grads = symm.empty(total, dtype=torch.float32, device=dev)
+      self.sq = symm.empty(8 * 48, dtype=torch.float64, device=dev)
+      self.flags = symm.empty(64, dtype=torch.int32, device=dev)
+      self.sq.zero_(); self.flags.zero_()
+      handles = [symm.rendezvous(t, group.group_name) for t in (self.grads, self.params, self.sq, self.flags)]
+    ptrs = []
+    for t, hd in zip((self.grads, self.params, self.sq, self.flags), handles):
+      off = int(getattr(hd, "offset", 0) or 0)
+      p = [int(b) + off for b in hd.buffer_ptrs]
+      if p[self.rank] != t.data_ptr():
+        raise RuntimeError("symmetric-memory handle does not describe the tensor it was made for")
+      ptrs.append(p)
+    self._handles = handles
+    engine.rebind(self.params, self.grads)
+    torch.cuda.synchronize(dev)
+    dist.barrier(group)                      # every rank's buffers are initialised before anybody's kernel touches them
+    engine.dp_bind(self.rank, self.world, *ptrs, grid=grid)
+    self.shard = engine.dp_shard()
+
+  def step(self, lr=1e-3, clipnorm=100.0, t=0):
+    self.eng.adam_step_dp(lr=lr, clipnorm=clipnorm, t=t)
+
+  def gather_optimizer_state(self):
+    """Adam moments are maintained per shard; assemble the full vectors on every rank (checkpointing)."""
+    b, e = self.shard
+    for t in (self.eng.adam_m, self.eng.adam_v):
+      t[:b].zero_(); t[e:].zero_()
+      dist.all_reduce(t, op=dist.ReduceOp.SUM)

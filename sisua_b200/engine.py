@@ -134,6 +134,31 @@ class Engine:
                                            int(t), self._stream()))
     self.step_count = t if t > 0 else self.step_count + 1
 
+  # ---- data-parallel optimiser step over peer memory ---------------------------------------------------------------
+  def rebind(self, params: torch.Tensor, grads: torch.Tensor):
+    """Move the flat parameter / gradient buffers into caller-provided (symmetric) device memory."""
+    params.copy_(self.params)
+    grads.zero_()
+    self.params, self.grads = params, grads
+    self._check(self.lib.sisua_bind_buffers(self.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
+                                            _ptr(self.bn_moving)))
+
+  def dp_bind(self, rank: int, world: int, peer_grads, peer_params, peer_sq, peer_flags, grid: int = 0):
+    """sisua_dp_bind: lists of `world` device pointers (ints) to every rank's symmetric buffers."""
+    arr = lambda ps: (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in ps])
+    self._dp_keep = (arr(peer_grads), arr(peer_params), arr(peer_sq), arr(peer_flags))
+    self._check(self.lib.sisua_dp_bind(self.handle, int(rank), int(world), *self._dp_keep, int(grid)))
+
+  def adam_step_dp(self, lr=1e-3, beta1=0.9, beta2=0.999, eps_hat=1e-7, clipnorm=100.0, t=0):
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_adam_step_dp(self.handle, lr, beta1, beta2, eps_hat, clipnorm or 0.0, int(t), self._stream()))
+    self.step_count = t if t > 0 else self.step_count + 1
+
+  def dp_shard(self):
+    b, e = ctypes.c_int64(0), ctypes.c_int64(0)
+    self._check(self.lib.sisua_dp_shard(self.handle, ctypes.byref(b), ctypes.byref(e)))
+    return int(b.value), int(e.value)
+
   def infer(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, S=1, want_mean=True,
             want_disp=False, want_pi=False) -> Dict[str, torch.Tensor]:
     cfg = self.cfg

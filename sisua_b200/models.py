@@ -413,6 +413,9 @@ class SingleCellModel:
                          "variables description.")
     # the remaining keys of configs/base.yaml:45-62 are honoured or rejected, never silently swallowed
     dp_shard = bool(kwargs.pop("dp_shard", True))     # data parallel: False = `train` already is this rank's shard
+    dp_exchange = str(kwargs.pop("dp_exchange", "peer"))   # 'peer': one kernel over NVLink peer memory; 'nccl': all-reduce + Adam
+    if dp_exchange not in ("peer", "nccl"):
+      raise ValueError("dp_exchange must be 'peer' or 'nccl'")
     valid_interval = float(kwargs.pop("valid_interval", 0) or 0)          # seconds between validation passes (0: valid_freq only)
     allow_rollback = bool(kwargs.pop("allow_rollback", False))            # restore the best validated weights when stopping
     if int(kwargs.pop("earlystop_progress_length", 0) or 0) != 0:
@@ -436,14 +439,18 @@ class SingleCellModel:
     import torch.distributed as dist
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank() if world > 1 else 0
-    if world > 1 and not dp_shard:
-      DP.broadcast_parameters(eng.params, eng.bn_moving)
+    px = None
+    if world > 1 and dp_exchange == "peer":
+      px = getattr(self, "_peer_exchange", None)
+      if px is None:
+        px = self._peer_exchange = DP.PeerExchange(eng)    # moves params / grads into symmetric memory
     if world > 1 and dp_shard:
       b0, e0 = DP.shard_range(len(train), rank, world)
       n_common = len(train) // world                      # every rank takes the same number of steps
       train = train._take(np.arange(b0, b0 + n_common), train.name, recompute_library=False)
+    if world > 1:
       DP.broadcast_parameters(eng.params, eng.bn_moving)
-    reducer = DP.OverlappedAllReduce(eng)
+    reducer = DP.OverlappedAllReduce(eng) if px is None else None
     B = int(batch_size)
     if B > eng.cfg.max_batch:
       raise ValueError(f"batch_size {B} > max_batch {eng.cfg.max_batch}")
@@ -509,8 +516,9 @@ class SingleCellModel:
         self.step += 1
         if host_stream:
           xb, extras = hds.batch(ep, s)
-          host_losses.append(pipe.step(xb, None, step=self.step, lr=lr, clipnorm=cn, world=world,
-                                       allreduce=(lambda g: dist.all_reduce(g)) if world > 1 else None, seed=step_seed, **extras))
+          host_losses.append(pipe.step(xb, None, step=self.step, lr=lr, clipnorm=cn, world=world, peer=px,
+                                       allreduce=(lambda g: dist.all_reduce(g)) if (world > 1 and px is None) else None,
+                                       seed=step_seed, **extras))
         elif graphed is not None:
           graphed.step(perm[s * B:(s + 1) * B])
         else:
@@ -518,8 +526,11 @@ class SingleCellModel:
           # and draw the reparameterisation noise in-kernel (no per-step torch kernels on the hot path)
           eng.train_step_gather(cache["x"], perm[s * B:(s + 1) * B], y_all=cache.get("y"), library_all=cache.get("library"),
                                 mask_all=cache.get("mask"), terms=terms, loss=loss, seed=step_seed, step=self.step)
-          gscale = reducer()
-          eng.adam_step(lr=lr, clipnorm=cn, grad_scale=gscale, t=self.step)
+          if px is not None:      # reduce-scatter + clip + sharded Adam + all-gather: one kernel over peer memory
+            px.step(lr=lr, clipnorm=cn, t=self.step)
+          else:
+            gscale = reducer()
+            eng.adam_step(lr=lr, clipnorm=cn, grad_scale=gscale, t=self.step)
         done += 1
         if logging_interval and done % int(logging_interval) == 0 and not host_stream:
           log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
@@ -587,6 +598,8 @@ class SingleCellModel:
         t.copy_(b_)
     if world > 1:
       DP.average_moving_statistics(eng.bn_moving)
+      if px is not None:
+        px.gather_optimizer_state()      # the Adam moments were maintained per shard
     torch.cuda.current_stream(eng.device).synchronize()
     self.is_fitted = True
     return self

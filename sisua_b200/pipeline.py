@@ -185,9 +185,9 @@ class HostTrainPipeline:
     return self.slots[s]
 
   def _graph(self, s: int, fmt: str, lr: float, clipnorm: float, world: int = 1, split: bool = False, seed: int = 0,
-             with_eps: bool = True):
+             with_eps: bool = True, peer: bool = False):
     """(graph, None), or (backward graph, optimiser graph) when an all-reduce sits between them."""
-    key = (s, fmt, float(lr), float(clipnorm), int(world), bool(split), int(seed), bool(with_eps))
+    key = (s, fmt, float(lr), float(clipnorm), int(world), bool(split), int(seed), bool(with_eps), bool(peer))
     if key not in self.graphs:
       eng, sl = self.eng, self._slot(s)
       def fwd_bwd():
@@ -199,7 +199,10 @@ class HostTrainPipeline:
         eng.train_step(sl["x"], eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
                        loss=sl["loss"], seed=seed, step=-1)
       def optimise():
-        eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=0)
+        if peer:       # data parallel over peer memory: the exchange is part of the optimiser kernel (and of the graph)
+          eng.adam_step_dp(lr=lr, clipnorm=clipnorm, t=0)
+        else:
+          eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=0)
         self.host_loss[s].copy_(sl["loss"], non_blocking=True)
       if not split:
         self.graphs[key] = (_capture_step(eng, lambda: (fwd_bwd(), optimise())), None)
@@ -210,7 +213,7 @@ class HostTrainPipeline:
     return self.graphs[key]
 
   def step(self, x_host, eps_host: Optional[torch.Tensor], step: int, lr: float = 1e-3, clipnorm: float = 100.0,
-           world: int = 1, allreduce: Optional[Callable] = None, seed: int = 0, **host_extras):
+           world: int = 1, allreduce: Optional[Callable] = None, seed: int = 0, peer=None, **host_extras):
     """Enqueue one train step; returns the pinned host tensor that will hold the loss once the stream has drained
     (read it after `flush`; it is reused `depth` steps later)."""
     eng = self.eng
@@ -222,6 +225,9 @@ class HostTrainPipeline:
       out = self.host_loss[self.i % len(self.host_loss)]
       self.i += 1
       eng.train_step_host(x_host, eps_z=eps_host, host_loss=out, seed=seed, step=step, **host_extras)
+      if peer is not None:
+        eng.adam_step_dp(lr=lr, clipnorm=clipnorm, t=step)
+        return out
       if allreduce is not None:
         allreduce(eng.grads)
       eng.adam_step(lr=lr, clipnorm=clipnorm, grad_scale=1.0 / world, t=step)
@@ -236,7 +242,7 @@ class HostTrainPipeline:
                    torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
     if fmt == "u16" and sl["x16"] is None:
       sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
-    graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None, seed, eps_host is not None)
+    graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None, seed, eps_host is not None, peer is not None)
     if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
       eng.reset_step_counter(step - 1)
     main = torch.cuda.current_stream(eng.device)

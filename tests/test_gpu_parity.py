@@ -542,3 +542,57 @@ def test_tfp_parameterised_output_enums(x_dist, model, kw, mode):
   _close(out["disp"].cpu().numpy(), ref["theta"].numpy(), atol=1e-7, what="total_count")
   assert (out["pi_logit"] is not None) == (x_dist == "zinb")
   eng.close()
+
+
+def _flat_device_buffers(total):
+  z = lambda dt, n: torch.zeros(n, dtype=dt, device="cuda")
+  return z(torch.float32, total), z(torch.float32, total), z(torch.float64, 8 * 48), z(torch.int32, 64)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_peer_memory_optimizer_step_equals_allreduce_plus_adam(world):
+  """sisua_adam_step_dp (reduce-scatter over peer loads -> clipnorm -> sharded Adam -> all-gather by peer stores, one
+  kernel per rank, device-side barriers) against all-reduce(mean) + sisua_adam_step.  The `world` ranks are simulated on
+  ONE GPU: one engine and one stream per rank, plain device buffers standing in for the symmetric memory, small grids so
+  that all kernels are resident together (they wait for each other)."""
+  from sisua_b200.engine import Engine
+  cfg = C.make_step_config("vae", n_genes=203, max_batch=128, input_dropout=0.2)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg)); mov = PR.init_bn_moving(cfg)
+  ranks = [Engine(cfg, 0, flat_params=flat, bn_moving=mov) for _ in range(world)]
+  ref = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  total = ref.total
+  bufs = [_flat_device_buffers(total) for _ in range(world)]
+  for r, e in enumerate(ranks):
+    e.rebind(bufs[r][1], bufs[r][0])
+  for r, e in enumerate(ranks):
+    e.dp_bind(r, world, [b[0].data_ptr() for b in bufs], [b[1].data_ptr() for b in bufs], [b[2].data_ptr() for b in bufs],
+              [b[3].data_ptr() for b in bufs], grid=24)
+  streams = [torch.cuda.Stream() for _ in range(world)]
+  T = 4
+  for t in range(1, T + 1):
+    gsum = torch.zeros(total, device="cuda")
+    for r, e in enumerate(ranks):
+      batch = Hh.make_batch(cfg, 96, seed=10 * t + r)
+      e.train_step(seed=r, step=t, **batch)
+      gsum += e.grads
+    # clipnorm small enough to bite on some variables
+    torch.cuda.synchronize()
+    ref.grads.copy_(gsum / world)
+    ref.adam_step(lr=1e-3, clipnorm=0.05, t=t)
+    for r, e in enumerate(ranks):
+      with torch.cuda.stream(streams[r]):
+        e.adam_step_dp(lr=1e-3, clipnorm=0.05, t=t)
+    torch.cuda.synchronize()
+    for r, e in enumerate(ranks):
+      d = (e.params - ref.params).abs().max().item()
+      assert d <= 2e-6, f"step {t} rank {r}: parameters differ from all-reduce + Adam by {d:.3e}"
+  # the shards tile the buffer and each rank's moments equal the reference's on its shard
+  cover = torch.zeros(total, device="cuda")
+  for e in ranks:
+    b, en = e.dp_shard()
+    cover[b:en] += 1
+    assert torch.allclose(e.adam_m[b:en], ref.adam_m[b:en], rtol=1e-5, atol=1e-9)
+    assert torch.allclose(e.adam_v[b:en], ref.adam_v[b:en], rtol=1e-5, atol=1e-12)
+  assert bool((cover == 1).all())
+  for e in ranks + [ref]:
+    e.close()
