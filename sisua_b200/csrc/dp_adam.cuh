@@ -54,77 +54,88 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
-// All CTAs of this rank and (through CTA 0) all ranks: nobody passes before everybody has arrived and everybody's prior
-// writes (local and to peers) are visible.  `phase` in 0..2, `epoch` >= 1 monotone across calls.  Bounded spins.
-__device__ __forceinline__ void dp_barrier(const DpArgs& a, unsigned int epoch, int phase) {
-  __syncthreads();
-  const unsigned int ticket = (epoch - 1u) * 3u + (unsigned int)phase + 1u;          // 1, 2, 3, ... over the whole run
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    atomicAdd(&a.local[0], 1u);
-    if (blockIdx.x == 0) {
-      unsigned int spins = 0;
-      while (ld_acquire_gpu(&a.local[0]) < ticket * gridDim.x) { if (++spins > (1u << 28)) __trap(); }
-      for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + phase * kMaxRanks + a.rank, epoch);
-      for (int r = 0; r < a.world; ++r) {
-        spins = 0;
-        while (ld_acquire_sys(a.flags[a.rank] + phase * kMaxRanks + r) < epoch) { if (++spins > (1u << 28)) __trap(); }
-      }
-      __threadfence_system();
-      atomicExch(&a.local[1], ticket);
-    }
-    unsigned int spins = 0;
-    while (ld_acquire_gpu(&a.local[1]) < ticket) { if (++spins > (1u << 28)) __trap(); }
-  }
-  __syncthreads();
+__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int v, bool sys) {
+  unsigned int spins = 0;
+  while ((sys ? ld_acquire_sys(p) : ld_acquire_gpu(p)) < v) { if (++spins > (1u << 28)) __trap(); }     // bounded: a protocol bug traps
 }
 
+// Protocol of one call (epoch e, monotone over the run; flag word [phase][src] on rank dst = "src reached phase in epoch e"):
+//   phase 0  CTA 0 tells every rank "my gradients are final" (they were produced by earlier kernels of this stream);
+//            every CTA waits for all ranks' phase-0 words before it loads peer gradients;
+//   phase 1  after the local grid barrier CTA 0 publishes this rank's partial squared norms to every rank and raises its
+//            phase-1 word; everybody continues once all ranks' words are up (then the table is complete everywhere);
+//   phase 2  every CTA fences its peer stores (updated parameters) at system scope and arrives; CTA 0 raises the phase-2
+//            word and leaves only when all ranks' words are up, so the kernel completes -- and the next forward pass may
+//            read the parameters -- only after every rank's shard has landed here.  The other CTAs exit at once.
 __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
   __shared__ double part[kMaxSegments];
   __shared__ float seg_scale[kMaxSegments];
   __shared__ float lr_t_s;
   const unsigned int epoch = a.local[2] + 1u;       // (written only at the very end of the previous call)
   const int W = a.world;
+  const unsigned int* my_flags = a.flags[a.rank];
   // shard [lo, hi): whole float4s, the last rank takes the remainder
   const long long n4 = (a.total + 3) / 4, per4 = (n4 + W - 1) / W;
   const long long lo = (long long)a.rank * per4 * 4, hi = a.rank == W - 1 ? a.total : min(a.total, lo + per4 * 4);
   const float inv_w = 1.0f / (float)W;
   for (int i = threadIdx.x; i < a.st.n; i += blockDim.x) part[i] = 0.0;
 
-  // ---- every rank's gradients are final (its backward kernels precede this one on its stream)
-  dp_barrier(a, epoch, 0);
+  // ---- phase 0: every rank's gradients are final
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0)
+      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 0 * kMaxRanks + a.rank, epoch);
+    for (int r = 0; r < W; ++r) spin_until(my_flags + 0 * kMaxRanks + r, epoch, true);
+  }
+  __syncthreads();
 
   // ---- reduce-scatter: this rank's shard summed over all ranks, mean written back in place; partial squared norms
-  for (long long o = lo + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; o < hi; o += (long long)gridDim.x * blockDim.x * 4) {
-    float4 s = ld_volatile_f4(a.grads[a.rank] + o);
-    for (int k = 1; k < W; ++k) {                     // start at a different peer on every rank: spreads the NVLink traffic
-      const float4 q = ld_volatile_f4(a.grads[(a.rank + k) % W] + o);
-      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+  // (whole warps iterate together so that the warp-level reduction below can use full-mask shuffles)
+  for (long long w0 = lo + ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4; w0 < hi; w0 += (long long)gridDim.x * blockDim.x * 4) {
+    const long long o = w0 + (threadIdx.x & 31) * 4;
+    double sq = 0.0;
+    int seg = -1;
+    if (o < hi) {
+      float4 s = ld_volatile_f4(a.grads[a.rank] + o);
+      for (int k = 1; k < W; ++k) {                     // start at a different peer on every rank: spreads the NVLink traffic
+        const float4 q = ld_volatile_f4(a.grads[(a.rank + k) % W] + o);
+        s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+      }
+      s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
+      *reinterpret_cast<float4*>(a.grads[a.rank] + o) = s;
+      sq = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+      seg = find_segment(a.st, o);
     }
-    s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
-    *reinterpret_cast<float4*>(a.grads[a.rank] + o) = s;
-    const double sq = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
-    if (sq != 0.0) atomicAdd(&part[find_segment(a.st, o)], sq);
+    // a warp covers 128 consecutive floats: almost always one variable -> one shared atomic per warp
+    const int seg0 = __shfl_sync(0xffffffffu, seg, 0);
+    if (__all_sync(0xffffffffu, seg == seg0 || seg < 0)) {
+      sq = warp_sum(sq);
+      if ((threadIdx.x & 31) == 0 && seg0 >= 0 && sq != 0.0) atomicAdd(&part[seg0], sq);
+    } else if (seg >= 0 && sq != 0.0) {
+      atomicAdd(&part[seg], sq);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < a.st.n; i += blockDim.x)
     if (part[i] != 0.0) atomicAdd(&a.sq_local[i], part[i]);
-  // local grid barrier (phase-1 barrier below also is one, but the partials must be complete BEFORE they are published)
+
+  // ---- phase 1: grid barrier; CTA 0 publishes this rank's partial norms; all ranks' tables complete
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int done = atomicAdd(&a.local[3], 1u) + 1u;
-    if (done == epoch * gridDim.x) {                  // last CTA of this rank: publish this rank's row to every peer
-      for (int r = 0; r < W; ++r)
-        for (int i = 0; i < a.st.n; ++i) a.sqp[r][a.rank * kMaxSegments + i] = ld_volatile_f64(&a.sq_local[i]);
-      for (int i = 0; i < a.st.n; ++i) a.sq_local[i] = 0.0;      // ready for the next call
+    atomicAdd(&a.local[0], 1u);
+    if (blockIdx.x == 0) {
+      spin_until(&a.local[0], (2u * epoch - 1u) * gridDim.x, false);
+      for (int i = 0; i < a.st.n; ++i) {
+        const double v = ld_volatile_f64(&a.sq_local[i]);
+        for (int r = 0; r < W; ++r) a.sqp[r][a.rank * kMaxSegments + i] = v;
+        a.sq_local[i] = 0.0;                           // ready for the next call
+      }
       __threadfence_system();
-      atomicExch(&a.local[4], epoch);
+      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 1 * kMaxRanks + a.rank, epoch);
     }
-    unsigned int spins = 0;
-    while (ld_acquire_gpu(&a.local[4]) < epoch) { if (++spins > (1u << 28)) __trap(); }
+    for (int r = 0; r < W; ++r) spin_until(my_flags + 1 * kMaxRanks + r, epoch, true);
   }
-  dp_barrier(a, epoch, 1);
+  __syncthreads();
 
   // ---- clip scales (per variable over ALL ranks' partial sums), Keras / TF learning rate, sharded Adam, all-gather
   if (threadIdx.x < a.st.n) {
@@ -166,11 +177,19 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
     const float4 pn = make_float4(pa[0], pa[1], pa[2], pa[3]);
     for (int k = 0; k < W; ++k) *reinterpret_cast<float4*>(a.params[(a.rank + k) % W] + o) = pn;
   }
-  // ---- every rank's parameter buffer is complete before anybody's next forward pass reads it
-  dp_barrier(a, epoch, 2);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *a.step = a.step_override > 0 ? a.step_override : (*a.step + 1);
-    a.local[2] = epoch;
+
+  // ---- phase 2: every rank's parameter buffer is complete before anybody's next forward pass reads it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                            // this CTA's stores into the peers' parameter buffers
+    atomicAdd(&a.local[0], 1u);
+    if (blockIdx.x == 0) {
+      spin_until(&a.local[0], 2u * epoch * gridDim.x, false);
+      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 2 * kMaxRanks + a.rank, epoch);
+      for (int r = 0; r < W; ++r) spin_until(my_flags + 2 * kMaxRanks + r, epoch, true);
+      *a.step = a.step_override > 0 ? a.step_override : (*a.step + 1);
+      a.local[2] = epoch;
+    }
   }
 }
 

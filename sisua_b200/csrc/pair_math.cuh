@@ -44,9 +44,15 @@ PM_HD F2 bc(float a) { return mk(a, a); }
 #if PM_DEVICE_CODE
 __device__ __forceinline__ float2 as2(F2 a) { return make_float2(a.x, a.y); }
 __device__ __forceinline__ F2 fr2(float2 a) { return mk(a.x, a.y); }
+#ifdef SISUA_PM_SCALAR      // experiment: two scalar instructions instead of one packed fp32x2 instruction
+__device__ __forceinline__ F2 add(F2 a, F2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ F2 mul(F2 a, F2 b) { return mk(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return mk(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
 __device__ __forceinline__ F2 add(F2 a, F2 b) { return fr2(__fadd2_rn(as2(a), as2(b))); }
 __device__ __forceinline__ F2 mul(F2 a, F2 b) { return fr2(__fmul2_rn(as2(a), as2(b))); }
 __device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return fr2(__ffma2_rn(as2(a), as2(b), as2(c))); }
+#endif
 __device__ __forceinline__ float ex2s(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2s(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcps(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -37,3 +37,18 @@ eng.profile(True)
 for i in range(50): step(200 + i)
 prof = eng.profile_read()
 print(f"{os.environ.get('SISUA_NVCC_DEFS', '')!r}: step {total:.4f} ms  " + "  ".join(f"{k} {v[0] / 50:.4f}" for k, v in prof.items()) + f"  loss {float(loss):.3f}", flush=True)
+
+# ---- single-rank cost of the peer-memory optimiser kernel (world = 1: the exchange degenerates to barriers with itself)
+if len(sys.argv) > 4 and sys.argv[4] == "dp1":
+  z = lambda dt, n: torch.zeros(n, dtype=dt, device=dev)
+  g, p_, sq, fl = z(torch.float32, eng.total), z(torch.float32, eng.total), z(torch.float64, 8 * 48), z(torch.int32, 64)
+  eng.rebind(p_, g)
+  eng.dp_bind(0, 1, [g.data_ptr()], [p_.data_ptr()], [sq.data_ptr()], [fl.data_ptr()], grid=0)
+  def step_dp(i):
+    eng.train_step(X[(i % 4) * B:(i % 4 + 1) * B], terms=terms, loss=loss, seed=1, step=i + 1, **extra)
+    eng.adam_step_dp(t=i + 1)
+  for i in range(5): step_dp(1000 + i)
+  eng.profile(True)
+  for i in range(50): step_dp(2000 + i)
+  prof = eng.profile_read()
+  print("dp1 (world 1):", "  ".join(f"{k} {v[0] / 50:.4f}" for k, v in prof.items()), flush=True)
