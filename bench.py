@@ -150,7 +150,7 @@ class ClockSampler:
 
 
 def ncu_entry(kernel, B, G):
-  p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+  p = os.path.join(ROOT, "profiles", "r2_traffic.json")
   if not os.path.exists(p):
     return None
   with open(p) as f:
@@ -160,8 +160,8 @@ def ncu_entry(kernel, B, G):
 
 def ncu_traffic(kernel, B, G):
   """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-  (profiles/r1_traffic.json), if it was taken at this batch / gene count."""
-  p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+  (profiles/r2_traffic.json), if it was taken at this batch / gene count."""
+  p = os.path.join(ROOT, "profiles", "r2_traffic.json")
   if not os.path.exists(p):
     return None
   with open(p) as f:
