@@ -697,6 +697,13 @@ extern "C" int sisua_debug_copy(sisua_handle h, const char* name, float* dst, in
 // Launch geometry of the tcgen05 kernels for a train step of B cells (tests assert the walk depths they claim to cover).
 // out[9] = first layer (cell tiles, k-chunks, k-blocks per chunk) | output heads (cell tiles, gene chunks, gene tiles per
 // chunk) | first-layer weight gradient (gene tiles, cell chunks, cell tiles per chunk).  Zeros without the tcgen05 path.
+#ifdef SISUA_OUT_TRACE
+// development aid, only in -DSISUA_OUT_TRACE builds (not declared in include/sisua_b200.h): copies the clock stamps of CTA 0
+extern "C" int sisua_debug_out_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, sisua::tc::g_out_trace, sizeof(long long) * 4 * 64 * 8) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" int sisua_debug_geometry(sisua_handle h, int B, int32_t* out) {
   if (!h || !out || B < 1) return SISUA_ERR_INVALID;
   for (int i = 0; i < 9; ++i) out[i] = 0;

@@ -29,6 +29,15 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kOutThreads = kEpiThreads + 128;
 constexpr int kOutRegsService = 32, kOutRegsEpilogue = 112;
 constexpr int kMmaWarp = kEpiWarps, kLoadWarp = kEpiWarps + 1, kGradWarp = kEpiWarps + 2;
+
+// Development aid (-DSISUA_OUT_TRACE): CTA 0 stamps clock64() at the hand-over points of every role for each gene tile;
+// tools/trace_out_heads.py prints the timeline.  Compiled out of the product.
+#ifdef SISUA_OUT_TRACE
+__device__ long long g_out_trace[4][64][8];
+#define OUT_TR(role, i, k) do { if (blockIdx.x == 0 && (i) < 64) g_out_trace[role][i][k] = clock64(); } while (0)
+#else
+#define OUT_TR(role, i, k) do { } while (0)
+#endif
 constexpr int kTmemCols = 512;
 constexpr int kTmemDD = 192, kTmemDWO = 256, kDwoCols = 80;
 
@@ -243,8 +252,11 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       for (int i = 0; i < nt; ++i) {
         const int s = i & 1, ws = i % kWStages;
         const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH)), sW2 = sW1 + w_tile_bytes(NH);
+        OUT_TR(1, i, 0);
         mbar_wait_backoff(&bars[W_FULL + ws], (i / kWStages) & 1);
+        OUT_TR(1, i, 1);
         if (i >= 2) mbar_wait_backoff(&bars[ACC_FREE + s], ((i >> 1) - 1) & 1);
+        OUT_TR(1, i, 2);
         tc_fence_after();
         const uint32_t d_t = tmem + (uint32_t)(s * N);
         uint32_t acc = 0;
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         }
         umma_commit(&bars[ACC_FULL + s]);
         umma_commit(&bars[W_FREE + ws]);      // (training: the gradient issuer's commit is the stage's second arrival)
+        OUT_TR(1, i, 3);
       }
     }
   } else if (warp == kGradWarp) {
@@ -274,8 +287,11 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         const int s = i & 1, ws = i % kWStages;
         const uint32_t sW1 = smem_u32(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH));
         const uint32_t sG = sG0 + s * OutSmem::Gstage;
+        OUT_TR(2, i, 0);
         mbar_wait_backoff(&bars[G_FULL + s], (i >> 1) & 1);
+        OUT_TR(2, i, 1);
         if (i >= 2) mbar_wait_backoff(&bars[DWO_FREE + s], ((i >> 1) - 1) & 1);
+        OUT_TR(2, i, 2);
         tc_fence_after();
         // dD[cells, k] += G[cells, n] . W[n, k]   (A: G K-major, B: w1 then w2, MN-major).  Both halves of the weight
         // split are used: the fp16 rounding of a weight is the same for every cell, so with w1 alone the error of dD
@@ -302,6 +318,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         umma_commit(&bars[DWO_FULL + s]);
         umma_commit(&bars[W_FREE + ws]);
         if (i == nt - 1) umma_commit(&bars[DD_FULL]);
+        OUT_TR(2, i, 3);
       }
     }
   } else {
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
     auto flush_dwo = [&](int i) {            // tile i's weight / bias gradient: TMEM -> vector reds
       const int s = i & 1;
       mbar_wait_backoff(&bars[DWO_FULL + s], (i >> 1) & 1);
+      if (t == 0) OUT_TR(0, i + 2, 7);       // (stamped in the row of the tile whose trip does this flush)
       tc_fence_after();
       const int n = cell;                    // TMEM lane = output-unit row of the tile
       const int h = n >> 5, g = (tile_begin + i) * kGeneTile + (n & 31);
@@ -406,9 +424,15 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         }
       }
       const int ws = i % kWStages;
+      const int tr_role = (t == 0) ? 0 : 3;
+      const bool tr_on = (t == 0) || (t == kEpiThreads - 32);
+      if (tr_on) OUT_TR(tr_role, i, 0);
       mbar_wait_backoff(&bars[W_FULL + ws], (i / kWStages) & 1);   // bias values of this stage (bulk copy) visible to this thread
+      if (tr_on) OUT_TR(tr_role, i, 1);
       mbar_wait_backoff(&bars[ACC_FULL + s], (i >> 1) & 1);
+      if (tr_on) OUT_TR(tr_role, i, 2);
       if (TRAIN && i >= 2) mbar_wait_backoff(&bars[G_FREE + s], ((i >> 1) - 1) & 1);   // gradient GEMMs of tile i-2 consumed this G stage
+      if (tr_on) OUT_TR(tr_role, i, 3);
       tc_fence_after();
       const uint32_t tb = tmem + lane_addr + (uint32_t)(s * N + sub * 8);
       const float* bias_s = reinterpret_cast<const float*>(smem + OutSmem::W0 + ws * OutSmem::Wstage(NH) + 2 * w_tile_bytes(NH)) + sub * 8;
@@ -434,7 +458,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       // pairs are independent dependency chains the compiler interleaves; the trip loop is rolled on purpose (its code
       // stays inside the instruction cache).  The TMEM reads of trip j+1 are in flight while trip j is evaluated.
 #ifndef SISUA_OUT_NP
-#define SISUA_OUT_NP 1       // measured on the B200 (18 944 x 2 000, ZINB train): 1 pair 0.347 ms, 2 pairs 0.351 ms
+#define SISUA_OUT_NP 2       // measured on the B200 (18 944 x 2 000, ZINB train): 1 pair per trip 0.303 ms, 2 pairs 0.290 ms
 #endif
       constexpr int kNP = SISUA_OUT_NP, kGT = 2 * kNP;     // genes per trip
       float pa[kGT], pb[kGT], pl[kGT];
@@ -567,6 +591,7 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
           }
         }
       }
+      if (tr_on) OUT_TR(tr_role, i, 4);      // element math of this tile done
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -577,10 +602,12 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[G_FULL + s]);
+        if (tr_on) OUT_TR(tr_role, i, 5);
         // the weight-gradient tile of tile i-2 (not i-1): its MMAs were committed together with the release of the G stage
         // this warp waited for at the top of tile i, so the flush never waits for the slowest warp of the CTA (flushing
         // tile i-1 here made every tile a barrier across the 16 epilogue warps: 9 % of the kernel's samples were polls)
         if (i >= 2) flush_dwo(i - 2);
+        if (tr_on) OUT_TR(tr_role, i, 6);
       }
     }
     // per-cell log-likelihood: four gene slices per cell -> shared -> one atomic per cell and chunk

@@ -9,7 +9,9 @@
 //     count in 1..3 costs 3 more (18 before);
 //   * selected exponentials run on the FMA pipe as a degree-5 polynomial (Cody-Waite split, packed Horner steps) to
 //     balance the MUFU and FMA pipes;
-//   * counts above 3 or non-integer counts (rare, warp-uniform vote) fall back to the scalar routines of device_math.cuh.
+//   * counts above 3 (a quarter of the warp x gene-pair groups of a pbmc-like matrix hold one) stay packed and branch-free
+//     through Stirling's series with a shift-by-4 recurrence (core_big); only negative / NaN inputs (not count
+//     data) fall back to the scalar routines of device_math.cuh.
 // Compiles for the host as well (plain float arithmetic in place of the packed / MUFU instructions): tests/csrc/ builds
 // it with g++ and checks the formulas against a float64 restatement without a GPU.
 #pragma once
@@ -193,11 +195,13 @@ PM_HD Core core_zero(CoreState& c, bool nozi = false) {
 }
 
 PM_HD bool pair_nonzero(F2 x) { return x.x >= kEps || x.y >= kEps; }
-// counts 1..3 (the bulk of the non-zero entries) stay on the packed path; anything else takes the scalar routines
+// counts 1..3 (the bulk of the non-zero entries) take the closed forms of piece 2a; anything else >= 1 takes the Stirling
+// forms of piece 2b (valid for any positive count, integer or not); negative / NaN inputs go to the scalar routines
 PM_HD bool count_big(float x) {
   const float r = (x + 8388608.f) - 8388608.f;      // rint(x) for 0 <= x < 2^22
   return x >= kEps && !(x == r && x <= 3.f);
 }
+PM_HD bool count_odd(float x) { return x < 0.f || !(x == x); }
 
 // piece 2a: counts in {0, 1, 2, 3}, branch-free
 template <bool ZI, bool GRAD>
@@ -236,18 +240,89 @@ PM_HD void core_small(const CoreState& c, Core& o, bool nozi = false) {
   }
 }
 
-// piece 2b: a gene at which some cell of the warp holds a count above 3 or a non-integer count is redone by the scalar
-// routines of device_math.cuh (every lane of the warp calls them together); voted per GENE, so that one large count does
-// not drag its neighbours out of the packed path
+// piece 2b: any positive count (integer or not), still packed and branch-free.  The three log-gammas of
+//   L = lgamma(x + th) - lgamma(th) - lgamma(x + 1),   D = dL/dth = psi(x + th) - psi(th)
+// come from Stirling's series; an argument below 4 is shifted up by 4 through z (z+1) (z+2) (z+3) = u (u + 2),
+// u = z (z + 3) (value) and its derivative (2z + 3)(2u + 2) (digamma), selected per element.  The difference
+// lgamma(z2) - lgamma(z1) is arranged as (z1 - 1/2) ln(z2/z1) + (z2 - z1)(ln z2 - 1) with ln(z2/z1) taken of the
+// quotient, so that th >> x (z2/z1 -> 1) loses no more than the rounding of the quotient; the series are cut at
+// z^-5 (value) / z^-6 (digamma): truncation < 4e-8 / 6e-8 at z = 4.  9 MUFU operations per element on top of piece 1.
+struct Shifted { F2 zs, Pe, dPe; };
+template <bool GRAD>
+PM_HD Shifted shift4(F2 z) {
+  Shifted r;
+  const bool s0 = z.x < 4.f, s1 = z.y < 4.f;
+  const F2 u = mul(z, add(z, bc(3.f)));
+  const F2 P = mul(u, add(u, bc(2.f)));
+  r.zs = add(z, mk(s0 ? 4.f : 0.f, s1 ? 4.f : 0.f));
+  r.Pe = mk(s0 ? P.x : 1.f, s1 ? P.y : 1.f);            // (selected, not blended: P can be far below 1 ulp of 1)
+  r.dPe = bc(0.f);
+  if (GRAD) {
+    const F2 dP = mul(fma2(z, bc(2.f), bc(3.f)), fma2(u, bc(2.f), bc(2.f)));
+    r.dPe = mk(s0 ? dP.x : 0.f, s1 ? dP.y : 0.f);
+  }
+  return r;
+}
+PM_HD F2 stirling_corr(F2 r) {       // 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5), r = 1/z
+  const F2 r2 = mul(r, r);
+  return mul(r, fma2(r2, fma2(r2, bc(1.f / 1260.f), bc(-1.f / 360.f)), bc(1.f / 12.f)));
+}
+PM_HD F2 digamma_corr(F2 r) {        // 1/(12 z^2) - 1/(120 z^4) + 1/(252 z^6)
+  const F2 r2 = mul(r, r);
+  return mul(r2, fma2(r2, fma2(r2, bc(1.f / 252.f), bc(-1.f / 120.f)), bc(1.f / 12.f)));
+}
+
+template <bool ZI, bool GRAD>
+PM_HD void core_big(const CoreState& c, Core& o, bool nozi = false) {
+  const F2 x = c.x, th = c.th;
+  const Shifted s1 = shift4<GRAD>(th), s2 = shift4<GRAD>(add(th, x)), s3 = shift4<false>(add(x, bc(1.f)));
+  const F2 R12 = rcp(mul(s1.zs, s2.zs));
+  const F2 r1 = mul(R12, s2.zs), r2 = mul(R12, s1.zs), r3 = rcp(s3.zs);
+  const F2 lr = lg2(mul(s2.zs, r1));                      // log2(z2 / z1)
+  const F2 l2s = lg2(s2.zs), l3s = lg2(s3.zs);
+  const F2 dz = sub(s2.zs, s1.zs);
+  // log2 of the Stirling main terms; the 1/2 log(2 pi) of z2 and z1 cancel, z3's stays
+  F2 L2 = fma2(sub(s1.zs, bc(0.5f)), lr, mul(dz, sub(l2s, bc(kLog2e))));
+  L2 = sub(L2, fma2(sub(s3.zs, bc(0.5f)), l3s, fma2(s3.zs, bc(-kLog2e), bc(1.3257480647361593f))));   // 1/2 log2(2 pi)
+  const F2 C = sub(sub(stirling_corr(r2), stirling_corr(r1)), stirling_corr(r3));
+  const F2 RP = rcp(mul(s1.Pe, s2.Pe));
+  const F2 iP1 = mul(RP, s2.Pe), iP2 = mul(RP, s1.Pe);
+  L2 = add(fma2(C, bc(kLog2e), L2), lg2(mul(mul(s1.Pe, s3.Pe), iP2)));
+  const F2 mue = add(c.mu, bc(c.eps));
+  const F2 m = max2(mul(mue, c.Rt), kTiny);             // mu / (theta + mu)
+  F2 l2 = add(fma2(x, lg2(m), c.n0), L2);               // log2 units
+  if (ZI && !nozi) {
+    const F2 over = max2(sub(c.pi, bc(kLinkClamp)), 0.f);
+    l2 = add(l2, fma2(over, bc(-kLog2e), lg2(mul(c.Ep, c.Rp))));
+  }
+  const F2 llk1 = mul(l2, bc(kLn2));
+  const bool nz0 = x.x >= kEps, nz1 = x.y >= kEps;
+  o.llk = mk(nz0 ? llk1.x : o.llk.x, nz1 ? llk1.y : o.llk.y);
+  if (GRAD) {
+    // psi(z) = ln zs - 1/(2 zs) - digamma_corr(1/zs) - P'/P;   r2 - r1 = -(z2s - z1s) / (z1s z2s) exactly
+    F2 D = fma2(lr, bc(kLn2), mul(mul(dz, R12), bc(0.5f)));
+    D = sub(D, sub(digamma_corr(r2), digamma_corr(r1)));
+    D = add(D, fma2(s1.dPe, iP1, neg(mul(s2.dPe, iP2))));
+    const F2 Rmue = rcp(mue);
+    const F2 gmu1 = fma2(x, sub(Rmue, c.Rt), neg(c.rho));
+    const F2 gth1 = add(D, fma2(neg(x), c.Rt, c.dn0_dth));
+    o.gmu = mk(nz0 ? gmu1.x : o.gmu.x, nz1 ? gmu1.y : o.gmu.y);
+    o.gth = mk(nz0 ? gth1.x : o.gth.x, nz1 ? gth1.y : o.gth.y);
+    if (ZI) o.gl = mk(nz0 ? -c.Rp.x : o.gl.x, nz1 ? -c.Rp.y : o.gl.y);
+  }
+}
+
+// piece 2c: a gene at which some cell of the warp holds a NEGATIVE (or NaN) count -- never on the reference's inputs -- is
+// redone by the scalar routines of device_math.cuh (every lane of the warp calls them together)
 template <bool ZI, bool GRAD>
 PM_HD void core_general(const CoreState& c, Core& o, bool nozi = false) {
   float l, gm, gt, gg;
-  if (any_lane(count_big(c.x.x))) {
+  if (any_lane(count_odd(c.x.x))) {
     if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, c.eps, l, gm, gt, gg);
     else core_scalar_fallback<false, GRAD>(c.mu.x, c.th.x, c.pi.x, c.x.x, c.eps, l, gm, gt, gg);
     o.llk.x = l; o.gmu.x = gm; o.gth.x = gt; o.gl.x = gg;
   }
-  if (any_lane(count_big(c.x.y))) {
+  if (any_lane(count_odd(c.x.y))) {
     if (ZI && !nozi) core_scalar_fallback<ZI, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, c.eps, l, gm, gt, gg);
     else core_scalar_fallback<false, GRAD>(c.mu.y, c.th.y, c.pi.y, c.x.y, c.eps, l, gm, gt, gg);
     o.llk.y = l; o.gmu.y = gm; o.gth.y = gt; o.gl.y = gg;
@@ -257,18 +332,24 @@ PM_HD void core_general(const CoreState& c, Core& o, bool nozi = false) {
 // NP pairs in lock-step: zero-count terms for all, one warp vote, then the small-count or the general path for all
 template <bool ZI, bool GRAD, int NP>
 PM_HD void core_multi(CoreState (&c)[NP], Core (&o)[NP], bool nozi = false) {
-  bool nz = false, big = false;
+  bool nz = false, big = false, odd = false;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     o[p] = core_zero<ZI, GRAD>(c[p], nozi);
     nz = nz || pair_nonzero(c[p].x); big = big || count_big(c[p].x.x) || count_big(c[p].x.y);
+    odd = odd || count_odd(c[p].x.x) || count_odd(c[p].x.y);
   }
   if (!any_lane(nz)) return;                         // every cell of the warp has zeros at all these genes
+  if (!any_lane(big)) {
 #pragma unroll
-  for (int p = 0; p < NP; ++p) core_small<ZI, GRAD>(c[p], o[p], nozi);
-  if (any_lane(big)) {                               // (lanes with a large count got garbage from core_small: overwritten here)
+    for (int p = 0; p < NP; ++p) core_small<ZI, GRAD>(c[p], o[p], nozi);
+  } else {                                           // some cell holds a count above 3: Stirling forms for the whole warp
 #pragma unroll
-    for (int p = 0; p < NP; ++p) core_general<ZI, GRAD>(c[p], o[p], nozi);
+    for (int p = 0; p < NP; ++p) core_big<ZI, GRAD>(c[p], o[p], nozi);
+    if (any_lane(odd)) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) core_general<ZI, GRAD>(c[p], o[p], nozi);
+    }
   }
 }
 
