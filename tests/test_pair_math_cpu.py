@@ -168,3 +168,25 @@ def test_scvi_pair_matches_float64(lib, zi):
   assert (np.abs(out[:, 6] - b.grad.numpy()) <= tol(b.grad.numpy()) + 3e-7 * th.detach().numpy()).all()
   if zi:
     assert (np.abs(out[:, 7] - p.grad.numpy()) <= tol(p.grad.numpy()) + 3e-7 * th.detach().numpy()).all()
+
+
+def test_large_counts_and_dispersions_stay_on_the_packed_path(lib):
+  """Counts up to 5 000, means up to 3 000, inverse dispersions up to 10^4, fractional counts: all of them go through
+  the packed Stirling forms (core_big) -- no scalar fall-back -- and must agree with float64.  The absolute floors
+  cover theta >> mu, where theta * log(theta / (theta + mu)) cancels in fp32 whatever the formula."""
+  rng = np.random.default_rng(5); n = 40000
+  ra = rng.uniform(-6, 9, n); ra[:n // 4] = rng.uniform(20, 3000, n // 4)
+  rb = rng.uniform(-6, 9, n); rb[n // 8:n // 2] = 10 ** rng.uniform(1, 4, n // 2 - n // 8)
+  pi = rng.uniform(-8, 8, n)
+  x = np.floor(10 ** rng.uniform(0, 3.7, n)); x[::7] = rng.integers(0, 12, len(x[::7])); x[::13] = rng.uniform(0.1, 30, len(x[::13]))
+  ra, rb, pi, x = [v.astype(np.float32) for v in (ra, rb, pi, x)]
+  out = np.zeros((n, 6), dtype=np.float32)
+  lib.pm_elem_softplus(_p(ra), _p(rb), _p(pi), _p(x), n, 1, 1, _p(out))
+  llk, ga, gb, gl, mu, th = _reference(ra, rb, pi, x, 1)
+  assert np.isfinite(out).all()
+  err = np.abs(out[:, 0] - llk)
+  # (terms of size (x + theta) log(x + theta) cancel in the log-likelihood: fp32 leaves ~1e-7 of THEIR size)
+  assert (err <= 3e-5 * np.abs(llk) + 3e-4 + 2.5e-6 * (x + th)).all(), f"llk worst {err.max():.3e} at {np.argmax(err)}"
+  for k, g in enumerate((ga, gb, gl)):
+    e = np.abs(out[:, 1 + k] - g)
+    assert (e <= 2e-3 * np.abs(g) + 1e-4).all(), f"gradient {k}: worst {e.max():.3e} at {np.argmax(e)} (ref {g[np.argmax(e)]:.3e})"
