@@ -81,10 +81,9 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
   for (int i = threadIdx.x; i < a.st.n; i += blockDim.x) part[i] = 0.0;
 
   // ---- phase 0: every rank's gradients are final
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0)
-      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 0 * kMaxRanks + a.rank, epoch);
-    for (int r = 0; r < W; ++r) spin_until(my_flags + 0 * kMaxRanks + r, epoch, true);
+  if (threadIdx.x < W) {
+    if (blockIdx.x == 0) st_release_sys(a.flags[threadIdx.x] + 0 * kMaxRanks + a.rank, epoch);
+    spin_until(my_flags + 0 * kMaxRanks + threadIdx.x, epoch, true);
   }
   __syncthreads();
 
@@ -95,11 +94,16 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
     double sq = 0.0;
     int seg = -1;
     if (o < hi) {
-      float4 s = ld_volatile_f4(a.grads[a.rank] + o);
-      for (int k = 1; k < W; ++k) {                     // start at a different peer on every rank: spreads the NVLink traffic
-        const float4 q = ld_volatile_f4(a.grads[(a.rank + k) % W] + o);
-        s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
-      }
+      // all peer loads are issued before the first one is consumed: ONE NVLink round trip per shard element, not W - 1
+      // dependent ones (a rolled load-add loop serialised them: ~1.5 us each)
+      float4 q[kMaxRanks];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k)               // start at a different peer on every rank: spreads the NVLink traffic
+        if (k < W) q[k] = ld_volatile_f4(a.grads[(a.rank + k) % W] + o);
+      float4 s = q[0];
+#pragma unroll
+      for (int k = 1; k < kMaxRanks; ++k)
+        if (k < W) { s.x += q[k].x; s.y += q[k].y; s.z += q[k].z; s.w += q[k].w; }
       s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
       *reinterpret_cast<float4*>(a.grads[a.rank] + o) = s;
       sq = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
@@ -123,18 +127,21 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(&a.local[0], 1u);
-    if (blockIdx.x == 0) {
-      spin_until(&a.local[0], (2u * epoch - 1u) * gridDim.x, false);
-      for (int i = 0; i < a.st.n; ++i) {
-        const double v = ld_volatile_f64(&a.sq_local[i]);
-        for (int r = 0; r < W; ++r) a.sqp[r][a.rank * kMaxSegments + i] = v;
-        a.sq_local[i] = 0.0;                           // ready for the next call
-      }
-      __threadfence_system();
-      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 1 * kMaxRanks + a.rank, epoch);
-    }
-    for (int r = 0; r < W; ++r) spin_until(my_flags + 1 * kMaxRanks + r, epoch, true);
   }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) spin_until(&a.local[0], (2u * epoch - 1u) * gridDim.x, false);
+    __syncthreads();
+    // one thread per (variable, destination rank): the posted stores of the table travel in parallel
+    for (int j = threadIdx.x; j < a.st.n * W; j += blockDim.x) {
+      const int i = j / W, r = j - i * W;
+      a.sqp[r][a.rank * kMaxSegments + i] = ld_volatile_f64(&a.sq_local[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.st.n; i += blockDim.x) a.sq_local[i] = 0.0;      // ready for the next call
+    if (threadIdx.x < W) st_release_sys(a.flags[threadIdx.x] + 1 * kMaxRanks + a.rank, epoch);
+  }
+  if (threadIdx.x < W) spin_until(my_flags + 1 * kMaxRanks + threadIdx.x, epoch, true);
   __syncthreads();
 
   // ---- clip scales (per variable over ALL ranks' partial sums), Keras / TF learning rate, sharded Adam, all-gather
@@ -183,10 +190,16 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpArgs a) {
   if (threadIdx.x == 0) {
     __threadfence_system();                            // this CTA's stores into the peers' parameter buffers
     atomicAdd(&a.local[0], 1u);
-    if (blockIdx.x == 0) {
-      spin_until(&a.local[0], 2u * epoch * gridDim.x, false);
-      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 2 * kMaxRanks + a.rank, epoch);
-      for (int r = 0; r < W; ++r) spin_until(my_flags + 2 * kMaxRanks + r, epoch, true);
+    if (blockIdx.x == 0) spin_until(&a.local[0], 2u * epoch * gridDim.x, false);
+  }
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x < W) {
+      st_release_sys(a.flags[threadIdx.x] + 2 * kMaxRanks + a.rank, epoch);
+      spin_until(my_flags + 2 * kMaxRanks + threadIdx.x, epoch, true);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
       *a.step = a.step_override > 0 ? a.step_override : (*a.step + 1);
       a.local[2] = epoch;
     }
