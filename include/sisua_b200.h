@@ -179,6 +179,12 @@ int sisua_debug_force_chunks(sisua_handle h, int out_chunks, int enc_chunks, int
  * larger count produces inf -> NaN gradients (loud), never a silently clamped one. */
 int sisua_set_count_bound(sisua_handle h, float max_count);
 
+/* Per-step finiteness of the training loss (the reference's terminate_on_nan callback, configs/base.yaml:59, acts on
+ * every step): every training step whose loss sum is not finite sets a sticky word in mapped host memory.  Returns 1 if
+ * it is set, 0 if not, -1 on a bad handle; `reset` != 0 clears it.  No stream synchronisation: the word becomes visible
+ * when the step that produced it has run, so polling once per step sees a failure within the depth of the launch queue. */
+int sisua_nonfinite_flag(sisua_handle h, int reset);
+
 /* Noise of sisua_infer calls that pass eps_z / eps_l == NULL: call k after this draws Philox(seed; row, column / 4,
  * call_index + k, stream 0x100 + 2 s (z) / 0x101 + 2 s (library) for Monte-Carlo sample s). */
 int sisua_set_infer_seed(sisua_handle h, uint64_t seed, int64_t call_index);

@@ -87,6 +87,7 @@ struct sisua_model {
   double* stats = nullptr;     // [n_units][4][H]: sum, sumsq, sdy, sdyx
   double* sq = nullptr;        // [kMaxSegments]
   long long* d_step = nullptr;
+  int* nf_host = nullptr; int* nf_dev = nullptr;      // sticky "a training loss was not finite" word (mapped host memory)
   float* d_lr_t = nullptr;
   SegTable seg;
   uint8_t* packed_wout = nullptr;   // pre-packed fp16 (hi | lo | bias) output-head weight tiles (tcgen05 path)
@@ -613,6 +614,9 @@ extern "C" int sisua_create(const sisua_step_config* cfg, int device, sisua_hand
   WS(h->d_lr_t, 1);
 #undef WS
   CUDA_OK(h, cudaMemset(h->d_step, 0, sizeof(long long)));
+  CUDA_OK(h, cudaHostAlloc((void**)&h->nf_host, sizeof(int), cudaHostAllocMapped));
+  *h->nf_host = 0;
+  CUDA_OK(h, cudaHostGetDevicePointer((void**)&h->nf_dev, h->nf_host, 0));
   CUDA_OK(h, cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseFwdSmem));
   CUDA_OK(h, cudaFuncSetAttribute(latent_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatentFwdSmem));
@@ -634,6 +638,7 @@ extern "C" int sisua_destroy(sisua_handle h) {
   if (!h) return SISUA_ERR_INVALID;
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->nf_host) cudaFreeHost(h->nf_host);
   for (auto& v : h->sec_events)
     for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->hs.copy) {
@@ -989,6 +994,7 @@ static int forward_common(sisua_model* h, cudaStream_t st, bool training, const 
     memset(&a, 0, sizeof(a));
     a.terms = terms; a.mask = P > 0 ? mask : nullptr; a.mask_scale = (P > 0 && c.mask_norm == 1) ? h->mask_scale : nullptr;
     a.R = R; a.B = B; a.alpha = c.alpha; a.beta = c.beta; a.loss = loss;
+    a.nonfinite = training ? h->nf_dev : nullptr;
     if (training && c.batchnorm) {
       auto reg = [&](const Layer& L, int rows) {
         a.mu.sum[L.bn_index] = h->stats + (size_t)L.stat_index * 4 * kH;
@@ -1627,6 +1633,13 @@ extern "C" int sisua_set_grad_ready_event(sisua_handle h, void* cuda_event) {
 // The fused kernels hand d llk / d (head outputs) to the tensor cores as fp16 tiles; its entries are bounded by the
 // largest count (or predicted mean), and fp16 ends at 65504.  Declaring a bound above 2^15 makes the kernels scale the
 // tiles by a power of two (and the results back), instead of overflowing to inf -> NaN gradients.
+extern "C" int sisua_nonfinite_flag(sisua_handle h, int reset) {
+  if (!h || !h->nf_host) return -1;
+  const int v = *(volatile int*)h->nf_host;
+  if (reset) *(volatile int*)h->nf_host = 0;
+  return v != 0;
+}
+
 extern "C" int sisua_set_count_bound(sisua_handle h, float max_count) {
   if (!h || !(max_count >= 0.f)) return SISUA_ERR_INVALID;
   float s = 1.0f;

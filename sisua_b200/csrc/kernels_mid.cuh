@@ -432,6 +432,9 @@ struct ElboArgs {
   int R, B; float alpha, beta; float* loss;  // loss: device scalar, pre-zeroed
   // training: the last n_bn blocks of the grid fold the batch statistics into the moving ones (one block per BN layer)
   int n_bn; float* moving; float momentum; MovingUpdateArgs mu;
+  // training: sticky word in mapped HOST memory, set when a partial sum of the loss is not finite (SURVEY.md section 5:
+  // the reference's terminate_on_nan callback looks at every step; the host reads the word without a synchronisation)
+  volatile int* nonfinite;
 };
 __global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
   // (no early trigger: co-resident waiting CTAs slowed the running kernel down)
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(256) elbo_kernel(ElboArgs a) {
   }
   local = block_sum(local, scratch);
   if (threadIdx.x == 0 && a.loss) atomicAdd(a.loss, -local / (float)a.R);
+  if (threadIdx.x == 0 && a.nonfinite && !isfinite(local)) *a.nonfinite = 1;
 }
 
 // ------------------------------------------------------------------------------------------

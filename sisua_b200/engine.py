@@ -326,6 +326,13 @@ class Engine:
       self._check(self.lib.sisua_train_step_host(self.handle, ctypes.byref(hb), int(seed), int(step), hp(host_loss),
                                                  hp(host_terms), self._stream()))
 
+  def nonfinite(self, reset: bool = False) -> bool:
+    """True once a training step produced a non-finite loss (sisua_nonfinite_flag; sticky, read without a sync)."""
+    v = self.lib.sisua_nonfinite_flag(self.handle, 1 if reset else 0)
+    if v < 0:
+      raise _lib.SisuaError("sisua_nonfinite_flag: bad handle")
+    return bool(v)
+
   def set_count_bound(self, max_count: float):
     """Largest count the step will see (sisua_set_count_bound): keeps the fp16 gradient operand tiles in range."""
     self._check(self.lib.sisua_set_count_bound(self.handle, float(max_count)))

@@ -496,6 +496,8 @@ class SingleCellModel:
         graphed = GraphedGatherStep(eng, B, cache["x"], y_all=cache.get("y"), library_all=cache.get("library"),
                                     mask_all=cache.get("mask"), lr=lr, clipnorm=cn, seed=step_seed)
         terms, loss = graphed.terms, graphed.loss
+    eng.nonfinite(reset=True)
+    nan_events = [None, None]
     best, patience, done = float("inf"), 0, 0
     best_state, last_valid = None, time.perf_counter()
     log_buf: List[torch.Tensor] = []
@@ -532,6 +534,18 @@ class SingleCellModel:
             gscale = reducer()
             eng.adam_step(lr=lr, clipnorm=cn, grad_scale=gscale, t=self.step)
         done += 1
+        # per-step NaN watch (configs/base.yaml:59): the step kernels raise a word in mapped host memory, read here without
+        # a synchronisation.  One rank leaving alone would dead-lock the others, so N > 1 decides at the epoch boundary.
+        if terminate_on_nan and world == 1 and not host_stream and done % 8 == 0:
+          # bound the host's run-ahead to 16 steps, so the word below is never older than that (an event wait on a step
+          # that finished long ago costs nothing once the queue is full anyway)
+          if nan_events[1] is not None:
+            nan_events[1].synchronize()
+          nan_events = [torch.cuda.Event(), nan_events[0]]
+          nan_events[0].record(torch.cuda.current_stream(eng.device))
+        if terminate_on_nan and world == 1 and eng.nonfinite():
+          eng.nonfinite(reset=True)
+          raise FloatingPointError(f"training loss is not finite at or before step {self.step} (terminate_on_nan, configs/base.yaml:59)")
         if logging_interval and done % int(logging_interval) == 0 and not host_stream:
           log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
         due = valid_freq and done % int(valid_freq) == 0
@@ -741,6 +755,39 @@ class SingleCellModel:
         class_name, dataset, metadata, _ = pickle.load(f)
       assert class_name == self.__class__.__name__
       self.dataset, self.metadata = dataset, metadata
+    self.is_fitted = True
+    return self
+
+  def export_keras(self, filepath, name_map=None):
+    r""" Writes the weights as an ``.npz`` keyed by Keras variable names with Keras tensor conventions
+    (``Dense.kernel`` = [in, out], BatchNormalization ``gamma / beta / moving_mean / moving_variance``, ``Adam/.../m|v``,
+    ``Adam/iter``): what ``{v.name: v.numpy() for v in keras_model.variables}`` holds on the reference's side
+    (sisua_b200/keras_layout.py; the reference's TF checkpoints, single_cell_model.py:295-306, need TensorFlow). """
+    from . import keras_layout as KL
+    snap = self._snapshot()
+    arrays = KL.to_keras(self.engine.cfg, snap["params"], snap["bn_moving"], snap["adam_m"], snap["adam_v"], step=snap["step"],
+                         name_map=name_map)
+    with open(filepath, "wb") as f:
+      np.savez(f, **arrays)
+    return self
+
+  def import_keras(self, filepath_or_arrays, name_map=None, strict=True):
+    r""" Loads Keras-named arrays (an ``.npz`` path or a dict) into the model: kernels are transposed into the K-major
+    flat layout, Adam slots and the step counter are taken if present. """
+    from . import keras_layout as KL
+    if isinstance(filepath_or_arrays, (str, os.PathLike)):
+      with np.load(filepath_or_arrays, allow_pickle=False) as z:
+        arrays = {k: z[k] for k in z.files}
+    else:
+      arrays = dict(filepath_or_arrays)
+    eng = self.engine
+    flat, moving, m, v, step = KL.from_keras(eng.cfg, arrays, name_map=name_map, strict=strict)
+    eng.params.copy_(torch.from_numpy(flat))
+    eng.bn_moving.copy_(torch.from_numpy(moving).reshape(eng.bn_moving.shape))
+    if m is not None and v is not None:
+      eng.adam_m.copy_(torch.from_numpy(m)); eng.adam_v.copy_(torch.from_numpy(v))
+    if step is not None:
+      self.step = int(step)
     self.is_fitted = True
     return self
 

@@ -128,3 +128,39 @@ def test_fit_argument_handling_and_host_streaming(tmp_path):
   assert abs(loss[-1] - l2[-6:].mean()) < 0.25 * abs(l2[-6:].mean())
   p = m2.plot_learning_curves(path=os.path.join(tmp_path, "curves.csv"))
   assert p is not None
+
+
+@pytest.mark.gpu
+def test_terminate_on_nan_acts_within_the_epoch():
+  """A non-finite training loss raises a word in mapped host memory from inside the step (sisua_nonfinite_flag); fit()
+  polls it every step, so terminate_on_nan stops the run long before the end of the epoch (configs/base.yaml:59)."""
+  sco = _data(n=2048)
+  m = _make("vae", seed=3)
+  m.fit(sco, batch_size=64, epochs=1, max_iter=2)          # builds the engine
+  eng = m.engine
+  assert not eng.nonfinite()
+  eng.params[:64].fill_(float("nan"))                      # poison the first encoder weights
+  with pytest.raises(FloatingPointError):
+    m.fit(sco, batch_size=64, epochs=1, terminate_on_nan=True)
+  assert m.step < 2 + 2048 // 64, m.step                   # left before the epoch's 32 steps were issued
+  assert not eng.nonfinite()                               # fit() cleared the word when it raised
+
+
+@pytest.mark.gpu
+def test_keras_named_weight_exchange(tmp_path):
+  """export_keras / import_keras: a model rebuilt from the Keras-named arrays predicts exactly like the original."""
+  sco = _data(n=512)
+  m = _make("vae", seed=4)
+  m.fit(sco, batch_size=64, epochs=1)
+  path = os.path.join(tmp_path, "weights_keras.npz")
+  m.export_keras(path)
+  with np.load(path) as z:
+    assert z["encoder/dense/kernel:0"].shape == (60, 64) and "Adam/iter:0" in z.files
+  m2 = _make("vae", seed=99)
+  m2.metadata, m2.dataset = m.metadata, m.dataset
+  m2.import_keras(path)
+  assert m2.step == m.step
+  z1 = m.encode(sco.X[:32])
+  z2 = m2.encode(sco.X[:32])
+  a, b = (z1[0] if isinstance(z1, tuple) else z1), (z2[0] if isinstance(z2, tuple) else z2)
+  assert torch.equal(a.mean(), b.mean())
