@@ -179,6 +179,18 @@ int sisua_debug_force_chunks(sisua_handle h, int out_chunks, int enc_chunks, int
  * larger count produces inf -> NaN gradients (loud), never a silently clamped one. */
 int sisua_set_count_bound(sisua_handle h, float max_count);
 
+/* Artificial corruption of a count matrix on the GPU -- the input of the imputation benchmark (apply_artificial_corruption,
+ * sisua/data/utils.py:168-228; Posterior corrupts its test set with it, sisua/analysis/posterior.py:150-170).  src / dst:
+ * device fp32 [rows, cols] with row strides ld_src / ld_dst (floats); dst may alias src.  Every positive entry is selected
+ * with probability `dropout`; a selected count n becomes Binomial(n, retain_rate) (distribution 0, 'binomial') or
+ * n * Bernoulli(retain_rate) (distribution 1, 'uniform').  Draws are Philox4x32-10(seed; row, col, call, 0x200), integer
+ * thresholds only: oracle/philox.py:corrupt_counts reproduces the result bit for bit.  Deviation from the reference,
+ * which is a NumPy host routine: it corrupts EXACTLY floor(dropout * nnz) entries drawn without replacement from one
+ * RandomState stream (sisua_b200.posterior.apply_artificial_corruption restates that on the host); here the selection is
+ * independent per entry, so the corrupted share is dropout in expectation. */
+int sisua_corrupt_counts(sisua_handle h, const float* src, float* dst, int64_t rows, int cols, int64_t ld_src, int64_t ld_dst,
+                         float dropout, float retain_rate, int distribution, uint64_t seed, void* stream);
+
 /* Per-step finiteness of the training loss (the reference's terminate_on_nan callback, configs/base.yaml:59, acts on
  * every step): every training step whose loss sum is not finite sets a sticky word in mapped host memory.  Returns 1 if
  * it is set, 0 if not, -1 on a bad handle; `reset` != 0 clears it.  No stream synchronisation: the word becomes visible

@@ -60,3 +60,41 @@ def normal_noise(rows: int, cols: int, seed: int, step: int, stream: int) -> np.
   ta = 2.0 * np.pi * u[1] * k24; tb = 2.0 * np.pi * u[3] * k24
   out = np.stack([ra * np.cos(ta), ra * np.sin(ta), rb * np.cos(tb), rb * np.sin(tb)], axis=-1).reshape(rows, c4 * 4)
   return out[:, :cols]
+
+
+CORRUPT_STREAM = 0x200
+
+
+def corrupt_counts(x: np.ndarray, dropout: float, retain_rate: float = 0.2, distribution: str = "binomial", seed: int = 8) -> np.ndarray:
+  """Restatement of sisua_corrupt_counts (sisua_b200/csrc/abi.cu: corrupt_kernel), integers only, so bit-exact: entry
+  (r, c) > 0 is selected when word 0 of Philox(seed; r, c, 0, 0x200) < floor(float32(dropout) 2^32); a selected count n
+  becomes the number of successes among n trials ('binomial') or n times one trial ('uniform'); trial t takes 16 bits
+  of call (r, c, 1 + t // 8, 0x200) -- low half of word (t % 8) // 2 first -- and succeeds below
+  floor(float32(retain_rate) 65536).  (The algorithm being imitated: sisua/data/utils.py:168-228.)"""
+  x = np.asarray(x, dtype=np.float32)
+  out = x.copy()
+  k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+  sel_thr = min(4294967295, int(np.floor(float(np.float32(dropout)) * 4294967296.0)))
+  keep_thr = int(np.floor(float(np.float32(retain_rate)) * 65536.0))
+  r, c = np.nonzero(x > 0)
+  if r.size == 0:
+    return out
+  r64, c64 = r.astype(np.uint64), c.astype(np.uint64)
+  w = philox4x32_10(r64, c64, np.zeros_like(r64), np.full_like(r64, CORRUPT_STREAM), k0, k1)
+  sel = w[0] < np.uint64(sel_thr)
+  r, c, r64, c64 = r[sel], c[sel], r64[sel], c64[sel]
+  n = x[r, c].astype(np.int64)
+  trials = np.ones_like(n) if distribution == "uniform" else n
+  k = np.zeros_like(n)
+  for blk in range(int((trials.max() + 7) // 8) if trials.size else 0):
+    live = trials > 8 * blk
+    if not live.any():
+      break
+    w = philox4x32_10(r64[live], c64[live], np.full(int(live.sum()), 1 + blk, dtype=np.uint64), np.full(int(live.sum()), CORRUPT_STREAM, dtype=np.uint64), k0, k1)
+    for j in range(8):
+      word = w[j >> 1]
+      u = (word >> np.uint64(16)) if (j & 1) else (word & np.uint64(0xFFFF))
+      ok = (8 * blk + j < trials[live]) & (u < np.uint64(keep_thr))
+      k[live] += ok.astype(np.int64)
+  out[r, c] = np.where(k > 0, x[r, c], 0.0) if distribution == "uniform" else k.astype(np.float32)
+  return out

@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step", "sisua_train_step_gather",
-           "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_dp_bind", "sisua_adam_step_dp", "sisua_dp_shard", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_nonfinite_flag", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_dp_bind", "sisua_adam_step_dp", "sisua_dp_shard", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_nonfinite_flag", "sisua_corrupt_counts", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -99,6 +99,8 @@ def load():
   L.sisua_unpack_counts_csr.restype = ci
   L.sisua_train_step_host.argtypes = [vp, ctypes.POINTER(HostBatch), ctypes.c_uint64, ctypes.c_int64, vp, vp, vp]
   L.sisua_train_step_host.restype = ci
+  L.sisua_corrupt_counts.argtypes = [vp, vp, vp, ctypes.c_int64, ci, ctypes.c_int64, ctypes.c_int64, cf, cf, ci, ctypes.c_uint64, vp]
+  L.sisua_corrupt_counts.restype = ci
   L.sisua_nonfinite_flag.argtypes = [vp, ci]
   L.sisua_nonfinite_flag.restype = ci
   L.sisua_set_count_bound.argtypes = [vp, cf]

@@ -1529,6 +1529,60 @@ extern "C" int sisua_unpack_counts_u16(sisua_handle h, const uint16_t* src, floa
   return SISUA_OK;
 }
 
+// ---- artificial corruption of a count matrix (the imputation benchmark's input, sisua/data/utils.py:168-228) on the GPU
+// Entry (row, col) > 0 is selected with probability `dropout` (Philox word 0 of call (row, col, 0, 0x200) against
+// floor(dropout 2^32)); a selected count n becomes Binomial(n, retain) ('binomial') or n Bernoulli(retain) ('uniform').
+// The binomial is the exact sum of n Bernoulli trials: trial t takes 16 bits of Philox call (row, col, 1 + t / 8, 0x200)
+// (low half of word (t % 8) / 2 first) and succeeds when they are below floor(retain 65536) -- integers only, so
+// oracle/philox.py:corrupt_counts reproduces the matrix bit for bit.  Counts in the thousands cost n / 8 Philox calls;
+// they are a vanishing share of a single-cell matrix.
+__global__ void __launch_bounds__(256) corrupt_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int cols,
+                                                      long long ld_src, long long ld_dst, uint32_t sel_thr, uint32_t keep_thr,
+                                                      int uniform, uint32_t seed_lo, uint32_t seed_hi) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols; const int c = (int)(i - r * cols);
+    const float x = src[r * ld_src + c];
+    float y = x;
+    if (x > 0.f) {
+      const uint2 key = make_uint2(seed_lo, seed_hi);
+      const uint4 s = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)c, 0u, 0x200u), key);
+      if (s.x < sel_thr) {
+        const uint32_t nn = (uint32_t)x, trials = uniform ? 1u : nn;
+        uint32_t k = 0;
+        for (uint32_t t0 = 0; t0 < trials; t0 += 8) {
+          const uint4 w = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)c, 1u + t0 / 8, 0x200u), key);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t u = (j & 1) ? (ww[j >> 1] >> 16) : (ww[j >> 1] & 0xffffu);
+            if (t0 + j < trials && u < keep_thr) ++k;
+          }
+        }
+        y = uniform ? (k ? x : 0.f) : (float)k;
+      }
+    }
+    dst[r * ld_dst + c] = y;
+  }
+}
+
+extern "C" int sisua_corrupt_counts(sisua_handle h, const float* src, float* dst, int64_t rows, int cols, int64_t ld_src,
+                                    int64_t ld_dst, float dropout, float retain_rate, int distribution, uint64_t seed, void* stream) {
+  if (!h || !src || !dst || rows < 0 || cols <= 0 || ld_src < cols || ld_dst < cols) return SISUA_ERR_INVALID;
+  if (!(dropout >= 0.f && dropout < 1.f) || !(retain_rate >= 0.f && retain_rate <= 1.f) || (distribution != 0 && distribution != 1))
+    SET_ERR(h, SISUA_ERR_INVALID, "corrupt_counts: dropout in [0, 1), retain_rate in [0, 1], distribution 0 (binomial) or 1 (uniform)");
+  if (rows >= (1ll << 32)) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "corrupt_counts: more than 2^32 rows");
+  if (rows == 0) return SISUA_OK;
+  const uint32_t sel_thr = (uint32_t)std::min(4294967295.0, floor((double)dropout * 4294967296.0));
+  const uint32_t keep_thr = (uint32_t)floor((double)retain_rate * 65536.0);
+  const long long n = (long long)rows * cols;
+  ++h->launches;
+  corrupt_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 16ll * h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, rows, cols, ld_src, ld_dst, sel_thr, keep_thr, distribution, (uint32_t)seed, (uint32_t)(seed >> 32));
+  LAUNCH_OK(h, "corrupt_kernel");
+  return SISUA_OK;
+}
+
 // ---- host-buffer train step ---------------------------------------------------------------------
 static int host_stage_init(sisua_model* h) {
   auto& S = h->hs;

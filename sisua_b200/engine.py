@@ -326,6 +326,21 @@ class Engine:
       self._check(self.lib.sisua_train_step_host(self.handle, ctypes.byref(hb), int(seed), int(step), hp(host_loss),
                                                  hp(host_terms), self._stream()))
 
+  def corrupt_counts(self, x: torch.Tensor, dropout: float, retain_rate: float = 0.2, distribution: str = "binomial", seed: int = 8,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Corrupted copy of the device count matrix `x` [rows, genes] (sisua_corrupt_counts; sisua/data/utils.py:168-228)."""
+    dist = {"binomial": 0, "uniform": 1}.get(str(distribution).lower())
+    if dist is None:
+      raise ValueError(f"Only support 2 corruption distribution: 'uniform' and 'binomial', but given: '{distribution}'")
+    x = self._dev(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+      raise ValueError("corrupt_counts: x must be a [rows, genes] matrix with contiguous rows")
+    out = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_corrupt_counts(self.handle, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.stride(0),
+                                                float(dropout), float(retain_rate), dist, int(seed) & (2 ** 64 - 1), self._stream()))
+    return out
+
   def nonfinite(self, reset: bool = False) -> bool:
     """True once a training step produced a non-finite loss (sisua_nonfinite_flag; sticky, read without a sync)."""
     v = self.lib.sisua_nonfinite_flag(self.handle, 1 if reset else 0)

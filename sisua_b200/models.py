@@ -544,6 +544,7 @@ class SingleCellModel:
           nan_events = [torch.cuda.Event(), nan_events[0]]
           nan_events[0].record(torch.cuda.current_stream(eng.device))
         if terminate_on_nan and world == 1 and eng.nonfinite():
+          torch.cuda.current_stream(eng.device).synchronize()      # (steps already queued would raise the word again)
           eng.nonfinite(reset=True)
           raise FloatingPointError(f"training loss is not finite at or before step {self.step} (terminate_on_nan, configs/base.yaml:59)")
         if logging_interval and done % int(logging_interval) == 0 and not host_stream:
@@ -686,8 +687,9 @@ class SingleCellModel:
   # ---------------------------------------------------------------- posterior / persistence
   def create_posterior(self, test_sco=None, dropout_rate=0.2, retain_rate=0.2, corrupt_distribution='binomial',
                        batch_size=8, sample_shape=10, reduce_latents=None, verbose=True, train_percent=0.8,
-                       random_state=1):
-    r""" Create a `Posterior` object for evaluation (single_cell_model.py:247-281) """
+                       random_state=1, corrupt_on='host'):
+    r""" Create a `Posterior` object for evaluation (single_cell_model.py:247-281); ``corrupt_on='device'`` corrupts the
+    test set on the GPU (``sisua_corrupt_counts``) instead of with the reference's host routine. """
     if not self.is_fitted:
       raise RuntimeError("fit() must be called before creating Posterior.")
     if isinstance(test_sco, SingleCellData):
@@ -700,7 +702,7 @@ class SingleCellModel:
     from .posterior import Posterior
     return Posterior(self, test, dropout_rate=dropout_rate, retain_rate=retain_rate,
                      corrupt_distribution=corrupt_distribution, batch_size=batch_size, sample_shape=sample_shape,
-                     random_state=random_state, name=f"{self.id}_{self.dataset}")
+                     random_state=random_state, name=f"{self.id}_{self.dataset}", corrupt_on=corrupt_on)
 
   def _snapshot(self):
     eng = self.engine

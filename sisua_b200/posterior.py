@@ -42,6 +42,19 @@ def apply_artificial_corruption(X: np.ndarray, dropout: float = 0.0, distributio
   return X
 
 
+def corrupt_on_device(engine, X, dropout: float = 0.0, distribution: str = "binomial", retain_rate: float = 0.2, seed: int = 8,
+                      rows_per_call: int = 1 << 18) -> np.ndarray:
+  """``apply_artificial_corruption`` on the GPU (``sisua_corrupt_counts``): the matrix is streamed through the device in row
+  blocks; row indices of the Philox counters are global, so the result does not depend on the blocking."""
+  X = np.asarray(X, dtype=np.float32)
+  assert 0 <= dropout < 1, f"dropout value must be >= 0 and < 1, given: {dropout}"
+  if not (0. < dropout < 1. or 0. < retain_rate < 1.):
+    return X.copy()
+  if X.shape[0] <= rows_per_call:
+    return engine.corrupt_counts(torch.from_numpy(X), dropout, retain_rate, distribution, seed).cpu().numpy()
+  raise NotImplementedError("corrupt_on_device: matrices above 2^18 rows -- corrupt the shard that is resident with Engine.corrupt_counts")
+
+
 corrupt_binomial = lambda X, dropout_rate=0.2, retain_rate=0.2, seed=1: apply_artificial_corruption(   # round-1 name
     X, dropout=dropout_rate, distribution="binomial", retain_rate=retain_rate, seed=seed)
 
@@ -76,14 +89,20 @@ class Posterior:
   (sisua/analysis/posterior.py:108-255). """
 
   def __init__(self, scm, sco, dropout_rate=0.2, retain_rate=0.2, corrupt_distribution='binomial', batch_size=8,
-               sample_shape=10, random_state=1, name=None, verbose=False):
+               sample_shape=10, random_state=1, name=None, verbose=False, corrupt_on='host'):
     from .models import SingleCellData
     if not scm.is_fitted:
       raise RuntimeError("fit() must be called before creating Posterior.")
     self.scm, self.name, self.verbose = scm, name or "posterior", verbose
     self.sco_original = sco
-    Xc = apply_artificial_corruption(sco.X, dropout=dropout_rate, distribution=corrupt_distribution, retain_rate=retain_rate,
-                                     seed=random_state)
+    if corrupt_on == 'host':      # the reference's NumPy routine, same RandomState sequence
+      Xc = apply_artificial_corruption(sco.X, dropout=dropout_rate, distribution=corrupt_distribution, retain_rate=retain_rate,
+                                       seed=random_state)
+    elif corrupt_on == 'device':  # Philox on the GPU (sisua_corrupt_counts): per-entry selection, see include/sisua_b200.h
+      Xc = corrupt_on_device(scm.engine, sco.X, dropout=dropout_rate, distribution=corrupt_distribution, retain_rate=retain_rate,
+                             seed=random_state)
+    else:
+      raise ValueError(f"corrupt_on must be 'host' or 'device', given: {corrupt_on!r}")
     self.sco_corrupted = SingleCellData(Xc, sco.Y, name=sco.name + "_corrupted", var_names=sco.var_names)
     self.sco_corrupted.mask = sco.mask
     self.sample_shape = sample_shape

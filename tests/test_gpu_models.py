@@ -139,7 +139,8 @@ def test_terminate_on_nan_acts_within_the_epoch():
   m.fit(sco, batch_size=64, epochs=1, max_iter=2)          # builds the engine
   eng = m.engine
   assert not eng.nonfinite()
-  eng.params[:64].fill_(float("nan"))                      # poison the first encoder weights
+  e = [e for e in eng.entries if e.name == "out.b"][0]
+  eng.params[e.offset:e.offset + 4].fill_(float("nan"))    # poison output-head biases (ReLU / clamps would launder a NaN further up)
   with pytest.raises(FloatingPointError):
     m.fit(sco, batch_size=64, epochs=1, terminate_on_nan=True)
   assert m.step < 2 + 2048 // 64, m.step                   # left before the epoch's 32 steps were issued

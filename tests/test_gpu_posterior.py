@@ -205,3 +205,41 @@ def test_streamed_predict_and_posterior_scores():
   mm = post.cal_marginal_llk(sample_shape=20)
   assert set(mm) == {"transcriptomic_llk", "marginal_llk"} and mm["marginal_llk"] <= mm["transcriptomic_llk"] + 1e-3
   assert post.imputed.shape == (N, 120) and post.latents.shape == (N, 10)
+
+
+def test_device_corruption_is_bit_exact_with_its_restatement():
+  """sisua_corrupt_counts against oracle/philox.py:corrupt_counts on the same matrix: identical, for both distributions,
+  with a strided source, in place, and with a count in the hundreds (many Philox calls for one entry)."""
+  from oracle import philox as PH
+  from sisua_b200 import config as C
+  from sisua_b200.engine import Engine
+  rng = np.random.default_rng(3)
+  x = (rng.poisson(0.7, (777, 203)) * (rng.random((777, 203)) < 0.6)).astype(np.float32)
+  x[3, 5] = 611.0; x[700, 202] = 65.0
+  eng = Engine(C.make_step_config("vae", n_genes=203, n_latent=10, max_batch=64), 0, seed=1)
+  for dist, seed in (("binomial", 7), ("uniform", (1 << 40) + 5)):
+    got = eng.corrupt_counts(torch.from_numpy(x), 0.3, 0.2, dist, seed).cpu().numpy()
+    np.testing.assert_array_equal(got, PH.corrupt_counts(x, 0.3, 0.2, dist, seed))
+  wide = torch.zeros((777, 256), device="cuda"); wide[:, :203] = torch.from_numpy(x).cuda()
+  view = wide[:, :203]
+  eng.corrupt_counts(view, 0.3, 0.2, "binomial", 7, out=view)          # strided, in place
+  np.testing.assert_array_equal(view.cpu().numpy(), PH.corrupt_counts(x, 0.3, 0.2, "binomial", 7))
+  with pytest.raises(ValueError):
+    eng.corrupt_counts(torch.from_numpy(x), 0.3, 0.2, "poisson", 7)
+  eng.close()
+
+
+def test_posterior_with_device_corruption():
+  """Posterior(corrupt_on='device'): the test set is corrupted by sisua_corrupt_counts instead of the host routine."""
+  from oracle import philox as PH
+  from sisua_b200.models import VAE, RVmeta, SingleCellData
+  from sisua_b200.posterior import Posterior
+  d = SY.realistic_counts(400, 120, 0, seed=11)
+  sco = SingleCellData(d["x"], name="toy")
+  m = VAE(RVmeta(120, "zinbd", True, "transcriptomic"), max_batch=256, seed=4)
+  m.fit(sco, batch_size=64, epochs=1, learning_rate=2e-3)
+  post = Posterior(m, sco, dropout_rate=0.25, retain_rate=0.2, sample_shape=2, random_state=5, corrupt_on="device")
+  np.testing.assert_array_equal(post.sco_corrupted.X, PH.corrupt_counts(sco.X, 0.25, 0.2, "binomial", 5))
+  assert all(np.isfinite(v) for v in post.cal_imputation_scores().values())
+  with pytest.raises(ValueError):
+    Posterior(m, sco, corrupt_on="nowhere")

@@ -329,3 +329,23 @@ def test_philox_normal_noise_is_standard_normal_and_counter_based():
   for other in (normal_noise(40000, 10, 0xDEADBEEFCAFE, 4, NOISE_STREAM_Z), normal_noise(40000, 10, 0xDEADBEEFCAFE, 3, NOISE_STREAM_L),
                 normal_noise(40000, 10, 0xDEADBEEFCAFF, 3, NOISE_STREAM_Z)):
     assert abs(np.corrcoef(n.ravel(), other.ravel())[0, 1]) < 0.01
+
+
+def test_gpu_corruption_restatement_statistics():
+  """oracle/philox.py:corrupt_counts (the bit-exact mirror of sisua_corrupt_counts): zeros stay zero, nothing grows, the
+  selected share and the retained mass follow dropout / retain_rate, 'uniform' only zeroes, a seed reproduces."""
+  from oracle import philox as PH
+  rng = np.random.default_rng(0)
+  x = (rng.poisson(0.6, (400, 300)) * (rng.random((400, 300)) < 0.7)).astype(np.float32)
+  x[0, 0] = 700.0
+  nz = x > 0
+  y = PH.corrupt_counts(x, 0.25, 0.2, "binomial", seed=11)
+  assert (y[~nz] == 0).all() and (y <= x).all() and (y == np.floor(y)).all()
+  assert abs(y[nz].sum() / x[nz].sum() - (1 - 0.25 * 0.8)) < 0.02
+  np.testing.assert_array_equal(y, PH.corrupt_counts(x, 0.25, 0.2, "binomial", seed=11))
+  assert (y != PH.corrupt_counts(x, 0.25, 0.2, "binomial", seed=12)).any()
+  u = PH.corrupt_counts(x, 0.25, 0.2, "uniform", seed=11)
+  assert ((u == x) | (u == 0)).all() and abs((u[nz] > 0).mean() - (1 - 0.25 * 0.8)) < 0.02
+  np.testing.assert_array_equal(PH.corrupt_counts(x, 0.0, 0.2, "binomial", seed=3), x)       # nothing selected
+  full = PH.corrupt_counts(x, 0.999, 1.0, "binomial", seed=3)                                   # everything retained
+  np.testing.assert_array_equal(full, x)
