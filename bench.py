@@ -120,24 +120,30 @@ class ClockSampler:
     except Exception as e:      # noqa: BLE001
       self.err, self.t = f"NVML unavailable: {e}", None
 
-  def _run(self):
+  def sample(self):
+    """One NVML reading.  Also called from the timed loop itself every 64 steps: the poller thread can be starved of the
+    GIL by the launch loop (one run of this file came back with 3 samples where another had 122)."""
+    if self.t is None or self.err:
+      return
     nv = self.nv
     names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
              "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-    while not self._stop.is_set():
+    try:
+      self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+      self.mx.append(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
       try:
-        self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-        self.mx.append(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
-        try:
-          r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-        except Exception:      # noqa: BLE001
-          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for n, bit in names.items():
-          if r & bit:
-            self.reasons.add(n)
-      except Exception as e:      # noqa: BLE001
-        self.err = str(e)
-        return
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+      except Exception:      # noqa: BLE001
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+      for n, bit in names.items():
+        if r & bit:
+          self.reasons.add(n)
+    except Exception as e:      # noqa: BLE001
+      self.err = str(e)
+
+  def _run(self):
+    while not self._stop.is_set() and not self.err:
+      self.sample()
       time.sleep(0.001)
 
   def stop(self):
@@ -311,6 +317,8 @@ def main():
   e0.record()
   for i in range(a.steps):
     one_step(a.warmup + i)
+    if sampler and (i & 63) == 32:
+      sampler.sample()
   e1.record()
   sync_all()
   ms = e0.elapsed_time(e1)
