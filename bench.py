@@ -49,6 +49,9 @@ def parse():
   ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                   help="multi-GPU gradient exchange: 'peer' = one kernel over NVLink peer memory (reduce-scatter + sharded Adam + "
                        "all-gather), 'nccl' = two overlapped NCCL all-reduces + Adam")
+  ap.add_argument("--storage", default="uint16", choices=["float32", "uint16"],
+                  help="resident count shard in HBM: float32 (the reference's storage type) or uint16 (exact for counts, "
+                       "widened inside the streaming kernels: sisua_train_step_gather_u16)")
   ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of one step at the benchmarked shape")
   ap.add_argument("--no-latency", action="store_true", help="skip the batch-64 / 128 latency-regime measurement")
   return ap.parse_args()
@@ -287,13 +290,15 @@ def main():
   # indices (a fresh device permutation of the shard every epoch) into the HBM-resident matrix, gathered inside the
   # kernels; dropout masks and the reparameterisation noise are Philox streams of (seed, step) drawn in-kernel.
   perm = [torch.randperm(a.shard_cells, device=dev, generator=gen).to(torch.int32)]
+  # resident storage of the shard the training loop reads (the inference / latency sections below keep reading X)
+  X_res = X.to(torch.int32).to(torch.int16) if a.storage == "uint16" else X      # counts < 32 768 here: same bits as uint16
 
   def one_step(i):
     j = i % n_batches
     if j == 0 and i > 0:
       perm[0] = torch.randperm(a.shard_cells, device=dev, generator=gen).to(torch.int32)     # next epoch
     step_no[0] += 1
-    eng.train_step_gather(X, perm[0][j * B:(j + 1) * B], terms=terms, loss=loss, seed=rank, step=step_no[0])
+    eng.train_step_gather(X_res, perm[0][j * B:(j + 1) * B], terms=terms, loss=loss, seed=rank, step=step_no[0])
     if px is not None:       # reduce-scatter + clipnorm + sharded Adam + all-gather: ONE kernel over NVLink peer memory
       px.step(lr=1e-3, clipnorm=100.0, t=step_no[0])
     else:
@@ -424,8 +429,9 @@ def main():
     dur_s = per_step[dom] * 1e-3
     achieved = alg_bytes[dom] / dur_s / 1e9
     out = dict(base)
-    out["config"] = dict(out["config"], shuffle=True, eps="philox (in-kernel)",
-                         step_entry="sisua_train_step_gather + sisua_adam_step (what SingleCellModel.fit issues per step)")
+    out["config"] = dict(out["config"], shuffle=True, eps="philox (in-kernel)", resident_storage=a.storage,
+                         step_entry=("sisua_train_step_gather_u16" if a.storage == "uint16" else "sisua_train_step_gather") +
+                         " + sisua_adam_step (what SingleCellModel.fit issues per step)")
     out.update({
         "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss, "parity_at_bench_shape": parity,
         "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 fused (3xFP16 compensated forward, fp16 gradient GEMMs)"}[mode],

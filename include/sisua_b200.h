@@ -100,6 +100,20 @@ int sisua_train_step_gather(sisua_handle h, const float* x_all, const float* y_a
                             const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
                             uint64_t seed, int64_t step, float* terms, float* loss, void* stream);
 
+/* sisua_train_step_gather with the resident count matrix stored as uint16 [N, G] -- exact for count data below 65 536
+ * (what sisua/data/utils.py:427-431 keeps as float32): half the HBM of the shard and half the bytes of both streaming
+ * reads of a step.  The tcgen05 kernels widen the counts themselves when rows are 16-byte aligned (n_genes % 8 == 0,
+ * aligned base) and the heads are the plain (non-scVI) ones; otherwise the minibatch rows are first widened into an fp32
+ * staging buffer (same results, one extra pass).  rows may be NULL (rows 0 .. B-1).  Results are identical to the fp32
+ * entry point on the widened matrix. */
+int sisua_train_step_gather_u16(sisua_handle h, const uint16_t* x_all, const float* y_all, const float* library_all,
+                                const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                                uint64_t seed, int64_t step, float* terms, float* loss, void* stream);
+
+/* dst[b, :] = (float) x_all[rows[b], :] for b < n_rows (rows == NULL: rows 0 .. n_rows-1): feeds the fp32 entry points
+ * (sisua_infer*, validation) from a uint16 resident matrix, chunk by chunk. */
+int sisua_widen_rows_u16(sisua_handle h, const uint16_t* x_all, const int32_t* rows, float* dst, int n_rows, void* stream);
+
 /* Replaces one `self(**data, training=False, sample_shape=S)` call of SingleCellModel.predict
  * (single_cell_model.py:176-181) plus the parameter tensors the returned distributions hold.
  * eps_z [S,B,z], eps_l [S,B]; terms [5,S*B]; z_loc/z_scale [B,z]; out_mean/out_disp/out_pi [S*B,G]

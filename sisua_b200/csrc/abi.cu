@@ -104,6 +104,7 @@ struct sisua_model {
   cudaEvent_t ev_out_grads = nullptr;   // caller-owned: recorded once d loss / d (out.W, out.b) is final
   long long launches = 0;       // kernels launched through this handle (bench.py reports it)
   const int* ridx = nullptr;    // row gather of the current sisua_train_step_gather call (consumed by the tcgen05 kernels)
+  bool x_u16 = false;           // ... whose resident count matrix is uint16 (sisua_train_step_gather_u16)
   // data-parallel optimiser step over peer memory (sisua_dp_bind / sisua_adam_step_dp)
   DpArgs dp;
   bool dp_bound = false;
@@ -328,6 +329,14 @@ static int tc_set_attr(sisua_model* h) {
                                   tc::OutSmem::total(NH, TRAIN)));
   CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_TFP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::OutSmem::total(NH, TRAIN)));
+  if (TRAIN && VEC) {      // the uint16-count instances (sisua_train_step_gather_u16)
+    CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, true, tc::LINK_SOFTPLUS, tc::MODE_PLAIN, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, true)));
+    CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, true, tc::LINK_GENERIC, tc::MODE_PLAIN, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, true)));
+    CUDA_OK(h, cudaFuncSetAttribute(tc::out_heads_kernel<NH, true, true, tc::LINK_TFP, tc::MODE_PLAIN, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, tc::OutSmem::total(NH, true)));
+  }
   return SISUA_OK;
 }
 
@@ -335,6 +344,7 @@ template <int N0>
 static int tc_enc_attr(sisua_model* h) {
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0, true>::total));
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0, false>::total));
+  CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_fwd_kernel<N0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncFwdSmem<N0, true>::total));
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
   CUDA_OK(h, cudaFuncSetAttribute(tc::enc_first_bwd_kernel<N0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EncBwdSmem<N0>::total));
   return SISUA_OK;
@@ -393,7 +403,10 @@ static int tc_encoder_first(sisua_model* h, cudaStream_t st, const float* x, int
   const bool vec = (c.n_genes % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   dim3 grid(cell_tiles, chunks);
   ++h->launches;
-  if (N0 == 64) {
+  if (h->x_u16) {      // (the entry point has checked the 16-byte geometry)
+    if (N0 == 64) tc::enc_first_fwd_kernel<64, true, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64, true>::total, st>>>(a);
+    else tc::enc_first_fwd_kernel<128, true, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<128, true>::total, st>>>(a);
+  } else if (N0 == 64) {
     if (vec) tc::enc_first_fwd_kernel<64, true><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64, true>::total, st>>>(a);
     else tc::enc_first_fwd_kernel<64, false><<<grid, tc::kEncFwdThreads, tc::EncFwdSmem<64, false>::total, st>>>(a);
   } else {
@@ -535,7 +548,15 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
     else if (link == tc::LINK_TFP) tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_TFP><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);  \
     else tc::out_heads_kernel<NH, TRAIN, VEC, tc::LINK_GENERIC><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, TRAIN), st>>>(a);      \
   } while (0)
-  if (nh == 3) {
+#define TC_LAUNCH_U16(NH)                                                                                            \
+  do {                                                                                                              \
+    if (link == tc::LINK_SOFTPLUS) tc::out_heads_kernel<NH, true, true, tc::LINK_SOFTPLUS, tc::MODE_PLAIN, true><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);  \
+    else if (link == tc::LINK_TFP) tc::out_heads_kernel<NH, true, true, tc::LINK_TFP, tc::MODE_PLAIN, true><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);  \
+    else tc::out_heads_kernel<NH, true, true, tc::LINK_GENERIC, tc::MODE_PLAIN, true><<<grid, tc::kOutThreads, tc::OutSmem::total(NH, true), st>>>(a);      \
+  } while (0)
+  if (h->x_u16) {      // training step on uint16 resident counts (the entry point has checked the geometry)
+    if (nh == 3) TC_LAUNCH_U16(3); else TC_LAUNCH_U16(2);
+  } else if (nh == 3) {
     if (training) { if (vec) TC_LAUNCH(3, true, true); else TC_LAUNCH(3, true, false); }
     else { if (vec) TC_LAUNCH(3, false, true); else TC_LAUNCH(3, false, false); }
   } else {
@@ -543,6 +564,7 @@ static int tc_output_heads(sisua_model* h, cudaStream_t st, bool training, const
     else { if (vec) TC_LAUNCH(2, false, true); else TC_LAUNCH(2, false, false); }
   }
 #undef TC_LAUNCH
+#undef TC_LAUNCH_U16
   LAUNCH_OK(h, "out_heads_kernel (tcgen05)");
   return SISUA_OK;
 }
@@ -1209,11 +1231,53 @@ __global__ void __launch_bounds__(256) gather_bytes_kernel(const uint8_t* __rest
 // every step: sisua/data/_single_cell_base.py:593-601 shuffle -> batch): x_all [N,G], y_all [N,P], library_all [N,2],
 // mask_all [N], rows [B] int32 (device).  The tcgen05 kernels read the count rows through the index (no gathered copy
 // of the minibatch is ever written); the small per-cell side inputs are gathered by one tiny kernel each.
+// gather + widen rows of a uint16 count matrix into fp32 (rows == NULL: rows 0 .. n_rows-1)
+__global__ void __launch_bounds__(256) widen_rows_u16_kernel(const uint16_t* __restrict__ src, const int* __restrict__ ridx,
+                                                             float* __restrict__ dst, int B, int G) {
+  const long long n = (long long)B * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / G), g = (int)(i - (long long)b * G);
+    dst[i] = (float)src[(size_t)(ridx ? ridx[b] : b) * G + g];
+  }
+}
+
+extern "C" int sisua_widen_rows_u16(sisua_handle h, const uint16_t* x_all, const int32_t* rows, float* dst, int n_rows, void* stream) {
+  if (!h || !x_all || !dst || n_rows < 0) return SISUA_ERR_INVALID;
+  if (n_rows == 0) return SISUA_OK;
+  const int G = h->cfg.n_genes;
+  ++h->launches;
+  widen_rows_u16_kernel<<<std::max(1, std::min(8 * h->num_sms, (int)(((long long)n_rows * G + 255) / 256))), 256, 0, (cudaStream_t)stream>>>(
+      x_all, rows, dst, n_rows, G);
+  LAUNCH_OK(h, "widen_rows_u16_kernel");
+  return SISUA_OK;
+}
+
+static int train_step_gather_impl(sisua_handle h, const void* x_any, bool u16, const float* y_all, const float* library_all,
+                                  const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                                  uint64_t seed, int64_t step, float* terms, float* loss, void* stream);
+
 extern "C" int sisua_train_step_gather(sisua_handle h, const float* x_all, const float* y_all, const float* library_all,
                                        const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
                                        uint64_t seed, int64_t step, float* terms, float* loss, void* stream) {
+  return train_step_gather_impl(h, x_all, false, y_all, library_all, mask_all, rows, eps_z, eps_l, B, seed, step, terms, loss, stream);
+}
+
+// The same step with the resident count matrix stored as uint16 (exact for count data below 65 536: half the HBM of the
+// shard and half the bytes of both streaming reads).  The two tcgen05 kernels widen the counts themselves when the rows
+// are 16-byte aligned (n_genes a multiple of 8, aligned base) and the model's heads are the plain (non-scVI) ones;
+// otherwise the minibatch rows are widened into an fp32 staging buffer first.
+extern "C" int sisua_train_step_gather_u16(sisua_handle h, const uint16_t* x_all, const float* y_all, const float* library_all,
+                                           const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                                           uint64_t seed, int64_t step, float* terms, float* loss, void* stream) {
+  return train_step_gather_impl(h, x_all, true, y_all, library_all, mask_all, rows, eps_z, eps_l, B, seed, step, terms, loss, stream);
+}
+
+static int train_step_gather_impl(sisua_handle h, const void* x_any, bool u16, const float* y_all, const float* library_all,
+                                  const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
+                                  uint64_t seed, int64_t step, float* terms, float* loss, void* stream) {
   if (!h) return SISUA_ERR_INVALID;
-  if (!rows) return sisua_train_step(h, x_all, y_all, library_all, mask_all, eps_z, eps_l, B, seed, step, terms, loss, stream);
+  const float* x_all = reinterpret_cast<const float*>(x_any);
+  if (!rows && !u16) return sisua_train_step(h, x_all, y_all, library_all, mask_all, eps_z, eps_l, B, seed, step, terms, loss, stream);
   const sisua_step_config& c = h->cfg;
   if (B < 1 || B > c.max_batch) SET_ERR(h, SISUA_ERR_INVALID, "train_step_gather: B=%d outside [1, max_batch=%d]", B, c.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1224,34 +1288,44 @@ extern "C" int sisua_train_step_gather(sisua_handle h, const float* x_all, const
 #ifdef SISUA_WITH_TC
   tc_path = tc_heads_enabled(h);
 #endif
-  if (!tc_path) {       // cross-check path: dense copy of the counts
+  // uint16 counts stay uint16 all the way into the kernels when the geometry allows 16-byte copies
+  const int32_t* x_rows = rows;      // the index the tcgen05 kernels read the counts through
+  const bool u16_direct = u16 && tc_path && c.model_kind != SISUA_MODEL_SCVI && c.n_genes % 8 == 0 &&
+                          (reinterpret_cast<uintptr_t>(x_any) & 15) == 0;
+  if (u16 && !u16_direct) {
+    if (!h->gx && (rc = ws_alloc(h, &h->gx, R * c.n_genes)) != SISUA_OK) return rc;
+    if ((rc = sisua_widen_rows_u16(h, reinterpret_cast<const uint16_t*>(x_any), rows, h->gx, B, stream)) != SISUA_OK) return rc;
+    x = h->gx; x_rows = nullptr;      // (the minibatch is now a dense fp32 copy)
+  } else if (!tc_path) {       // cross-check path: dense copy of the counts
     if (!h->gx && (rc = ws_alloc(h, &h->gx, R * c.n_genes)) != SISUA_OK) return rc;
     ++h->launches;
     gather_rows_kernel<<<std::max(1, std::min(4 * h->num_sms, (int)(((long long)B * c.n_genes + 255) / 256))), 256, 0, st>>>(x_all, rows, h->gx, B, c.n_genes);
-    x = h->gx;
+    x = h->gx; x_rows = nullptr;
   }
-  if (y_all && c.n_proteins > 0) {
+  if (rows && y_all && c.n_proteins > 0) {
     if (!h->gy && (rc = ws_alloc(h, &h->gy, R * c.n_proteins)) != SISUA_OK) return rc;
     ++h->launches;
     gather_rows_kernel<<<(B * c.n_proteins + 255) / 256, 256, 0, st>>>(y_all, rows, h->gy, B, c.n_proteins);
     y = h->gy;
   }
-  if (library_all) {
+  if (rows && library_all) {
     if (!h->glib && (rc = ws_alloc(h, &h->glib, R * 2)) != SISUA_OK) return rc;
     ++h->launches;
     gather_rows_kernel<<<(B * 2 + 255) / 256, 256, 0, st>>>(library_all, rows, h->glib, B, 2);
     lib = h->glib;
   }
-  if (mask_all) {
+  if (rows && mask_all) {
     if (!h->gmask && (rc = ws_alloc(h, &h->gmask, R)) != SISUA_OK) return rc;
     ++h->launches;
     gather_bytes_kernel<<<(B + 255) / 256, 256, 0, st>>>(mask_all, rows, h->gmask, B);
     mask = h->gmask;
   }
   LAUNCH_OK(h, "row gather");
-  h->ridx = tc_path ? rows : nullptr;
+  h->ridx = tc_path ? x_rows : nullptr;
+  h->x_u16 = u16_direct;
   rc = sisua_train_step(h, x, y, lib, mask, eps_z, eps_l, B, seed, step, terms, loss, stream);
   h->ridx = nullptr;
+  h->x_u16 = false;
   return rc;
 }
 

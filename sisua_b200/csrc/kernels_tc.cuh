@@ -138,9 +138,11 @@ enum OutBar { ACC_FULL = 4, ACC_FREE = 6, G_FULL = 8, G_FREE = 10, DWO_FULL = 12
 // LINK: how the raw head outputs become (mean, inverse dispersion): the default softplus pair (packed fast path), TFP's
 // total_count / logits form of the 'zinb' / 'nb' enums (packed), or any other activation pair (scalar evaluation)
 enum OutLink { LINK_GENERIC = 0, LINK_SOFTPLUS = 1, LINK_TFP = 2 };
-template <int NH, bool TRAIN, bool VEC, int LINK, int MODE = MODE_PLAIN>
+// XU16 (VEC only): a.x points at uint16 counts (exact for count data; half the bytes of the likelihood's second read of x)
+template <int NH, bool TRAIN, bool VEC, int LINK, int MODE = MODE_PLAIN, bool XU16 = false>
 __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs a) {
   static_assert(TRAIN == (MODE == MODE_SCVI_TRAIN) || MODE == MODE_PLAIN, "only the plain and scVI-train modes run the gradient GEMMs");
+  static_assert(VEC || !XU16, "uint16 counts are implemented for the 16-byte aligned (VEC) geometry");
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int N = NH * 32;
   constexpr int NF = MODE == MODE_SCVI_LSE ? 32 : N;     // the logsumexp pass only needs head 0 (rows 0..31 of a tile)
@@ -397,8 +399,13 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
       const int g = (tile_begin + i) * kGeneTile + sub * 8;
       uint8_t* dst = xs_base + (i & 1) * kXsStage;
       const bool ok0 = row_ok && g < a.G && a.x, ok1 = row_ok && g + 4 < a.G && a.x;      // (x == NULL: decode only, zeros)
-      cp_async_16_zfill(dst, ok0 ? (const void*)(xrow + g) : (const void*)a.x, ok0 ? 16u : 0u);
-      cp_async_16_zfill(dst + kXsHalf, ok1 ? (const void*)(xrow + g + 4) : (const void*)a.x, ok1 ? 16u : 0u);
+      if (XU16) {          // the 8 counts of this thread are ONE 16-byte copy (G is a multiple of 8: whole or nothing)
+        const uint16_t* xrow16 = reinterpret_cast<const uint16_t*>(a.x) + (size_t)(a.ridx ? a.ridx[xb] : xb) * a.G;
+        cp_async_16_zfill(dst, ok0 ? (const void*)(xrow16 + g) : (const void*)a.x, ok0 ? 16u : 0u);
+      } else {
+        cp_async_16_zfill(dst, ok0 ? (const void*)(xrow + g) : (const void*)a.x, ok0 ? 16u : 0u);
+        cp_async_16_zfill(dst + kXsHalf, ok1 ? (const void*)(xrow + g + 4) : (const void*)a.x, ok1 ? 16u : 0u);
+      }
       cp_async_commit();
     };
     float xnext[VEC ? 1 : 8];
@@ -488,8 +495,13 @@ __global__ void __launch_bounds__(kOutThreads, 1) out_heads_kernel(OutHeadsArgs 
             pi[p] = pm::add(pm::mk(pl[2 * p], pl[2 * p + 1]), pm::mk(bl.x, bl.y));
           }
           const int pj = (j >> 1) + p;      // gene pair 0..3 of this thread's slice
-          const float2 xv = *reinterpret_cast<const float2*>(xs + (pj >> 1) * kXsHalf + (pj & 1) * 8);
-          x2[p] = pm::mk(xv.x, xv.y);
+          if (XU16) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(xs + pj * 4);
+            x2[p] = pm::mk(u16_to_float(w & 0xffffu), u16_to_float(w >> 16));
+          } else {
+            const float2 xv = *reinterpret_cast<const float2*>(xs + (pj >> 1) * kXsHalf + (pj & 1) * 8);
+            x2[p] = pm::mk(xv.x, xv.y);
+          }
         }
         if (j + kGT < 8) {
           tmem_ldn<kGT>(tb + j + kGT, pa);

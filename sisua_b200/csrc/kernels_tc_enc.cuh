@@ -110,7 +110,7 @@ __device__ __forceinline__ void store8_hi(uint8_t* tile, uint32_t off, const flo
 }
 
 struct EncFwdArgs {
-  const float* x;           // [B, G], or the resident [N, G] matrix when ridx is given
+  const float* x;           // [B, G], or the resident [N, G] matrix when ridx is given (uint16 entries in the XU16 kernels)
   const int* ridx;          // [B] rows of x that make up this minibatch (nullable: rows 0 .. B-1)
   const uint8_t* packed;    // packed W1 k-blocks
   float* A0;                // [B, ld0] pre-activations (zeroed by the caller when k_chunks > 1)
@@ -139,8 +139,11 @@ struct EncFwdSmem {
 
 enum EncBar { EB_A_FULL = 0, EB_W_FULL = 3, EB_STAGE_FREE = 6, EB_ACC_FULL = 9, EB_RAW_FULL = 10, EB_RAW_FREE = 13 };
 
-template <int N0, bool VEC>
+// XU16 (VEC only): the count matrix is stored as uint16 (exact for count data, half the HBM bytes); a row segment of 64
+// genes is 128 bytes = 8 async copies, and an item's 8 counts are ONE 16-byte shared-memory read.
+template <int N0, bool VEC, bool XU16 = false>
 __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwdArgs a) {
+  static_assert(VEC || !XU16, "uint16 counts are implemented for the 16-byte aligned (VEC) geometry");
   constexpr int CW = kEncFwdConvWarps, kMma = CW, kLoad = CW + 1, kStore = CW + 2;
   extern __shared__ __align__(128) uint8_t smem[];
   using S = EncFwdSmem<N0, VEC>;
@@ -232,20 +235,24 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
     // VEC: every converter thread issues four 16-byte async copies per k-block (rows (t >> 4) + 32 j, chunk t & 15 of the
     // 256-byte row segment), NR - 1 k-blocks ahead of the one it converts; cells / genes outside the matrix are zero-filled.
     // (A single loader warp issuing all 2048 copies of a tile was issue-bound: 1.5 TB/s.)
-    const float* cp_rows[4];              // this thread's four source rows (gathered through ridx when given)
+    // (XU16: two copies per thread -- rows (t >> 3) + 64 j, chunk t & 7 of the 128-byte row segment)
+    constexpr int NCP = XU16 ? 2 : 4, CHUNKS = XU16 ? 8 : 16, RSEG = XU16 ? 128 : 256, EPC = XU16 ? 8 : 4;   // copies, chunks / row, bytes / row, entries / chunk
+    constexpr int ESZ = XU16 ? 2 : 4;
+    const int cp_r = t / CHUNKS, cp_c = t % CHUNKS;
+    const uint8_t* cp_rows[NCP];          // this thread's source rows (gathered through ridx when given)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = min(row0 + (t >> 4) + 32 * j, a.B - 1);
-      cp_rows[j] = a.x + (size_t)(a.ridx ? a.ridx[r] : r) * a.G + kb_begin * 64 + (t & 15) * 4;
+    for (int j = 0; j < NCP; ++j) {
+      const int r = min(row0 + cp_r + (512 / CHUNKS) * j, a.B - 1);
+      cp_rows[j] = reinterpret_cast<const uint8_t*>(a.x) + ((size_t)(a.ridx ? a.ridx[r] : r) * a.G + kb_begin * 64 + cp_c * EPC) * ESZ;
     }
-    uint8_t* cp_dst = smem + S::raw + (t >> 4) * 256 + (t & 15) * 16;
+    uint8_t* cp_dst = smem + S::raw + cp_r * RSEG + cp_c * 16;
     auto issue = [&](int i) {
       const int rs = i % NR;
-      const bool c_ok = (kb_begin + i) * 64 + (t & 15) * 4 < a.G;
+      const bool c_ok = (kb_begin + i) * 64 + cp_c * EPC < a.G;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = c_ok && row0 + (t >> 4) + 32 * j < a.B;
-        cp_async_16_zfill(cp_dst + rs * kRawTile + j * 32 * 256, ok ? (const void*)(cp_rows[j] + (size_t)i * 64) : (const void*)a.x,
+      for (int j = 0; j < NCP; ++j) {
+        const bool ok = c_ok && row0 + cp_r + (512 / CHUNKS) * j < a.B;
+        cp_async_16_zfill(cp_dst + rs * kRawTile + j * (512 / CHUNKS) * RSEG, ok ? (const void*)(cp_rows[j] + (size_t)i * 64 * ESZ) : (const void*)a.x,
                           ok ? 16u : 0u);
       }
       cp_async_mbar_arrive_noinc(&bars[EB_RAW_FULL + rs]);
@@ -272,6 +279,14 @@ __global__ void __launch_bounds__(kEncFwdThreads, 1) enc_first_fwd_kernel(EncFwd
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
           const int r = rbase + RSTEP * j;
+          if (XU16) {         // 8 counts = one 16-byte read; a quarter warp (8 column groups of a row) covers 128 contiguous bytes
+            const uint4 w = *reinterpret_cast<const uint4*>(smem + S::raw + rs * kRawTile + r * 128 + cg * 16);
+            cur[j][0] = u16_to_float(w.x & 0xffffu); cur[j][1] = u16_to_float(w.x >> 16);
+            cur[j][2] = u16_to_float(w.y & 0xffffu); cur[j][3] = u16_to_float(w.y >> 16);
+            cur[j][4] = u16_to_float(w.z & 0xffffu); cur[j][5] = u16_to_float(w.z >> 16);
+            cur[j][6] = u16_to_float(w.w & 0xffffu); cur[j][7] = u16_to_float(w.w >> 16);
+            continue;
+          }
           const uint8_t* src = smem + S::raw + rs * kRawTile + r * 256 + cg * 32;
           const float4 p = *reinterpret_cast<const float4*>(src + (swap ? 16 : 0));
           const float4 q = *reinterpret_cast<const float4*>(src + (swap ? 0 : 16));

@@ -60,6 +60,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// exact widening of a 16-bit count without the quarter-rate integer -> float conversion: 2^23 + v has v in its low mantissa bits
+__device__ __forceinline__ float u16_to_float(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
+
 // register reallocation between warpgroups (sm_90a+): every warp of a warpgroup executes the same instruction
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

@@ -117,16 +117,34 @@ class Engine:
     for t in (x_all, y_all, library_all, mask_all, eps_z, eps_l):
       if t is not None and (not t.is_cuda or not t.is_contiguous()):
         raise ValueError("train_step_gather: inputs must be contiguous device tensors")
+    # a 16-bit integer matrix is the compact (uint16) resident storage of the counts (sisua_train_step_gather_u16)
+    if x_all.dtype in (torch.uint16, torch.int16):
+      entry = self.lib.sisua_train_step_gather_u16
+    elif x_all.dtype == torch.float32:
+      entry = self.lib.sisua_train_step_gather
+    else:
+      raise ValueError(f"train_step_gather: counts must be float32 or 16-bit integers, got {x_all.dtype}")
     B = rows.numel()
     if terms is None:
       terms = torch.empty((5, B), dtype=torch.float32, device=self.device)
     if loss is None:
       loss = torch.empty((1,), dtype=torch.float32, device=self.device)
     with torch.cuda.device(self.device):
-      self._check(self.lib.sisua_train_step_gather(self.handle, _ptr(x_all), _ptr(y_all), _ptr(library_all), _ptr(mask_all),
-                                                   _ptr(rows), _ptr(eps_z), _ptr(eps_l), B, int(seed), int(step), _ptr(terms),
-                                                   _ptr(loss), self._stream()))
+      self._check(entry(self.handle, _ptr(x_all), _ptr(y_all), _ptr(library_all), _ptr(mask_all), _ptr(rows), _ptr(eps_z), _ptr(eps_l), B,
+                        int(seed), int(step), _ptr(terms), _ptr(loss), self._stream()))
     return terms, loss
+
+  def widen_rows(self, x_u16: torch.Tensor, rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 copy of rows of a uint16 resident count matrix (sisua_widen_rows_u16); rows=None: the whole matrix."""
+    if x_u16.dtype not in (torch.uint16, torch.int16) or not x_u16.is_cuda or not x_u16.is_contiguous():
+      raise ValueError("widen_rows: x must be a contiguous 16-bit integer device matrix")
+    n = x_u16.shape[0] if rows is None else rows.numel()
+    if rows is not None and (rows.dtype != torch.int32 or not rows.is_cuda or not rows.is_contiguous()):
+      raise ValueError("widen_rows: rows must be a contiguous int32 device tensor")
+    out = torch.empty((n, x_u16.shape[1]), dtype=torch.float32, device=self.device) if out is None else out
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_widen_rows_u16(self.handle, _ptr(x_u16), _ptr(rows), _ptr(out), int(n), self._stream()))
+    return out
 
   def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps_hat=1e-7, clipnorm=100.0, grad_scale=1.0, t=0):
     with torch.cuda.device(self.device):

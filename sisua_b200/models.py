@@ -74,6 +74,16 @@ class SingleCellData:
     return out
 
 
+def _is_batch_iterable(x) -> bool:
+  """True for an iterable of minibatches (a generator, a tf.data-like object, a list of batch dicts) as opposed to a whole
+  dataset (SingleCellData, an array, a (X, Y) pair, a dict of arrays)."""
+  if isinstance(x, (SingleCellData, np.ndarray, torch.Tensor, dict)) or x is None:
+    return False
+  if isinstance(x, (tuple, list)):
+    return len(x) > 0 and all(isinstance(b, dict) and "inputs" in b for b in x)
+  return hasattr(x, "__iter__")
+
+
 def _to_data(x, require_meta=False) -> SingleCellData:
   if isinstance(x, SingleCellData):
     return x
@@ -231,9 +241,20 @@ class SingleCellModel:
       b["library"] = dev_cache["library"][idx]
     return b
 
-  def _upload(self, data: SingleCellData) -> Dict[str, torch.Tensor]:
+  def _upload(self, data: SingleCellData, storage: str = "float32") -> Dict[str, torch.Tensor]:
     dev = self.engine.device
-    cache = dict(x=torch.from_numpy(data.X).to(dev))
+    X = data.X
+    compact = False
+    if storage in ("uint16", "auto") and X.size:
+      # counts are integers: uint16 holds them exactly in half the HBM (sisua_train_step_gather_u16 widens them in-kernel)
+      compact = float(X.min()) >= 0 and float(X.max()) < 65536 and all(
+          np.array_equal(X[s:s + 65536], np.rint(X[s:s + 65536])) for s in range(0, X.shape[0], 65536))
+      if storage == "uint16" and not compact:
+        raise ValueError("storage='uint16' needs non-negative integer counts below 65 536")
+    if compact:
+      cache = dict(x=torch.from_numpy(X.astype(np.uint16).view(np.int16)).to(dev))
+    else:
+      cache = dict(x=torch.from_numpy(X).to(dev))
     self.engine.set_count_bound(float(data.X.max()) if data.X.size else 0.0)     # keeps the fp16 gradient tiles in range
     if self.labels:
       if data.Y is None:
@@ -414,6 +435,9 @@ class SingleCellModel:
     # the remaining keys of configs/base.yaml:45-62 are honoured or rejected, never silently swallowed
     dp_shard = bool(kwargs.pop("dp_shard", True))     # data parallel: False = `train` already is this rank's shard
     dp_exchange = str(kwargs.pop("dp_exchange", "peer"))   # 'peer': one kernel over NVLink peer memory; 'nccl': all-reduce + Adam
+    storage = str(kwargs.pop("storage", "auto"))           # resident training shard: 'float32', 'uint16' (exact for counts) or 'auto'
+    if storage not in ("float32", "uint16", "auto"):
+      raise ValueError("storage must be 'float32', 'uint16' or 'auto'")
     if dp_exchange not in ("peer", "nccl"):
       raise ValueError("dp_exchange must be 'peer' or 'nccl'")
     valid_interval = float(kwargs.pop("valid_interval", 0) or 0)          # seconds between validation passes (0: valid_freq only)
@@ -430,6 +454,11 @@ class SingleCellModel:
       raise ValueError("the fused optimiser on the hot path is Adam (configs/base.yaml:46)")
     if sample_shape not in ((), None, [], 0, 1, (1,)):
       raise NotImplementedError("training uses sample_shape=() (configs/base.yaml:53)")
+    if _is_batch_iterable(train):
+      # an iterable of minibatch dicts -- what SingleCellOMIC.create_dataset / tf.data yields and odin-ai's fit consumes
+      # (sisua/data/_single_cell_base.py:582-601): every batch goes through sisua_train_step + sisua_adam_step as it comes
+      return self._fit_batches(train, epochs=epochs, max_iter=max_iter, lr=float(learning_rate), clipnorm=float(clipnorm or 0.0),
+                               terminate_on_nan=terminate_on_nan, logging_interval=logging_interval, verbose=verbose)
     train = _to_data(train)
     valid = _to_data(valid) if valid is not None else None
     eng = self.engine
@@ -487,7 +516,7 @@ class SingleCellModel:
       pipe = HostTrainPipeline(eng, B)
       host_losses = []
     else:
-      cache = self._upload(train)
+      cache = self._upload(train, storage)
       # launch-bound regime (the reference's minibatch sizes): replay the whole step as one CUDA graph
       use_graph = (cuda_graph is True) or (cuda_graph == 'auto' and B <= 2048 and world == 1)
       if use_graph:
@@ -757,6 +786,54 @@ class SingleCellModel:
         class_name, dataset, metadata, _ = pickle.load(f)
       assert class_name == self.__class__.__name__
       self.dataset, self.metadata = dataset, metadata
+    self.is_fitted = True
+    return self
+
+  def _fit_batches(self, batches, epochs, max_iter, lr, clipnorm, terminate_on_nan, logging_interval, verbose):
+    eng = self.engine
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+      raise NotImplementedError("fit(iterable of batches) is single-GPU; shard a SingleCellData over ranks instead")
+    names = ["loss", "llk_" + self.posteriors[0].name] + (["llk_" + self.posteriors[1].name] if self.labels else []) + \
+        ["kl_" + self._latents.name] + (["kl_Library"] if self._kind == C.MODEL_SCVI else [])
+    for n in names:
+      self.train_history.setdefault(n, [])
+      self.valid_history.setdefault(n, [])
+    eng.nonfinite(reset=True)
+    eng.reset_step_counter(self.step)
+    limit = int(max_iter) if (max_iter is not None and max_iter > 0) else None
+    done, log_buf = 0, []
+    for ep in range(max(1, int(epochs or 1))):
+      seen = 0
+      for b in batches:
+        if limit is not None and done >= limit:
+          break
+        inputs = b["inputs"] if isinstance(b, dict) else b
+        x, y = (tuple(inputs) + (None,))[:2] if isinstance(inputs, (tuple, list)) else (inputs, None)
+        extra = b if isinstance(b, dict) else {}
+        if self.labels and y is None:
+          raise ValueError("this model has a label head: every batch needs inputs=(x, y)")
+        if self._kind == C.MODEL_SCVI and extra.get("library") is None:
+          raise ValueError("scVI batches need 'library' ([B, 2]: mean and variance of the log library size)")
+        self.step += 1
+        terms, loss = eng.train_step(x, y=y if self.labels else None, library=extra.get("library") if self._kind == C.MODEL_SCVI else None,
+                                     mask=extra.get("mask") if self.labels else None, seed=self._seed, step=self.step)
+        eng.adam_step(lr=lr, clipnorm=clipnorm, t=self.step)
+        done += 1; seen += 1
+        if terminate_on_nan and eng.nonfinite():
+          torch.cuda.current_stream(eng.device).synchronize()
+          eng.nonfinite(reset=True)
+          raise FloatingPointError(f"training loss is not finite at or before step {self.step} (terminate_on_nan, configs/base.yaml:59)")
+        if logging_interval and done % int(logging_interval) == 0:
+          log_buf.append(torch.cat([loss, terms[1:].mean(dim=1)]))
+      if log_buf:
+        for row in torch.stack(log_buf).cpu().numpy():
+          self._log(self.train_history, names, self._select(row))
+        if verbose:
+          print(f"epoch {ep + 1} loss {self.train_history['loss'][-1]:.3f}")
+        log_buf = []
+      if seen == 0 or (limit is not None and done >= limit):      # exhausted generator / step budget reached
+        break
     self.is_fitted = True
     return self
 

@@ -165,3 +165,43 @@ def test_keras_named_weight_exchange(tmp_path):
   z2 = m2.encode(sco.X[:32])
   a, b = (z1[0] if isinstance(z1, tuple) else z1), (z2[0] if isinstance(z2, tuple) else z2)
   assert torch.equal(a.mean(), b.mean())
+
+
+@pytest.mark.gpu
+def test_fit_accepts_an_iterable_of_batch_dicts():
+  """fit(iterable of dict(inputs, library, mask)) -- the minibatch dicts SingleCellOMIC.create_dataset yields
+  (sisua/data/_single_cell_base.py:582-601) -- trains batch by batch; a generator is consumed once."""
+  sco = _data(n=640, p=6, labels_percent=0.5)
+  m = _make("sisua", seed=5)
+  m.set_metadata(sco)
+
+  def batches():
+    for s in range(0, 640, 64):
+      yield dict(inputs=(sco.X[s:s + 64], sco.Y[s:s + 64]), mask=sco.mask[s:s + 64])
+
+  m.fit(list(batches()), epochs=3, learning_rate=2e-3, logging_interval=1)
+  loss = np.array(m.train_history["loss"])
+  assert len(loss) == 30 and np.isfinite(loss).all() and loss[-5:].mean() < loss[:5].mean()
+  assert m.step == 30 and m.is_fitted
+  m.fit(batches(), epochs=3, logging_interval=1)           # a generator: one pass, then it is exhausted
+  assert m.step == 40
+  v = _make("scvi", seed=5); v.set_metadata(sco)
+  with pytest.raises(ValueError):
+    v.fit([dict(inputs=sco.X[:64])], epochs=1)              # scVI needs the library statistics with every batch
+
+
+@pytest.mark.gpu
+def test_fit_with_uint16_resident_storage():
+  """fit(storage='uint16'): the training shard lives in HBM as uint16 and trains exactly like the float32 shard (same
+  seeds -> same minibatches, masks and noise); non-integer data is refused."""
+  sco = _data(n=1024, g=64)
+  a = _make("vae", g=64, seed=6); b = _make("vae", g=64, seed=6)
+  a.fit(sco, batch_size=128, epochs=3, learning_rate=2e-3, logging_interval=1, storage="uint16")
+  b.fit(sco, batch_size=128, epochs=3, learning_rate=2e-3, logging_interval=1, storage="float32")
+  la, lb = np.array(a.train_history["loss"]), np.array(b.train_history["loss"])
+  assert len(la) == 24 and np.isfinite(la).all()
+  np.testing.assert_allclose(la, lb, rtol=2e-3)
+  frac = SingleCellData(sco.X + 0.5, name="frac")
+  with pytest.raises(ValueError):
+    _make("vae", g=64, seed=6).fit(frac, batch_size=128, epochs=1, storage="uint16")
+  _make("vae", g=64, seed=6).fit(frac, batch_size=128, epochs=1, storage="auto")      # falls back to float32

@@ -523,6 +523,44 @@ def test_row_gather_step_equals_step_on_gathered_copy(model, kw, G, mode):
   a.close(); b.close()
 
 
+@pytest.mark.parametrize("model,kw,G,mode", [("vae", {}, 2000, C.GEMM_TC_3XFP16), ("vae", dict(x_dist="nbd"), 328, C.GEMM_TC_3XFP16),
+                                             ("sisua", dict(n_proteins=10), 520, C.GEMM_TC_3XFP16), ("vae", {}, 203, C.GEMM_TC_3XFP16),
+                                             ("scvi", {}, 328, C.GEMM_TC_3XFP16), ("vae", {}, 328, C.GEMM_FP32_UNFUSED)])
+def test_uint16_resident_counts_equal_float32(model, kw, G, mode):
+  """sisua_train_step_gather_u16 (the resident shard stored as uint16, widened inside the two tcgen05 kernels) against
+  sisua_train_step_gather on the float32 copy of the same matrix: same terms, loss and gradients.  G = 203 (rows not
+  16-byte aligned), scVI and the un-fused mode take the staged widening instead of the in-kernel one."""
+  from sisua_b200.engine import Engine
+  N, B = 1000, 200
+  cfg = C.make_step_config(model, n_genes=G, gemm_mode=mode, max_batch=256, input_dropout=0.3, **kw)
+  flat = Hh.randomize_norm_params(cfg, PR.init_flat_params(cfg))
+  mov = PR.init_bn_moving(cfg)
+  full = Hh.make_batch(cfg, N, seed=4)
+  full["x"][3, 5] = 4000.0; full["x"][7, G - 1] = 65535.0       # large counts survive the 16-bit storage
+  rows = np.random.default_rng(0).permutation(N)[:B].astype(np.int32)
+  a = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  b = Engine(cfg, 0, flat_params=flat, bn_moving=mov)
+  for e in (a, b):
+    e.set_count_bound(65535.0)
+  dev = lambda v, dt=torch.float32: None if v is None else torch.from_numpy(np.ascontiguousarray(v)).to("cuda", dt)
+  x16 = torch.from_numpy(full["x"].astype(np.uint16).view(np.int16)).cuda()
+  side = dict(y_all=dev(full.get("y")), library_all=dev(full.get("library")), mask_all=dev(full.get("mask"), torch.uint8))
+  ta, la = a.train_step_gather(x16, dev(rows, torch.int32), seed=9, step=2, **side)
+  tb, lb = b.train_step_gather(dev(full["x"]), dev(rows, torch.int32), seed=9, step=2, **side)
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(ta.cpu().numpy(), tb.cpu().numpy(), rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(float(la), float(lb), rtol=1e-6)
+  assert np.isfinite(float(la)) and torch.isfinite(ta).all()
+  ga, gb = a.grads_dict(), b.grads_dict()
+  tol = 1e-6 if mode == C.GEMM_FP32_UNFUSED else 3e-3      # (atomics order + fp16 operand rounding, as in the gather test)
+  for k in ga:
+    np.testing.assert_allclose(ga[k], gb[k], rtol=1e-4 if mode == C.GEMM_FP32_UNFUSED else 0.0,
+                               atol=tol * (np.abs(gb[k]).max() + 1e-12) + 1e-9, err_msg=k)
+  np.testing.assert_array_equal(a.widen_rows(x16, dev(rows, torch.int32)).cpu().numpy(), full["x"][rows])
+  np.testing.assert_array_equal(a.widen_rows(x16).cpu().numpy(), full["x"])
+  a.close(); b.close()
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("model,kw", [("vae", {}), ("sisua", dict(n_proteins=10)), ("dca", {})])
 @pytest.mark.parametrize("x_dist", ["zinb", "nb"])
