@@ -124,8 +124,9 @@ class ClockSampler:
       self.err, self.t = f"NVML unavailable: {e}", None
 
   def sample(self):
-    """One NVML reading.  Also called from the timed loop itself every 64 steps: the poller thread can be starved of the
-    GIL by the launch loop (one run of this file came back with 3 samples where another had 122)."""
+    """One NVML reading.  Also called once from the main thread while the timed steps are still draining: the poller thread
+    can be starved by the launch loop (one run came back with 3 samples where another had 122).  Not called inside the
+    loop: an NVML query takes ~10 ms and stalled the launch queue (0.53 -> 0.75 ms per step when sampled every 64 steps)."""
     if self.t is None or self.err:
       return
     nv = self.nv
@@ -322,9 +323,9 @@ def main():
   e0.record()
   for i in range(a.steps):
     one_step(a.warmup + i)
-    if sampler and (i & 63) == 32:
-      sampler.sample()
   e1.record()
+  if sampler:
+    sampler.sample()      # the queue is still draining here: a reading inside the timed region even if the poller thread starved
   sync_all()
   ms = e0.elapsed_time(e1)
   launches = eng.launch_count() - launches0

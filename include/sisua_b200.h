@@ -110,6 +110,11 @@ int sisua_train_step_gather_u16(sisua_handle h, const uint16_t* x_all, const flo
                                 const uint8_t* mask_all, const int32_t* rows, const float* eps_z, const float* eps_l, int B,
                                 uint64_t seed, int64_t step, float* terms, float* loss, void* stream);
 
+/* sisua_unpack_counts_csr into a uint16 [rows, G] matrix (the input type of sisua_train_step_gather_u16): a host pipeline
+ * that ships CSR minibatches never materialises them in fp32. */
+int sisua_unpack_counts_csr_u16(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals, uint16_t* dst,
+                                int rows, void* stream);
+
 /* dst[b, :] = (float) x_all[rows[b], :] for b < n_rows (rows == NULL: rows 0 .. n_rows-1): feeds the fp32 entry points
  * (sisua_infer*, validation) from a uint16 resident matrix, chunk by chunk. */
 int sisua_widen_rows_u16(sisua_handle h, const uint16_t* x_all, const int32_t* rows, float* dst, int n_rows, void* stream);

@@ -1581,6 +1581,37 @@ __global__ void __launch_bounds__(256) unpack_csr_kernel(const int* __restrict__
   }
 }
 
+// same, into a uint16 matrix (what sisua_train_step_gather_u16 reads): half the bytes written here and read by the step
+__global__ void __launch_bounds__(256) unpack_csr_u16_kernel(const int* __restrict__ indptr, const uint16_t* __restrict__ cols,
+                                                             const uint16_t* __restrict__ vals, uint16_t* __restrict__ dst, int rows, int G) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  uint16_t* row = dst + (size_t)warp * G;
+  if ((G & 7) == 0) {
+    uint4* r4 = reinterpret_cast<uint4*>(row);
+    for (int i = lane; i < G / 8; i += 32) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int i = lane; i < G; i += 32) row[i] = 0;
+  }
+  __syncwarp();
+  const int b = indptr[warp], e = indptr[warp + 1];
+  for (int i = b + lane; i < e; i += 32) {
+    const int c = cols[i];
+    if (c < G) row[c] = vals[i];
+  }
+}
+
+extern "C" int sisua_unpack_counts_csr_u16(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals,
+                                           uint16_t* dst, int rows, void* stream) {
+  if (!h || !indptr || !dst || rows < 0) return SISUA_ERR_INVALID;
+  if (h->cfg.n_genes > 65536) SET_ERR(h, SISUA_ERR_UNSUPPORTED, "unpack_counts_csr_u16: uint16 column ids need n_genes <= 65536");
+  if (reinterpret_cast<uintptr_t>(dst) & 15) SET_ERR(h, SISUA_ERR_INVALID, "unpack_counts_csr_u16: dst must be 16-byte aligned");
+  ++h->launches;
+  unpack_csr_u16_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(indptr, cols, vals, dst, rows, h->cfg.n_genes);
+  LAUNCH_OK(h, "unpack_csr_u16_kernel");
+  return SISUA_OK;
+}
+
 extern "C" int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals,
                                        float* dst, int rows, void* stream) {
   if (!h || !indptr || !dst || rows < 0) return SISUA_ERR_INVALID;

@@ -95,7 +95,10 @@ class Engine:
   # -------------------------------------------------------------------------------------------
   def train_step(self, x, y=None, library=None, mask=None, eps_z=None, eps_l=None, terms=None, loss=None,
                  seed: int = 0, step: int = -1):
-    """forward + backward on device tensors (or host arrays, copied). Returns (terms [5,B], loss [1])."""
+    """forward + backward on device tensors (or host arrays, copied). Returns (terms [5,B], loss [1]).  A 16-bit integer
+    device matrix `x` is taken as uint16 counts (sisua_train_step_gather_u16 without a row index)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype in (torch.int16, torch.uint16):
+      return self._train_step_u16(x, y, library, mask, eps_z, eps_l, terms, loss, seed, step)
     x = self._dev(x); y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l)
     mask = self._dev(mask, torch.uint8)
     B = x.shape[0]
@@ -106,6 +109,18 @@ class Engine:
     with torch.cuda.device(self.device):
       self._check(self.lib.sisua_train_step(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), _ptr(eps_z),
                                             _ptr(eps_l), B, int(seed), int(step), _ptr(terms), _ptr(loss), self._stream()))
+    return terms, loss
+
+  def _train_step_u16(self, x, y, library, mask, eps_z, eps_l, terms, loss, seed, step):
+    y = self._dev(y); library = self._dev(library); eps_z = self._dev(eps_z); eps_l = self._dev(eps_l); mask = self._dev(mask, torch.uint8)
+    if not x.is_contiguous():
+      raise ValueError("train_step: 16-bit counts must be contiguous")
+    B = x.shape[0]
+    terms = torch.empty((5, B), dtype=torch.float32, device=self.device) if terms is None else terms
+    loss = torch.empty((1,), dtype=torch.float32, device=self.device) if loss is None else loss
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_train_step_gather_u16(self.handle, _ptr(x), _ptr(y), _ptr(library), _ptr(mask), None, _ptr(eps_z),
+                                                       _ptr(eps_l), B, int(seed), int(step), _ptr(terms), _ptr(loss), self._stream()))
     return terms, loss
 
   def train_step_gather(self, x_all, rows, y_all=None, library_all=None, mask_all=None, eps_z=None, eps_l=None, terms=None,
@@ -301,14 +316,15 @@ class Engine:
     end = self.total if self.entries[-1].name == "out.b" else ents["out.b"].offset + ents["out.b"].size
     return ev, (begin, end)
 
-  def unpack_counts_csr(self, indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, dst_f32: torch.Tensor):
-    """device CSR minibatch (int32 indptr [rows+1], 16-bit cols / vals) -> dense fp32 [rows, G] on the current stream."""
+  def unpack_counts_csr(self, indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, dst: torch.Tensor):
+    """device CSR minibatch (int32 indptr [rows+1], 16-bit cols / vals) -> dense [rows, G] on the current stream; `dst`
+    float32, or 16-bit integers (the compact form `train_step` accepts directly)."""
     rows = indptr.numel() - 1
-    if dst_f32.shape != (rows, self.cfg.n_genes) or dst_f32.dtype != torch.float32 or indptr.dtype != torch.int32:
+    if dst.shape != (rows, self.cfg.n_genes) or dst.dtype not in (torch.float32, torch.int16, torch.uint16) or indptr.dtype != torch.int32:
       raise ValueError("unpack_counts_csr: bad shapes / dtypes")
+    fn = self.lib.sisua_unpack_counts_csr if dst.dtype == torch.float32 else self.lib.sisua_unpack_counts_csr_u16
     with torch.cuda.device(self.device):
-      self._check(self.lib.sisua_unpack_counts_csr(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst_f32), rows,
-                                                   self._stream()))
+      self._check(fn(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst), rows, self._stream()))
 
   def train_step_host(self, x, *, y=None, library=None, mask=None, eps_z=None, eps_l=None, host_loss=None, host_terms=None,
                       seed: int = 0, step: int = -1):

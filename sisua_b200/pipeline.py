@@ -177,7 +177,7 @@ class HostTrainPipeline:
       eng, B = self.eng, self.batch
       dev, G = eng.device, eng.cfg.n_genes
       self.slots[s] = dict(
-          x=torch.empty((B, G), device=dev), x16=None, csr=None,
+          x=None, x16=None, csr=None,
           eps=torch.zeros((B, eng.cfg.n_latent), device=dev),
           terms=torch.empty((5, B), device=dev), loss=torch.empty((1,), device=dev),
           filled=torch.cuda.Event(), consumed=torch.cuda.Event())
@@ -191,12 +191,13 @@ class HostTrainPipeline:
     if key not in self.graphs:
       eng, sl = self.eng, self._slot(s)
       def fwd_bwd():
+        # integer formats stay 16-bit on the device: CSR is scattered into the slot's uint16 matrix, a dense uint16 batch
+        # is used as it arrived, and the step's streaming kernels widen the counts themselves (sisua_train_step_gather_u16)
         if fmt == "csr":
-          eng.unpack_counts_csr(*sl["csr"], sl["x"])
-        elif fmt == "u16":
-          eng.unpack_counts_u16(sl["x16"], sl["x"])
+          eng.unpack_counts_csr(*sl["csr"], sl["x16"])
+        x_dev = sl["x"] if fmt == "f32" else sl["x16"]
         # eps from the host when one is shipped (tests), otherwise Philox noise drawn in-kernel
-        eng.train_step(sl["x"], eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
+        eng.train_step(x_dev, eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
                        loss=sl["loss"], seed=seed, step=-1)
       def optimise():
         if peer:       # data parallel over peer memory: the exchange is part of the optimiser kernel (and of the graph)
@@ -240,7 +241,9 @@ class HostTrainPipeline:
       cap = self.batch * eng.cfg.n_genes
       sl["csr"] = (torch.zeros(self.batch + 1, device=eng.device, dtype=torch.int32),
                    torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
-    if fmt == "u16" and sl["x16"] is None:
+    if fmt == "f32" and sl["x"] is None:
+      sl["x"] = torch.empty((self.batch, eng.cfg.n_genes), device=eng.device)
+    if fmt in ("u16", "csr") and sl["x16"] is None:
       sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
     graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None, seed, eps_host is not None, peer is not None)
     if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
