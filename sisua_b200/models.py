@@ -526,6 +526,10 @@ class SingleCellModel:
                                     mask_all=cache.get("mask"), lr=lr, clipnorm=cn, seed=step_seed)
         terms, loss = graphed.terms, graphed.loss
     eng.nonfinite(reset=True)
+    ep_loss = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)] if host_stream else None
+    ep_pending = None
+    nan_slot = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    nan_pending = None
     nan_events = [None, None]
     best, patience, done = float("inf"), 0, 0
     best_state, last_valid = None, time.perf_counter()
@@ -605,11 +609,26 @@ class SingleCellModel:
               stop = True
               break
       if host_stream and host_losses:
-        vals = np.array(pipe.flush_all(host_losses), dtype=np.float64)[:, None]
         host_losses = []
-        for row in vals:
-          self.train_history["loss"].append(float(row[0]))
-        bad = not np.isfinite(vals).all()
+        if pipe.last_loss_dev is not None:
+          # epoch-end loss WITHOUT draining the pipeline: the last step's device loss is copied to a pinned slot behind
+          # the queued work and read one epoch later (a full synchronisation here cost one step's latency per epoch --
+          # 7-step epochs lost 8 % to it)
+          slot = ep_loss[ep % 2]
+          slot.copy_(pipe.last_loss_dev, non_blocking=True)
+          ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(eng.device))
+          harvested = []
+          if ep_pending is not None:
+            ep_pending[0].synchronize()
+            harvested.append(float(ep_pending[1].item()))
+          ep_pending = (ev, slot)
+          vals = np.array(harvested, dtype=np.float64)[:, None] if harvested else None
+        else:
+          vals = np.array(pipe.flush_all([pipe.host_loss[(pipe.i - 1) % len(pipe.host_loss)]]), dtype=np.float64)[-1:, None]
+        if vals is not None:
+          for row in vals:
+            self.train_history["loss"].append(float(row[0]))
+        bad = vals is not None and not np.isfinite(vals).all()
       elif log_buf:
         vals = torch.stack(log_buf).cpu().numpy()
         log_buf = []
@@ -618,16 +637,34 @@ class SingleCellModel:
         bad = not np.isfinite(vals[:, 0]).all()
       else:
         vals, bad = None, False
-      if world > 1 and terminate_on_nan:       # collective decision: a rank leaving alone would dead-lock the others
-        flag = torch.tensor([1.0 if bad else 0.0], device=eng.device)
+      if world > 1 and terminate_on_nan:
+        # collective decision (a rank leaving alone would dead-lock the others), taken one epoch late so that reading the
+        # reduced flag never drains the pipeline: every rank sees the same flag at the same epoch
+        flag = torch.tensor([1.0 if (bad or eng.nonfinite()) else 0.0], device=eng.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        bad = bool(flag.item() > 0)
+        nslot = nan_slot[ep % 2]
+        nslot.copy_(flag, non_blocking=True)
+        nev = torch.cuda.Event(); nev.record(torch.cuda.current_stream(eng.device))
+        bad = False
+        if nan_pending is not None:
+          nan_pending[0].synchronize()
+          bad = bool(nan_pending[1].item() > 0)
+        nan_pending = (nev, nslot)
       if terminate_on_nan and bad:
         raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
       if verbose and vals is not None:
         print(f"epoch {ep + 1}/{epochs} loss {vals[-1, 0]:.3f}")
       if stop:
         break
+    if nan_pending is not None:         # the last epoch's collective flag
+      nan_pending[0].synchronize()
+      if nan_pending[1].item() > 0:
+        raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
+    if ep_pending is not None:          # the last epoch's loss
+      ep_pending[0].synchronize()
+      self.train_history["loss"].append(float(ep_pending[1].item()))
+      if terminate_on_nan and world == 1 and not np.isfinite(self.train_history["loss"][-1]):
+        raise FloatingPointError("training loss is not finite (terminate_on_nan, configs/base.yaml:59)")
     if timing is not None and t_start is not None:
       torch.cuda.current_stream(eng.device).synchronize()
       if world > 1:

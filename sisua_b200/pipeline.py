@@ -171,6 +171,7 @@ class HostTrainPipeline:
     self.slots = [None] * depth
     self.graphs = {}
     self.i = 0
+    self.last_loss_dev = None      # device scalar of the most recent graph-replayed step (None after an eager step)
 
   def _slot(self, s: int):
     if self.slots[s] is None:
@@ -225,6 +226,7 @@ class HostTrainPipeline:
     if not graphable:
       out = self.host_loss[self.i % len(self.host_loss)]
       self.i += 1
+      self.last_loss_dev = None
       eng.train_step_host(x_host, eps_z=eps_host, host_loss=out, seed=seed, step=step, **host_extras)
       if peer is not None:
         eng.adam_step_dp(lr=lr, clipnorm=clipnorm, t=step)
@@ -271,6 +273,7 @@ class HostTrainPipeline:
       allreduce(eng.grads)
       graph_opt.replay()
     eng.step_count += 1
+    self.last_loss_dev = sl["loss"]
     return self.host_loss[s]
 
   def flush(self, losses: List[torch.Tensor]):
