@@ -1,5 +1,5 @@
 """Per-section device time of the train step at the bench shape (GPU box): quick A/B of kernel variants.
-Usage: python tools/time_sections.py [batch] [genes] [model]"""
+Usage: python tools/time_sections.py [batch] [genes] [model] [dp1] [u16]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,8 +23,10 @@ if model == "scvi":
 if model == "sisua":
   extra["y"] = torch.rand((B, 10), device=dev) * 5; extra["mask"] = (torch.rand(B, device=dev) < 0.1).to(torch.uint8)
 terms = torch.empty((5, B), device=dev); loss = torch.empty((1,), device=dev)
+U16 = "u16" in sys.argv[4:]       # resident counts as uint16 (what bench.py / fit() use by default for count data)
+Xs = X.to(torch.int32).to(torch.int16) if U16 else X
 def step(i):
-  eng.train_step(X[(i % 4) * B:(i % 4 + 1) * B], terms=terms, loss=loss, seed=1, step=i + 1, **extra)
+  eng.train_step(Xs[(i % 4) * B:(i % 4 + 1) * B], terms=terms, loss=loss, seed=1, step=i + 1, **extra)
   eng.adam_step(t=i + 1)
 for i in range(5): step(i)
 torch.cuda.synchronize()
@@ -39,7 +41,7 @@ prof = eng.profile_read()
 print(f"{os.environ.get('SISUA_NVCC_DEFS', '')!r}: step {total:.4f} ms  " + "  ".join(f"{k} {v[0] / 50:.4f}" for k, v in prof.items()) + f"  loss {float(loss):.3f}", flush=True)
 
 # ---- single-rank cost of the peer-memory optimiser kernel (world = 1: the exchange degenerates to barriers with itself)
-if len(sys.argv) > 4 and sys.argv[4] == "dp1":
+if "dp1" in sys.argv[4:]:
   z = lambda dt, n: torch.zeros(n, dtype=dt, device=dev)
   g, p_, sq, fl = z(torch.float32, eng.total), z(torch.float32, eng.total), z(torch.float64, 8 * 48), z(torch.int32, 64)
   eng.rebind(p_, g)
