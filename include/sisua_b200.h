@@ -115,6 +115,14 @@ int sisua_train_step_gather_u16(sisua_handle h, const uint16_t* x_all, const flo
 int sisua_unpack_counts_csr_u16(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals, uint16_t* dst,
                                 int rows, void* stream);
 
+/* Packed CSR minibatch ("delta-8") -> uint16 [rows, G]: one 16-bit word per stored entry, low byte = column advance from
+ * the row's previous entry (the first from column 0), high byte = count.  (advance 255, count 0) is a pure skip for gaps of
+ * 255 and more; count 255 escapes to the row's next unread element of `big` (big_ptr [rows + 1] offsets into it).  indptr
+ * [rows + 1] offsets into `ents`.  2 bytes per non-zero over PCIe instead of 4 (CSR) or 4 G per cell (float32 rows).
+ * sisua_b200/pipeline.py:Csr8Batch builds it. */
+int sisua_unpack_counts_csr8_u16(sisua_handle h, const int32_t* indptr, const int32_t* big_ptr, const uint16_t* ents,
+                                 const uint16_t* big, uint16_t* dst, int rows, void* stream);
+
 /* dst[b, :] = (float) x_all[rows[b], :] for b < n_rows (rows == NULL: rows 0 .. n_rows-1): feeds the fp32 entry points
  * (sisua_infer*, validation) from a uint16 resident matrix, chunk by chunk. */
 int sisua_widen_rows_u16(sisua_handle h, const uint16_t* x_all, const int32_t* rows, float* dst, int n_rows, void* stream);

@@ -10,7 +10,7 @@ from .config import StepConfig
 _LIB = None
 
 EXPORTS = ["sisua_create", "sisua_destroy", "sisua_param_layout", "sisua_bind_buffers", "sisua_train_step", "sisua_train_step_gather",
-           "sisua_train_step_gather_u16", "sisua_widen_rows_u16", "sisua_unpack_counts_csr_u16", "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_dp_bind", "sisua_adam_step_dp", "sisua_dp_shard", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_nonfinite_flag", "sisua_corrupt_counts", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
+           "sisua_train_step_gather_u16", "sisua_widen_rows_u16", "sisua_unpack_counts_csr_u16", "sisua_unpack_counts_csr8_u16", "sisua_infer", "sisua_infer_ex", "sisua_forward_train_mode", "sisua_decode", "sisua_marginal_llk", "sisua_adam_step", "sisua_dp_bind", "sisua_adam_step_dp", "sisua_dp_shard", "sisua_debug_buffer", "sisua_debug_copy", "sisua_debug_geometry", "sisua_debug_force_chunks", "sisua_launch_count", "sisua_set_step", "sisua_set_infer_seed", "sisua_set_count_bound", "sisua_nonfinite_flag", "sisua_corrupt_counts", "sisua_set_grad_ready_event", "sisua_unpack_counts_u16", "sisua_unpack_counts_csr", "sisua_train_step_host", "sisua_tc_selftest", "sisua_profile_enable", "sisua_profile_read", "sisua_last_error", "sisua_version"]
 
 
 class ParamDesc(ctypes.Structure):
@@ -63,6 +63,8 @@ def load():
   L.sisua_widen_rows_u16.restype = ci
   L.sisua_unpack_counts_csr_u16.argtypes = [vp, vp, vp, vp, vp, ci, vp]
   L.sisua_unpack_counts_csr_u16.restype = ci
+  L.sisua_unpack_counts_csr8_u16.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
+  L.sisua_unpack_counts_csr8_u16.restype = ci
   L.sisua_infer.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci] + [vp] * 10
   L.sisua_infer.restype = ci
   L.sisua_infer_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci] + [vp] * 12

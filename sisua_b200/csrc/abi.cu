@@ -1612,6 +1612,57 @@ extern "C" int sisua_unpack_counts_csr_u16(sisua_handle h, const int32_t* indptr
   return SISUA_OK;
 }
 
+// Packed CSR ("delta-8"): one 16-bit word per stored entry, low byte = column advance from the previous entry of the row
+// (the first from column 0), high byte = count.  An advance of 255 with count 0 is a pure skip (gaps >= 255); count 255
+// is an escape whose real value is the next unread element of `big` for that row (big_ptr[row] .. big_ptr[row+1]).
+// Half the PCIe bytes of the (uint16 column, uint16 count) form.  One warp per row: zero-fill, then 32 entries at a time
+// with a warp scan over the advances and a ballot over the escapes.
+__global__ void __launch_bounds__(256) unpack_csr8_u16_kernel(const int* __restrict__ indptr, const int* __restrict__ big_ptr,
+                                                              const uint16_t* __restrict__ ents, const uint16_t* __restrict__ big,
+                                                              uint16_t* __restrict__ dst, int rows, int G) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  uint16_t* row = dst + (size_t)warp * G;
+  if ((G & 7) == 0) {
+    uint4* r4 = reinterpret_cast<uint4*>(row);
+    for (int i = lane; i < G / 8; i += 32) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int i = lane; i < G; i += 32) row[i] = 0;
+  }
+  __syncwarp();
+  const int b = indptr[warp], e = indptr[warp + 1];
+  int col0 = 0, big0 = big_ptr[warp];
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t w = i < e ? ents[i] : 0u;
+    int adv = (int)(w & 0xffu);
+    const uint32_t v8 = w >> 8;
+    // inclusive scan of the advances: this entry's column
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, adv, d);
+      if (lane >= d) adv += o;
+    }
+    const int col = col0 + adv;
+    const unsigned esc = __ballot_sync(0xffffffffu, i < e && v8 == 255u);
+    uint32_t val = v8;
+    if (v8 == 255u && i < e) val = big[big0 + __popc(esc & ((1u << lane) - 1u))];
+    if (i < e && val != 0u && col < G) row[col] = (uint16_t)val;
+    col0 += __shfl_sync(0xffffffffu, adv, 31);
+    big0 += __popc(esc);
+  }
+}
+
+extern "C" int sisua_unpack_counts_csr8_u16(sisua_handle h, const int32_t* indptr, const int32_t* big_ptr, const uint16_t* ents,
+                                            const uint16_t* big, uint16_t* dst, int rows, void* stream) {
+  if (!h || !indptr || !big_ptr || !dst || rows < 0) return SISUA_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(dst) & 15) SET_ERR(h, SISUA_ERR_INVALID, "unpack_counts_csr8_u16: dst must be 16-byte aligned");
+  ++h->launches;
+  unpack_csr8_u16_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(indptr, big_ptr, ents, big, dst, rows, h->cfg.n_genes);
+  LAUNCH_OK(h, "unpack_csr8_u16_kernel");
+  return SISUA_OK;
+}
+
 extern "C" int sisua_unpack_counts_csr(sisua_handle h, const int32_t* indptr, const uint16_t* cols, const uint16_t* vals,
                                        float* dst, int rows, void* stream) {
   if (!h || !indptr || !dst || rows < 0) return SISUA_ERR_INVALID;

@@ -326,6 +326,16 @@ class Engine:
     with torch.cuda.device(self.device):
       self._check(fn(self.handle, _ptr(indptr), _ptr(cols), _ptr(vals), _ptr(dst), rows, self._stream()))
 
+  def unpack_counts_csr8(self, indptr: torch.Tensor, big_ptr: torch.Tensor, ents: torch.Tensor, big: torch.Tensor, dst_u16: torch.Tensor):
+    """device packed-CSR minibatch (pipeline.Csr8Batch layout) -> dense 16-bit [rows, G] on the current stream."""
+    rows = indptr.numel() - 1
+    if (dst_u16.shape != (rows, self.cfg.n_genes) or dst_u16.dtype not in (torch.int16, torch.uint16) or indptr.dtype != torch.int32
+        or big_ptr.dtype != torch.int32 or big_ptr.numel() != rows + 1):
+      raise ValueError("unpack_counts_csr8: bad shapes / dtypes")
+    with torch.cuda.device(self.device):
+      self._check(self.lib.sisua_unpack_counts_csr8_u16(self.handle, _ptr(indptr), _ptr(big_ptr), _ptr(ents), _ptr(big), _ptr(dst_u16), rows,
+                                                        self._stream()))
+
   def train_step_host(self, x, *, y=None, library=None, mask=None, eps_z=None, eps_l=None, host_loss=None, host_terms=None,
                       seed: int = 0, step: int = -1):
     """One train step from HOST tensors (sisua_train_step_host): `x` is a pinned float32 / 16-bit [B,G] tensor or a

@@ -510,7 +510,9 @@ class SingleCellModel:
       # the dataset stays in (pinned) host memory and every step ships its minibatch over PCIe: CSR for integer counts
       # (single-cell matrices are 70-96 % zeros), the library's host-buffer entry point otherwise
       from .pipeline import HostDataset, HostTrainPipeline
-      hds = HostDataset(train, B, shuffle=shuffle, seed=rng_seed, with_y=bool(self.labels), with_library=self._kind == C.MODEL_SCVI)
+      # plain VAE / DCA steps replay a CUDA graph per slot: those take the 2-bytes-per-non-zero packed CSR form
+      hds = HostDataset(train, B, shuffle=shuffle, seed=rng_seed, with_y=bool(self.labels), with_library=self._kind == C.MODEL_SCVI,
+                        packed=(self._kind in (C.MODEL_VAE, C.MODEL_DCA) and not self.labels))
       eng.set_count_bound(hds.max_count)
       eng.reset_step_counter(self.step)
       pipe = HostTrainPipeline(eng, B)

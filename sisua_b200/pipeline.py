@@ -53,6 +53,82 @@ class CsrBatch:
     return self.indptr.numel() * 4 + self.cols.numel() * 2 + self.vals.numel() * 2
 
 
+def encode_csr8(X):
+  """Packed CSR ("delta-8", include/sisua_b200.h: sisua_unpack_counts_csr8_u16) of a non-negative integer matrix [n, G] with
+  counts below 65 536: (indptr int64 [n + 1] into ents, ents uint16, big_ptr int64 [n + 1] into big, big uint16)."""
+  import numpy as np
+  X = np.ascontiguousarray(X)
+  n = X.shape[0]
+  r, c = np.nonzero(X)
+  v = X[r, c].astype(np.int64)
+  first = np.ones(r.size, dtype=bool)
+  first[1:] = r[1:] != r[:-1]
+  prev = np.empty_like(c)
+  prev[1:] = c[:-1]
+  prev[first] = 0
+  delta = (c - prev).astype(np.int64)                 # advance from the previous entry of the row (first: from column 0)
+  skips = delta // 255                                # pure-skip words (advance 255, count 0) in front of the entry
+  rem = delta - 255 * skips
+  words_per = skips + 1
+  tot = int(words_per.sum())
+  ents = np.full(tot, 255, dtype=np.uint16)           # skip words by default: advance 255, count 0
+  pos = np.cumsum(words_per) - 1                      # position of each real entry
+  v8 = np.minimum(v, 255)
+  ents[pos] = (rem | (v8 << 8)).astype(np.uint16)
+  indptr = np.zeros(n + 1, dtype=np.int64)
+  np.add.at(indptr, r + 1, words_per)
+  indptr = np.cumsum(indptr)
+  esc = v >= 255
+  big = v[esc].astype(np.uint16)
+  big_ptr = np.zeros(n + 1, dtype=np.int64)
+  np.add.at(big_ptr, r[esc] + 1, 1)
+  big_ptr = np.cumsum(big_ptr)
+  return indptr, ents, big_ptr, big
+
+
+def decode_csr8(indptr, ents, big_ptr, big, genes):
+  """NumPy inverse of `encode_csr8` (tests, and the documentation of the format)."""
+  import numpy as np
+  n = len(indptr) - 1
+  X = np.zeros((n, genes), dtype=np.float32)
+  for i in range(n):
+    col, k = 0, int(big_ptr[i])
+    for w in ents[int(indptr[i]):int(indptr[i + 1])]:
+      col += int(w) & 0xff
+      val = int(w) >> 8
+      if val == 255:
+        val = int(big[k]); k += 1
+      if val:
+        X[i, col] = val
+  return X
+
+
+class Csr8Batch:
+  """Pinned host packed-CSR form of one minibatch (see `encode_csr8`): 2 bytes per non-zero over PCIe."""
+
+  def __init__(self, X):
+    import numpy as np
+    X = np.ascontiguousarray(X)
+    if X.min() < 0 or X.max() >= 65536 or not np.array_equal(X, np.rint(X)):
+      raise ValueError("Csr8Batch needs non-negative integer counts below 65536")
+    ip, ents, bp, big = encode_csr8(X)
+    self.rows, self.genes = X.shape
+    self.indptr = _pin(torch.from_numpy(ip.astype(np.int32)))
+    self.big_ptr = _pin(torch.from_numpy(bp.astype(np.int32)))
+    self.ents = _pin(torch.from_numpy(ents.view(np.int16)))
+    self.big = _pin(torch.from_numpy(np.concatenate([big, np.zeros(1, np.uint16)]).view(np.int16)))      # never empty
+
+  @classmethod
+  def view(cls, rows, genes, indptr, big_ptr, ents, big) -> "Csr8Batch":
+    b = cls.__new__(cls)
+    b.rows, b.genes, b.indptr, b.big_ptr, b.ents, b.big = rows, genes, indptr, big_ptr, ents, big
+    return b
+
+  @property
+  def nbytes(self) -> int:
+    return (self.indptr.numel() + self.big_ptr.numel()) * 4 + (self.ents.numel() + self.big.numel()) * 2
+
+
 class HostDataset:
   """A training set kept in pinned HOST memory and served as minibatches for `HostTrainPipeline` (what `fit(data_on='host')`
   uses).  Mirrors the reference's input pipeline (sisua/data/_single_cell_base.py:593-601: map -> cache -> shuffle ->
@@ -61,7 +137,10 @@ class HostDataset:
   pointers, uint16 gene ids and counts; single-cell matrices are 70-96 % zeros), so a minibatch is three pinned slices
   plus B + 1 rebased row pointers; anything else stays dense float32."""
 
-  def __init__(self, data, batch: int, shuffle: bool = True, seed: int = 0, with_y: bool = False, with_library: bool = False):
+  def __init__(self, data, batch: int, shuffle: bool = True, seed: int = 0, with_y: bool = False, with_library: bool = False,
+               packed: bool = False):
+    """`packed`: cache integer counts in the 2-bytes-per-non-zero packed CSR form (`Csr8Batch`) instead of 4-byte CSR; only
+    the CUDA-graph path of `HostTrainPipeline` consumes it."""
     import numpy as np
     X = np.asarray(data.X)
     N, G = X.shape
@@ -78,7 +157,18 @@ class HostDataset:
           integer = False
           break
     self.csr = integer
-    if integer:
+    self.packed = bool(packed and integer)
+    if self.packed:
+      ips, ents_l, bps, big_l = [np.zeros(1, np.int64)], [], [np.zeros(1, np.int64)], []
+      for s in range(0, N, 32768):
+        ip, ents, bp, big = encode_csr8(X[order[s:s + 32768]])
+        ips.append(ip[1:] + ips[-1][-1]); bps.append(bp[1:] + bps[-1][-1]); ents_l.append(ents); big_l.append(big)
+      self.indptr, self.big_ptr = np.concatenate(ips), np.concatenate(bps)
+      self.ents = _pin(torch.from_numpy(np.concatenate(ents_l).view(np.int16)))
+      self.big = _pin(torch.from_numpy(np.concatenate(big_l + [np.zeros(1, np.uint16)]).view(np.int16)))
+      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
+      self._bp = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
+    elif integer:
       counts = np.zeros(N + 1, dtype=np.int64)
       cols_l, vals_l = [], []
       for s in range(0, N, 32768):
@@ -103,7 +193,15 @@ class HostDataset:
     """(x, extras): minibatch s of the cached order; x is a `CsrBatch` view or a pinned float32 [B, G] slice."""
     B = self.B
     lo, hi = s * B, (s + 1) * B
-    if self.csr:
+    if self.packed:
+      a, b = int(self.indptr[lo]), int(self.indptr[hi])
+      a2, b2 = int(self.big_ptr[lo]), int(self.big_ptr[hi])
+      ip = self._ip[self.batches_served % len(self._ip)]; bp = self._bp[self.batches_served % len(self._bp)]
+      ip.copy_(torch.from_numpy((self.indptr[lo:hi + 1] - a).astype("int32")))
+      bp.copy_(torch.from_numpy((self.big_ptr[lo:hi + 1] - a2).astype("int32")))
+      x = Csr8Batch.view(B, self.genes, ip, bp, self.ents[a:b], self.big[a2:max(b2, a2 + 1)])
+      self.h2d_bytes += x.nbytes
+    elif self.csr:
       a, b = int(self.indptr[lo]), int(self.indptr[hi])
       ip = self._ip[self.batches_served % len(self._ip)]
       ip.copy_(torch.from_numpy((self.indptr[lo:hi + 1] - a).astype("int32")))
@@ -178,7 +276,7 @@ class HostTrainPipeline:
       eng, B = self.eng, self.batch
       dev, G = eng.device, eng.cfg.n_genes
       self.slots[s] = dict(
-          x=None, x16=None, csr=None,
+          x=None, x16=None, csr=None, csr8=None,
           eps=torch.zeros((B, eng.cfg.n_latent), device=dev),
           terms=torch.empty((5, B), device=dev), loss=torch.empty((1,), device=dev),
           filled=torch.cuda.Event(), consumed=torch.cuda.Event())
@@ -196,6 +294,8 @@ class HostTrainPipeline:
         # is used as it arrived, and the step's streaming kernels widen the counts themselves (sisua_train_step_gather_u16)
         if fmt == "csr":
           eng.unpack_counts_csr(*sl["csr"], sl["x16"])
+        elif fmt == "csr8":
+          eng.unpack_counts_csr8(*sl["csr8"], sl["x16"])
         x_dev = sl["x"] if fmt == "f32" else sl["x16"]
         # eps from the host when one is shipped (tests), otherwise Philox noise drawn in-kernel
         eng.train_step(x_dev, eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
@@ -219,11 +319,14 @@ class HostTrainPipeline:
     """Enqueue one train step; returns the pinned host tensor that will hold the loss once the stream has drained
     (read it after `flush`; it is reused `depth` steps later)."""
     eng = self.eng
+    is_csr8 = isinstance(x_host, Csr8Batch)
     is_csr = isinstance(x_host, CsrBatch)
-    rows = x_host.rows if is_csr else x_host.shape[0]
+    rows = x_host.rows if (is_csr or is_csr8) else x_host.shape[0]
     graphable = (self.use_graph and not host_extras and rows == self.batch and
                  eng.cfg.model_kind in (0, 2) and eng.cfg.n_proteins == 0)
     if not graphable:
+      if is_csr8:
+        raise ValueError("packed CSR minibatches are only consumed by the CUDA-graph path (plain VAE / DCA, full batches)")
       out = self.host_loss[self.i % len(self.host_loss)]
       self.i += 1
       self.last_loss_dev = None
@@ -238,22 +341,39 @@ class HostTrainPipeline:
     s = self.i % self.depth
     self.i += 1
     sl = self._slot(s)
-    fmt = "csr" if is_csr else ("u16" if x_host.dtype in (torch.int16, torch.uint16) else "f32")
+    fmt = "csr8" if is_csr8 else ("csr" if is_csr else ("u16" if x_host.dtype in (torch.int16, torch.uint16) else "f32"))
+    if fmt == "csr8" and sl.get("csr8") is None:      # worst-case capacities: the graph bakes the addresses in
+      cap = self.batch * eng.cfg.n_genes
+      i32 = lambda n: torch.zeros(n, device=eng.device, dtype=torch.int32)
+      i16 = lambda n: torch.zeros(n, device=eng.device, dtype=torch.int16)
+      sl["csr8"] = (i32(self.batch + 1), i32(self.batch + 1), i16(cap + cap // 255 + 8), i16(cap + 8))
     if fmt == "csr" and sl["csr"] is None:      # worst-case capacity: the graph bakes the addresses in
       cap = self.batch * eng.cfg.n_genes
       sl["csr"] = (torch.zeros(self.batch + 1, device=eng.device, dtype=torch.int32),
                    torch.zeros(cap, device=eng.device, dtype=torch.int16), torch.zeros(cap, device=eng.device, dtype=torch.int16))
     if fmt == "f32" and sl["x"] is None:
       sl["x"] = torch.empty((self.batch, eng.cfg.n_genes), device=eng.device)
-    if fmt in ("u16", "csr") and sl["x16"] is None:
+    if fmt in ("u16", "csr", "csr8") and sl["x16"] is None:
       sl["x16"] = torch.zeros((self.batch, eng.cfg.n_genes), device=eng.device, dtype=torch.int16)
     graph, graph_opt = self._graph(s, fmt, lr, clipnorm, world, allreduce is not None, seed, eps_host is not None, peer is not None)
     if eng.step_count != step - 1:             # the graph follows the device-side step counter (dropout masks, Adam t)
       eng.reset_step_counter(step - 1)
     main = torch.cuda.current_stream(eng.device)
+    # Host-side throttle: the H2D copies of this slot's previous use must have been DONE before more batches are prepared.
+    # The dataset hands out its rebased row-pointer arrays from a small pinned ring; without the wait a host running many
+    # steps ahead of the copy engine would overwrite a ring entry whose DMA has not happened yet.  (`depth` steps of
+    # run-ahead remain, which is what hides the host's per-step cost.)
+    if sl.get("used"):
+      sl["filled"].synchronize()
+    sl["used"] = True
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(sl["consumed"])
-      if fmt == "csr":
+      if fmt == "csr8":
+        ip, bp, ee, bb = sl["csr8"]
+        ip.copy_(x_host.indptr, non_blocking=True); bp.copy_(x_host.big_ptr, non_blocking=True)
+        ee[:x_host.ents.numel()].copy_(x_host.ents, non_blocking=True)
+        bb[:x_host.big.numel()].copy_(x_host.big, non_blocking=True)
+      elif fmt == "csr":
         nnz = x_host.cols.numel()
         ip, cc, vv = sl["csr"]
         ip.copy_(x_host.indptr, non_blocking=True)

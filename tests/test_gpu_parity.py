@@ -264,6 +264,19 @@ def test_host_count_formats_roundtrip():
   assert torch.equal(dst.cpu(), torch.from_numpy(X))
   assert c.nbytes < X.nbytes
   assert quantize_counts(X + 0.5).dtype == torch.float32     # non-integer data stays fp32
+  # 16-bit destinations (what the step reads directly) and the packed 2-bytes-per-non-zero form
+  from sisua_b200.pipeline import Csr8Batch
+  X2 = X.copy()
+  X2[3, :] = 0; X2[3, 557] = 7; X2[4, :] = 0; X2[5, 0] = 255; X2[5, 1] = 254; X2[5, 300] = 65535; X2[6, :] = 0; X2[6, 255] = 1; X2[6, 510] = 2
+  d16 = torch.full((100, 558), -1, device="cuda", dtype=torch.int16)
+  c2 = CsrBatch(X2)
+  eng.unpack_counts_csr(c2.indptr.cuda(), c2.cols.cuda(), c2.vals.cuda(), d16)
+  np.testing.assert_array_equal(d16.cpu().numpy().view(np.uint16).astype(np.float32), X2)
+  d16.fill_(-1)
+  c8 = Csr8Batch(X2)
+  eng.unpack_counts_csr8(c8.indptr.cuda(), c8.big_ptr.cuda(), c8.ents.cuda(), c8.big.cuda(), d16)
+  np.testing.assert_array_equal(d16.cpu().numpy().view(np.uint16).astype(np.float32), X2)
+  assert c8.nbytes < 0.6 * c2.nbytes
   eng.close()
 
 
