@@ -10,6 +10,9 @@ import torch
 from .engine import Engine
 
 
+kRing = 8      # pinned row-pointer buffers a HostDataset cycles through; HostTrainPipeline keeps at most `depth` (< kRing) steps in flight
+
+
 def _pin(t: torch.Tensor) -> torch.Tensor:
   """Page-locked when a CUDA device is present (asynchronous H2D); plain host memory otherwise, so the format helpers
   also work on a machine without a GPU (tests, data preparation)."""
@@ -166,8 +169,8 @@ class HostDataset:
       self.indptr, self.big_ptr = np.concatenate(ips), np.concatenate(bps)
       self.ents = _pin(torch.from_numpy(np.concatenate(ents_l).view(np.int16)))
       self.big = _pin(torch.from_numpy(np.concatenate(big_l + [np.zeros(1, np.uint16)]).view(np.int16)))
-      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
-      self._bp = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
+      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(kRing)]
+      self._bp = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(kRing)]
     elif integer:
       counts = np.zeros(N + 1, dtype=np.int64)
       cols_l, vals_l = [], []
@@ -179,7 +182,7 @@ class HostDataset:
       self.indptr = np.cumsum(counts)
       self.cols = _pin(torch.from_numpy(np.concatenate(cols_l).view(np.int16)))
       self.vals = _pin(torch.from_numpy(np.concatenate(vals_l).view(np.int16)))
-      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(4)]
+      self._ip = [_pin(torch.empty(self.B + 1, dtype=torch.int32)) for _ in range(kRing)]
     else:
       self.dense = _pin(torch.from_numpy(np.ascontiguousarray(X[order], dtype=np.float32)))
     self.y = _pin(torch.from_numpy(np.ascontiguousarray(data.Y[order], dtype=np.float32))) if (with_y and data.Y is not None) else None
@@ -259,6 +262,7 @@ class HostTrainPipeline:
   which stages on its own copy stream."""
 
   def __init__(self, eng: Engine, batch: int, depth: int = 2, use_graph: bool = True):
+    assert 1 <= depth < kRing
     self.eng = eng
     self.batch = batch
     self.depth = depth
