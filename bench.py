@@ -212,7 +212,8 @@ def main():
                      "sharding": f"{a.gpus} rank(s), cells sharded; gradient exchange + optimiser: " +
                                  ("one kernel over NVLink peer memory (reduce-scatter, sharded Adam, all-gather)" if a.exchange == "peer"
                                   else "NCCL all-reduce of the flat gradient buffer, then Adam"),
-                     "l2": "inputs larger than L2: each step streams a fresh minibatch of a >= 1 GB resident shard"}}
+                     "l2": "inputs larger than L2: each step streams a fresh minibatch of a >= 1 GB resident shard",
+                     "shuffle": True, "eps": "drawn inside the step (Philox in-kernel)", "resident_storage": a.storage}}
 
   # ------------------------------------------------------------------ reference arm (CPU)
   if a.impl == "reference":
@@ -430,9 +431,10 @@ def main():
     dur_s = per_step[dom] * 1e-3
     achieved = alg_bytes[dom] / dur_s / 1e9
     out = dict(base)
-    out["config"] = dict(out["config"], shuffle=True, eps="philox (in-kernel)", resident_storage=a.storage,
-                         step_entry=("sisua_train_step_gather_u16" if a.storage == "uint16" else "sisua_train_step_gather") +
-                         " + sisua_adam_step (what SingleCellModel.fit issues per step)")
+    # (config is identical on both arms; the entry points are this arm's own business)
+    out["step_entry"] = (("sisua_train_step_gather_u16" if a.storage == "uint16" else "sisua_train_step_gather") +
+                         " + " + ("sisua_adam_step_dp" if (world > 1 and a.exchange == "peer") else "sisua_adam_step") +
+                         " (what SingleCellModel.fit issues per step)")
     out.update({
         "value": value, "ms_per_step": ms / a.steps, "final_loss": final_loss, "parity_at_bench_shape": parity,
         "gemm_mode": {0: "fp32 CUDA-core, un-fused", 1: "tcgen05 fused (3xFP16 compensated forward, fp16 gradient GEMMs)"}[mode],
