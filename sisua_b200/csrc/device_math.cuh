@@ -299,7 +299,7 @@ __device__ __forceinline__ void count_core_fast(const float (&mu)[U], const floa
   }
 }
 
-// scalar fall-back of the pair-wise epilogue mathematics (pair_math.cuh) for counts above 3 / non-integer counts; every
+// scalar fall-back of the pair-wise epilogue mathematics (pair_math.cuh) for negative / NaN inputs (not count data); every
 // lane of the warp calls it together (count_core_fast votes warp-wide)
 namespace pm {
 template <bool ZI, bool GRAD>

@@ -5,9 +5,10 @@
 //        dD    += G . W_out          (gradient wrt the decoder activations, TMEM-resident across gene tiles)
 //        dW_out = G^T . [d | 1]      (weight and bias gradient of the gene tile, flushed with vector reds)
 // Forward products are error-compensated 3xFP16 (d = d1 + d2, w = w1 + w2; d1w1 + d1w2 + d2w1 accumulated in
-// fp32), i.e. fp32-grade logits; the two gradient GEMMs use single fp16 operands (2^-11 relative).
+// fp32), i.e. fp32-grade logits; the two gradient GEMMs take G as one fp16 operand and both halves of W / d.
 // One CTA owns a tile of 128 cells and walks a chunk of 32-gene tiles; roles: 16 epilogue warps (TMEM lane
-// quarter x 8-gene slice), 1 MMA-issuing thread, 1 bulk-copy (TMA) thread streaming pre-packed weight tiles.
+// quarter x 8-gene slice) and a service warpgroup: forward-MMA issuer, bulk-copy (TMA) thread streaming pre-packed weight
+// tiles, gradient-MMA issuer.  The counts arrive as fp32 or (XU16) uint16 and are widened in the epilogue.
 #pragma once
 #include "device_math.cuh"
 #include "kernels_mid.cuh"
