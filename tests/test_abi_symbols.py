@@ -96,3 +96,26 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     assert int(got[cname]) == ctypes.sizeof(st), cname
     for fname, _ in st._fields_:
       assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+
+
+def test_product_never_touches_the_oracle():
+  """The oracle is test infrastructure: no module of the package imports it (comments may cite it), and importing the
+  package does not pull it in."""
+  import ast
+  import pathlib
+  import subprocess
+  import sys
+  root = pathlib.Path(__file__).resolve().parents[1]
+  for path in (root / "sisua_b200").glob("*.py"):
+    tree = ast.parse(path.read_text())
+    for node in ast.walk(tree):
+      names = []
+      if isinstance(node, ast.Import):
+        names = [a.name for a in node.names]
+      elif isinstance(node, ast.ImportFrom):
+        names = [node.module or ""]
+      assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{path.name} imports the oracle"
+  code = "import sys; import sisua_b200.models, sisua_b200.posterior, sisua_b200.pipeline, sisua_b200.streamed; " \
+         "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+  out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(root))
+  assert out.returncode == 0 and out.stdout.strip() == "False", out.stdout + out.stderr
