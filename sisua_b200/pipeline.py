@@ -294,12 +294,10 @@ class HostTrainPipeline:
     if key not in self.graphs:
       eng, sl = self.eng, self._slot(s)
       def fwd_bwd():
-        # integer formats stay 16-bit on the device: CSR is scattered into the slot's uint16 matrix, a dense uint16 batch
-        # is used as it arrived, and the step's streaming kernels widen the counts themselves (sisua_train_step_gather_u16)
-        if fmt == "csr":
-          eng.unpack_counts_csr(*sl["csr"], sl["x16"])
-        elif fmt == "csr8":
-          eng.unpack_counts_csr8(*sl["csr8"], sl["x16"])
+        # integer formats stay 16-bit on the device: CSR was decoded into the slot's uint16 matrix on the COPY stream right
+        # behind its H2D transfer (`step`), i.e. under the kernels of the previous step and off this graph's critical path;
+        # a dense uint16 batch is used as it arrived; the step's streaming kernels widen the counts themselves
+        # (sisua_train_step_gather_u16)
         x_dev = sl["x"] if fmt == "f32" else sl["x16"]
         # eps from the host when one is shipped (tests), otherwise Philox noise drawn in-kernel
         eng.train_step(x_dev, eps_z=sl["eps"] if (with_eps and eng.cfg.model_kind != 2) else None, terms=sl["terms"],
@@ -377,12 +375,14 @@ class HostTrainPipeline:
         ip.copy_(x_host.indptr, non_blocking=True); bp.copy_(x_host.big_ptr, non_blocking=True)
         ee[:x_host.ents.numel()].copy_(x_host.ents, non_blocking=True)
         bb[:x_host.big.numel()].copy_(x_host.big, non_blocking=True)
+        eng.unpack_counts_csr8(ip, bp, ee, bb, sl["x16"])        # decode on the copy stream, behind the transfer
       elif fmt == "csr":
         nnz = x_host.cols.numel()
         ip, cc, vv = sl["csr"]
         ip.copy_(x_host.indptr, non_blocking=True)
         cc[:nnz].copy_(x_host.cols, non_blocking=True)
         vv[:nnz].copy_(x_host.vals, non_blocking=True)
+        eng.unpack_counts_csr(ip, cc, vv, sl["x16"])
       elif fmt == "u16":
         sl["x16"].copy_(x_host.view(torch.int16), non_blocking=True)
       else:
