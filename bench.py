@@ -283,8 +283,23 @@ def main():
   px = reducer = None
   if world > 1:
     if a.exchange == "peer":
-      px = PeerExchange(eng)          # moves the flat parameter / gradient buffers into symmetric (peer-mapped) memory
-    else:
+      # moves the flat parameter / gradient buffers into symmetric (peer-mapped) memory.  If any rank cannot set it up
+      # (no P2P between the visible GPUs, symmetric memory unavailable) every rank falls back to the NCCL arm together
+      # and the JSON line says so -- the run must not die for it.
+      err = None
+      try:
+        px = PeerExchange(eng)
+      except Exception as e:      # noqa: BLE001
+        err, px = f"{type(e).__name__}: {e}", None
+      ok = torch.tensor([0.0 if err else 1.0], device=dev)
+      dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+      if ok.item() < 1.0:
+        if rank == 0:
+          print(f"[bench] peer-memory exchange unavailable ({err or 'on another rank'}); using the NCCL all-reduce arm", file=sys.stderr)
+        px, a.exchange = None, "nccl"
+        base["config"]["sharding"] = (f"{a.gpus} rank(s), cells sharded; gradient exchange + optimiser: NCCL all-reduce of the flat gradient "
+                                      "buffer, then Adam (peer-memory exchange was requested but could not be set up)")
+    if px is None:
       reducer = OverlappedAllReduce(eng)
     broadcast_parameters(eng.params, eng.bn_moving)
 

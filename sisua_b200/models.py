@@ -472,7 +472,19 @@ class SingleCellModel:
     if world > 1 and dp_exchange == "peer":
       px = getattr(self, "_peer_exchange", None)
       if px is None:
-        px = self._peer_exchange = DP.PeerExchange(eng)    # moves params / grads into symmetric memory
+        # moves params / grads into symmetric memory; if ANY rank cannot (no P2P between the GPUs, no symmetric memory),
+        # all ranks fall back to the NCCL all-reduce together -- a rank on its own path would dead-lock the others
+        err = None
+        try:
+          px = DP.PeerExchange(eng)
+        except Exception as e:      # noqa: BLE001
+          err, px = f"{type(e).__name__}: {e}", None
+        ok = torch.tensor([0.0 if err else 1.0], device=eng.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0:
+          warnings.warn(f"peer-memory gradient exchange unavailable ({err or 'on another rank'}); using the NCCL all-reduce")
+          px = None
+        self._peer_exchange = px
     if world > 1 and dp_shard:
       b0, e0 = DP.shard_range(len(train), rank, world)
       n_common = len(train) // world                      # every rank takes the same number of steps
